@@ -1,0 +1,114 @@
+"""Build and load libcaf_b200.so (the C ABI in include/caf_b200.h) with ctypes.
+
+The library is compiled IN-TREE by nvcc for sm_100a only; there is no other backend and no CPU
+fallback: `load()` raises if the shared object is missing, and handle creation fails loudly when no
+sm_100 GPU is visible.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import shutil
+import subprocess
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_PKG)
+CSRC = os.path.join(_PKG, "csrc")
+SO_PATH = os.path.join(_PKG, "libcaf_b200.so")
+HEADER = os.path.join(_ROOT, "include", "caf_b200.h")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-lineinfo", "-std=c++17",
+    "-Xcompiler", "-fPIC", "-shared",
+]
+
+
+def _sources():
+    return [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh"))] + [HEADER]
+
+
+def needs_build() -> bool:
+    if not os.path.exists(SO_PATH):
+        return True
+    so_m = os.path.getmtime(SO_PATH)
+    return any(os.path.getmtime(s) > so_m for s in _sources())
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """nvcc -gencode arch=compute_100a,code=sm_100a ... -> caf_cookoff_b200/libcaf_b200.so"""
+    if not force and not needs_build():
+        return SO_PATH
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        raise RuntimeError("nvcc not found: cannot build libcaf_b200.so (no prebuilt fallback exists)")
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + [
+        "-o", SO_PATH, os.path.join(CSRC, "caf_b200.cu")]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    if verbose:
+        print(res.stderr)
+    return SO_PATH
+
+
+class Peak(C.Structure):
+    """caf_b200_peak"""
+    _fields_ = [("value", C.c_double), ("freq_hz", C.c_double),
+                ("doppler_idx", C.c_uint64), ("delay_idx", C.c_uint64)]
+
+
+# every symbol include/caf_b200.h declares: name -> (restype, argtypes)
+_vp, _sz, _u32, _dbl, _int = C.c_void_p, C.c_size_t, C.c_uint32, C.c_double, C.c_int
+_PK = C.POINTER(Peak)
+_batch = [_vp, _vp, _vp, _sz, _sz, _vp, _sz, _u32, _vp, _vp, _vp, _vp]
+_surf = [_vp, _vp, _vp, _sz, _vp, _sz, _u32, _vp, _vp, _vp, _vp]
+_peak = [_vp, _vp, _vp, _sz, _vp, _sz, _u32, _vp]
+_shift = [_vp, _vp, _sz, _dbl, _u32, _vp]
+_xcor = [_vp, _vp, _vp, _sz, _vp]
+SYMBOLS = {
+    "caf_b200_create": (_int, [_int, C.POINTER(_vp)]),
+    "caf_b200_create_on_stream": (_int, [_int, _vp, C.POINTER(_vp)]),
+    "caf_b200_destroy": (_int, [_vp]),
+    "caf_b200_sync": (_int, [_vp]),
+    "caf_b200_last_error": (C.c_char_p, []),
+    "caf_b200_version": (C.c_char_p, []),
+    "caf_b200_launch_count": (C.c_uint64, [_vp]),
+    "caf_b200_host_alloc": (_int, [C.POINTER(_vp), _sz]),
+    "caf_b200_host_free": (_int, [_vp]),
+    "caf_b200_apply_freq_shift_f64": (_int, _shift),
+    "caf_b200_apply_freq_shift_f32": (_int, _shift),
+    "caf_b200_apply_shift_f64": (_int, _shift),
+    "caf_b200_apply_shift_f32": (_int, _shift),
+    "caf_b200_xcor_f64": (_int, _xcor),
+    "caf_b200_xcor_f32": (_int, _xcor),
+    "caf_b200_surface_f64": (_int, _surf),
+    "caf_b200_surface_f32": (_int, _surf),
+    "caf_b200_peak_f64": (_int, _peak),
+    "caf_b200_peak_f32": (_int, _peak),
+    "caf_b200_batch_f64": (_int, _batch),
+    "caf_b200_batch_f32": (_int, _batch),
+    "caf_b200_batch_f64_dev": (_int, _batch),
+    "caf_b200_batch_f32_dev": (_int, _batch),
+    "caf_b200_peak_pack": (None, [_PK, C.c_uint64, C.POINTER(C.c_uint64)]),
+    "caf_b200_peak_resolve": (None, [C.POINTER(C.c_uint64), _sz, _PK]),
+}
+
+_lib = None
+
+
+def load():
+    """dlopen the in-tree library and type every entry point.  Raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(SO_PATH):
+            raise RuntimeError(
+                f"{SO_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a).  There is no CPU fallback.")
+        lib = C.CDLL(SO_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(lib, name)   # AttributeError if the header and the library ever disagree
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib

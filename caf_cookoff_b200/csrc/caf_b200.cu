@@ -1,0 +1,509 @@
+// caf_b200.cu — C ABI (include/caf_b200.h) over the sm_100a kernels in caf_kernels.cuh.
+//
+// Host-side responsibilities only: argument checks that mirror the reference's panics
+// (/root/reference/caf_rust/src/caf/xcor_rustfft.rs:54-55), workspace management, H2D/D2H,
+// kernel launches on the handle's stream.  No CPU compute path exists here: without an
+// sm_100 device create() fails (CAF_B200_ENODEVICE).
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/caf_b200.h"
+#include "caf_kernels.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            char b_[512];                                                                          \
+            snprintf(b_, sizeof b_, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            return fail(CAF_B200_ECUDA, b_);                                                       \
+        }                                                                                          \
+    } while (0)
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) { cudaFree(p); p = nullptr; cap = 0; }
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+template <typename T> struct Tables { caf::cx<T>* tw1 = nullptr; caf::cx<T>* tw2 = nullptr; caf::cx<T>* g = nullptr; };
+
+}  // namespace
+
+struct caf_b200_handle_s {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    unsigned long long launches = 0;
+    Tables<double> td;
+    Tables<float> tf;
+    int occ_d = 1, occ_f = 1;   // resident CTAs per SM of the surface kernel
+    DevBuf needle, hay, hperm, freqs, surface, rowval, rowidx, peaks, scratch;
+    void* h_peaks = nullptr;    // pinned staging for peaks
+    size_t h_peaks_cap = 0;
+};
+
+namespace {
+
+template <typename T> Tables<T>& tables(caf_b200_handle h);
+template <> Tables<double>& tables<double>(caf_b200_handle h) { return h->td; }
+template <> Tables<float>& tables<float>(caf_b200_handle h) { return h->tf; }
+
+template <typename T> size_t smem_bytes() {
+    return sizeof(caf::cx<T>) * (2 * caf::kL0 + 2 * 2 * 48) + 16 * sizeof(unsigned long long) + 16 * sizeof(T);
+}
+
+template <typename T>
+cudaError_t upload_tables(Tables<T>& t, cudaStream_t s) {
+    using C = caf::cx<T>;
+    const long double TWO_PI = 6.283185307179586476925286766559005768L;
+    std::vector<C> tw1(16 * 256), tw2(256), g(4096);
+    for (int k = 0; k < 16; ++k)
+        for (int tt = 0; tt < 256; ++tt) {
+            long double a = -TWO_PI * (long double)((k * tt) % 4096) / 4096.0L;
+            tw1[k * 256 + tt].x = (T)cosl(a); tw1[k * 256 + tt].y = (T)sinl(a);
+        }
+    for (int a_ = 0; a_ < 16; ++a_)
+        for (int b_ = 0; b_ < 16; ++b_) {
+            long double a = -TWO_PI * (long double)((a_ * b_) % 256) / 256.0L;
+            tw2[a_ * 16 + b_].x = (T)cosl(a); tw2[a_ * 16 + b_].y = (T)sinl(a);
+        }
+    for (int n = 0; n < 4096; ++n) {
+        long double a = TWO_PI * (long double)n / 8192.0L;
+        g[n].x = (T)cosl(a); g[n].y = (T)sinl(a);
+    }
+    cudaError_t e;
+    if ((e = cudaMalloc(&t.tw1, sizeof(C) * tw1.size())) != cudaSuccess) return e;
+    if ((e = cudaMalloc(&t.tw2, sizeof(C) * tw2.size())) != cudaSuccess) return e;
+    if ((e = cudaMalloc(&t.g, sizeof(C) * g.size())) != cudaSuccess) return e;
+    if ((e = cudaMemcpyAsync(t.tw1, tw1.data(), sizeof(C) * tw1.size(), cudaMemcpyHostToDevice, s)) != cudaSuccess) return e;
+    if ((e = cudaMemcpyAsync(t.tw2, tw2.data(), sizeof(C) * tw2.size(), cudaMemcpyHostToDevice, s)) != cudaSuccess) return e;
+    if ((e = cudaMemcpyAsync(t.g, g.data(), sizeof(C) * g.size(), cudaMemcpyHostToDevice, s)) != cudaSuccess) return e;
+    return cudaStreamSynchronize(s);   // the host vectors die at scope exit
+}
+
+template <typename T, int MODE>
+cudaError_t configure_kernel(int* occ_out) {
+    auto k = caf::caf_rows_kernel<T, MODE>;
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<T>());
+    if (e != cudaSuccess) return e;
+    if (occ_out) {
+        int occ = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, caf::kThreads, smem_bytes<T>());
+        if (e != cudaSuccess) return e;
+        *occ_out = occ < 1 ? 1 : occ;
+    }
+    return cudaSuccess;
+}
+
+template <typename T>
+cudaError_t configure_all(int* occ) {
+    cudaError_t e;
+    if ((e = configure_kernel<T, caf::kSurface>(occ)) != cudaSuccess) return e;
+    if ((e = configure_kernel<T, caf::kSpectrum>(nullptr)) != cudaSuccess) return e;
+    if ((e = configure_kernel<T, caf::kSpectrumFull>(nullptr)) != cudaSuccess) return e;
+    if ((e = configure_kernel<T, caf::kXcorFull>(nullptr)) != cudaSuccess) return e;
+    if ((e = configure_kernel<T, caf::kXcorHalf>(nullptr)) != cudaSuccess) return e;
+    return cudaSuccess;
+}
+
+template <typename T, int MODE>
+cudaError_t launch_rows(caf_b200_handle h, const caf::RowArgs<T>& a, long long n_items) {
+    if (n_items <= 0) return cudaSuccess;
+    const int occ = std::is_same<T, double>::value ? h->occ_d : h->occ_f;
+    long long cap = (long long)h->sm_count * occ;
+    int grid = (int)(n_items < cap ? n_items : cap);
+    caf::caf_rows_kernel<T, MODE><<<grid, caf::kThreads, smem_bytes<T>(), h->stream>>>(a);
+    h->launches++;
+    return cudaGetLastError();
+}
+
+template <typename T>
+caf::RowArgs<T> base_args(caf_b200_handle h) {
+    caf::RowArgs<T> a{};
+    Tables<T>& t = tables<T>(h);
+    a.tw1 = t.tw1; a.tw2 = t.tw2; a.g = t.g;
+    a.dt = 0.0; a.L = 0; a.D = 1; a.P = 1;
+    return a;
+}
+
+// The whole device-side pipeline for p pairs; every pointer is device memory.
+template <typename T>
+int run_batch_dev(caf_b200_handle h, const caf::cx<T>* needles, const caf::cx<T>* hays, size_t p, size_t l,
+                  const double* freqs, size_t d, uint32_t fs, T* surface, T* rowval,
+                  unsigned long long* rowidx, caf::PeakOut* peaks) {
+    using namespace caf;
+    if (p == 0) return CAF_B200_OK;
+    if (l == 0 || d == 0) {
+        // empty rows: xcor_peak_idx = 0, xcor_peak_val = 0.0 (mod.rs:143-144); find_peak -> dummy row
+        if (d && rowval) CK(cudaMemsetAsync(rowval, 0, sizeof(T) * p * d, h->stream));
+        if (d && rowidx) CK(cudaMemsetAsync(rowidx, 0, sizeof(unsigned long long) * p * d, h->stream));
+        if (peaks) {
+            std::vector<PeakOut> z(p);
+            for (auto& q : z) { q.value = 0.0; q.freq_hz = 0.0; q.doppler_idx = ~0ull; q.delay_idx = 0; }
+            CK(cudaMemcpyAsync(peaks, z.data(), sizeof(PeakOut) * p, cudaMemcpyHostToDevice, h->stream));
+            CK(cudaStreamSynchronize(h->stream));
+        }
+        return CAF_B200_OK;
+    }
+    CK(h->hperm.ensure(sizeof(cx<T>) * kM * p));
+    // row peaks are needed internally for find_peak even when the caller does not want them
+    T* rv = rowval; unsigned long long* ri = rowidx;
+    if (peaks && (!rv || !ri)) {
+        CK(h->scratch.ensure((sizeof(T) + sizeof(unsigned long long)) * p * d + 16));
+        ri = reinterpret_cast<unsigned long long*>(h->scratch.p);
+        rv = reinterpret_cast<T*>(ri + p * d);
+    }
+    RowArgs<T> a = base_args<T>(h);
+    a.hperm = reinterpret_cast<cx<T>*>(h->hperm.p);
+    a.L = (int)l; a.P = (int)p;
+    // K0: H = FFT(haystack)/n once per pair (the reference recomputes it per row, xcor_rustfft.rs:58-59)
+    a.in = hays; a.D = 1;
+    CK((launch_rows<T, kSpectrum>(h, a, (long long)p)));
+    // K1: fused shift -> FFT -> xH -> IFFT -> |.|^2 -> row argmax
+    a.in = needles; a.D = (int)d; a.freqs = freqs; a.dt = 1.0 / (double)fs;
+    a.out = surface; a.row_peak_val = rv; a.row_peak_idx = ri;
+    CK((launch_rows<T, kSurface>(h, a, (long long)p * (long long)d)));
+    // K3: find_peak per pair
+    if (peaks) {
+        caf_peak_kernel<T><<<(unsigned)p, 256, 0, h->stream>>>(rv, ri, freqs, (int)d, peaks);
+        h->launches++;
+        CK(cudaGetLastError());
+    }
+    return CAF_B200_OK;
+}
+
+void to_public(const caf::PeakOut& s, caf_b200_peak* o) {
+    o->value = s.value; o->freq_hz = s.freq_hz; o->doppler_idx = s.doppler_idx; o->delay_idx = s.delay_idx;
+}
+
+template <typename T>
+int check_common(caf_b200_handle h, const void* needle, const void* hay, size_t p, size_t l, const double* freqs,
+                 size_t d, uint32_t fs) {
+    if (!h) return fail(CAF_B200_EINVAL, "null handle");
+    if (p && l && (!needle || !hay)) return fail(CAF_B200_EINVAL, "null needle/haystack");
+    if (d && !freqs) return fail(CAF_B200_EINVAL, "null freqs_hz");
+    if (fs == 0) return fail(CAF_B200_EINVAL, "fs must be non-zero");
+    if (l > (size_t)caf::kL0)
+        return fail(CAF_B200_EUNSUPPORTED, "l > 4096: rows longer than 8192 delay cells are not built yet");
+    if (p > (1u << 30) || d > (1u << 30) || (double)p * (double)d > 2.0e9)
+        return fail(CAF_B200_EUNSUPPORTED, "p*d too large");
+    return CAF_B200_OK;
+}
+
+// Host-pointer batch: stage in, run, stage out.
+template <typename T>
+int run_batch_host(caf_b200_handle h, const caf::cx<T>* needles, const caf::cx<T>* hays, size_t p, size_t l,
+                   const double* freqs, size_t d, uint32_t fs, T* surface, T* rowval, uint64_t* rowidx,
+                   caf_b200_peak* peaks) {
+    using namespace caf;
+    int rc = check_common<T>(h, needles, hays, p, l, freqs, d, fs);
+    if (rc) return rc;
+    CK(cudaSetDevice(h->device));
+    if (p == 0) return CAF_B200_OK;
+    const size_t n = 2 * l, rows = p * d;
+    cudaStream_t s = h->stream;
+    if (l) {
+        CK(h->needle.ensure(sizeof(cx<T>) * p * l));
+        CK(h->hay.ensure(sizeof(cx<T>) * p * l));
+        CK(cudaMemcpyAsync(h->needle.p, needles, sizeof(cx<T>) * p * l, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(h->hay.p, hays, sizeof(cx<T>) * p * l, cudaMemcpyHostToDevice, s));
+    }
+    if (d) {
+        CK(h->freqs.ensure(sizeof(double) * d));
+        CK(cudaMemcpyAsync(h->freqs.p, freqs, sizeof(double) * d, cudaMemcpyHostToDevice, s));
+    }
+    T* d_surface = nullptr;
+    if (surface && rows && n) { CK(h->surface.ensure(sizeof(T) * rows * n)); d_surface = (T*)h->surface.p; }
+    T* d_rv = nullptr; unsigned long long* d_ri = nullptr;
+    if (rows && (rowval || rowidx || peaks)) {
+        CK(h->rowval.ensure(sizeof(T) * rows)); CK(h->rowidx.ensure(sizeof(unsigned long long) * rows));
+        d_rv = (T*)h->rowval.p; d_ri = (unsigned long long*)h->rowidx.p;
+    }
+    PeakOut* d_pk = nullptr;
+    if (peaks) {
+        CK(h->peaks.ensure(sizeof(PeakOut) * p)); d_pk = (PeakOut*)h->peaks.p;
+        if (h->h_peaks_cap < sizeof(PeakOut) * p) {
+            if (h->h_peaks) cudaFreeHost(h->h_peaks);
+            h->h_peaks = nullptr; h->h_peaks_cap = 0;
+            CK(cudaMallocHost(&h->h_peaks, sizeof(PeakOut) * p));
+            h->h_peaks_cap = sizeof(PeakOut) * p;
+        }
+    }
+    rc = run_batch_dev<T>(h, (const cx<T>*)h->needle.p, (const cx<T>*)h->hay.p, p, l, (const double*)h->freqs.p, d,
+                          fs, d_surface, d_rv, d_ri, d_pk);
+    if (rc) return rc;
+    if (d_surface) CK(cudaMemcpyAsync(surface, d_surface, sizeof(T) * rows * n, cudaMemcpyDeviceToHost, s));
+    if (rowval && rows) CK(cudaMemcpyAsync(rowval, d_rv, sizeof(T) * rows, cudaMemcpyDeviceToHost, s));
+    if (rowidx && rows) CK(cudaMemcpyAsync(rowidx, d_ri, sizeof(uint64_t) * rows, cudaMemcpyDeviceToHost, s));
+    if (peaks) CK(cudaMemcpyAsync(h->h_peaks, d_pk, sizeof(PeakOut) * p, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (peaks)
+        for (size_t i = 0; i < p; ++i) to_public(reinterpret_cast<PeakOut*>(h->h_peaks)[i], &peaks[i]);
+    return CAF_B200_OK;
+}
+
+template <typename T>
+int run_shift(caf_b200_handle h, const caf::cx<T>* in, size_t n, double f, uint32_t fs, caf::cx<T>* out) {
+    using namespace caf;
+    if (!h) return fail(CAF_B200_EINVAL, "null handle");
+    if (n && (!in || !out)) return fail(CAF_B200_EINVAL, "null samples");
+    if (fs == 0) return fail(CAF_B200_EINVAL, "fs must be non-zero");
+    if (n == 0) return CAF_B200_OK;
+    CK(cudaSetDevice(h->device));
+    CK(h->needle.ensure(sizeof(cx<T>) * n));
+    CK(h->scratch.ensure(sizeof(cx<T>) * n));
+    cudaStream_t s = h->stream;
+    CK(cudaMemcpyAsync(h->needle.p, in, sizeof(cx<T>) * n, cudaMemcpyHostToDevice, s));
+    const double dt = 1.0 / (double)fs;   // mod.rs:53
+    long long blocks = (long long)((n + 255) / 256);
+    if (blocks > 4 * h->sm_count) blocks = 4 * h->sm_count;
+    caf_apply_shift_kernel<T><<<(unsigned)blocks, 256, 0, s>>>((const cx<T>*)h->needle.p, (cx<T>*)h->scratch.p,
+                                                              (long long)n, f * dt);
+    h->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, h->scratch.p, sizeof(cx<T>) * n, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return CAF_B200_OK;
+}
+
+template <typename T>
+int run_xcor(caf_b200_handle h, const caf::cx<T>* a_, const caf::cx<T>* b_, size_t n, caf::cx<T>* out) {
+    using namespace caf;
+    if (!h) return fail(CAF_B200_EINVAL, "null handle");
+    if (n && (!a_ || !b_ || !out)) return fail(CAF_B200_EINVAL, "null operand");
+    if (n == 0) return CAF_B200_OK;
+    if (!(n == (size_t)kM || n <= (size_t)kL0))
+        return fail(CAF_B200_EUNSUPPORTED, "xcor: n must be 8192 or <= 4096 in this build");
+    CK(cudaSetDevice(h->device));
+    cudaStream_t s = h->stream;
+    CK(h->needle.ensure(sizeof(cx<T>) * n)); CK(h->hay.ensure(sizeof(cx<T>) * n));
+    CK(h->hperm.ensure(sizeof(cx<T>) * kM)); CK(h->scratch.ensure(sizeof(cx<T>) * (kM + n)));
+    CK(cudaMemcpyAsync(h->hay.p, a_, sizeof(cx<T>) * n, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(h->needle.p, b_, sizeof(cx<T>) * n, cudaMemcpyHostToDevice, s));
+    RowArgs<T> a = base_args<T>(h);
+    a.hperm = (cx<T>*)h->hperm.p; a.P = 1; a.D = 1; a.L = (int)n;
+    cx<T>* y = (cx<T>*)h->scratch.p;
+    cx<T>* res = y;
+    if (n == (size_t)kM) {
+        a.in = (const cx<T>*)h->hay.p;
+        CK((launch_rows<T, kSpectrumFull>(h, a, 1)));
+        a.in = (const cx<T>*)h->needle.p; a.out = y;
+        CK((launch_rows<T, kXcorFull>(h, a, 1)));
+    } else {
+        a.in = (const cx<T>*)h->hay.p;
+        CK((launch_rows<T, kSpectrum>(h, a, 1)));
+        a.in = (const cx<T>*)h->needle.p; a.out = y;
+        CK((launch_rows<T, kXcorHalf>(h, a, 1)));
+        res = y + kM;
+        caf_fold_circular_kernel<T><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(y, res, (int)n);
+        h->launches++;
+        CK(cudaGetLastError());
+    }
+    CK(cudaMemcpyAsync(out, res, sizeof(cx<T>) * n, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return CAF_B200_OK;
+}
+
+}  // namespace
+
+// ================================================ C ABI ================================================
+extern "C" {
+
+const char* caf_b200_last_error(void) { return g_err.c_str(); }
+const char* caf_b200_version(void) { return "caf_b200 0.1 (sm_100a)"; }
+
+int caf_b200_create_on_stream(int device, void* cuda_stream, caf_b200_handle* out) {
+    if (!out) return fail(CAF_B200_EINVAL, "null out");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(CAF_B200_ENODEVICE, std::string("no CUDA device (there is no CPU fallback): ") +
+                                            (e != cudaSuccess ? cudaGetErrorString(e) : "device count 0"));
+    if (device < 0 || device >= ndev) return fail(CAF_B200_EINVAL, "device index out of range");
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(CAF_B200_ENODEVICE, std::string("device is sm_") + std::to_string(prop.major * 10 + prop.minor) +
+                                            ", this library carries sm_100a code only (no fallback)");
+    CK(cudaSetDevice(device));
+    caf_b200_handle h = new (std::nothrow) caf_b200_handle_s();
+    if (!h) return fail(CAF_B200_EINVAL, "out of host memory");
+    h->device = device;
+    h->sm_count = prop.multiProcessorCount;
+    if (cuda_stream) { h->stream = (cudaStream_t)cuda_stream; h->own_stream = false; }
+    else {
+        e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess) { delete h; return fail(CAF_B200_ECUDA, cudaGetErrorString(e)); }
+        h->own_stream = true;
+    }
+    if ((e = upload_tables<double>(h->td, h->stream)) != cudaSuccess ||
+        (e = upload_tables<float>(h->tf, h->stream)) != cudaSuccess ||
+        (e = configure_all<double>(&h->occ_d)) != cudaSuccess ||
+        (e = configure_all<float>(&h->occ_f)) != cudaSuccess) {
+        std::string m = std::string("handle setup failed: ") + cudaGetErrorString(e);
+        caf_b200_destroy(h);
+        return fail(CAF_B200_ECUDA, m);
+    }
+    *out = h;
+    return CAF_B200_OK;
+}
+
+int caf_b200_create(int device, caf_b200_handle* out) { return caf_b200_create_on_stream(device, nullptr, out); }
+
+int caf_b200_destroy(caf_b200_handle h) {
+    if (!h) return CAF_B200_OK;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    for (DevBuf* b : {&h->needle, &h->hay, &h->hperm, &h->freqs, &h->surface, &h->rowval, &h->rowidx, &h->peaks, &h->scratch})
+        b->release();
+    for (void* q : {(void*)h->td.tw1, (void*)h->td.tw2, (void*)h->td.g, (void*)h->tf.tw1, (void*)h->tf.tw2, (void*)h->tf.g})
+        if (q) cudaFree(q);
+    if (h->h_peaks) cudaFreeHost(h->h_peaks);
+    if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return CAF_B200_OK;
+}
+
+int caf_b200_sync(caf_b200_handle h) {
+    if (!h) return fail(CAF_B200_EINVAL, "null handle");
+    CK(cudaStreamSynchronize(h->stream));
+    return CAF_B200_OK;
+}
+
+uint64_t caf_b200_launch_count(caf_b200_handle h) { return h ? h->launches : 0; }
+
+int caf_b200_host_alloc(void** out, size_t bytes) {
+    if (!out) return fail(CAF_B200_EINVAL, "null out");
+    *out = nullptr;
+    if (bytes == 0) return CAF_B200_OK;
+    CK(cudaMallocHost(out, bytes));
+    return CAF_B200_OK;
+}
+int caf_b200_host_free(void* p) {
+    if (p) CK(cudaFreeHost(p));
+    return CAF_B200_OK;
+}
+
+int caf_b200_apply_freq_shift_f64(caf_b200_handle h, const caf_c128* in, size_t n, double f, uint32_t fs, caf_c128* out) {
+    return run_shift<double>(h, (const double2*)in, n, f, fs, (double2*)out);
+}
+int caf_b200_apply_freq_shift_f32(caf_b200_handle h, const caf_c64* in, size_t n, double f, uint32_t fs, caf_c64* out) {
+    return run_shift<float>(h, (const float2*)in, n, f, fs, (float2*)out);
+}
+int caf_b200_apply_shift_f64(caf_b200_handle h, const caf_c128* in, size_t n, double f, uint32_t fs, caf_c128* out) {
+    return caf_b200_apply_freq_shift_f64(h, in, n, f, fs, out);
+}
+int caf_b200_apply_shift_f32(caf_b200_handle h, const caf_c64* in, size_t n, double f, uint32_t fs, caf_c64* out) {
+    return caf_b200_apply_freq_shift_f32(h, in, n, f, fs, out);
+}
+
+int caf_b200_xcor_f64(caf_b200_handle h, const caf_c128* a, const caf_c128* b, size_t n, caf_c128* out) {
+    return run_xcor<double>(h, (const double2*)a, (const double2*)b, n, (double2*)out);
+}
+int caf_b200_xcor_f32(caf_b200_handle h, const caf_c64* a, const caf_c64* b, size_t n, caf_c64* out) {
+    return run_xcor<float>(h, (const float2*)a, (const float2*)b, n, (float2*)out);
+}
+
+int caf_b200_batch_f64(caf_b200_handle h, const caf_c128* needles, const caf_c128* hays, size_t p, size_t l,
+                       const double* freqs, size_t d, uint32_t fs, double* surface, double* rv, uint64_t* ri,
+                       caf_b200_peak* peaks) {
+    return run_batch_host<double>(h, (const double2*)needles, (const double2*)hays, p, l, freqs, d, fs, surface, rv, ri, peaks);
+}
+int caf_b200_batch_f32(caf_b200_handle h, const caf_c64* needles, const caf_c64* hays, size_t p, size_t l,
+                       const double* freqs, size_t d, uint32_t fs, float* surface, float* rv, uint64_t* ri,
+                       caf_b200_peak* peaks) {
+    return run_batch_host<float>(h, (const float2*)needles, (const float2*)hays, p, l, freqs, d, fs, surface, rv, ri, peaks);
+}
+
+int caf_b200_surface_f64(caf_b200_handle h, const caf_c128* needle, const caf_c128* hay, size_t l, const double* freqs,
+                         size_t d, uint32_t fs, double* surface, double* rv, uint64_t* ri, caf_b200_peak* peak) {
+    return caf_b200_batch_f64(h, needle, hay, 1, l, freqs, d, fs, surface, rv, ri, peak);
+}
+int caf_b200_surface_f32(caf_b200_handle h, const caf_c64* needle, const caf_c64* hay, size_t l, const double* freqs,
+                         size_t d, uint32_t fs, float* surface, float* rv, uint64_t* ri, caf_b200_peak* peak) {
+    return caf_b200_batch_f32(h, needle, hay, 1, l, freqs, d, fs, surface, rv, ri, peak);
+}
+int caf_b200_peak_f64(caf_b200_handle h, const caf_c128* needle, const caf_c128* hay, size_t l, const double* freqs,
+                      size_t d, uint32_t fs, caf_b200_peak* peak) {
+    if (!peak) return fail(CAF_B200_EINVAL, "null peak");
+    return caf_b200_batch_f64(h, needle, hay, 1, l, freqs, d, fs, nullptr, nullptr, nullptr, peak);
+}
+int caf_b200_peak_f32(caf_b200_handle h, const caf_c64* needle, const caf_c64* hay, size_t l, const double* freqs,
+                      size_t d, uint32_t fs, caf_b200_peak* peak) {
+    if (!peak) return fail(CAF_B200_EINVAL, "null peak");
+    return caf_b200_batch_f32(h, needle, hay, 1, l, freqs, d, fs, nullptr, nullptr, nullptr, peak);
+}
+
+static_assert(sizeof(caf_b200_peak) == sizeof(caf::PeakOut), "peak layouts must match");
+
+int caf_b200_batch_f64_dev(caf_b200_handle h, const caf_c128* needles, const caf_c128* hays, size_t p, size_t l,
+                           const double* freqs, size_t d, uint32_t fs, double* surface, double* rv, uint64_t* ri,
+                           caf_b200_peak* peaks) {
+    int rc = check_common<double>(h, needles, hays, p, l, freqs, d, fs);
+    if (rc) return rc;
+    CK(cudaSetDevice(h->device));
+    return run_batch_dev<double>(h, (const double2*)needles, (const double2*)hays, p, l, freqs, d, fs, surface, rv,
+                                 (unsigned long long*)ri, (caf::PeakOut*)peaks);
+}
+int caf_b200_batch_f32_dev(caf_b200_handle h, const caf_c64* needles, const caf_c64* hays, size_t p, size_t l,
+                           const double* freqs, size_t d, uint32_t fs, float* surface, float* rv, uint64_t* ri,
+                           caf_b200_peak* peaks) {
+    int rc = check_common<float>(h, needles, hays, p, l, freqs, d, fs);
+    if (rc) return rc;
+    CK(cudaSetDevice(h->device));
+    return run_batch_dev<float>(h, (const float2*)needles, (const float2*)hays, p, l, freqs, d, fs, surface, rv,
+                                (unsigned long long*)ri, (caf::PeakOut*)peaks);
+}
+
+// ---- multi-GPU peak words: [0] = bits(value), [1] = global doppler row (UINT64_MAX if none),
+//      [2] = delay index, [3] = bits(freq_hz) ----
+void caf_b200_peak_pack(const caf_b200_peak* local, uint64_t global_row_offset, uint64_t words[4]) {
+    double v = local->value, f = local->freq_hz;
+    std::memcpy(&words[0], &v, 8);
+    words[1] = (local->doppler_idx == UINT64_MAX) ? UINT64_MAX : local->doppler_idx + global_row_offset;
+    words[2] = local->delay_idx;
+    std::memcpy(&words[3], &f, 8);
+}
+
+void caf_b200_peak_resolve(const uint64_t* words, size_t world, caf_b200_peak* out) {
+    caf_b200_peak best; best.value = 0.0; best.freq_hz = 0.0; best.doppler_idx = UINT64_MAX; best.delay_idx = 0;
+    for (size_t r = 0; r < world; ++r) {
+        const uint64_t* w = words + 4 * r;
+        double v, f;
+        std::memcpy(&v, &w[0], 8); std::memcpy(&f, &w[3], 8);
+        if (w[1] == UINT64_MAX) continue;
+        // find_peak (mod.rs:36-40): strict > in row order  ==  larger value, ties to the lower global row
+        if (v > best.value || (v == best.value && v > 0.0 && w[1] < best.doppler_idx)) {
+            best.value = v; best.freq_hz = f; best.doppler_idx = w[1]; best.delay_idx = w[2];
+        }
+    }
+    *out = best;
+}
+
+}  // extern "C"

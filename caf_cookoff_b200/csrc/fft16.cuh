@@ -1,0 +1,93 @@
+// fft16.cuh — in-register complex helpers and the 16-point butterfly used by every pass.
+//
+// Replaces the arithmetic the reference delegates to rustfft 3.0.1 / FFTW3
+// (/root/reference/caf_rust/src/caf/xcor_rustfft.rs:59,61,76 and xcor_fftw.rs:59,61,76):
+// unnormalised forward (e^{-j...}) and inverse (e^{+j...}) DFTs.  Written from scratch for
+// sm_100a: one thread owns 16 complex values in registers, the DFT-16 is a 4x4 Cooley-Tukey
+// with compile-time twiddles, and everything is templated on the scalar (double / float).
+#pragma once
+#include <cuda_runtime.h>
+
+namespace caf {
+
+template <typename T> struct cx_of;
+template <> struct cx_of<double> { using type = double2; };
+template <> struct cx_of<float>  { using type = float2; };
+template <typename T> using cx = typename cx_of<T>::type;
+
+template <typename T> __device__ __forceinline__ cx<T> mk(T x, T y) { cx<T> r; r.x = x; r.y = y; return r; }
+template <typename C> __device__ __forceinline__ C cadd(C a, C b) { C r; r.x = a.x + b.x; r.y = a.y + b.y; return r; }
+template <typename C> __device__ __forceinline__ C csub(C a, C b) { C r; r.x = a.x - b.x; r.y = a.y - b.y; return r; }
+// a * b
+template <typename C> __device__ __forceinline__ C cmul(C a, C b) {
+    C r; r.x = a.x * b.x - a.y * b.y; r.y = a.x * b.y + a.y * b.x; return r;
+}
+// a * conj(b)
+template <typename C> __device__ __forceinline__ C cmulc(C a, C b) {
+    C r; r.x = a.x * b.x + a.y * b.y; r.y = a.y * b.x - a.x * b.y; return r;
+}
+// a * (INV ? conj(w) : w)
+template <bool INV, typename C> __device__ __forceinline__ C ctw(C a, C w) { return INV ? cmulc(a, w) : cmul(a, w); }
+
+template <typename T, bool INV>
+__device__ __forceinline__ void radix4(cx<T>& a0, cx<T>& a1, cx<T>& a2, cx<T>& a3) {
+    cx<T> t0 = cadd(a0, a2), t1 = csub(a0, a2), t2 = cadd(a1, a3), t3 = csub(a1, a3);
+    a0 = cadd(t0, t2);
+    a2 = csub(t0, t2);
+    if (!INV) {  // W4 = -j
+        a1 = mk<T>(t1.x + t3.y, t1.y - t3.x);
+        a3 = mk<T>(t1.x - t3.y, t1.y + t3.x);
+    } else {     // W4^-1 = +j
+        a1 = mk<T>(t1.x - t3.y, t1.y + t3.x);
+        a3 = mk<T>(t1.x + t3.y, t1.y - t3.x);
+    }
+}
+
+// a *= W16^E (forward sign e^{-2 pi j E/16}; conjugated when INV)
+template <typename T, int E, bool INV>
+__device__ __forceinline__ cx<T> mul_w16(cx<T> a) {
+    constexpr T C1 = (T)0.92387953251128675613L;  // cos(pi/8)
+    constexpr T S1 = (T)0.38268343236508977173L;  // sin(pi/8)
+    constexpr T R  = (T)0.70710678118654752440L;  // sqrt(1/2)
+    if constexpr (E == 0) return a;
+    else if constexpr (E == 4) return INV ? mk<T>(-a.y, a.x) : mk<T>(a.y, -a.x);
+    else if constexpr (E == 2) return INV ? mk<T>(R * (a.x - a.y), R * (a.x + a.y)) : mk<T>(R * (a.x + a.y), R * (a.y - a.x));
+    else if constexpr (E == 6) return INV ? mk<T>(-R * (a.x + a.y), R * (a.x - a.y)) : mk<T>(R * (a.y - a.x), -R * (a.x + a.y));
+    else {
+        constexpr T wr = (E == 1) ? C1 : (E == 3) ? S1 : -C1;                 // E in {1,3,9}
+        constexpr T wi_f = (E == 1) ? -S1 : (E == 3) ? -C1 : S1;              // forward imaginary part
+        constexpr T wi = INV ? -wi_f : wi_f;
+        return mk<T>(a.x * wr - a.y * wi, a.x * wi + a.y * wr);
+    }
+}
+
+// In-place 16-point DFT, natural order in and out: v[k] <- sum_i v[i] e^{-+2 pi j i k/16}
+template <typename T, bool INV>
+__device__ __forceinline__ void fft16(cx<T> (&v)[16]) {
+    // stage A: i = c + 4a  ->  A[c][ka] left at v[c + 4 ka]
+#pragma unroll
+    for (int c = 0; c < 4; ++c) radix4<T, INV>(v[c], v[c + 4], v[c + 8], v[c + 12]);
+    // twiddle W16^{c ka}
+    v[1 + 4]  = mul_w16<T, 1, INV>(v[1 + 4]);
+    v[1 + 8]  = mul_w16<T, 2, INV>(v[1 + 8]);
+    v[1 + 12] = mul_w16<T, 3, INV>(v[1 + 12]);
+    v[2 + 4]  = mul_w16<T, 2, INV>(v[2 + 4]);
+    v[2 + 8]  = mul_w16<T, 4, INV>(v[2 + 8]);
+    v[2 + 12] = mul_w16<T, 6, INV>(v[2 + 12]);
+    v[3 + 4]  = mul_w16<T, 3, INV>(v[3 + 4]);
+    v[3 + 8]  = mul_w16<T, 6, INV>(v[3 + 8]);
+    v[3 + 12] = mul_w16<T, 9, INV>(v[3 + 12]);
+    // stage B: over c for each ka -> X[ka + 4 kb] left at v[4 ka + kb]
+#pragma unroll
+    for (int ka = 0; ka < 4; ++ka) radix4<T, INV>(v[4 * ka], v[4 * ka + 1], v[4 * ka + 2], v[4 * ka + 3]);
+    // 4x4 register transpose back to natural order (pure renaming once unrolled)
+    cx<T> o[16];
+#pragma unroll
+    for (int ka = 0; ka < 4; ++ka)
+#pragma unroll
+        for (int kb = 0; kb < 4; ++kb) o[ka + 4 * kb] = v[4 * ka + kb];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = o[i];
+}
+
+}  // namespace caf

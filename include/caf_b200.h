@@ -1,0 +1,142 @@
+/*
+ * caf_b200.h — C ABI of the B200-native filterbank cross-ambiguity function (libcaf_b200.so).
+ *
+ * The reference (Teque5/caf_cookoff, caf_rust) has no FFI: its boundary is the Rust crate API
+ *     pub trait CafSurface { caf_surface, find_peak, apply_freq_shift }   caf_rust/src/caf/mod.rs:23-66
+ *     pub struct CafSurfaceRow                                            caf_rust/src/caf/mod.rs:17-22
+ *     struct Xcor { new, run }  (crate-private)                           caf_rust/src/caf/xcor_rustfft.rs:14-78
+ * Each entry point below names the reference function it replaces; INTEGRATION.md shows the Rust
+ * `extern "C"` block + trait impl a maintainer adds to bind them (rust/ holds that shim as source).
+ *
+ * Conventions
+ *  - every function returns 0 on success, a negative caf_b200_status otherwise; the message of the
+ *    last failure on the calling thread is caf_b200_last_error().  Nothing aborts or throws.
+ *    (The reference panics instead — xcor_rustfft.rs:54-55 assert!, unwrap()s; the Rust shim turns a
+ *    non-zero status into panic! to preserve that.)
+ *  - caf_c128 / caf_c64 are interleaved (re, im) and layout-identical to num_complex::Complex<f64> /
+ *    Complex<f32> (#[repr(C)]) and to numpy complex128 / complex64.
+ *  - pointers are caller-owned HOST memory unless the function name ends in _dev (device memory on the
+ *    handle's device; those calls are asynchronous on the handle's stream — caf_b200_sync() to wait).
+ *  - a handle owns one device, one stream, the twiddle tables and a grow-only workspace.  A handle is
+ *    not thread-safe; distinct handles are independent.
+ *  - there is NO CPU fallback: if no sm_100 device is usable, create() fails.
+ *
+ * Sizes.  l = samples per input signal (needle and haystack must be equal length, as the reference's
+ * Xcor asserts).  A surface row has n = 2*l delay cells (both inputs zero-padded at the end to 2*l,
+ * mod.rs:130-131); cell k < l is lag +k, cell k > l is lag k - 2l.  This build runs rows in on-chip
+ * memory for l <= 4096 (the reference's only shape is l = 4096); larger l returns CAF_B200_EUNSUPPORTED.
+ */
+#ifndef CAF_B200_H
+#define CAF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct caf_b200_handle_s* caf_b200_handle;
+
+typedef struct { double re, im; } caf_c128;   /* == num_complex::Complex64  (utils.rs:8-9) */
+typedef struct { float re, im; } caf_c64;     /* == num_complex::Complex32 */
+
+typedef enum {
+    CAF_B200_OK = 0,
+    CAF_B200_EINVAL = -1,        /* null pointer / bad argument */
+    CAF_B200_ELENGTH = -2,       /* needle.len() != haystack.len()  (xcor_rustfft.rs:54-55 assert) */
+    CAF_B200_EUNSUPPORTED = -3,  /* size outside what this build implements */
+    CAF_B200_ECUDA = -4,         /* CUDA runtime error (message in last_error) */
+    CAF_B200_ENODEVICE = -5      /* no usable sm_100 GPU — there is no CPU fallback */
+} caf_b200_status;
+
+/* Result of CafSurface::find_peak (mod.rs:31-42).  When no row beats the dummy 0.0 row (empty or
+ * all-zero surface) the reference returns (0.0, 0): value = 0, freq_hz = 0, delay_idx = 0 and
+ * doppler_idx = UINT64_MAX. */
+typedef struct {
+    double value;          /* |xcor|^2 at the peak */
+    double freq_hz;        /* freqs_hz[doppler_idx] */
+    uint64_t doppler_idx;  /* first row holding the maximum (rows in freqs_hz order) */
+    uint64_t delay_idx;    /* xcor_peak_idx of that row */
+} caf_b200_peak;
+
+/* ---- lifecycle ------------------------------------------------------------------------------- */
+int caf_b200_create(int device, caf_b200_handle* out);
+/* Same, but all work is issued on an existing CUDA stream (a cudaStream_t passed as void*). */
+int caf_b200_create_on_stream(int device, void* cuda_stream, caf_b200_handle* out);
+int caf_b200_destroy(caf_b200_handle h);
+int caf_b200_sync(caf_b200_handle h);
+const char* caf_b200_last_error(void);
+const char* caf_b200_version(void);
+/* number of kernels this handle has launched since creation (bench.py's gpu_launches) */
+uint64_t caf_b200_launch_count(caf_b200_handle h);
+
+/* pinned host buffers: surfaces DMA straight into them (any host pointer is accepted, pinned is faster) */
+int caf_b200_host_alloc(void** out, size_t bytes);
+int caf_b200_host_free(void* p);
+
+/* ---- CafSurface::apply_freq_shift (mod.rs:46-65); README.md:124 calls it apply_shift ------------ */
+/* out[i] = in[i] * e^{+j 2 pi freq_hz i / fs}.  in == out allowed. */
+int caf_b200_apply_freq_shift_f64(caf_b200_handle h, const caf_c128* in, size_t n, double freq_hz,
+                                  uint32_t fs, caf_c128* out);
+int caf_b200_apply_freq_shift_f32(caf_b200_handle h, const caf_c64* in, size_t n, double freq_hz,
+                                  uint32_t fs, caf_c64* out);
+int caf_b200_apply_shift_f64(caf_b200_handle h, const caf_c128* in, size_t n, double freq_hz,
+                             uint32_t fs, caf_c128* out);   /* alias */
+int caf_b200_apply_shift_f32(caf_b200_handle h, const caf_c64* in, size_t n, double freq_hz,
+                             uint32_t fs, caf_c64* out);    /* alias */
+
+/* ---- Xcor::run (xcor_rustfft.rs:51-78 / xcor_fftw.rs:51-78) ----------------------------------------
+ * out = IFFT( FFT(a) * conj(FFT(b)) / n ), unnormalised transforms: the length-n CIRCULAR correlation
+ * out[k] = sum_m a[(m+k) mod n] conj(b[m]).  n == 8192 or n <= 4096 in this build. */
+int caf_b200_xcor_f64(caf_b200_handle h, const caf_c128* a, const caf_c128* b, size_t n, caf_c128* out);
+int caf_b200_xcor_f32(caf_b200_handle h, const caf_c64* a, const caf_c64* b, size_t n, caf_c64* out);
+
+/* ---- CafSurface::caf_surface + find_peak (mod.rs:121-166, 31-42) -----------------------------------
+ * needle, haystack: l samples each.  freqs_hz: d doppler shifts.  fs: sample rate (u32 as in the trait).
+ * surface: d x 2l row-major |xcor|^2 (norm_sqr, mod.rs:147) or NULL to skip materialising it.
+ * row_peak_val / row_peak_idx: CafSurfaceRow::xcor_peak_val / xcor_peak_idx per row, or NULL.
+ * peak: find_peak over the rows in freqs_hz order, or NULL. */
+int caf_b200_surface_f64(caf_b200_handle h, const caf_c128* needle, const caf_c128* haystack, size_t l,
+                         const double* freqs_hz, size_t d, uint32_t fs,
+                         double* surface, double* row_peak_val, uint64_t* row_peak_idx, caf_b200_peak* peak);
+int caf_b200_surface_f32(caf_b200_handle h, const caf_c64* needle, const caf_c64* haystack, size_t l,
+                         const double* freqs_hz, size_t d, uint32_t fs,
+                         float* surface, float* row_peak_val, uint64_t* row_peak_idx, caf_b200_peak* peak);
+
+/* peak only: caf_surface followed by find_peak with the surface never leaving the chip */
+int caf_b200_peak_f64(caf_b200_handle h, const caf_c128* needle, const caf_c128* haystack, size_t l,
+                      const double* freqs_hz, size_t d, uint32_t fs, caf_b200_peak* peak);
+int caf_b200_peak_f32(caf_b200_handle h, const caf_c64* needle, const caf_c64* haystack, size_t l,
+                      const double* freqs_hz, size_t d, uint32_t fs, caf_b200_peak* peak);
+
+/* p independent pairs, each l samples, one shared doppler grid: needles / haystacks are [p][l],
+ * surface [p][d][2l] or NULL, row_peak_* [p][d] or NULL, peaks [p] or NULL. */
+int caf_b200_batch_f64(caf_b200_handle h, const caf_c128* needles, const caf_c128* haystacks, size_t p,
+                       size_t l, const double* freqs_hz, size_t d, uint32_t fs,
+                       double* surface, double* row_peak_val, uint64_t* row_peak_idx, caf_b200_peak* peaks);
+int caf_b200_batch_f32(caf_b200_handle h, const caf_c64* needles, const caf_c64* haystacks, size_t p,
+                       size_t l, const double* freqs_hz, size_t d, uint32_t fs,
+                       float* surface, float* row_peak_val, uint64_t* row_peak_idx, caf_b200_peak* peaks);
+
+/* device-resident variants: every pointer is device memory (peaks too); asynchronous on the handle's
+ * stream.  Same argument meaning as the batch calls. */
+int caf_b200_batch_f64_dev(caf_b200_handle h, const caf_c128* needles, const caf_c128* haystacks, size_t p,
+                           size_t l, const double* freqs_hz, size_t d, uint32_t fs,
+                           double* surface, double* row_peak_val, uint64_t* row_peak_idx, caf_b200_peak* peaks);
+int caf_b200_batch_f32_dev(caf_b200_handle h, const caf_c64* needles, const caf_c64* haystacks, size_t p,
+                           size_t l, const double* freqs_hz, size_t d, uint32_t fs,
+                           float* surface, float* row_peak_val, uint64_t* row_peak_idx, caf_b200_peak* peaks);
+
+/* ---- multi-GPU peak reduction (doppler rows or pairs sharded across ranks) ----
+ * Each rank computes the peak of its shard, packs it with its GLOBAL first-row offset into 4 uint64
+ * words, the caller all-gathers (or all-reduces a zero-initialised 4*world buffer with SUM/MAX) the
+ * words over NCCL, and every rank resolves the same winner with find_peak's tie-break (lowest global
+ * doppler row).  Pure host helpers; no GPU work. */
+void caf_b200_peak_pack(const caf_b200_peak* local, uint64_t global_row_offset, uint64_t words[4]);
+void caf_b200_peak_resolve(const uint64_t* words, size_t world, caf_b200_peak* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CAF_B200_H */
