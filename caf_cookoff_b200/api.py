@@ -47,7 +47,7 @@ class Handle:
     def __init__(self, device: int = 0, stream: Optional[int] = None):
         self._lib = _lib.load()
         self._h = C.c_void_p()
-        if stream:
+        if stream is not None:
             _check(self._lib.caf_b200_create_on_stream(int(device), C.c_void_p(int(stream)), C.byref(self._h)))
         else:
             _check(self._lib.caf_b200_create(int(device), C.byref(self._h)))

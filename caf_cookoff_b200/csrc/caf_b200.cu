@@ -63,8 +63,12 @@ struct caf_b200_handle_s {
     Tables<float> tf;
     int occ_d = 1, occ_f = 1;   // resident CTAs per SM of the surface kernel
     DevBuf needle, hay, hperm, freqs, surface, rowval, rowidx, peaks, scratch;
+    unsigned int* done_counter = nullptr;   // last-CTA-done ticket of the fused find_peak
     void* h_peaks = nullptr;    // pinned staging for peaks
     size_t h_peaks_cap = 0;
+    bool profiling = false;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // around spectrum | rows | peak
+    bool ev_valid = false;
 };
 
 namespace {
@@ -73,9 +77,7 @@ template <typename T> Tables<T>& tables(caf_b200_handle h);
 template <> Tables<double>& tables<double>(caf_b200_handle h) { return h->td; }
 template <> Tables<float>& tables<float>(caf_b200_handle h) { return h->tf; }
 
-template <typename T> size_t smem_bytes() {
-    return sizeof(caf::cx<T>) * (2 * caf::kL0 + 2 * 2 * 48) + 16 * sizeof(unsigned long long) + 16 * sizeof(T);
-}
+template <typename T> size_t smem_bytes() { return caf::SmemLayout<T>::kTotal; }
 
 template <typename T>
 cudaError_t upload_tables(Tables<T>& t, cudaStream_t s) {
@@ -124,7 +126,7 @@ template <typename T>
 cudaError_t configure_all(int* occ) {
     cudaError_t e;
     if ((e = configure_kernel<T, caf::kSurface>(occ)) != cudaSuccess) return e;
-    if ((e = configure_kernel<T, caf::kSpectrum>(nullptr)) != cudaSuccess) return e;
+    if ((e = configure_kernel<T, caf::kSpectrumHalf>(nullptr)) != cudaSuccess) return e;
     if ((e = configure_kernel<T, caf::kSpectrumFull>(nullptr)) != cudaSuccess) return e;
     if ((e = configure_kernel<T, caf::kXcorFull>(nullptr)) != cudaSuccess) return e;
     if ((e = configure_kernel<T, caf::kXcorHalf>(nullptr)) != cudaSuccess) return e;
@@ -170,7 +172,6 @@ int run_batch_dev(caf_b200_handle h, const caf::cx<T>* needles, const caf::cx<T>
         }
         return CAF_B200_OK;
     }
-    CK(h->hperm.ensure(sizeof(cx<T>) * kM * p));
     // row peaks are needed internally for find_peak even when the caller does not want them
     T* rv = rowval; unsigned long long* ri = rowidx;
     if (peaks && (!rv || !ri)) {
@@ -179,21 +180,27 @@ int run_batch_dev(caf_b200_handle h, const caf::cx<T>* needles, const caf::cx<T>
         rv = reinterpret_cast<T*>(ri + p * d);
     }
     RowArgs<T> a = base_args<T>(h);
-    a.hperm = reinterpret_cast<cx<T>*>(h->hperm.p);
-    a.L = (int)l; a.P = (int)p;
-    // K0: H = FFT(haystack)/n once per pair (the reference recomputes it per row, xcor_rustfft.rs:58-59)
-    a.in = hays; a.D = 1;
-    CK((launch_rows<T, kSpectrum>(h, a, (long long)p)));
-    // K1: fused shift -> FFT -> xH -> IFFT -> |.|^2 -> row argmax
-    a.in = needles; a.D = (int)d; a.freqs = freqs; a.dt = 1.0 / (double)fs;
+    a.L = (int)l; a.P = (int)p; a.D = (int)d;
+    a.in = needles; a.in2 = hays; a.freqs = freqs; a.dt = 1.0 / (double)fs;   // dt: mod.rs:53
     a.out = surface; a.row_peak_val = rv; a.row_peak_idx = ri;
+    const bool fused_peak = peaks && p == 1;      // single pair: find_peak rides in the same launch
+    if (fused_peak) { a.peak = peaks; a.done_counter = h->done_counter; }
+    const bool prof = h->profiling;
+    if (prof) {
+        for (auto& e : h->ev) if (!e) CK(cudaEventCreate(&e));
+        h->ev_valid = false;
+        CK(cudaEventRecord(h->ev[0], h->stream));
+        CK(cudaEventRecord(h->ev[1], h->stream));
+    }
+    // one fused launch: per pair FFT(s1) -> TMEM, then per row shift -> FFT -> xH -> IFFT -> |.|^2 -> argmax
     CK((launch_rows<T, kSurface>(h, a, (long long)p * (long long)d)));
-    // K3: find_peak per pair
-    if (peaks) {
+    if (prof) CK(cudaEventRecord(h->ev[2], h->stream));
+    if (peaks && !fused_peak) {
         caf_peak_kernel<T><<<(unsigned)p, 256, 0, h->stream>>>(rv, ri, freqs, (int)d, peaks);
         h->launches++;
         CK(cudaGetLastError());
     }
+    if (prof) { CK(cudaEventRecord(h->ev[3], h->stream)); h->ev_valid = true; }
     return CAF_B200_OK;
 }
 
@@ -316,7 +323,7 @@ int run_xcor(caf_b200_handle h, const caf::cx<T>* a_, const caf::cx<T>* b_, size
         CK((launch_rows<T, kXcorFull>(h, a, 1)));
     } else {
         a.in = (const cx<T>*)h->hay.p;
-        CK((launch_rows<T, kSpectrum>(h, a, 1)));
+        CK((launch_rows<T, kSpectrumHalf>(h, a, 1)));
         a.in = (const cx<T>*)h->needle.p; a.out = y;
         CK((launch_rows<T, kXcorHalf>(h, a, 1)));
         res = y + kM;
@@ -337,7 +344,7 @@ extern "C" {
 const char* caf_b200_last_error(void) { return g_err.c_str(); }
 const char* caf_b200_version(void) { return "caf_b200 0.1 (sm_100a)"; }
 
-int caf_b200_create_on_stream(int device, void* cuda_stream, caf_b200_handle* out) {
+static int create_impl(int device, bool own_stream, void* cuda_stream, caf_b200_handle* out) {
     if (!out) return fail(CAF_B200_EINVAL, "null out");
     *out = nullptr;
     int ndev = 0;
@@ -356,13 +363,15 @@ int caf_b200_create_on_stream(int device, void* cuda_stream, caf_b200_handle* ou
     if (!h) return fail(CAF_B200_EINVAL, "out of host memory");
     h->device = device;
     h->sm_count = prop.multiProcessorCount;
-    if (cuda_stream) { h->stream = (cudaStream_t)cuda_stream; h->own_stream = false; }
+    if (!own_stream) { h->stream = (cudaStream_t)cuda_stream; h->own_stream = false; }   // 0 = legacy default stream
     else {
         e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
         if (e != cudaSuccess) { delete h; return fail(CAF_B200_ECUDA, cudaGetErrorString(e)); }
         h->own_stream = true;
     }
-    if ((e = upload_tables<double>(h->td, h->stream)) != cudaSuccess ||
+    if ((e = cudaMalloc(&h->done_counter, sizeof(unsigned int))) != cudaSuccess ||
+        (e = cudaMemsetAsync(h->done_counter, 0, sizeof(unsigned int), h->stream)) != cudaSuccess ||
+        (e = upload_tables<double>(h->td, h->stream)) != cudaSuccess ||
         (e = upload_tables<float>(h->tf, h->stream)) != cudaSuccess ||
         (e = configure_all<double>(&h->occ_d)) != cudaSuccess ||
         (e = configure_all<float>(&h->occ_f)) != cudaSuccess) {
@@ -374,7 +383,10 @@ int caf_b200_create_on_stream(int device, void* cuda_stream, caf_b200_handle* ou
     return CAF_B200_OK;
 }
 
-int caf_b200_create(int device, caf_b200_handle* out) { return caf_b200_create_on_stream(device, nullptr, out); }
+int caf_b200_create(int device, caf_b200_handle* out) { return create_impl(device, true, nullptr, out); }
+int caf_b200_create_on_stream(int device, void* cuda_stream, caf_b200_handle* out) {
+    return create_impl(device, false, cuda_stream, out);
+}
 
 int caf_b200_destroy(caf_b200_handle h) {
     if (!h) return CAF_B200_OK;
@@ -385,6 +397,8 @@ int caf_b200_destroy(caf_b200_handle h) {
     for (void* q : {(void*)h->td.tw1, (void*)h->td.tw2, (void*)h->td.g, (void*)h->tf.tw1, (void*)h->tf.tw2, (void*)h->tf.g})
         if (q) cudaFree(q);
     if (h->h_peaks) cudaFreeHost(h->h_peaks);
+    if (h->done_counter) cudaFree(h->done_counter);
+    for (auto& e : h->ev) if (e) cudaEventDestroy(e);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return CAF_B200_OK;
@@ -397,6 +411,53 @@ int caf_b200_sync(caf_b200_handle h) {
 }
 
 uint64_t caf_b200_launch_count(caf_b200_handle h) { return h ? h->launches : 0; }
+
+int caf_b200_set_profiling(caf_b200_handle h, int on) {
+    if (!h) return fail(CAF_B200_EINVAL, "null handle");
+    h->profiling = on != 0;
+    return CAF_B200_OK;
+}
+
+int caf_b200_last_kernel_ms(caf_b200_handle h, float* spectrum_ms, float* rows_ms, float* peak_ms) {
+    if (!h) return fail(CAF_B200_EINVAL, "null handle");
+    if (!h->ev_valid) return fail(CAF_B200_EINVAL, "no profiled call recorded (caf_b200_set_profiling first)");
+    CK(cudaEventSynchronize(h->ev[3]));
+    float a = 0, b = 0, c = 0;
+    CK(cudaEventElapsedTime(&a, h->ev[0], h->ev[1]));
+    CK(cudaEventElapsedTime(&b, h->ev[1], h->ev[2]));
+    CK(cudaEventElapsedTime(&c, h->ev[2], h->ev[3]));
+    if (spectrum_ms) *spectrum_ms = a;
+    if (rows_ms) *rows_ms = b;
+    if (peak_ms) *peak_ms = c;
+    return CAF_B200_OK;
+}
+
+int caf_b200_probe_fma_tflops(caf_b200_handle h, int is_f64, double* tflops) {
+    if (!h || !tflops) return fail(CAF_B200_EINVAL, "null argument");
+    CK(cudaSetDevice(h->device));
+    CK(h->scratch.ensure(64));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    const int iters = is_f64 ? 4096 : 16384, blocks = h->sm_count * 4, threads = 512;
+    double best = 0.0;
+    for (int rep = 0; rep < 4; ++rep) {
+        CK(cudaEventRecord(e0, h->stream));
+        if (is_f64) caf::caf_fma_probe_kernel<double><<<blocks, threads, 0, h->stream>>>((double*)h->scratch.p, iters, 1.0);
+        else caf::caf_fma_probe_kernel<float><<<blocks, threads, 0, h->stream>>>((float*)h->scratch.p, iters, 1.0f);
+        h->launches++;
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(e1, h->stream));
+        CK(cudaEventSynchronize(e1));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        double fl = 2.0 * 64.0 * (double)iters * (double)blocks * (double)threads;
+        double tf = fl / ((double)ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    *tflops = best;
+    return CAF_B200_OK;
+}
 
 int caf_b200_host_alloc(void** out, size_t bytes) {
     if (!out) return fail(CAF_B200_EINVAL, "null out");

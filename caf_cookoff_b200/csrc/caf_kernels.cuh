@@ -1,15 +1,21 @@
-// caf_kernels.cuh — the fused filterbank-CAF row kernel for sm_100a (N = 8192 point rows).
+// caf_kernels.cuh — the fused filterbank-CAF kernel for sm_100a (rows of N = 8192 delay cells).
 //
-// One CTA (512 threads = 16 warps) owns one doppler row at a time and keeps the whole row in
-// REGISTERS (16 complex values per thread); shared memory is only the exchange fabric between
-// passes.  What it replaces in the reference, per row (paths relative to /root/reference):
-//   caf_rust/src/caf/mod.rs:46-65        apply_freq_shift  -> phasor folded into the load
-//   caf_rust/src/caf/xcor_rustfft.rs:60-61  FFT(shifted)   -> two 4096-point DIF FFTs (see below)
-//   caf_rust/src/caf/xcor_rustfft.rs:64-73  conj, product, /n -> one multiply with H = FFT(s1)/n
-//   caf_rust/src/caf/xcor_rustfft.rs:76     IFFT           -> two 4096-point DIT IFFTs + radix-2
-//   caf_rust/src/caf/mod.rs:141-153      norm_sqr + strict-> argmax -> fused epilogue
-// FFT(haystack) (xcor_rustfft.rs:58-59, recomputed per row by the reference) is computed once
-// per pair by the same code in SPECTRUM mode.
+// One persistent CTA (512 threads = 16 warps) per SM owns one doppler row at a time and keeps the
+// whole row in REGISTERS (16 complex values per thread).  Row-invariant operands — the needle samples
+// and H = FFT(haystack)/n that every row of a pair re-uses — live in TENSOR MEMORY (TMEM, 256 KB/SM),
+// used here as a software-managed per-thread scratchpad through tcgen05.st / tcgen05.ld: each thread
+// owns exactly the 16 needle samples and the 16 H bins it needs, 512 B, which is the whole TMEM.
+// Shared memory holds the exchange fabric between passes (128 KB) and the twiddle tables (72 KB).
+// After the per-pair prologue a row touches HBM/L2 only to write its |xcor|^2 cells.
+//
+// What it replaces in the reference, per row (paths relative to /root/reference):
+//   caf_rust/src/caf/mod.rs:46-65            apply_freq_shift  -> phasor folded into the load
+//   caf_rust/src/caf/xcor_rustfft.rs:58-59   FFT(haystack), recomputed per row there -> once per pair per CTA
+//   caf_rust/src/caf/xcor_rustfft.rs:60-61   FFT(shifted)      -> two 4096-point DIF FFTs (see below)
+//   caf_rust/src/caf/xcor_rustfft.rs:64-73   conj, product, /n -> one multiply with H
+//   caf_rust/src/caf/xcor_rustfft.rs:76      IFFT              -> two 4096-point DIT IFFTs + radix-2
+//   caf_rust/src/caf/mod.rs:141-153          norm_sqr + strict-> argmax -> fused epilogue
+//   caf_rust/src/caf/mod.rs:31-42            find_peak         -> last-CTA-done reduction (single pair)
 //
 // Math.  The padded needle x[n] is zero for n >= 4096 (mod.rs:130), so with k = 2q + r
 //   X[2q+r] = FFT_4096( x[n] * W_8192^{r n} )[q],           r in {0,1}
@@ -18,11 +24,10 @@
 // The inverse is the mirror image: y[n] = A[n] + W_8192^{-n} B[n], y[n+4096] = A[n] - W_8192^{-n} B[n]
 // with A/B the 4096-point inverse transforms of the even/odd bins.  Forward runs decimation in
 // frequency (natural in, digit-reversed out), inverse runs decimation in time (digit-reversed in,
-// natural out), so the spectrum is never reordered; H is stored pre-permuted in that order.
+// natural out), so the spectrum is never reordered; H is kept in that digit-reversed order.
 //
 // Thread map.  warp w (0..15), lane = 16 r + h: the two half-warps of a warp work on the two
-// pipelines r = 0/1 with identical indices, so twiddle / needle loads coalesce to one address
-// set per warp.  4096 = 16 x 16 x 16:
+// pipelines r = 0/1 with identical indices, so twiddle loads broadcast.  4096 = 16 x 16 x 16:
 //   pass 1  radix-16 over i,  elements n = t + 256 i,      t = 16 w + h      (twiddle W_4096^{t k1})
 //   X1      block exchange    S_r[k1][t]  ->  warp k1 owns sub-transform k1
 //   pass 2  radix-16 over i', elements t = h + 16 i'                          (twiddle W_256^{h k2})
@@ -31,6 +36,7 @@
 //   ... multiply by H, then passes 1', 2', 3' mirror 3, 2, 1 with conjugated twiddles.
 #pragma once
 #include <cstdint>
+#include <type_traits>
 #include "fft16.cuh"
 
 namespace caf {
@@ -40,29 +46,132 @@ constexpr int kL0 = 4096;   // points per pipeline
 constexpr int kM = 8192;    // transform length of one row
 
 enum Mode : int {
-    kSurface = 0,      // needle (half zero) x phasor -> |xcor|^2 (+ row argmax)
-    kSpectrum = 1,     // haystack (half zero)        -> H (pre-permuted, scaled 1/8192)
-    kSpectrumFull = 2, // full 8192-sample input      -> H            (standalone xcor operand a)
+    kSurface = 0,      // needle (half zero) x phasor -> |xcor|^2 (+ row argmax, + peak); H computed in-kernel
+    kSpectrumHalf = 1, // half-zero input             -> H in global memory (standalone xcor operand a, n <= 4096)
+    kSpectrumFull = 2, // full 8192-sample input      -> H in global memory (standalone xcor operand a, n = 8192)
     kXcorFull = 3,     // full 8192-sample input b    -> complex xcor (standalone xcor, n = 8192)
     kXcorHalf = 4      // half-zero input b, no shift -> complex linear xcor (standalone xcor, n <= 4096)
 };
 
+struct PeakOut {
+    double value;
+    double freq_hz;
+    unsigned long long doppler_idx;   // ~0ull when no row beat the dummy row
+    unsigned long long delay_idx;
+};
+
 template <typename T>
 struct RowArgs {
-    const cx<T>* in;        // kSurface/kSpectrum: [P][L]; *Full modes: [P][8192]
-    cx<T>* hperm;           // [P][8192]  (written by spectrum modes, read otherwise)
+    const cx<T>* in;        // kSurface: needles [P][L]; *Half: [P][L]; *Full: [P][8192]
+    const cx<T>* in2;       // kSurface: haystacks [P][L]
+    cx<T>* hperm;           // [P][8192]  standalone-xcor spectrum (written by kSpectrum*, read by kXcor*)
     const double* freqs;    // [D] doppler shifts, Hz (kSurface only)
     void* out;              // kSurface: T [P*D][2L] or null; kXcor*: cx<T> [P][8192]
     T* row_peak_val;        // [P*D] or null
     unsigned long long* row_peak_idx;  // [P*D] or null
+    PeakOut* peak;          // kSurface, P == 1: fused find_peak result (or null)
+    unsigned int* done_counter;   // kSurface, P == 1: last-CTA-done ticket (self-resetting)
     const cx<T>* tw1;       // [16][256]  W_4096^{k1 t}
     const cx<T>* tw2;       // [16][16]   W_256^{a b}
-    const cx<T>* g;         // [4096]     W_8192^{-n}
+    const cx<T>* g;         // [4096]     W_8192^{-n}   (first 256 entries are staged in smem)
     double dt;              // 1/fs (mod.rs:53)
     int L;                  // samples per input signal (<= 4096)
     int D;                  // doppler rows per pair
     int P;                  // pairs
 };
+
+// ------------------------------------------------------------------------------------------------
+// shared-memory carve-up
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+struct SmemLayout {
+    static constexpr size_t kS = sizeof(cx<T>) * 2 * kL0;        // exchange fabric [2][4096]
+    static constexpr size_t kTw1 = sizeof(cx<T>) * 16 * 256;
+    static constexpr size_t kTw2 = sizeof(cx<T>) * 256;
+    static constexpr size_t kG = sizeof(cx<T>) * 256;
+    static constexpr size_t kPtab = sizeof(cx<T>) * 2 * 2 * 48;  // [2 buf][2 r][3][16]
+    static constexpr size_t kRed = 16 * 8 + 16 * 8;              // argmax scratch
+    static constexpr size_t kMisc = 64;                          // tmem base, flags
+    static constexpr size_t offTw1 = kS, offTw2 = offTw1 + kTw1, offG = offTw2 + kTw2, offPtab = offG + kG,
+                            offRed = offPtab + kPtab, offMisc = offRed + kRed, kTotal = offMisc + kMisc;
+};
+
+template <typename T>
+struct Ctx {
+    cx<T>* S;        // exchange fabric
+    cx<T>* Sr;       // this thread's pipeline half
+    cx<T>* Sw;       // this warp's 256-entry region inside Sr
+    const cx<T>* tw1;
+    const cx<T>* tw2;
+    const cx<T>* g256;
+    cx<T>* ptab;
+    int w, lane, r, h, t;
+};
+
+// ------------------------------------------------------------------------------------------------
+// TMEM scratchpad: tcgen05.st / tcgen05.ld, shape 32x32b (thread i of a warp <-> TMEM lane 32*(warp%4)+i).
+// One call moves 4 complex values (x16 words for complex128, x8 for complex64).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_st_x16(uint32_t taddr, const uint32_t (&r)[16]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};\n"
+                 :: "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+                    "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_x8(uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_st_x8(uint32_t taddr, const uint32_t (&r)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};\n"
+                 :: "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory"); }
+
+template <typename T> struct TmemGeom;
+template <> struct TmemGeom<double> { static constexpr int kColsPerC = 4, kColsPerGroup = 128, kAlloc = 512; };
+template <> struct TmemGeom<float>  { static constexpr int kColsPerC = 2, kColsPerGroup = 64,  kAlloc = 256; };
+
+// 4 complex values <-> TMEM columns [taddr, taddr + 4*kColsPerC)
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, double2 (&o)[4]) {
+    uint32_t r[16];
+    tmem_ld_x16(taddr, r);
+    tmem_wait_ld();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        o[i].x = __hiloint2double((int)r[4 * i + 1], (int)r[4 * i]);
+        o[i].y = __hiloint2double((int)r[4 * i + 3], (int)r[4 * i + 2]);
+    }
+}
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const double2 (&v)[4]) {
+    uint32_t r[16];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        r[4 * i] = (uint32_t)__double2loint(v[i].x); r[4 * i + 1] = (uint32_t)__double2hiint(v[i].x);
+        r[4 * i + 2] = (uint32_t)__double2loint(v[i].y); r[4 * i + 3] = (uint32_t)__double2hiint(v[i].y);
+    }
+    tmem_st_x16(taddr, r);
+}
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, float2 (&o)[4]) {
+    uint32_t r[8];
+    tmem_ld_x8(taddr, r);
+    tmem_wait_ld();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { o[i].x = __uint_as_float(r[2 * i]); o[i].y = __uint_as_float(r[2 * i + 1]); }
+}
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const float2 (&v)[4]) {
+    uint32_t r[8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { r[2 * i] = __float_as_uint(v[i].x); r[2 * i + 1] = __float_as_uint(v[i].y); }
+    tmem_st_x8(taddr, r);
+}
 
 template <typename T>
 __device__ __forceinline__ cx<T> ldg(const cx<T>* p) { return __ldg(p); }
@@ -79,63 +188,214 @@ __device__ __forceinline__ double2 unit_phasor(double n, double phi, double exac
     return make_double2(c, s);
 }
 
+// ------------------------------------------------------------------------------------------------
+// forward: v[i] = u_r[t + 256 i]  ->  v[k3] = U_r[w + 16 h + 256 k3]          (xcor_rustfft.rs:59,61)
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ void forward_4096(cx<T> (&v)[16], const Ctx<T>& c) {
+    fft16<T, false>(v);
+#pragma unroll
+    for (int k = 1; k < 16; ++k) v[k] = cmul(v[k], c.tw1[k * 256 + c.t]);
+    __syncthreads();   // every earlier reader of the fabric (previous item's X4 / X2) is done
+#pragma unroll
+    for (int k = 0; k < 16; ++k) c.Sr[k * 256 + c.t] = v[k];
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = c.Sw[c.h + 16 * i];
+
+    fft16<T, false>(v);
+#pragma unroll
+    for (int k = 1; k < 16; ++k) v[k] = cmul(v[k], c.tw2[k * 16 + c.h]);
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) c.Sw[k * 16 + (c.h ^ k)] = v[k];
+    __syncwarp();
+#pragma unroll
+    for (int m = 0; m < 16; ++m) v[m] = c.Sw[c.h * 16 + (m ^ c.h)];
+
+    fft16<T, false>(v);
+}
+
+// ------------------------------------------------------------------------------------------------
+// inverse: v[k3] = Y_r[w + 16 h + 256 k3]  ->  v[n1] = A_r[t + 256 n1]  (unnormalised, xcor_rustfft.rs:76)
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ void inverse_4096(cx<T> (&v)[16], const Ctx<T>& c) {
+    fft16<T, true>(v);
+#pragma unroll
+    for (int k = 1; k < 16; ++k) v[k] = cmulc(v[k], c.tw2[k * 16 + c.h]);
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) c.Sw[k * 16 + (c.h ^ k)] = v[k];
+    __syncwarp();
+#pragma unroll
+    for (int m = 0; m < 16; ++m) v[m] = c.Sw[c.h * 16 + (m ^ c.h)];
+
+    fft16<T, true>(v);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) v[k] = cmulc(v[k], c.tw1[c.w * 256 + 16 * k + c.h]);
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) c.Sw[16 * k + c.h] = v[k];
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) v[k] = c.Sr[k * 256 + c.t];
+
+    fft16<T, true>(v);
+}
+
+// multiply by W_32^{-J} = e^{+2 pi j J/32}, J = 0..7 (compile-time constant)
+template <typename T, int J>
+__device__ __forceinline__ cx<T> mul_w32_inv(cx<T> a) {
+    constexpr T Cc[8] = {(T)1.0L, (T)0.98078528040323044913L, (T)0.92387953251128675613L, (T)0.83146961230254523708L,
+                         (T)0.70710678118654752440L, (T)0.55557023301960222474L, (T)0.38268343236508977173L,
+                         (T)0.19509032201612826785L};
+    constexpr T Ss[8] = {(T)0.0L, (T)0.19509032201612826785L, (T)0.38268343236508977173L, (T)0.55557023301960222474L,
+                         (T)0.70710678118654752440L, (T)0.83146961230254523708L, (T)0.92387953251128675613L,
+                         (T)0.98078528040323044913L};
+    if constexpr (J == 0) return a;
+    else return mk<T>(a.x * Cc[J] - a.y * Ss[J], a.x * Ss[J] + a.y * Cc[J]);
+}
+
+// argmax helper: larger value wins, ties go to the lower index (== first strict-> maximum, mod.rs:148)
+template <typename T>
+__device__ __forceinline__ void amax_take(T& best, int& bidx, T m, int k) {
+    if (m > best || (m == best && k < bidx)) { best = m; bidx = k; }
+}
+
 template <typename T, int MODE>
 __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> a) {
     using C = cx<T>;
+    using SL = SmemLayout<T>;
+    using TG = TmemGeom<T>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    C* S = reinterpret_cast<C*>(smem_raw);                 // [2][4096] exchange fabric
-    C* ptab = S + 2 * kL0;                                  // [2 buf][2 r][3][16] phasor factors
-    unsigned long long* red_idx = reinterpret_cast<unsigned long long*>(ptab + 2 * 2 * 48);
-    T* red_val = reinterpret_cast<T*>(red_idx + 16);
+    C* S = reinterpret_cast<C*>(smem_raw);
+    C* tw1s = reinterpret_cast<C*>(smem_raw + SL::offTw1);
+    C* tw2s = reinterpret_cast<C*>(smem_raw + SL::offTw2);
+    C* g256s = reinterpret_cast<C*>(smem_raw + SL::offG);
+    C* ptab = reinterpret_cast<C*>(smem_raw + SL::offPtab);
+    unsigned long long* red_idx = reinterpret_cast<unsigned long long*>(smem_raw + SL::offRed);
+    double* red_val = reinterpret_cast<double*>(smem_raw + SL::offRed + 128);
+    uint32_t* misc = reinterpret_cast<uint32_t*>(smem_raw + SL::offMisc);
 
     const int tid = threadIdx.x;
-    const int w = tid >> 5, lane = tid & 31, r = lane >> 4, h = lane & 15;
-    const int t = 16 * w + h;
-    C* Sr = S + r * kL0;
-    constexpr bool kHalfZero = (MODE == kSurface || MODE == kSpectrum || MODE == kXcorHalf);
-    constexpr bool kComplexOut = (MODE == kXcorFull || MODE == kXcorHalf);
-    constexpr bool kWritesH = (MODE == kSpectrum || MODE == kSpectrumFull);
+    Ctx<T> c;
+    c.w = tid >> 5; c.lane = tid & 31; c.r = c.lane >> 4; c.h = c.lane & 15; c.t = 16 * c.w + c.h;
+    c.S = S; c.Sr = S + c.r * kL0; c.Sw = c.Sr + c.w * 256;
+    c.tw1 = tw1s; c.tw2 = tw2s; c.g256 = g256s; c.ptab = ptab;
+    const int w = c.w, lane = c.lane, r = c.r, h = c.h, t = c.t;
 
-    const int rows_per_pair = (MODE == kSurface) ? a.D : 1;
-    const long long n_items = (long long)a.P * rows_per_pair;
+    constexpr bool kHalfZero = (MODE == kSurface || MODE == kSpectrumHalf || MODE == kXcorHalf);
+    constexpr bool kWritesH = (MODE == kSpectrumHalf || MODE == kSpectrumFull);
+    constexpr bool kUseTmem = (MODE == kSurface);
+
+    // ---- stage the twiddle tables in shared memory (once per CTA) ----
+    for (int i = tid; i < 16 * 256; i += kThreads) tw1s[i] = ldg<T>(a.tw1 + i);
+    if (tid < 256) { tw2s[tid] = ldg<T>(a.tw2 + tid); g256s[tid] = ldg<T>(a.g + tid); }
+
+    // ---- TMEM: the tensor memory of this SM becomes the per-thread operand store ----
+    uint32_t tm_h = 0, tm_n = 0;
+    if (kUseTmem) {
+        if (w == 0) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n"
+                         :: "l"((uint64_t)__cvta_generic_to_shared(&misc[0])), "n"(TG::kAlloc));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;\n");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;\n");
+        const uint32_t base = misc[0] + ((uint32_t)(32 * (w & 3)) << 16) + (uint32_t)(TG::kColsPerGroup * (w >> 2));
+        tm_h = base;                              // 16 H bins
+        tm_n = base + 16 * TG::kColsPerC;         // 16 needle samples
+    } else {
+        __syncthreads();
+    }
 
     // phasor factor tables for one item: ptab[buf][r][0][i] = e^{j2pi 256 i phi_r}, [1][a] = 16 a, [2][b] = b
-    auto fill_ptab = [&](int buf, long long item) {
+    auto fill_ptab = [&](int buf, double phi) {
         if (tid < 96) {
             const int rr = tid / 48, e = tid % 48, which = e >> 4, idx = e & 15;
             const int n = idx << (which == 0 ? 8 : which == 1 ? 4 : 0);
-            double phi = 0.0;
-            if (MODE == kSurface) phi = a.freqs[item % a.D] * a.dt;
             // r/8192 * n is exact in binary
             double2 p = unit_phasor((double)n, phi, (double)(rr * n) * (1.0 / 8192.0));
             ptab[(buf * 2 + rr) * 48 + e] = mk<T>((T)p.x, (T)p.y);
         }
     };
+    // v[i] *= phasor_r(t + 256 i)
+    auto phasor_mul = [&](C (&v)[16], int buf) {
+        const C* pt = ptab + (buf * 2 + r) * 48;
+        const C pth = cmul(pt[16 + w], pt[32 + h]);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = cmul(v[i], cmul(pth, pt[i]));
+    };
+    // v[i] = src[t + 256 i]  (zero beyond L)
+    auto load_half = [&](C (&v)[16], const C* src, int L) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const int n = t + 256 * i;
+            v[i] = (n < L) ? ldg<T>(src + n) : mk<T>((T)0, (T)0);
+        }
+    };
+
+    // ---- work split: contiguous ranges of (pair, row) items so a CTA changes pair as rarely as possible ----
+    const int rows_per_pair = (MODE == kSurface) ? a.D : 1;
+    const long long n_items = (long long)a.P * rows_per_pair;
+    const long long lo = n_items * blockIdx.x / gridDim.x, hi = n_items * (blockIdx.x + 1) / gridDim.x;
 
     int buf = 0;
-    if (kHalfZero) {
-        if ((long long)blockIdx.x < n_items) fill_ptab(0, blockIdx.x);
-        __syncthreads();
-    }
+    long long cur_pair = -1;
+    C v[16];
 
-    for (long long item = blockIdx.x; item < n_items; item += gridDim.x, buf ^= 1) {
+    for (long long item = lo; item < hi; ++item, buf ^= 1) {
         const long long pair = (MODE == kSurface) ? item / a.D : item;
-        C v[16];
+        const int row = (MODE == kSurface) ? (int)(item - pair * a.D) : 0;
 
-        // ---------------- load + phasor (mod.rs:46-65 folded with the radix-2 twiddle) ----------------
-        if (kHalfZero) {
-            const C* src = a.in + pair * a.L;
-            const C* pt = ptab + (buf * 2 + r) * 48;
-            const C pth = cmul(pt[16 + w], pt[32 + h]);
+        if constexpr (MODE == kSurface) {
+            if (pair != cur_pair) {
+                // ---- per-pair prologue: H = FFT(haystack)/n into TMEM, needle into TMEM ----
+                cur_pair = pair;
+                __syncthreads();                  // nobody still reads ptab[buf] of an earlier item
+                fill_ptab(buf, 0.0);
+                load_half(v, a.in2 + pair * a.L, a.L);
+                __syncthreads();
+                phasor_mul(v, buf);
+                forward_4096<T>(v, c);
+                const T sc = (T)(1.0 / 8192.0);   // the /n of xcor_rustfft.rs:72 (n = transform length)
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const int n = t + 256 * i;
-                C s = mk<T>((T)0, (T)0);
-                if (n < a.L) s = ldg<T>(src + n);
-                v[i] = s;
+                for (int q = 0; q < 4; ++q) {
+                    C tmp[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) tmp[i] = mk<T>(v[4 * q + i].x * sc, v[4 * q + i].y * sc);
+                    tmem_st4(tm_h + 4 * q * TG::kColsPerC, tmp);
+                }
+                load_half(v, a.in + pair * a.L, a.L);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    C tmp[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) tmp[i] = v[4 * q + i];
+                    tmem_st4(tm_n + 4 * q * TG::kColsPerC, tmp);
+                }
+                tmem_wait_st();
+                __syncthreads();                  // ptab[buf] (phi = 0) is dead from here
+                fill_ptab(buf, a.freqs[row] * a.dt);
+                __syncthreads();
             }
+            // ---- needle samples back from TMEM ----
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = cmul(v[i], cmul(pth, pt[i]));
+            for (int q = 0; q < 4; ++q) {
+                C tmp[4];
+                tmem_ld4(tm_n + 4 * q * TG::kColsPerC, tmp);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) v[4 * q + i] = tmp[i];
+            }
+            phasor_mul(v, buf);
+        } else if constexpr (kHalfZero) {
+            __syncthreads();
+            fill_ptab(buf, 0.0);
+            load_half(v, a.in + pair * a.L, a.L);
+            __syncthreads();
+            phasor_mul(v, buf);
         } else {
             // general 8192-sample input: explicit first radix-2 stage
             const C* src = a.in + pair * kM;
@@ -148,160 +408,161 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
             }
         }
 
-        // ---------------- forward pass 1 ----------------
-        fft16<T, false>(v);
-#pragma unroll
-        for (int k = 1; k < 16; ++k) v[k] = cmul(v[k], ldg<T>(a.tw1 + k * 256 + t));
-        __syncthreads();   // previous item's X4 reads are complete before S is overwritten
-#pragma unroll
-        for (int k = 0; k < 16; ++k) Sr[k * 256 + t] = v[k];
-        __syncthreads();
-        // phasors of the next item are produced here; the barrier after X4 orders them
-        if (kHalfZero && item + gridDim.x < n_items) fill_ptab(buf ^ 1, item + gridDim.x);
-        C* Sw = Sr + w * 256;
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = Sw[h + 16 * i];
-
-        // ---------------- forward pass 2 ----------------
-        fft16<T, false>(v);
-#pragma unroll
-        for (int k = 1; k < 16; ++k) v[k] = cmul(v[k], ldg<T>(a.tw2 + k * 16 + h));
-        __syncwarp();
-#pragma unroll
-        for (int k = 0; k < 16; ++k) Sw[k * 16 + (h ^ k)] = v[k];
-        __syncwarp();
-#pragma unroll
-        for (int m = 0; m < 16; ++m) v[m] = Sw[h * 16 + (m ^ h)];
-
-        // ---------------- forward pass 3 ----------------
-        fft16<T, false>(v);   // v[k3] = X_r[w + 16 h + 256 k3]
+        // ---------------- forward transform ----------------
+        forward_4096<T>(v, c);
+        // phasors of the next row are produced while the fabric is quiet; the block barrier inside
+        // inverse_4096 orders them before their first use
+        if constexpr (MODE == kSurface) {
+            if (item + 1 < hi && (item + 1) / a.D == pair) fill_ptab(buf ^ 1, a.freqs[row + 1] * a.dt);
+        }
 
         C* hp = a.hperm + pair * kM;
-        if (kWritesH) {
-            const T sc = (T)(1.0 / 8192.0);   // the /n of xcor_rustfft.rs:72 (n = transform length)
+        if constexpr (kWritesH) {
+            const T sc = (T)(1.0 / 8192.0);
 #pragma unroll
             for (int k = 0; k < 16; ++k) hp[(k * 16 + w) * 32 + lane] = mk<T>(v[k].x * sc, v[k].y * sc);
-            continue;
-        }
-
-        // ---------------- H * conj(X)  (xcor_rustfft.rs:64-73) ----------------
+        } else {
+            // ---------------- H * conj(X)  (xcor_rustfft.rs:64-73) ----------------
+            if constexpr (kUseTmem) {
 #pragma unroll
-        for (int k = 0; k < 16; ++k) v[k] = cmulc(ldg<T>(hp + (k * 16 + w) * 32 + lane), v[k]);
-
-        // ---------------- inverse pass 1' ----------------
-        fft16<T, true>(v);
+                for (int q = 0; q < 4; ++q) {
+                    C hv[4];
+                    tmem_ld4(tm_h + 4 * q * TG::kColsPerC, hv);
 #pragma unroll
-        for (int k = 1; k < 16; ++k) v[k] = cmulc(v[k], ldg<T>(a.tw2 + k * 16 + h));
-        __syncwarp();
+                    for (int i = 0; i < 4; ++i) v[4 * q + i] = cmulc(hv[i], v[4 * q + i]);
+                }
+            } else {
 #pragma unroll
-        for (int k = 0; k < 16; ++k) Sw[k * 16 + (h ^ k)] = v[k];
-        __syncwarp();
-#pragma unroll
-        for (int m = 0; m < 16; ++m) v[m] = Sw[h * 16 + (m ^ h)];
-
-        // ---------------- inverse pass 2' ----------------
-        fft16<T, true>(v);
-#pragma unroll
-        for (int k = 0; k < 16; ++k) v[k] = cmulc(v[k], ldg<T>(a.tw1 + w * 256 + 16 * k + h));
-        __syncwarp();
-#pragma unroll
-        for (int k = 0; k < 16; ++k) Sw[16 * k + h] = v[k];
-        __syncthreads();
-#pragma unroll
-        for (int k = 0; k < 16; ++k) v[k] = Sr[k * 256 + t];
-
-        // ---------------- inverse pass 3' ----------------
-        fft16<T, true>(v);   // v[n1] = A_r[t + 256 n1]
-
-        // ---------------- radix-2 combine across the two pipelines (partner lane ^ 16) ----------------
-        // r = 0 keeps n1 = 0..7, r = 1 keeps n1 = 8..15; each thread ends with 8 (A, B) pairs.
-        C ya[8], yb[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            C send = r ? v[j] : v[j + 8];
-            C recv;
-            recv.x = __shfl_xor_sync(0xffffffffu, send.x, 16);
-            recv.y = __shfl_xor_sync(0xffffffffu, send.y, 16);
-            C A = r ? recv : v[j];
-            C B = r ? v[j + 8] : recv;
-            const int n = t + 256 * (j + 8 * r);
-            B = cmul(B, ldg<T>(a.g + n));
-            ya[j] = cadd(A, B);    // lag index n
-            yb[j] = csub(A, B);    // lag index n + 4096
-        }
-
-        if (kComplexOut) {
-            C* o = reinterpret_cast<C*>(a.out) + pair * kM;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int n = t + 256 * (j + 8 * r);
-                o[n] = ya[j];
-                o[n + kL0] = yb[j];
+                for (int k = 0; k < 16; ++k) v[k] = cmulc(ldg<T>(hp + (k * 16 + w) * 32 + lane), v[k]);
             }
-            continue;
-        }
 
-        // ---------------- |.|^2, store, row argmax (mod.rs:141-153) ----------------
-        const int L = a.L, nout = 2 * L, skip = kM - nout;
-        T* orow = a.out ? reinterpret_cast<T*>(a.out) + item * (long long)nout : nullptr;
-        T best = (T)0;
-        int bidx = 0;
+            // ---------------- inverse transform ----------------
+            inverse_4096<T>(v, c);   // v[n1] = A_r[t + 256 n1]
+
+            // ---------------- radix-2 combine across the two pipelines (partner lane ^ 16) ----------------
+            // r = 0 ends up with n1 = 0..7, r = 1 with n1 = 8..15.  B' = B * W_8192^{-n},
+            // n = t + 256 (j + 8 r):  W_8192^{-n} = g[t] * W_32^{-j} * (+j)^r
+            const C gt = g256s[t];
+            const int L = a.L, nout = 2 * L, skip = kM - nout;
+            T* orow = (MODE == kSurface && a.out) ? reinterpret_cast<T*>(a.out) + item * (long long)nout : nullptr;
+            C* ocx = (MODE != kSurface) ? reinterpret_cast<C*>(a.out) + pair * kM : nullptr;
+            T best = (T)0;
+            int bidx = 0;
+            auto emit = [&](C y, int kp) {
+                if constexpr (MODE == kSurface) {
+                    const T m = y.x * y.x + y.y * y.y;                   // norm_sqr, mod.rs:147
+                    // reference index: 2L-point circular layout (identity when L = 4096)
+                    int k = -1;
+                    if (kp <= L) k = kp; else if (kp > kM - L) k = kp - skip;
+                    if (k >= 0 && k < nout) {
+                        if (orow) orow[k] = m;
+                        amax_take<T>(best, bidx, m, k);
+                    }
+                } else {
+                    ocx[kp] = y;
+                }
+            };
+            auto combine = [&](auto jtag) {
+                constexpr int j = decltype(jtag)::value;
+                C send = r ? v[j] : v[j + 8];
+                C recv;
+                recv.x = __shfl_xor_sync(0xffffffffu, send.x, 16);
+                recv.y = __shfl_xor_sync(0xffffffffu, send.y, 16);
+                const C A = r ? recv : v[j];
+                C B = r ? v[j + 8] : recv;
+                B = mul_w32_inv<T, j>(cmul(B, gt));
+                if (r) B = mk<T>(-B.y, B.x);            // * (+j)
+                const int n = t + 256 * (j + 8 * r);
+                emit(cadd(A, B), n);                    // lag index n
+                emit(csub(A, B), n + kL0);              // lag index n + 4096
+            };
+            combine(std::integral_constant<int, 0>{}); combine(std::integral_constant<int, 1>{});
+            combine(std::integral_constant<int, 2>{}); combine(std::integral_constant<int, 3>{});
+            combine(std::integral_constant<int, 4>{}); combine(std::integral_constant<int, 5>{});
+            combine(std::integral_constant<int, 6>{}); combine(std::integral_constant<int, 7>{});
+
+            if constexpr (MODE == kSurface) {
+                // ---------------- row argmax (mod.rs:141-153) ----------------
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int n = t + 256 * (j + 8 * r);
+                for (int off = 16; off > 0; off >>= 1) {
+                    T ov = __shfl_xor_sync(0xffffffffu, best, off);
+                    int oi = __shfl_xor_sync(0xffffffffu, bidx, off);
+                    amax_take<T>(best, bidx, ov, oi);
+                }
+                // red_* were last read before the block barriers of this item -> no hazard
+                if (lane == 0) { red_val[w] = (double)best; red_idx[w] = (unsigned long long)bidx; }
+                __syncthreads();
+                if (w == 0) {
+                    double bv = (lane < 16) ? red_val[lane] : 0.0;
+                    int bi = (lane < 16) ? (int)red_idx[lane] : 0x7fffffff;
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                const C y = half ? yb[j] : ya[j];
-                const int kp = n + half * kL0;                       // lag index in the 8192-point row
-                const T m = y.x * y.x + y.y * y.y;                   // norm_sqr, mod.rs:147
-                // reference index: 2L-point circular layout (identity when L = 4096)
-                int k = -1;
-                if (kp <= L) k = kp; else if (kp > kM - L) k = kp - skip;
-                if (k >= 0 && k < nout) {
-                    if (orow) orow[k] = m;
-                    if (m > best || (m == best && k < bidx)) { best = m; bidx = k; }
+                    for (int off = 8; off > 0; off >>= 1) {
+                        double ov = __shfl_xor_sync(0xffffffffu, bv, off);
+                        int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+                        amax_take<double>(bv, bi, ov, oi);
+                    }
+                    if (lane == 0) {
+                        if (!(bv > 0.0)) bi = 0;   // nothing beat the initial max = 0.0 (mod.rs:143-144)
+                        if (a.row_peak_val) a.row_peak_val[item] = (T)bv;
+                        if (a.row_peak_idx) a.row_peak_idx[item] = (unsigned long long)bi;
+                    }
                 }
             }
         }
-        // warp reduce: larger value wins, ties go to the lower index (== first strict-> maximum)
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-            T ov = __shfl_xor_sync(0xffffffffu, best, off);
-            int oi = __shfl_xor_sync(0xffffffffu, bidx, off);
-            if (ov > best || (ov == best && oi < bidx)) { best = ov; bidx = oi; }
-        }
-        // red_* were last read before the two block barriers above (previous item) -> no hazard
-        if (lane == 0) { red_val[w] = best; red_idx[w] = (unsigned long long)bidx; }
+    }
+
+    if constexpr (kUseTmem) {
+        asm volatile("tcgen05.fence::before_thread_sync;\n");
         __syncthreads();
-        if (w == 0) {
-            T bv = (lane < 16) ? red_val[lane] : (T)0;
-            int bi = (lane < 16) ? (int)red_idx[lane] : 0x7fffffff;
-#pragma unroll
-            for (int off = 8; off > 0; off >>= 1) {
-                T ov = __shfl_xor_sync(0xffffffffu, bv, off);
-                int oi = __shfl_xor_sync(0xffffffffu, bi, off);
-                if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+        if (w == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" :: "r"(misc[0]), "n"(TG::kAlloc));
+    }
+
+    // ---------------- fused find_peak (mod.rs:31-42), single pair: the last CTA to finish reduces the rows ----------------
+    if constexpr (MODE == kSurface) {
+        if (a.peak != nullptr && a.done_counter != nullptr) {
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) {
+                unsigned int ticket = atomicAdd(a.done_counter, 1u);
+                misc[1] = (ticket == gridDim.x - 1) ? 1u : 0u;
             }
-            if (lane == 0) {
-                if (!(bv > (T)0)) bi = 0;   // nothing beat the initial max = 0.0 (mod.rs:143-144)
-                if (a.row_peak_val) a.row_peak_val[item] = bv;
-                if (a.row_peak_idx) a.row_peak_idx[item] = (unsigned long long)bi;
+            __syncthreads();
+            if (misc[1]) {
+                __threadfence();
+                double best = 0.0;
+                int brow = 0x7fffffff;
+                for (int d = tid; d < a.D; d += kThreads) {
+                    double val = (double)__ldcg(a.row_peak_val + d);
+                    if (val > best) { best = val; brow = d; }      // d ascending per thread: first max kept
+                }
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) {
+                    double ov = __shfl_xor_sync(0xffffffffu, best, off);
+                    int oi = __shfl_xor_sync(0xffffffffu, brow, off);
+                    amax_take<double>(best, brow, ov, oi);
+                }
+                if (lane == 0) { red_val[w] = best; red_idx[w] = (unsigned long long)(unsigned int)brow; }
+                __syncthreads();
+                if (tid == 0) {
+                    for (int q = 1; q < 16; ++q) amax_take<double>(best, brow, red_val[q], (int)red_idx[q]);
+                    PeakOut p;
+                    if (best > 0.0 && brow != 0x7fffffff) {
+                        p.value = best; p.freq_hz = a.freqs[brow];
+                        p.doppler_idx = (unsigned long long)brow; p.delay_idx = __ldcg(a.row_peak_idx + brow);
+                    } else {   // dummy row of find_peak: (0.0, 0)
+                        p.value = 0.0; p.freq_hz = 0.0; p.doppler_idx = ~0ull; p.delay_idx = 0;
+                    }
+                    *a.peak = p;
+                    *a.done_counter = 0u;   // ready for the next launch on this stream
+                }
             }
         }
     }
 }
 
 // ---------------------------------------------------------------------------------------------
-// find_peak (mod.rs:31-42): strict > over rows from a dummy 0.0 row  ->  first row holding the max.
-// One block per pair.
+// find_peak (mod.rs:31-42) for batches: one block per pair.
 // ---------------------------------------------------------------------------------------------
-struct PeakOut {
-    double value;
-    double freq_hz;
-    unsigned long long doppler_idx;   // ~0ull when no row beat the dummy row
-    unsigned long long delay_idx;
-};
-
 template <typename T>
 __global__ void __launch_bounds__(256) caf_peak_kernel(const T* __restrict__ row_val,
                                                        const unsigned long long* __restrict__ row_idx,
@@ -313,19 +574,18 @@ __global__ void __launch_bounds__(256) caf_peak_kernel(const T* __restrict__ row
     int brow = 0x7fffffff;
     for (int d = threadIdx.x; d < D; d += blockDim.x) {
         double v = (double)row_val[base + d];
-        if (v > best || (v == best && v > 0.0 && d < brow)) { best = v; brow = d; }
+        if (v > best) { best = v; brow = d; }
     }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
         double ov = __shfl_xor_sync(0xffffffffu, best, off);
         int oi = __shfl_xor_sync(0xffffffffu, brow, off);
-        if (ov > best || (ov == best && oi < brow)) { best = ov; brow = oi; }
+        amax_take<double>(best, brow, ov, oi);
     }
     if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = best; si[threadIdx.x >> 5] = brow; }
     __syncthreads();
     if (threadIdx.x == 0) {
-        for (int q = 1; q < 8; ++q)
-            if (sv[q] > best || (sv[q] == best && si[q] < brow)) { best = sv[q]; brow = si[q]; }
+        for (int q = 1; q < 8; ++q) amax_take<double>(best, brow, sv[q], si[q]);
         PeakOut p;
         if (best > 0.0 && brow != 0x7fffffff) {
             p.value = best; p.freq_hz = freqs[brow];
@@ -361,6 +621,26 @@ __global__ void caf_fold_circular_kernel(const cx<T>* __restrict__ y, cx<T>* __r
         cx<T> b = (k == 0) ? mk<T>((T)0, (T)0) : y[kM - n + k];
         out[k] = cadd(a, b);
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// fp64 / fp32 FMA-pipe peak probe (bench.py's roofline denominator; MEASURED_PEAKS.json carries only
+// HBM and bf16).  8 independent dependent-FMA chains per thread, 2 flops per FMA.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(512) caf_fma_probe_kernel(T* sink, int iters, T seed) {
+    T a0 = seed + (T)threadIdx.x, a1 = a0 + (T)1, a2 = a0 + (T)2, a3 = a0 + (T)3;
+    T a4 = a0 + (T)4, a5 = a0 + (T)5, a6 = a0 + (T)6, a7 = a0 + (T)7;
+    const T m = (T)0.999999, c = (T)1e-6;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+            a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+        }
+    }
+    T r = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+    if (r == (T)123456789) sink[0] = r;   // never true; keeps the chains alive
 }
 
 }  // namespace caf

@@ -62,7 +62,8 @@ typedef struct {
 
 /* ---- lifecycle ------------------------------------------------------------------------------- */
 int caf_b200_create(int device, caf_b200_handle* out);
-/* Same, but all work is issued on an existing CUDA stream (a cudaStream_t passed as void*). */
+/* Same, but all work is issued on an existing CUDA stream (a cudaStream_t passed as void*; NULL is the
+ * legacy default stream, exactly as in the CUDA runtime). */
 int caf_b200_create_on_stream(int device, void* cuda_stream, caf_b200_handle* out);
 int caf_b200_destroy(caf_b200_handle h);
 int caf_b200_sync(caf_b200_handle h);
@@ -70,6 +71,15 @@ const char* caf_b200_last_error(void);
 const char* caf_b200_version(void);
 /* number of kernels this handle has launched since creation (bench.py's gpu_launches) */
 uint64_t caf_b200_launch_count(caf_b200_handle h);
+
+/* Per-kernel device times of the LAST surface/batch call on this handle, in milliseconds, measured with
+ * CUDA events on the handle's stream.  Off by default (the events cost a little); when on, every
+ * surface/batch call records spectrum (FFT(s1)), rows (the fused row kernel) and peak (find_peak). */
+int caf_b200_set_profiling(caf_b200_handle h, int on);
+int caf_b200_last_kernel_ms(caf_b200_handle h, float* spectrum_ms, float* rows_ms, float* peak_ms);
+/* FMA-pipe peak probe used as the roofline denominator: runs a dependent-FMA kernel on every SM and
+ * returns achieved TFLOP/s (2 flops per FMA).  is_f64 != 0 -> double, else float. */
+int caf_b200_probe_fma_tflops(caf_b200_handle h, int is_f64, double* tflops);
 
 /* pinned host buffers: surfaces DMA straight into them (any host pointer is accepted, pinned is faster) */
 int caf_b200_host_alloc(void** out, size_t bytes);
