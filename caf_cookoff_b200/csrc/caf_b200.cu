@@ -108,9 +108,9 @@ cudaError_t upload_tables(Tables<T>& t, cudaStream_t s) {
     return cudaStreamSynchronize(s);   // the host vectors die at scope exit
 }
 
-template <typename T, int MODE>
+template <typename T, int MODE, bool FULL = false>
 cudaError_t configure_kernel(int* occ_out) {
-    auto k = caf::caf_rows_kernel<T, MODE>;
+    auto k = caf::caf_rows_kernel<T, MODE, FULL>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<T>());
     if (e != cudaSuccess) return e;
     if (occ_out) {
@@ -125,7 +125,8 @@ cudaError_t configure_kernel(int* occ_out) {
 template <typename T>
 cudaError_t configure_all(int* occ) {
     cudaError_t e;
-    if ((e = configure_kernel<T, caf::kSurface>(occ)) != cudaSuccess) return e;
+    if ((e = configure_kernel<T, caf::kSurface, true>(occ)) != cudaSuccess) return e;
+    if ((e = configure_kernel<T, caf::kSurface, false>(nullptr)) != cudaSuccess) return e;
     if ((e = configure_kernel<T, caf::kSpectrumHalf>(nullptr)) != cudaSuccess) return e;
     if ((e = configure_kernel<T, caf::kSpectrumFull>(nullptr)) != cudaSuccess) return e;
     if ((e = configure_kernel<T, caf::kXcorFull>(nullptr)) != cudaSuccess) return e;
@@ -133,13 +134,13 @@ cudaError_t configure_all(int* occ) {
     return cudaSuccess;
 }
 
-template <typename T, int MODE>
+template <typename T, int MODE, bool FULL = false>
 cudaError_t launch_rows(caf_b200_handle h, const caf::RowArgs<T>& a, long long n_items) {
     if (n_items <= 0) return cudaSuccess;
     const int occ = std::is_same<T, double>::value ? h->occ_d : h->occ_f;
     long long cap = (long long)h->sm_count * occ;
     int grid = (int)(n_items < cap ? n_items : cap);
-    caf::caf_rows_kernel<T, MODE><<<grid, caf::kThreads, smem_bytes<T>(), h->stream>>>(a);
+    caf::caf_rows_kernel<T, MODE, FULL><<<grid, caf::kThreads, smem_bytes<T>(), h->stream>>>(a);
     h->launches++;
     return cudaGetLastError();
 }
@@ -193,7 +194,8 @@ int run_batch_dev(caf_b200_handle h, const caf::cx<T>* needles, const caf::cx<T>
         CK(cudaEventRecord(h->ev[1], h->stream));
     }
     // one fused launch: per pair FFT(s1) -> TMEM, then per row shift -> FFT -> xH -> IFFT -> |.|^2 -> argmax
-    CK((launch_rows<T, kSurface>(h, a, (long long)p * (long long)d)));
+    if (l == (size_t)kL0) CK((launch_rows<T, kSurface, true>(h, a, (long long)p * (long long)d)));
+    else CK((launch_rows<T, kSurface, false>(h, a, (long long)p * (long long)d)));
     if (prof) CK(cudaEventRecord(h->ev[2], h->stream));
     if (peaks && !fused_peak) {
         caf_peak_kernel<T><<<(unsigned)p, 256, 0, h->stream>>>(rv, ri, freqs, (int)d, peaks);

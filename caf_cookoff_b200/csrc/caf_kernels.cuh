@@ -26,8 +26,8 @@
 // frequency (natural in, digit-reversed out), inverse runs decimation in time (digit-reversed in,
 // natural out), so the spectrum is never reordered; H is kept in that digit-reversed order.
 //
-// Thread map.  warp w (0..15), lane = 16 r + h: the two half-warps of a warp work on the two
-// pipelines r = 0/1 with identical indices, so twiddle loads broadcast.  4096 = 16 x 16 x 16:
+// Thread map.  warp w (0..15), lane = h[2:0] | r<<3 | h[3]<<4: each warp works on both pipelines
+// r = 0/1 with identical indices h, so twiddle loads broadcast between adjacent quarter-warps.  4096 = 16 x 16 x 16:
 //   pass 1  radix-16 over i,  elements n = t + 256 i,      t = 16 w + h      (twiddle W_4096^{t k1})
 //   X1      block exchange    S_r[k1][t]  ->  warp k1 owns sub-transform k1
 //   pass 2  radix-16 over i', elements t = h + 16 i'                          (twiddle W_256^{h k2})
@@ -176,6 +176,12 @@ __device__ __forceinline__ void tmem_st4(uint32_t taddr, const float2 (&v)[4]) {
 template <typename T>
 __device__ __forceinline__ cx<T> ldg(const cx<T>* p) { return __ldg(p); }
 
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n"
+                 :: "r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+
 // fractional part helper: cycles -> (cos, sin)(2 pi cycles), evaluated in fp64 for both variants
 __device__ __forceinline__ double2 unit_phasor(double n, double phi, double exact_sub) {
     // phase(cycles) = n*phi - exact_sub; product split with an FMA so no bits of n*phi are lost
@@ -263,7 +269,8 @@ __device__ __forceinline__ void amax_take(T& best, int& bidx, T m, int k) {
     if (m > best || (m == best && k < bidx)) { best = m; bidx = k; }
 }
 
-template <typename T, int MODE>
+// FULL = the reference's shape, L == 4096: every one of the 8192 cells is an output cell (no index remap).
+template <typename T, int MODE, bool FULL>
 __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> a) {
     using C = cx<T>;
     using SL = SmemLayout<T>;
@@ -280,7 +287,10 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
 
     const int tid = threadIdx.x;
     Ctx<T> c;
-    c.w = tid >> 5; c.lane = tid & 31; c.r = c.lane >> 4; c.h = c.lane & 15; c.t = 16 * c.w + c.h;
+    // lane = h[2:0] | r << 3 | h[3] << 4: the two pipelines sit in adjacent quarter-warps, so a 128-bit
+    // twiddle load (same address for both r) costs 2 shared-memory wavefronts instead of 4
+    c.w = tid >> 5; c.lane = tid & 31; c.r = (c.lane >> 3) & 1; c.h = (c.lane & 7) | ((c.lane >> 1) & 8);
+    c.t = 16 * c.w + c.h;
     c.S = S; c.Sr = S + c.r * kL0; c.Sw = c.Sr + c.w * 256;
     c.tw1 = tw1s; c.tw2 = tw2s; c.g256 = g256s; c.ptab = ptab;
     const int w = c.w, lane = c.lane, r = c.r, h = c.h, t = c.t;
@@ -289,9 +299,20 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
     constexpr bool kWritesH = (MODE == kSpectrumHalf || MODE == kSpectrumFull);
     constexpr bool kUseTmem = (MODE == kSurface);
 
-    // ---- stage the twiddle tables in shared memory (once per CTA) ----
-    for (int i = tid; i < 16 * 256; i += kThreads) tw1s[i] = ldg<T>(a.tw1 + i);
-    if (tid < 256) { tw2s[tid] = ldg<T>(a.tw2 + tid); g256s[tid] = ldg<T>(a.g + tid); }
+    // ---- stage the twiddle tables in shared memory (once per CTA), asynchronously: the copies fly
+    //      while TMEM is allocated and the first operands are fetched ----
+    {
+        constexpr int kChunks1 = (int)(SL::kTw1 / 16), kChunks2 = (int)(SL::kTw2 / 16);
+        const char* g1 = reinterpret_cast<const char*>(a.tw1);
+        const char* g2 = reinterpret_cast<const char*>(a.tw2);
+        const char* g3 = reinterpret_cast<const char*>(a.g);
+        for (int i = tid; i < kChunks1; i += kThreads) cp_async16(smem_raw + SL::offTw1 + 16 * i, g1 + 16 * i);
+        for (int i = tid; i < kChunks2; i += kThreads) {
+            cp_async16(smem_raw + SL::offTw2 + 16 * i, g2 + 16 * i);
+            cp_async16(smem_raw + SL::offG + 16 * i, g3 + 16 * i);
+        }
+        asm volatile("cp.async.commit_group;\n" ::: "memory");
+    }
 
     // ---- TMEM: the tensor memory of this SM becomes the per-thread operand store ----
     uint32_t tm_h = 0, tm_n = 0;
@@ -341,26 +362,32 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
     const int rows_per_pair = (MODE == kSurface) ? a.D : 1;
     const long long n_items = (long long)a.P * rows_per_pair;
     const long long lo = n_items * blockIdx.x / gridDim.x, hi = n_items * (blockIdx.x + 1) / gridDim.x;
+    int pair = (int)(lo / rows_per_pair), row = (int)(lo - (long long)pair * rows_per_pair);   // one division per CTA
+
+    // The inverse of pipeline r = 1 runs on (-1)^q H: its output comes out rotated by 2048 samples, i.e. register j
+    // of an r = 1 lane holds B[t + 256 (j + 8)] and register j + 8 holds B[t + 256 j].  Both partners of the final
+    // radix-2 then send register j + 8 and keep register j — no per-lane register selection.  q = w + 16 h + 256 k3
+    // has the parity of w, so the sign is one factor per thread, folded into the 1/n scaling of H.
+    const T hsign = (r && (w & 1)) ? (T)-1 : (T)1;
 
     int buf = 0;
-    long long cur_pair = -1;
+    int cur_pair = -1;
+    bool tables_ready = false;
     C v[16];
 
     for (long long item = lo; item < hi; ++item, buf ^= 1) {
-        const long long pair = (MODE == kSurface) ? item / a.D : item;
-        const int row = (MODE == kSurface) ? (int)(item - pair * a.D) : 0;
-
         if constexpr (MODE == kSurface) {
             if (pair != cur_pair) {
                 // ---- per-pair prologue: H = FFT(haystack)/n into TMEM, needle into TMEM ----
                 cur_pair = pair;
                 __syncthreads();                  // nobody still reads ptab[buf] of an earlier item
                 fill_ptab(buf, 0.0);
-                load_half(v, a.in2 + pair * a.L, a.L);
+                load_half(v, a.in2 + (long long)pair * a.L, a.L);
+                if (!tables_ready) { cp_async_wait_all(); tables_ready = true; }
                 __syncthreads();
                 phasor_mul(v, buf);
                 forward_4096<T>(v, c);
-                const T sc = (T)(1.0 / 8192.0);   // the /n of xcor_rustfft.rs:72 (n = transform length)
+                const T sc = (T)(1.0 / 8192.0) * hsign;   // the /n of xcor_rustfft.rs:72 (n = transform length)
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     C tmp[4];
@@ -368,7 +395,7 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
                     for (int i = 0; i < 4; ++i) tmp[i] = mk<T>(v[4 * q + i].x * sc, v[4 * q + i].y * sc);
                     tmem_st4(tm_h + 4 * q * TG::kColsPerC, tmp);
                 }
-                load_half(v, a.in + pair * a.L, a.L);
+                load_half(v, a.in + (long long)pair * a.L, a.L);
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     C tmp[4];
@@ -393,12 +420,13 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
         } else if constexpr (kHalfZero) {
             __syncthreads();
             fill_ptab(buf, 0.0);
-            load_half(v, a.in + pair * a.L, a.L);
+            load_half(v, a.in + (long long)pair * a.L, a.L);
+            if (!tables_ready) { cp_async_wait_all(); tables_ready = true; }
             __syncthreads();
             phasor_mul(v, buf);
         } else {
             // general 8192-sample input: explicit first radix-2 stage
-            const C* src = a.in + pair * kM;
+            const C* src = a.in + (long long)pair * kM;
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
                 const int n = t + 256 * i;
@@ -406,17 +434,20 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
                 if (r == 0) v[i] = cadd(x0, x1);
                 else v[i] = cmulc(csub(x0, x1), ldg<T>(a.g + n));   // * W_8192^{+n} = conj(g[n])
             }
+            if (!tables_ready) { cp_async_wait_all(); tables_ready = true; }
+            __syncthreads();
         }
 
         // ---------------- forward transform ----------------
         forward_4096<T>(v, c);
         // phasors of the next row are produced while the fabric is quiet; the block barrier inside
         // inverse_4096 orders them before their first use
+        const bool next_same_pair = (MODE == kSurface) && (item + 1 < hi) && (row + 1 < a.D);
         if constexpr (MODE == kSurface) {
-            if (item + 1 < hi && (item + 1) / a.D == pair) fill_ptab(buf ^ 1, a.freqs[row + 1] * a.dt);
+            if (next_same_pair) fill_ptab(buf ^ 1, a.freqs[row + 1] * a.dt);
         }
 
-        C* hp = a.hperm + pair * kM;
+        C* hp = a.hperm + (long long)pair * kM;
         if constexpr (kWritesH) {
             const T sc = (T)(1.0 / 8192.0);
 #pragma unroll
@@ -433,30 +464,42 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
                 }
             } else {
 #pragma unroll
-                for (int k = 0; k < 16; ++k) v[k] = cmulc(ldg<T>(hp + (k * 16 + w) * 32 + lane), v[k]);
+                for (int k = 0; k < 16; ++k) {
+                    C hv = ldg<T>(hp + (k * 16 + w) * 32 + lane);
+                    v[k] = cmulc(mk<T>(hv.x * hsign, hv.y * hsign), v[k]);
+                }
             }
 
             // ---------------- inverse transform ----------------
-            inverse_4096<T>(v, c);   // v[n1] = A_r[t + 256 n1]
+            inverse_4096<T>(v, c);   // r = 0: v[n1] = A[t + 256 n1];  r = 1: v[n1] = B[t + 256 (n1 ^ 8)]
 
-            // ---------------- radix-2 combine across the two pipelines (partner lane ^ 16) ----------------
-            // r = 0 ends up with n1 = 0..7, r = 1 with n1 = 8..15.  B' = B * W_8192^{-n},
-            // n = t + 256 (j + 8 r):  W_8192^{-n} = g[t] * W_32^{-j} * (+j)^r
-            const C gt = g256s[t];
-            const int L = a.L, nout = 2 * L, skip = kM - nout;
+            // ---------------- radix-2 combine across the two pipelines (partner lane ^ 8) ----------------
+            // lane r handles n = t + 256 (j + 8 r), j = 0..7:   y[n] = A + B', y[n + 4096] = A - B',
+            // B' = B W_8192^{-n},  W_8192^{-n} = g[t] (+j)^r W_32^{-j}
+            C gt = g256s[t];
+            if (r) gt = mk<T>(-gt.y, gt.x);
+            const int L = FULL ? kL0 : a.L;
+            const int nout = 2 * L, skip = kM - nout;
             T* orow = (MODE == kSurface && a.out) ? reinterpret_cast<T*>(a.out) + item * (long long)nout : nullptr;
-            C* ocx = (MODE != kSurface) ? reinterpret_cast<C*>(a.out) + pair * kM : nullptr;
-            T best = (T)0;
-            int bidx = 0;
-            auto emit = [&](C y, int kp) {
+            C* ocx = (MODE != kSurface) ? reinterpret_cast<C*>(a.out) + (long long)pair * kM : nullptr;
+            // two running maxima (cells n < 4096 and n >= 4096), each visited in ascending index order, so a
+            // strict > keeps the first maximum exactly as mod.rs:148 does
+            T best0 = (T)0, best1 = (T)0;
+            int bidx0 = 0, bidx1 = 0;
+            auto emit = [&](C y, int kp, T& best, int& bidx) {
                 if constexpr (MODE == kSurface) {
                     const T m = y.x * y.x + y.y * y.y;                   // norm_sqr, mod.rs:147
-                    // reference index: 2L-point circular layout (identity when L = 4096)
-                    int k = -1;
-                    if (kp <= L) k = kp; else if (kp > kM - L) k = kp - skip;
-                    if (k >= 0 && k < nout) {
-                        if (orow) orow[k] = m;
-                        amax_take<T>(best, bidx, m, k);
+                    if constexpr (FULL) {
+                        if (orow) orow[kp] = m;
+                        if (m > best) { best = m; bidx = kp; }
+                    } else {
+                        // reference index: 2L-point circular layout
+                        int k = -1;
+                        if (kp <= L) k = kp; else if (kp > kM - L) k = kp - skip;
+                        if (k >= 0 && k < nout) {
+                            if (orow) orow[k] = m;
+                            if (m > best) { best = m; bidx = k; }
+                        }
                     }
                 } else {
                     ocx[kp] = y;
@@ -464,17 +507,15 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
             };
             auto combine = [&](auto jtag) {
                 constexpr int j = decltype(jtag)::value;
-                C send = r ? v[j] : v[j + 8];
                 C recv;
-                recv.x = __shfl_xor_sync(0xffffffffu, send.x, 16);
-                recv.y = __shfl_xor_sync(0xffffffffu, send.y, 16);
+                recv.x = __shfl_xor_sync(0xffffffffu, v[j + 8].x, 8);
+                recv.y = __shfl_xor_sync(0xffffffffu, v[j + 8].y, 8);
                 const C A = r ? recv : v[j];
-                C B = r ? v[j + 8] : recv;
-                B = mul_w32_inv<T, j>(cmul(B, gt));
-                if (r) B = mk<T>(-B.y, B.x);            // * (+j)
+                const C B = r ? v[j] : recv;
+                const C Bp = cmul(B, mul_w32_inv<T, j>(gt));
                 const int n = t + 256 * (j + 8 * r);
-                emit(cadd(A, B), n);                    // lag index n
-                emit(csub(A, B), n + kL0);              // lag index n + 4096
+                emit(cadd(A, Bp), n, best0, bidx0);             // lag index n
+                emit(csub(A, Bp), n + kL0, best1, bidx1);       // lag index n + 4096
             };
             combine(std::integral_constant<int, 0>{}); combine(std::integral_constant<int, 1>{});
             combine(std::integral_constant<int, 2>{}); combine(std::integral_constant<int, 3>{});
@@ -483,6 +524,9 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
 
             if constexpr (MODE == kSurface) {
                 // ---------------- row argmax (mod.rs:141-153) ----------------
+                T best = best0;
+                int bidx = bidx0;
+                if (best1 > best) { best = best1; bidx = bidx1; }   // every index of half 1 is above half 0
 #pragma unroll
                 for (int off = 16; off > 0; off >>= 1) {
                     T ov = __shfl_xor_sync(0xffffffffu, best, off);
@@ -509,7 +553,10 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
                 }
             }
         }
+        // next item
+        if (++row == rows_per_pair) { row = 0; ++pair; }
     }
+    if (!tables_ready) cp_async_wait_all();
 
     if constexpr (kUseTmem) {
         asm volatile("tcgen05.fence::before_thread_sync;\n");
