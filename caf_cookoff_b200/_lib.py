@@ -14,7 +14,7 @@ import subprocess
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
 CSRC = os.path.join(_PKG, "csrc")
-SO_PATH = os.path.join(_PKG, "libcaf_b200.so")
+SO_PATH = os.environ.get("CAF_B200_SO") or os.path.join(_PKG, "libcaf_b200.so")   # override: development builds
 HEADER = os.path.join(_ROOT, "include", "caf_b200.h")
 
 NVCC_FLAGS = [
@@ -77,6 +77,7 @@ SYMBOLS = {
     "caf_b200_set_profiling": (_int, [_vp, _int]),
     "caf_b200_last_kernel_ms": (_int, [_vp, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "caf_b200_probe_fma_tflops": (_int, [_vp, _int, C.POINTER(C.c_double)]),
+    "caf_b200_debug_trace": (_int, [_vp, _vp, _sz]),
     "caf_b200_host_alloc": (_int, [C.POINTER(_vp), _sz]),
     "caf_b200_host_free": (_int, [_vp]),
     "caf_b200_apply_freq_shift_f64": (_int, _shift),

@@ -6,6 +6,7 @@
 // sm_100 device create() fails (CAF_B200_ENODEVICE).
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -63,6 +64,8 @@ struct caf_b200_handle_s {
     Tables<float> tf;
     int occ_d = 1, occ_f = 1;   // resident CTAs per SM of the surface kernel
     DevBuf needle, hay, hperm, freqs, surface, rowval, rowidx, peaks, scratch;
+    int stagger = 0;
+    long long* trace = nullptr;   // CAF_TRACE builds: device buffer for phase stamps
     unsigned int* done_counter = nullptr;   // last-CTA-done ticket of the fused find_peak
     void* h_peaks = nullptr;    // pinned staging for peaks
     size_t h_peaks_cap = 0;
@@ -151,6 +154,8 @@ caf::RowArgs<T> base_args(caf_b200_handle h) {
     Tables<T>& t = tables<T>(h);
     a.tw1 = t.tw1; a.tw2 = t.tw2; a.g = t.g;
     a.dt = 0.0; a.L = 0; a.D = 1; a.P = 1;
+    a.stagger = h->stagger;
+    a.trace = h->trace;
     return a;
 }
 
@@ -365,6 +370,7 @@ static int create_impl(int device, bool own_stream, void* cuda_stream, caf_b200_
     if (!h) return fail(CAF_B200_EINVAL, "out of host memory");
     h->device = device;
     h->sm_count = prop.multiProcessorCount;
+    if (const char* e_ = getenv("CAF_B200_STAGGER")) h->stagger = atoi(e_);
     if (!own_stream) { h->stream = (cudaStream_t)cuda_stream; h->own_stream = false; }   // 0 = legacy default stream
     else {
         e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
@@ -459,6 +465,22 @@ int caf_b200_probe_fma_tflops(caf_b200_handle h, int is_f64, double* tflops) {
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     *tflops = best;
     return CAF_B200_OK;
+}
+
+/* development hook (CAF_TRACE builds): copy the per-warp phase stamps of the last surface launch to `out`
+ * (n_cta * 16 * 8 * 24 int64).  Allocates the trace buffer on first use; returns EUNSUPPORTED otherwise. */
+int caf_b200_debug_trace(caf_b200_handle h, long long* out, size_t n_cta) {
+#ifdef CAF_TRACE
+    if (!h) return fail(CAF_B200_EINVAL, "null handle");
+    const size_t bytes = sizeof(long long) * 512 * 16 * 8 * 24;
+    if (!h->trace) { CK(cudaMalloc(&h->trace, bytes)); CK(cudaMemset(h->trace, 0, bytes)); return CAF_B200_OK; }
+    CK(cudaStreamSynchronize(h->stream));
+    if (out) CK(cudaMemcpy(out, h->trace, sizeof(long long) * n_cta * 16 * 8 * 24, cudaMemcpyDeviceToHost));
+    return CAF_B200_OK;
+#else
+    (void)h; (void)out; (void)n_cta;
+    return fail(CAF_B200_EUNSUPPORTED, "library built without CAF_TRACE");
+#endif
 }
 
 int caf_b200_host_alloc(void** out, size_t bytes) {

@@ -78,6 +78,8 @@ struct RowArgs {
     int L;                  // samples per input signal (<= 4096)
     int D;                  // doppler rows per pair
     int P;                  // pairs
+    int stagger;            // cycles group 0 idles before its first item (phase offset between the groups)
+    long long* trace;       // CAF_TRACE builds only: [cta][warp][8 items][24 slots] clock64 stamps
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -106,7 +108,14 @@ struct Ctx {
     const cx<T>* g256;
     cx<T>* ptab;
     int w, lane, r, h, t;
+    long long* tr;   // CAF_TRACE: this warp's slot array for the current item (lane 0 writes)
 };
+
+#ifdef CAF_TRACE
+#define CAF_TR(c_, slot_) do { if ((c_).tr && (c_).lane == 0) (c_).tr[slot_] = clock64(); } while (0)
+#else
+#define CAF_TR(c_, slot_) do { } while (0)
+#endif
 
 // ------------------------------------------------------------------------------------------------
 // TMEM scratchpad: tcgen05.st / tcgen05.ld, shape 32x32b (thread i of a warp <-> TMEM lane 32*(warp%4)+i).
@@ -195,62 +204,98 @@ __device__ __forceinline__ double2 unit_phasor(double n, double phi, double exac
 }
 
 // ------------------------------------------------------------------------------------------------
-// forward: v[i] = u_r[t + 256 i]  ->  v[k3] = U_r[w + 16 h + 256 k3]          (xcor_rustfft.rs:59,61)
+// Two warp groups per CTA.  Group r (8 warps, 256 threads) owns pipeline r of the current row from the
+// phasor to its 4096-point inverse; its passes are fenced by a NAMED barrier over 256 threads, so the two
+// groups drift apart and one group's shared-memory exchange overlaps the other group's fp64 butterflies.
+// The only coupling is the final radix-2: group 1 posts B' = B W_8192^{-n} into its (then idle) half of
+// the fabric, group 0 consumes it (mbarrier full/empty pair) and runs the |.|^2 / argmax / store epilogue.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void bar_group(int r) { asm volatile("bar.sync %0, 256;\n" :: "r"(r + 1) : "memory"); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* mb, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" :: "r"((uint32_t)__cvta_generic_to_shared(mb)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* mb) {
+    asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.shared::cta.b64 st, [%0];\n}\n"
+                 :: "r"((uint32_t)__cvta_generic_to_shared(mb)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* mb, int parity) {
+    const uint32_t addr = (uint32_t)__cvta_generic_to_shared(mb);
+    asm volatile("{\n.reg .pred p;\nWAIT_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}\n"
+                 :: "r"(addr), "r"(parity) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward: v[i] = u_r[t + 256 i]  ->  v[k3] = U_r[k1 + 16 h + 256 k3]          (xcor_rustfft.rs:59,61)
+// `empty_mb` (group 1 only): the mailbox barrier to wait on before the fabric half is overwritten.
 // ------------------------------------------------------------------------------------------------
 template <typename T>
-__device__ __forceinline__ void forward_4096(cx<T> (&v)[16], const Ctx<T>& c) {
+__device__ __forceinline__ void forward_4096(cx<T> (&v)[16], const Ctx<T>& c, uint64_t* empty_mb, int empty_parity) {
     fft16<T, false>(v);
 #pragma unroll
     for (int k = 1; k < 16; ++k) v[k] = cmul(v[k], c.tw1[k * 256 + c.t]);
-    __syncthreads();   // every earlier reader of the fabric (previous item's X4 / X2) is done
+    CAF_TR(c, 3);
+    if (empty_mb) mbar_wait(empty_mb, empty_parity);   // group 0 has drained the previous row's mailbox
+    bar_group(c.r);    // every earlier reader of this half of the fabric (previous X4 / X2) is done
 #pragma unroll
     for (int k = 0; k < 16; ++k) c.Sr[k * 256 + c.t] = v[k];
-    __syncthreads();
+    CAF_TR(c, 4);
+    bar_group(c.r);
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = c.Sw[c.h + 16 * i];
+    CAF_TR(c, 5);
 
     fft16<T, false>(v);
 #pragma unroll
     for (int k = 1; k < 16; ++k) v[k] = cmul(v[k], c.tw2[k * 16 + c.h]);
+    CAF_TR(c, 6);
     __syncwarp();
 #pragma unroll
     for (int k = 0; k < 16; ++k) c.Sw[k * 16 + (c.h ^ k)] = v[k];
     __syncwarp();
 #pragma unroll
     for (int m = 0; m < 16; ++m) v[m] = c.Sw[c.h * 16 + (m ^ c.h)];
+    CAF_TR(c, 7);
 
     fft16<T, false>(v);
+    CAF_TR(c, 8);
 }
 
 // ------------------------------------------------------------------------------------------------
-// inverse: v[k3] = Y_r[w + 16 h + 256 k3]  ->  v[n1] = A_r[t + 256 n1]  (unnormalised, xcor_rustfft.rs:76)
+// inverse: v[k3] = Y_r[k1 + 16 h + 256 k3]  ->  v[n1] = A_r[t + 256 n1]  (unnormalised, xcor_rustfft.rs:76)
 // ------------------------------------------------------------------------------------------------
 template <typename T>
 __device__ __forceinline__ void inverse_4096(cx<T> (&v)[16], const Ctx<T>& c) {
     fft16<T, true>(v);
 #pragma unroll
     for (int k = 1; k < 16; ++k) v[k] = cmulc(v[k], c.tw2[k * 16 + c.h]);
+    CAF_TR(c, 10);
     __syncwarp();
 #pragma unroll
     for (int k = 0; k < 16; ++k) c.Sw[k * 16 + (c.h ^ k)] = v[k];
     __syncwarp();
 #pragma unroll
     for (int m = 0; m < 16; ++m) v[m] = c.Sw[c.h * 16 + (m ^ c.h)];
+    CAF_TR(c, 11);
 
     fft16<T, true>(v);
 #pragma unroll
     for (int k = 0; k < 16; ++k) v[k] = cmulc(v[k], c.tw1[c.w * 256 + 16 * k + c.h]);
+    CAF_TR(c, 12);
     __syncwarp();
 #pragma unroll
     for (int k = 0; k < 16; ++k) c.Sw[16 * k + c.h] = v[k];
-    __syncthreads();
+    CAF_TR(c, 13);
+    bar_group(c.r);
 #pragma unroll
     for (int k = 0; k < 16; ++k) v[k] = c.Sr[k * 256 + c.t];
+    CAF_TR(c, 14);
 
     fft16<T, true>(v);
+    CAF_TR(c, 15);
 }
 
-// multiply by W_32^{-J} = e^{+2 pi j J/32}, J = 0..7 (compile-time constant)
+// multiply by W_32^{-J} = e^{+2 pi j J/32}, J = 0..15 (compile-time constant)
 template <typename T, int J>
 __device__ __forceinline__ cx<T> mul_w32_inv(cx<T> a) {
     constexpr T Cc[8] = {(T)1.0L, (T)0.98078528040323044913L, (T)0.92387953251128675613L, (T)0.83146961230254523708L,
@@ -260,7 +305,9 @@ __device__ __forceinline__ cx<T> mul_w32_inv(cx<T> a) {
                          (T)0.70710678118654752440L, (T)0.83146961230254523708L, (T)0.92387953251128675613L,
                          (T)0.98078528040323044913L};
     if constexpr (J == 0) return a;
-    else return mk<T>(a.x * Cc[J] - a.y * Ss[J], a.x * Ss[J] + a.y * Cc[J]);
+    else if constexpr (J == 8) return mk<T>(-a.y, a.x);                                   // +j
+    else if constexpr (J < 8) return mk<T>(a.x * Cc[J] - a.y * Ss[J], a.x * Ss[J] + a.y * Cc[J]);
+    else return mk<T>(-a.x * Ss[J - 8] - a.y * Cc[J - 8], a.x * Cc[J - 8] - a.y * Ss[J - 8]);   // (+j) * W_32^{-(J-8)}
 }
 
 // argmax helper: larger value wins, ties go to the lower index (== first strict-> maximum, mod.rs:148)
@@ -268,6 +315,8 @@ template <typename T>
 __device__ __forceinline__ void amax_take(T& best, int& bidx, T m, int k) {
     if (m > best || (m == best && k < bidx)) { best = m; bidx = k; }
 }
+
+template <int I> using ic = std::integral_constant<int, I>;
 
 // FULL = the reference's shape, L == 4096: every one of the 8192 cells is an output cell (no index remap).
 template <typename T, int MODE, bool FULL>
@@ -284,16 +333,22 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
     unsigned long long* red_idx = reinterpret_cast<unsigned long long*>(smem_raw + SL::offRed);
     double* red_val = reinterpret_cast<double*>(smem_raw + SL::offRed + 128);
     uint32_t* misc = reinterpret_cast<uint32_t*>(smem_raw + SL::offMisc);
+    uint64_t* mb_full = reinterpret_cast<uint64_t*>(smem_raw + SL::offMisc + 16);
+    uint64_t* mb_empty = reinterpret_cast<uint64_t*>(smem_raw + SL::offMisc + 24);
 
     const int tid = threadIdx.x;
     Ctx<T> c;
-    // lane = h[2:0] | r << 3 | h[3] << 4: the two pipelines sit in adjacent quarter-warps, so a 128-bit
-    // twiddle load (same address for both r) costs 2 shared-memory wavefronts instead of 4
-    c.w = tid >> 5; c.lane = tid & 31; c.r = (c.lane >> 3) & 1; c.h = (c.lane & 7) | ((c.lane >> 1) & 8);
+    // group r = tid / 256.  Inside a warp: lane = h[2:0] | sub << 3 | h[3] << 4; the warp's two sub-transforms
+    // k1 = 2 * warp_in_group + sub sit in adjacent quarter-warps, so a 128-bit W_256 twiddle load (same address
+    // for both) costs 2 shared-memory wavefronts instead of 4.
+    const int hw_warp = tid >> 5;
+    c.lane = tid & 31; c.r = tid >> 8;
+    c.h = (c.lane & 7) | ((c.lane >> 1) & 8);
+    c.w = 2 * (hw_warp & 7) + ((c.lane >> 3) & 1);     // k1: the 256-point sub-transform this thread works in
     c.t = 16 * c.w + c.h;
     c.S = S; c.Sr = S + c.r * kL0; c.Sw = c.Sr + c.w * 256;
     c.tw1 = tw1s; c.tw2 = tw2s; c.g256 = g256s; c.ptab = ptab;
-    const int w = c.w, lane = c.lane, r = c.r, h = c.h, t = c.t;
+    const int w = c.w, lane = c.lane, r = c.r, h = c.h, t = c.t, tg = tid & 255, wg = hw_warp & 7;
 
     constexpr bool kHalfZero = (MODE == kSurface || MODE == kSpectrumHalf || MODE == kXcorHalf);
     constexpr bool kWritesH = (MODE == kSpectrumHalf || MODE == kSpectrumFull);
@@ -313,11 +368,16 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
         }
         asm volatile("cp.async.commit_group;\n" ::: "memory");
     }
+    if (tid == 0) {
+        mbar_init(mb_full, 256);
+        mbar_init(mb_empty, 256);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
 
     // ---- TMEM: the tensor memory of this SM becomes the per-thread operand store ----
     uint32_t tm_h = 0, tm_n = 0;
     if (kUseTmem) {
-        if (w == 0) {
+        if (hw_warp == 0) {
             asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n"
                          :: "l"((uint64_t)__cvta_generic_to_shared(&misc[0])), "n"(TG::kAlloc));
             asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
@@ -325,21 +385,21 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
         asm volatile("tcgen05.fence::before_thread_sync;\n");
         __syncthreads();
         asm volatile("tcgen05.fence::after_thread_sync;\n");
-        const uint32_t base = misc[0] + ((uint32_t)(32 * (w & 3)) << 16) + (uint32_t)(TG::kColsPerGroup * (w >> 2));
+        const uint32_t base = misc[0] + ((uint32_t)(32 * (hw_warp & 3)) << 16) + (uint32_t)(TG::kColsPerGroup * (hw_warp >> 2));
         tm_h = base;                              // 16 H bins
         tm_n = base + 16 * TG::kColsPerC;         // 16 needle samples
     } else {
         __syncthreads();
     }
 
-    // phasor factor tables for one item: ptab[buf][r][0][i] = e^{j2pi 256 i phi_r}, [1][a] = 16 a, [2][b] = b
+    // phasor factor tables of this group's pipeline: ptab[buf][r][0][i] = e^{j2pi 256 i phi_r}, [1][a] = 16 a, [2][b] = b
     auto fill_ptab = [&](int buf, double phi) {
-        if (tid < 96) {
-            const int rr = tid / 48, e = tid % 48, which = e >> 4, idx = e & 15;
+        if (tg < 48) {
+            const int e = tg, which = e >> 4, idx = e & 15;
             const int n = idx << (which == 0 ? 8 : which == 1 ? 4 : 0);
             // r/8192 * n is exact in binary
-            double2 p = unit_phasor((double)n, phi, (double)(rr * n) * (1.0 / 8192.0));
-            ptab[(buf * 2 + rr) * 48 + e] = mk<T>((T)p.x, (T)p.y);
+            double2 p = unit_phasor((double)n, phi, (double)(r * n) * (1.0 / 8192.0));
+            ptab[(buf * 2 + r) * 48 + e] = mk<T>((T)p.x, (T)p.y);
         }
     };
     // v[i] *= phasor_r(t + 256 i)
@@ -364,30 +424,45 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
     const long long lo = n_items * blockIdx.x / gridDim.x, hi = n_items * (blockIdx.x + 1) / gridDim.x;
     int pair = (int)(lo / rows_per_pair), row = (int)(lo - (long long)pair * rows_per_pair);   // one division per CTA
 
-    // The inverse of pipeline r = 1 runs on (-1)^q H: its output comes out rotated by 2048 samples, i.e. register j
-    // of an r = 1 lane holds B[t + 256 (j + 8)] and register j + 8 holds B[t + 256 j].  Both partners of the final
-    // radix-2 then send register j + 8 and keep register j — no per-lane register selection.  q = w + 16 h + 256 k3
-    // has the parity of w, so the sign is one factor per thread, folded into the 1/n scaling of H.
-    const T hsign = (r && (w & 1)) ? (T)-1 : (T)1;
-
     int buf = 0;
     int cur_pair = -1;
     bool tables_ready = false;
+    int posts = 0;            // mailbox posts so far (group 1) / mailbox reads so far (group 0)
+    bool drain_pending = false;   // group 1: a posted mailbox that group 0 may still be reading
     C v[16];
 
+    auto empty_gate = [&](uint64_t*& mb, int& par) {
+        // group 1 must not overwrite its fabric half while group 0 still reads the last mailbox from it
+        if (r == 1 && drain_pending) { mb = mb_empty; par = (posts - 1) & 1; drain_pending = false; }
+        else { mb = nullptr; par = 0; }
+    };
+
+    if (r == 0 && a.stagger > 0 && lo < hi) {
+        // start group 0 half a pass behind group 1: from then on one group's exchange overlaps the other's math
+        const long long t0 = clock64();
+        while (clock64() - t0 < a.stagger) { }
+    }
+
+    c.tr = nullptr;
     for (long long item = lo; item < hi; ++item, buf ^= 1) {
+#ifdef CAF_TRACE
+        c.tr = (a.trace && item - lo < 8) ? a.trace + ((((long long)blockIdx.x * 16 + hw_warp) * 8 + (item - lo)) * 24) : nullptr;
+#endif
+        CAF_TR(c, 0);
         if constexpr (MODE == kSurface) {
             if (pair != cur_pair) {
-                // ---- per-pair prologue: H = FFT(haystack)/n into TMEM, needle into TMEM ----
+                // ---- per-pair prologue: H_r = FFT_r(haystack)/n into TMEM, needle into TMEM ----
                 cur_pair = pair;
-                __syncthreads();                  // nobody still reads ptab[buf] of an earlier item
+                bar_group(r);                     // nobody in this group still reads ptab[buf] of an earlier item
                 fill_ptab(buf, 0.0);
                 load_half(v, a.in2 + (long long)pair * a.L, a.L);
-                if (!tables_ready) { cp_async_wait_all(); tables_ready = true; }
-                __syncthreads();
+                if (!tables_ready) { cp_async_wait_all(); __syncthreads(); tables_ready = true; }
+                else bar_group(r);
                 phasor_mul(v, buf);
-                forward_4096<T>(v, c);
-                const T sc = (T)(1.0 / 8192.0) * hsign;   // the /n of xcor_rustfft.rs:72 (n = transform length)
+                uint64_t* mb; int par;
+                empty_gate(mb, par);
+                forward_4096<T>(v, c, mb, par);
+                const T sc = (T)(1.0 / 8192.0);   // the /n of xcor_rustfft.rs:72 (n = transform length)
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     C tmp[4];
@@ -404,10 +479,11 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
                     tmem_st4(tm_n + 4 * q * TG::kColsPerC, tmp);
                 }
                 tmem_wait_st();
-                __syncthreads();                  // ptab[buf] (phi = 0) is dead from here
+                bar_group(r);                     // ptab[buf] (phi = 0) is dead from here
                 fill_ptab(buf, a.freqs[row] * a.dt);
-                __syncthreads();
+                bar_group(r);
             }
+            CAF_TR(c, 1);
             // ---- needle samples back from TMEM ----
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -417,12 +493,13 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
                 for (int i = 0; i < 4; ++i) v[4 * q + i] = tmp[i];
             }
             phasor_mul(v, buf);
+            CAF_TR(c, 2);
         } else if constexpr (kHalfZero) {
-            __syncthreads();
+            bar_group(r);
             fill_ptab(buf, 0.0);
             load_half(v, a.in + (long long)pair * a.L, a.L);
-            if (!tables_ready) { cp_async_wait_all(); tables_ready = true; }
-            __syncthreads();
+            if (!tables_ready) { cp_async_wait_all(); __syncthreads(); tables_ready = true; }
+            else bar_group(r);
             phasor_mul(v, buf);
         } else {
             // general 8192-sample input: explicit first radix-2 stage
@@ -434,24 +511,27 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
                 if (r == 0) v[i] = cadd(x0, x1);
                 else v[i] = cmulc(csub(x0, x1), ldg<T>(a.g + n));   // * W_8192^{+n} = conj(g[n])
             }
-            if (!tables_ready) { cp_async_wait_all(); tables_ready = true; }
-            __syncthreads();
+            if (!tables_ready) { cp_async_wait_all(); __syncthreads(); tables_ready = true; }
         }
 
         // ---------------- forward transform ----------------
-        forward_4096<T>(v, c);
-        // phasors of the next row are produced while the fabric is quiet; the block barrier inside
+        {
+            uint64_t* mb; int par;
+            empty_gate(mb, par);
+            forward_4096<T>(v, c, mb, par);
+        }
+        // phasors of the next row are produced while the fabric is quiet; the group barrier inside
         // inverse_4096 orders them before their first use
-        const bool next_same_pair = (MODE == kSurface) && (item + 1 < hi) && (row + 1 < a.D);
         if constexpr (MODE == kSurface) {
-            if (next_same_pair) fill_ptab(buf ^ 1, a.freqs[row + 1] * a.dt);
+            if ((item + 1 < hi) && (row + 1 < a.D)) fill_ptab(buf ^ 1, a.freqs[row + 1] * a.dt);
         }
 
+        // standalone-xcor spectrum layout in global memory: [k3][k1][r][h]
         C* hp = a.hperm + (long long)pair * kM;
         if constexpr (kWritesH) {
             const T sc = (T)(1.0 / 8192.0);
 #pragma unroll
-            for (int k = 0; k < 16; ++k) hp[(k * 16 + w) * 32 + lane] = mk<T>(v[k].x * sc, v[k].y * sc);
+            for (int k = 0; k < 16; ++k) hp[((k * 16 + w) * 2 + r) * 16 + h] = mk<T>(v[k].x * sc, v[k].y * sc);
         } else {
             // ---------------- H * conj(X)  (xcor_rustfft.rs:64-73) ----------------
             if constexpr (kUseTmem) {
@@ -464,95 +544,107 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
                 }
             } else {
 #pragma unroll
-                for (int k = 0; k < 16; ++k) {
-                    C hv = ldg<T>(hp + (k * 16 + w) * 32 + lane);
-                    v[k] = cmulc(mk<T>(hv.x * hsign, hv.y * hsign), v[k]);
-                }
+                for (int k = 0; k < 16; ++k) v[k] = cmulc(ldg<T>(hp + ((k * 16 + w) * 2 + r) * 16 + h), v[k]);
             }
 
+            CAF_TR(c, 9);
             // ---------------- inverse transform ----------------
-            inverse_4096<T>(v, c);   // r = 0: v[n1] = A[t + 256 n1];  r = 1: v[n1] = B[t + 256 (n1 ^ 8)]
+            inverse_4096<T>(v, c);   // v[n1] = A_r[t + 256 n1]
 
-            // ---------------- radix-2 combine across the two pipelines (partner lane ^ 8) ----------------
-            // lane r handles n = t + 256 (j + 8 r), j = 0..7:   y[n] = A + B', y[n + 4096] = A - B',
-            // B' = B W_8192^{-n},  W_8192^{-n} = g[t] (+j)^r W_32^{-j}
-            C gt = g256s[t];
-            if (r) gt = mk<T>(-gt.y, gt.x);
-            const int L = FULL ? kL0 : a.L;
-            const int nout = 2 * L, skip = kM - nout;
-            T* orow = (MODE == kSurface && a.out) ? reinterpret_cast<T*>(a.out) + item * (long long)nout : nullptr;
-            C* ocx = (MODE != kSurface) ? reinterpret_cast<C*>(a.out) + (long long)pair * kM : nullptr;
-            // two running maxima (cells n < 4096 and n >= 4096), each visited in ascending index order, so a
-            // strict > keeps the first maximum exactly as mod.rs:148 does
-            T best0 = (T)0, best1 = (T)0;
-            int bidx0 = 0, bidx1 = 0;
-            auto emit = [&](C y, int kp, T& best, int& bidx) {
-                if constexpr (MODE == kSurface) {
-                    const T m = y.x * y.x + y.y * y.y;                   // norm_sqr, mod.rs:147
-                    if constexpr (FULL) {
-                        if (orow) orow[kp] = m;
-                        if (m > best) { best = m; bidx = kp; }
-                    } else {
-                        // reference index: 2L-point circular layout
-                        int k = -1;
-                        if (kp <= L) k = kp; else if (kp > kM - L) k = kp - skip;
-                        if (k >= 0 && k < nout) {
-                            if (orow) orow[k] = m;
-                            if (m > best) { best = m; bidx = k; }
+            // ---------------- final radix-2 across the pipelines:  y[n] = A + B', y[n + 4096] = A - B',
+            //                  B' = B W_8192^{-n},  n = t + 256 n1,  W_8192^{-n} = g[t] W_32^{-n1} ----------------
+            if (r == 1) {
+                const C gt = g256s[t];
+                auto post = [&](auto jt) {
+                    constexpr int j = decltype(jt)::value;
+                    v[j] = cmul(v[j], mul_w32_inv<T, j>(gt));
+                };
+                post(ic<0>{}); post(ic<1>{}); post(ic<2>{}); post(ic<3>{}); post(ic<4>{}); post(ic<5>{}); post(ic<6>{}); post(ic<7>{});
+                post(ic<8>{}); post(ic<9>{}); post(ic<10>{}); post(ic<11>{}); post(ic<12>{}); post(ic<13>{}); post(ic<14>{}); post(ic<15>{});
+                CAF_TR(c, 16);
+                bar_group(1);                 // all X4 reads of this half are done: it becomes the mailbox
+#pragma unroll
+                for (int k = 0; k < 16; ++k) c.Sr[k * 256 + t] = v[k];
+                mbar_arrive(mb_full);
+                CAF_TR(c, 17);
+                ++posts;
+                drain_pending = true;
+            } else {
+                const int L = FULL ? kL0 : a.L;
+                const int nout = 2 * L, skip = kM - nout;
+                T* orow = (MODE == kSurface && a.out) ? reinterpret_cast<T*>(a.out) + item * (long long)nout : nullptr;
+                C* ocx = (MODE != kSurface) ? reinterpret_cast<C*>(a.out) + (long long)pair * kM : nullptr;
+                // two running maxima (cells n < 4096 and n >= 4096), each visited in ascending index order, so a
+                // strict > keeps the first maximum exactly as mod.rs:148 does
+                T best0 = (T)0, best1 = (T)0;
+                int bidx0 = 0, bidx1 = 0;
+                auto emit = [&](C y, int kp, T& best, int& bidx) {
+                    if constexpr (MODE == kSurface) {
+                        const T m = y.x * y.x + y.y * y.y;                   // norm_sqr, mod.rs:147
+                        if constexpr (FULL) {
+                            if (orow) orow[kp] = m;
+                            if (m > best) { best = m; bidx = kp; }
+                        } else {
+                            // reference index: 2L-point circular layout
+                            int k = -1;
+                            if (kp <= L) k = kp; else if (kp > kM - L) k = kp - skip;
+                            if (k >= 0 && k < nout) {
+                                if (orow) orow[k] = m;
+                                if (m > best) { best = m; bidx = k; }
+                            }
                         }
+                    } else {
+                        ocx[kp] = y;
                     }
-                } else {
-                    ocx[kp] = y;
+                };
+                CAF_TR(c, 16);
+                mbar_wait(mb_full, posts & 1);
+                CAF_TR(c, 17);
+                const C* mail = S + kL0;
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                    const C Bp = mail[k * 256 + t];
+                    const int n = t + 256 * k;
+                    emit(cadd(v[k], Bp), n, best0, bidx0);             // lag index n
+                    emit(csub(v[k], Bp), n + kL0, best1, bidx1);       // lag index n + 4096
                 }
-            };
-            auto combine = [&](auto jtag) {
-                constexpr int j = decltype(jtag)::value;
-                C recv;
-                recv.x = __shfl_xor_sync(0xffffffffu, v[j + 8].x, 8);
-                recv.y = __shfl_xor_sync(0xffffffffu, v[j + 8].y, 8);
-                const C A = r ? recv : v[j];
-                const C B = r ? v[j] : recv;
-                const C Bp = cmul(B, mul_w32_inv<T, j>(gt));
-                const int n = t + 256 * (j + 8 * r);
-                emit(cadd(A, Bp), n, best0, bidx0);             // lag index n
-                emit(csub(A, Bp), n + kL0, best1, bidx1);       // lag index n + 4096
-            };
-            combine(std::integral_constant<int, 0>{}); combine(std::integral_constant<int, 1>{});
-            combine(std::integral_constant<int, 2>{}); combine(std::integral_constant<int, 3>{});
-            combine(std::integral_constant<int, 4>{}); combine(std::integral_constant<int, 5>{});
-            combine(std::integral_constant<int, 6>{}); combine(std::integral_constant<int, 7>{});
+                mbar_arrive(mb_empty);
+                CAF_TR(c, 18);
+                ++posts;
 
-            if constexpr (MODE == kSurface) {
-                // ---------------- row argmax (mod.rs:141-153) ----------------
-                T best = best0;
-                int bidx = bidx0;
-                if (best1 > best) { best = best1; bidx = bidx1; }   // every index of half 1 is above half 0
+                if constexpr (MODE == kSurface) {
+                    // ---------------- row argmax (mod.rs:141-153) ----------------
+                    T best = best0;
+                    int bidx = bidx0;
+                    if (best1 > best) { best = best1; bidx = bidx1; }   // every index of half 1 is above half 0
 #pragma unroll
-                for (int off = 16; off > 0; off >>= 1) {
-                    T ov = __shfl_xor_sync(0xffffffffu, best, off);
-                    int oi = __shfl_xor_sync(0xffffffffu, bidx, off);
-                    amax_take<T>(best, bidx, ov, oi);
-                }
-                // red_* were last read before the block barriers of this item -> no hazard
-                if (lane == 0) { red_val[w] = (double)best; red_idx[w] = (unsigned long long)bidx; }
-                __syncthreads();
-                if (w == 0) {
-                    double bv = (lane < 16) ? red_val[lane] : 0.0;
-                    int bi = (lane < 16) ? (int)red_idx[lane] : 0x7fffffff;
-#pragma unroll
-                    for (int off = 8; off > 0; off >>= 1) {
-                        double ov = __shfl_xor_sync(0xffffffffu, bv, off);
-                        int oi = __shfl_xor_sync(0xffffffffu, bi, off);
-                        amax_take<double>(bv, bi, ov, oi);
+                    for (int off = 16; off > 0; off >>= 1) {
+                        T ov = __shfl_xor_sync(0xffffffffu, best, off);
+                        int oi = __shfl_xor_sync(0xffffffffu, bidx, off);
+                        amax_take<T>(best, bidx, ov, oi);
                     }
-                    if (lane == 0) {
-                        if (!(bv > 0.0)) bi = 0;   // nothing beat the initial max = 0.0 (mod.rs:143-144)
-                        if (a.row_peak_val) a.row_peak_val[item] = (T)bv;
-                        if (a.row_peak_idx) a.row_peak_idx[item] = (unsigned long long)bi;
+                    // red_* were last read before the group barriers of this item -> no hazard
+                    if (lane == 0) { red_val[wg] = (double)best; red_idx[wg] = (unsigned long long)bidx; }
+                    bar_group(0);
+                    if (wg == 0) {
+                        double bv = (lane < 8) ? red_val[lane] : 0.0;
+                        int bi = (lane < 8) ? (int)red_idx[lane] : 0x7fffffff;
+#pragma unroll
+                        for (int off = 4; off > 0; off >>= 1) {
+                            double ov = __shfl_xor_sync(0xffffffffu, bv, off);
+                            int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+                            amax_take<double>(bv, bi, ov, oi);
+                        }
+                        if (lane == 0) {
+                            if (!(bv > 0.0)) bi = 0;   // nothing beat the initial max = 0.0 (mod.rs:143-144)
+                            if (a.row_peak_val) a.row_peak_val[item] = (T)bv;
+                            if (a.row_peak_idx) a.row_peak_idx[item] = (unsigned long long)bi;
+                        }
                     }
                 }
             }
         }
+        CAF_TR(c, 19);
         // next item
         if (++row == rows_per_pair) { row = 0; ++pair; }
     }
@@ -561,7 +653,7 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
     if constexpr (kUseTmem) {
         asm volatile("tcgen05.fence::before_thread_sync;\n");
         __syncthreads();
-        if (w == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" :: "r"(misc[0]), "n"(TG::kAlloc));
+        if (hw_warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" :: "r"(misc[0]), "n"(TG::kAlloc));
     }
 
     // ---------------- fused find_peak (mod.rs:31-42), single pair: the last CTA to finish reduces the rows ----------------
@@ -588,7 +680,7 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
                     int oi = __shfl_xor_sync(0xffffffffu, brow, off);
                     amax_take<double>(best, brow, ov, oi);
                 }
-                if (lane == 0) { red_val[w] = best; red_idx[w] = (unsigned long long)(unsigned int)brow; }
+                if (lane == 0) { red_val[hw_warp] = best; red_idx[hw_warp] = (unsigned long long)(unsigned int)brow; }
                 __syncthreads();
                 if (tid == 0) {
                     for (int q = 1; q < 16; ++q) amax_take<double>(best, brow, red_val[q], (int)red_idx[q]);

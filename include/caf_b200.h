@@ -81,6 +81,9 @@ int caf_b200_last_kernel_ms(caf_b200_handle h, float* spectrum_ms, float* rows_m
  * returns achieved TFLOP/s (2 flops per FMA).  is_f64 != 0 -> double, else float. */
 int caf_b200_probe_fma_tflops(caf_b200_handle h, int is_f64, double* tflops);
 
+/* development hook: phase time stamps of the row kernel; only in -DCAF_TRACE builds (else EUNSUPPORTED) */
+int caf_b200_debug_trace(caf_b200_handle h, long long* out, size_t n_cta);
+
 /* pinned host buffers: surfaces DMA straight into them (any host pointer is accepted, pinned is faster) */
 int caf_b200_host_alloc(void** out, size_t bytes);
 int caf_b200_host_free(void* p);

@@ -1,0 +1,35 @@
+"""Development: dump the per-warp phase timeline of the row kernel (needs the -DCAF_TRACE build).
+   CAF_B200_SO=scripts/micro/libcaf_b200_trace.so python scripts/trace_rows.py"""
+import os, sys, ctypes as C
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from caf_cookoff_b200 import _lib, read_file_c64, bench_shifts, surface_arrays, default_handle
+D = os.path.join(ROOT, "tests/golden/data/")
+needle = read_file_c64(D + "chirp_0_raw.c64"); hay = read_file_c64(D + "chirp_0_T+202samp_F+69.25Hz.c64")[:4096]
+sh = bench_shifts()
+h = default_handle(); lib = _lib.load()
+lib.caf_b200_debug_trace(h.raw, None, 0)            # allocate
+for _ in range(3): surface_arrays(needle, hay, sh, 48000, want_surface=True)
+ncta = 148
+buf = np.zeros((ncta, 16, 8, 24), dtype=np.int64)
+assert lib.caf_b200_debug_trace(h.raw, buf.ctypes.data_as(C.c_void_p), ncta) == 0
+names = {0:"item start",1:"row start",2:"phasor done",3:"f1+tw done",4:"X1 written",5:"X1 read iss",6:"f2+tw done",7:"X2 done",8:"f3 done",9:"H mul done",10:"i1+tw done",11:"X3 done",12:"i2+tw done",13:"X4 written",14:"X4 read iss",15:"i3 done",16:"G1 tw done/G0 at wait",17:"G1 posted/G0 got mail",18:"G0 emitted",19:"item end"}
+for cta in (0, 77):
+    t0 = buf[cta][buf[cta] > 0].min()
+    print(f"=== CTA {cta}: cycles since first stamp; columns = warp 0 (G0), warp 7 (G0), warp 8 (G1), warp 15 (G1)")
+    for item in range(3):
+        print(f"-- item {item}")
+        prev = None
+        for s in range(20):
+            vals = [int(buf[cta, w, item, s] - t0) if buf[cta, w, item, s] > 0 else -1 for w in (0, 7, 8, 15)]
+            print(f"{s:2d} {names[s]:24s} " + " ".join(f"{v:8d}" for v in vals))
+# summary: per-row duration across CTAs
+dur = []
+for cta in range(ncta):
+    for item in range(3):
+        a, b = buf[cta, 0, item, 1], buf[cta, 0, item, 19]
+        if a > 0 and b > 0: dur.append(b - a)
+print("row duration (warp 0) cycles: median", np.median(dur), "min", np.min(dur), "max", np.max(dur))
+pro = [buf[c, 0, 0, 1] - buf[c, 0, 0, 0] for c in range(ncta) if buf[c, 0, 0, 1] > 0]
+print("prologue (item start -> row start) cycles: median", np.median(pro))
