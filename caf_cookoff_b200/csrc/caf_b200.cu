@@ -67,6 +67,9 @@ struct caf_b200_handle_s {
     int stagger = 0;
     long long* trace = nullptr;   // CAF_TRACE builds: device buffer for phase stamps
     unsigned int* done_counter = nullptr;   // last-CTA-done ticket of the fused find_peak
+    void* hshare = nullptr;                 // single-pair launches: H published by CTA 0 (8192 complex128)
+    unsigned int* hflag = nullptr;          // [2] publish counters, monotonic
+    unsigned int epoch = 0;
     void* h_peaks = nullptr;    // pinned staging for peaks
     size_t h_peaks_cap = 0;
     bool profiling = false;
@@ -191,6 +194,9 @@ int run_batch_dev(caf_b200_handle h, const caf::cx<T>* needles, const caf::cx<T>
     a.out = surface; a.row_peak_val = rv; a.row_peak_idx = ri;
     const bool fused_peak = peaks && p == 1;      // single pair: find_peak rides in the same launch
     if (fused_peak) { a.peak = peaks; a.done_counter = h->done_counter; }
+    if (p == 1 && d > 1) {                        // one pair over many CTAs: CTA 0 publishes H, the rest consume it
+        a.hshare = reinterpret_cast<cx<T>*>(h->hshare); a.hflag = h->hflag; a.epoch = ++h->epoch;
+    }
     const bool prof = h->profiling;
     if (prof) {
         for (auto& e : h->ev) if (!e) CK(cudaEventCreate(&e));
@@ -377,7 +383,10 @@ static int create_impl(int device, bool own_stream, void* cuda_stream, caf_b200_
         if (e != cudaSuccess) { delete h; return fail(CAF_B200_ECUDA, cudaGetErrorString(e)); }
         h->own_stream = true;
     }
-    if ((e = cudaMalloc(&h->done_counter, sizeof(unsigned int))) != cudaSuccess ||
+    if ((e = cudaMalloc(&h->hshare, sizeof(double2) * caf::kM)) != cudaSuccess ||
+        (e = cudaMalloc(&h->hflag, 2 * sizeof(unsigned int))) != cudaSuccess ||
+        (e = cudaMemsetAsync(h->hflag, 0, 2 * sizeof(unsigned int), h->stream)) != cudaSuccess ||
+        (e = cudaMalloc(&h->done_counter, sizeof(unsigned int))) != cudaSuccess ||
         (e = cudaMemsetAsync(h->done_counter, 0, sizeof(unsigned int), h->stream)) != cudaSuccess ||
         (e = upload_tables<double>(h->td, h->stream)) != cudaSuccess ||
         (e = upload_tables<float>(h->tf, h->stream)) != cudaSuccess ||
@@ -406,6 +415,8 @@ int caf_b200_destroy(caf_b200_handle h) {
         if (q) cudaFree(q);
     if (h->h_peaks) cudaFreeHost(h->h_peaks);
     if (h->done_counter) cudaFree(h->done_counter);
+    if (h->hshare) cudaFree(h->hshare);
+    if (h->hflag) cudaFree(h->hflag);
     for (auto& e : h->ev) if (e) cudaEventDestroy(e);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
     delete h;

@@ -79,6 +79,9 @@ struct RowArgs {
     int D;                  // doppler rows per pair
     int P;                  // pairs
     int stagger;            // cycles group 0 idles before its first item (phase offset between the groups)
+    cx<T>* hshare;          // kSurface, P == 1: H published by CTA 0 for every other CTA, [16][512] per-thread order
+    unsigned int* hflag;    // [2] per-group publish counters (monotonic across launches)
+    unsigned int epoch;     // this launch's counter value
     long long* trace;       // CAF_TRACE builds only: [cta][warp][8 items][24 slots] clock64 stamps
 };
 
@@ -148,16 +151,25 @@ template <typename T> struct TmemGeom;
 template <> struct TmemGeom<double> { static constexpr int kColsPerC = 4, kColsPerGroup = 128, kAlloc = 512; };
 template <> struct TmemGeom<float>  { static constexpr int kColsPerC = 2, kColsPerGroup = 64,  kAlloc = 256; };
 
-// 4 complex values <-> TMEM columns [taddr, taddr + 4*kColsPerC)
-__device__ __forceinline__ void tmem_ld4(uint32_t taddr, double2 (&o)[4]) {
-    uint32_t r[16];
-    tmem_ld_x16(taddr, r);
-    tmem_wait_ld();
+// 4 complex values <-> TMEM columns [taddr, taddr + 4*kColsPerC).  Loads are split into issue / unpack so
+// several can be in flight behind a single tcgen05.wait::ld.
+struct Raw4d { uint32_t r[16]; };
+struct Raw4f { uint32_t r[8]; };
+template <typename T> struct raw4_of;
+template <> struct raw4_of<double> { using type = Raw4d; };
+template <> struct raw4_of<float>  { using type = Raw4f; };
+__device__ __forceinline__ void tmem_ld4_issue(uint32_t taddr, Raw4d& q) { tmem_ld_x16(taddr, q.r); }
+__device__ __forceinline__ void tmem_ld4_issue(uint32_t taddr, Raw4f& q) { tmem_ld_x8(taddr, q.r); }
+__device__ __forceinline__ void tmem_unpack4(const Raw4d& q, double2 (&o)[4]) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        o[i].x = __hiloint2double((int)r[4 * i + 1], (int)r[4 * i]);
-        o[i].y = __hiloint2double((int)r[4 * i + 3], (int)r[4 * i + 2]);
+        o[i].x = __hiloint2double((int)q.r[4 * i + 1], (int)q.r[4 * i]);
+        o[i].y = __hiloint2double((int)q.r[4 * i + 3], (int)q.r[4 * i + 2]);
     }
+}
+__device__ __forceinline__ void tmem_unpack4(const Raw4f& q, float2 (&o)[4]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { o[i].x = __uint_as_float(q.r[2 * i]); o[i].y = __uint_as_float(q.r[2 * i + 1]); }
 }
 __device__ __forceinline__ void tmem_st4(uint32_t taddr, const double2 (&v)[4]) {
     uint32_t r[16];
@@ -167,13 +179,6 @@ __device__ __forceinline__ void tmem_st4(uint32_t taddr, const double2 (&v)[4]) 
         r[4 * i + 2] = (uint32_t)__double2loint(v[i].y); r[4 * i + 3] = (uint32_t)__double2hiint(v[i].y);
     }
     tmem_st_x16(taddr, r);
-}
-__device__ __forceinline__ void tmem_ld4(uint32_t taddr, float2 (&o)[4]) {
-    uint32_t r[8];
-    tmem_ld_x8(taddr, r);
-    tmem_wait_ld();
-#pragma unroll
-    for (int i = 0; i < 4; ++i) { o[i].x = __uint_as_float(r[2 * i]); o[i].y = __uint_as_float(r[2 * i + 1]); }
 }
 __device__ __forceinline__ void tmem_st4(uint32_t taddr, const float2 (&v)[4]) {
     uint32_t r[8];
@@ -212,6 +217,13 @@ __device__ __forceinline__ double2 unit_phasor(double n, double phi, double exac
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void bar_group(int r) { asm volatile("bar.sync %0, 256;\n" :: "r"(r + 1) : "memory"); }
 
+// Ping-pong of the fp64 pipe between the two groups (the FlashAttention-3 warpgroup schedule): a group runs its
+// butterfly blocks only while it holds the token, and does its shared-memory exchange while the other group
+// computes.  pp_acquire = bar.sync on the own barrier (256 waiters + 256 arrivals from the other group),
+// pp_release = bar.arrive on the other group's barrier.
+__device__ __forceinline__ void pp_acquire(int r) { asm volatile("bar.sync %0, 512;\n" :: "r"(3 + r) : "memory"); }
+__device__ __forceinline__ void pp_release(int r) { asm volatile("bar.arrive %0, 512;\n" :: "r"(4 - r) : "memory"); }
+
 __device__ __forceinline__ void mbar_init(uint64_t* mb, int count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" :: "r"((uint32_t)__cvta_generic_to_shared(mb)), "r"(count) : "memory");
 }
@@ -232,8 +244,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t* mb, int parity) {
 template <typename T>
 __device__ __forceinline__ void forward_4096(cx<T> (&v)[16], const Ctx<T>& c, uint64_t* empty_mb, int empty_parity) {
     fft16<T, false>(v);
-#pragma unroll
-    for (int k = 1; k < 16; ++k) v[k] = cmul(v[k], c.tw1[k * 256 + c.t]);
+    twiddle_powers<false>(v, c.tw1[256 + c.t]);                 // W_4096^{t k}
+    pp_release(c.r);
     CAF_TR(c, 3);
     if (empty_mb) mbar_wait(empty_mb, empty_parity);   // group 0 has drained the previous row's mailbox
     bar_group(c.r);    // every earlier reader of this half of the fabric (previous X4 / X2) is done
@@ -245,9 +257,10 @@ __device__ __forceinline__ void forward_4096(cx<T> (&v)[16], const Ctx<T>& c, ui
     for (int i = 0; i < 16; ++i) v[i] = c.Sw[c.h + 16 * i];
     CAF_TR(c, 5);
 
+    pp_acquire(c.r);
     fft16<T, false>(v);
-#pragma unroll
-    for (int k = 1; k < 16; ++k) v[k] = cmul(v[k], c.tw2[k * 16 + c.h]);
+    twiddle_powers<false>(v, c.tw2[16 + c.h]);                  // W_256^{h k}
+    pp_release(c.r);
     CAF_TR(c, 6);
     __syncwarp();
 #pragma unroll
@@ -257,7 +270,8 @@ __device__ __forceinline__ void forward_4096(cx<T> (&v)[16], const Ctx<T>& c, ui
     for (int m = 0; m < 16; ++m) v[m] = c.Sw[c.h * 16 + (m ^ c.h)];
     CAF_TR(c, 7);
 
-    fft16<T, false>(v);
+    pp_acquire(c.r);
+    fft16<T, false>(v);    // returns holding the token
     CAF_TR(c, 8);
 }
 
@@ -266,9 +280,9 @@ __device__ __forceinline__ void forward_4096(cx<T> (&v)[16], const Ctx<T>& c, ui
 // ------------------------------------------------------------------------------------------------
 template <typename T>
 __device__ __forceinline__ void inverse_4096(cx<T> (&v)[16], const Ctx<T>& c) {
-    fft16<T, true>(v);
-#pragma unroll
-    for (int k = 1; k < 16; ++k) v[k] = cmulc(v[k], c.tw2[k * 16 + c.h]);
+    fft16<T, true>(v);     // entered holding the token
+    twiddle_powers<true>(v, c.tw2[16 + c.h]);                   // conj W_256^{h k}
+    pp_release(c.r);
     CAF_TR(c, 10);
     __syncwarp();
 #pragma unroll
@@ -278,9 +292,10 @@ __device__ __forceinline__ void inverse_4096(cx<T> (&v)[16], const Ctx<T>& c) {
     for (int m = 0; m < 16; ++m) v[m] = c.Sw[c.h * 16 + (m ^ c.h)];
     CAF_TR(c, 11);
 
+    pp_acquire(c.r);
     fft16<T, true>(v);
-#pragma unroll
-    for (int k = 0; k < 16; ++k) v[k] = cmulc(v[k], c.tw1[c.w * 256 + 16 * k + c.h]);
+    twiddle_geometric<true>(v, c.tw1[c.w * 256 + c.h], c.tw2[16 + c.w]);   // conj W_4096^{k1 (16 k + h)}
+    pp_release(c.r);
     CAF_TR(c, 12);
     __syncwarp();
 #pragma unroll
@@ -291,7 +306,8 @@ __device__ __forceinline__ void inverse_4096(cx<T> (&v)[16], const Ctx<T>& c) {
     for (int k = 0; k < 16; ++k) v[k] = c.Sr[k * 256 + c.t];
     CAF_TR(c, 14);
 
-    fft16<T, true>(v);
+    pp_acquire(c.r);
+    fft16<T, true>(v);     // returns holding the token
     CAF_TR(c, 15);
 }
 
@@ -404,10 +420,16 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
     };
     // v[i] *= phasor_r(t + 256 i)
     auto phasor_mul = [&](C (&v)[16], int buf) {
+        // phasor(t + 256 i) = [e^{j 2 pi 16 w phi} e^{j 2 pi h phi}] * (e^{j 2 pi 256 phi})^i: two product chains of 8
         const C* pt = ptab + (buf * 2 + r) * 48;
-        const C pth = cmul(pt[16 + w], pt[32 + h]);
+        const C d1 = pt[1];
+        C qa = cmul(pt[16 + w], pt[32 + h]), qb = cmul(qa, pt[8]);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = cmul(v[i], cmul(pth, pt[i]));
+        for (int i = 0; i < 8; ++i) {
+            v[i] = cmul(v[i], qa);
+            v[i + 8] = cmul(v[i + 8], qb);
+            if (i < 7) { qa = cmul(qa, d1); qb = cmul(qb, d1); }
+        }
     };
     // v[i] = src[t + 256 i]  (zero beyond L)
     auto load_half = [&](C (&v)[16], const C* src, int L) {
@@ -420,16 +442,38 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
 
     // ---- work split: contiguous ranges of (pair, row) items so a CTA changes pair as rarely as possible ----
     const int rows_per_pair = (MODE == kSurface) ? a.D : 1;
-    const long long n_items = (long long)a.P * rows_per_pair;
-    const long long lo = n_items * blockIdx.x / gridDim.x, hi = n_items * (blockIdx.x + 1) / gridDim.x;
-    int pair = (int)(lo / rows_per_pair), row = (int)(lo - (long long)pair * rows_per_pair);   // one division per CTA
+    const long long n_items = (long long)a.P * rows_per_pair;     // host guarantees < 2^31
+    const int lo = (int)(n_items * blockIdx.x / gridDim.x), hi = (int)(n_items * (blockIdx.x + 1) / gridDim.x);
+    int pair = lo / rows_per_pair, row = lo - pair * rows_per_pair;   // one division per CTA
 
     int buf = 0;
     int cur_pair = -1;
     bool tables_ready = false;
     int posts = 0;            // mailbox posts so far (group 1) / mailbox reads so far (group 0)
     bool drain_pending = false;   // group 1: a posted mailbox that group 0 may still be reading
+    bool h_from_share = false;    // consumer CTA: H still has to be fetched from CTA 0's publication
+    int peak_pending = -1;        // group 0: item whose per-warp maxima wait in red_* for the deferred reduction
     C v[16];
+
+    // fold the 8 per-warp maxima of a finished row (parked in red_*[slot]) into its row peak: warp 0 of group 0
+    auto flush_peak = [&](int slot) {
+        if (r == 0 && wg == 0 && peak_pending >= 0) {
+            double bv = (lane < 8) ? red_val[slot * 8 + lane] : 0.0;
+            int bi = (lane < 8) ? (int)red_idx[slot * 8 + lane] : 0x7fffffff;
+#pragma unroll
+            for (int off = 4; off > 0; off >>= 1) {
+                double ov = __shfl_xor_sync(0xffffffffu, bv, off);
+                int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+                amax_take<double>(bv, bi, ov, oi);
+            }
+            if (lane == 0) {
+                if (!(bv > 0.0)) bi = 0;   // nothing beat the initial max = 0.0 (mod.rs:143-144)
+                if (a.row_peak_val) a.row_peak_val[peak_pending] = (T)bv;
+                if (a.row_peak_idx) a.row_peak_idx[peak_pending] = (unsigned long long)bi;
+            }
+        }
+        peak_pending = -1;
+    };
 
     auto empty_gate = [&](uint64_t*& mb, int& par) {
         // group 1 must not overwrite its fabric half while group 0 still reads the last mailbox from it
@@ -437,6 +481,7 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
         else { mb = nullptr; par = 0; }
     };
 
+    if (r == 0) pp_release(0);     // group 1 computes first: hand it the token
     if (r == 0 && a.stagger > 0 && lo < hi) {
         // start group 0 half a pass behind group 1: from then on one group's exchange overlaps the other's math
         const long long t0 = clock64();
@@ -444,7 +489,7 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
     }
 
     c.tr = nullptr;
-    for (long long item = lo; item < hi; ++item, buf ^= 1) {
+    for (int item = lo; item < hi; ++item, buf ^= 1) {
 #ifdef CAF_TRACE
         c.tr = (a.trace && item - lo < 8) ? a.trace + ((((long long)blockIdx.x * 16 + hw_warp) * 8 + (item - lo)) * 24) : nullptr;
 #endif
@@ -452,23 +497,43 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
         if constexpr (MODE == kSurface) {
             if (pair != cur_pair) {
                 // ---- per-pair prologue: H_r = FFT_r(haystack)/n into TMEM, needle into TMEM ----
+                // Single pair split over many CTAs: only CTA 0 transforms the haystack and publishes H through L2;
+                // the others start their first row at once and pick H up just before they need it.
                 cur_pair = pair;
+                const bool shared_h = (a.hshare != nullptr);
+                const bool producer = !shared_h || blockIdx.x == 0;
                 bar_group(r);                     // nobody in this group still reads ptab[buf] of an earlier item
-                fill_ptab(buf, 0.0);
-                load_half(v, a.in2 + (long long)pair * a.L, a.L);
+                if (producer) {
+                    fill_ptab(buf, 0.0);
+                    load_half(v, a.in2 + (long long)pair * a.L, a.L);
+                }
                 if (!tables_ready) { cp_async_wait_all(); __syncthreads(); tables_ready = true; }
                 else bar_group(r);
-                phasor_mul(v, buf);
-                uint64_t* mb; int par;
-                empty_gate(mb, par);
-                forward_4096<T>(v, c, mb, par);
-                const T sc = (T)(1.0 / 8192.0);   // the /n of xcor_rustfft.rs:72 (n = transform length)
+                if (producer) {
+                    pp_acquire(r);
+                    phasor_mul(v, buf);
+                    uint64_t* mb; int par;
+                    empty_gate(mb, par);
+                    forward_4096<T>(v, c, mb, par);
+                    const T sc = (T)(1.0 / 8192.0);   // the /n of xcor_rustfft.rs:72 (n = transform length)
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    C tmp[4];
+                    for (int q = 0; q < 4; ++q) {
+                        C tmp[4];
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) tmp[i] = mk<T>(v[4 * q + i].x * sc, v[4 * q + i].y * sc);
-                    tmem_st4(tm_h + 4 * q * TG::kColsPerC, tmp);
+                        for (int i = 0; i < 4; ++i) {
+                            tmp[i] = mk<T>(v[4 * q + i].x * sc, v[4 * q + i].y * sc);
+                            if (shared_h) __stcg(a.hshare + (4 * q + i) * kThreads + tid, tmp[i]);
+                        }
+                        tmem_st4(tm_h + 4 * q * TG::kColsPerC, tmp);
+                    }
+                    pp_release(r);
+                    if (shared_h) {
+                        __threadfence();
+                        bar_group(r);
+                        if (tg == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;\n" :: "l"(a.hflag + r), "r"(a.epoch) : "memory");
+                    }
+                } else {
+                    h_from_share = true;
                 }
                 load_half(v, a.in + (long long)pair * a.L, a.L);
 #pragma unroll
@@ -484,14 +549,19 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
                 bar_group(r);
             }
             CAF_TR(c, 1);
-            // ---- needle samples back from TMEM ----
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
+            // ---- needle samples back from TMEM: four loads in flight behind one wait ----
+            {
+                typename raw4_of<T>::type q0, q1, q2, q3;
+                tmem_ld4_issue(tm_n + 0 * TG::kColsPerC, q0); tmem_ld4_issue(tm_n + 4 * TG::kColsPerC, q1);
+                tmem_ld4_issue(tm_n + 8 * TG::kColsPerC, q2); tmem_ld4_issue(tm_n + 12 * TG::kColsPerC, q3);
+                tmem_wait_ld();
                 C tmp[4];
-                tmem_ld4(tm_n + 4 * q * TG::kColsPerC, tmp);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) v[4 * q + i] = tmp[i];
+                tmem_unpack4(q0, tmp); v[0] = tmp[0]; v[1] = tmp[1]; v[2] = tmp[2]; v[3] = tmp[3];
+                tmem_unpack4(q1, tmp); v[4] = tmp[0]; v[5] = tmp[1]; v[6] = tmp[2]; v[7] = tmp[3];
+                tmem_unpack4(q2, tmp); v[8] = tmp[0]; v[9] = tmp[1]; v[10] = tmp[2]; v[11] = tmp[3];
+                tmem_unpack4(q3, tmp); v[12] = tmp[0]; v[13] = tmp[1]; v[14] = tmp[2]; v[15] = tmp[3];
             }
+            pp_acquire(r);
             phasor_mul(v, buf);
             CAF_TR(c, 2);
         } else if constexpr (kHalfZero) {
@@ -500,6 +570,7 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
             load_half(v, a.in + (long long)pair * a.L, a.L);
             if (!tables_ready) { cp_async_wait_all(); __syncthreads(); tables_ready = true; }
             else bar_group(r);
+            pp_acquire(r);
             phasor_mul(v, buf);
         } else {
             // general 8192-sample input: explicit first radix-2 stage
@@ -512,6 +583,7 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
                 else v[i] = cmulc(csub(x0, x1), ldg<T>(a.g + n));   // * W_8192^{+n} = conj(g[n])
             }
             if (!tables_ready) { cp_async_wait_all(); __syncthreads(); tables_ready = true; }
+            pp_acquire(r);
         }
 
         // ---------------- forward transform ----------------
@@ -520,6 +592,7 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
             empty_gate(mb, par);
             forward_4096<T>(v, c, mb, par);
         }
+        if constexpr (MODE == kSurface) flush_peak((buf ^ 1) & 1);   // previous row's maxima: two group barriers have passed
         // phasors of the next row are produced while the fabric is quiet; the group barrier inside
         // inverse_4096 orders them before their first use
         if constexpr (MODE == kSurface) {
@@ -532,15 +605,45 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
             const T sc = (T)(1.0 / 8192.0);
 #pragma unroll
             for (int k = 0; k < 16; ++k) hp[((k * 16 + w) * 2 + r) * 16 + h] = mk<T>(v[k].x * sc, v[k].y * sc);
+            pp_release(r);
         } else {
             // ---------------- H * conj(X)  (xcor_rustfft.rs:64-73) ----------------
             if constexpr (kUseTmem) {
+                if (h_from_share) {
+                    // first row of a consumer CTA: H arrives from CTA 0 through L2; keep it in TMEM for later rows
+                    h_from_share = false;
+                    if (tg == 0) {
+                        unsigned int seen;
+                        do {
+                            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(seen) : "l"(a.hflag + r) : "memory");
+                        } while ((int)(seen - a.epoch) < 0);
+                    }
+                    bar_group(r);
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    C hv[4];
-                    tmem_ld4(tm_h + 4 * q * TG::kColsPerC, hv);
+                    for (int q = 0; q < 4; ++q) {
+                        C hv[4];
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) v[4 * q + i] = cmulc(hv[i], v[4 * q + i]);
+                        for (int i = 0; i < 4; ++i) hv[i] = __ldcg(a.hshare + (4 * q + i) * kThreads + tid);
+                        tmem_st4(tm_h + 4 * q * TG::kColsPerC, hv);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) v[4 * q + i] = cmulc(hv[i], v[4 * q + i]);
+                    }
+                    tmem_wait_st();
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        typename raw4_of<T>::type qa, qb;
+                        tmem_ld4_issue(tm_h + (8 * q) * TG::kColsPerC, qa);
+                        tmem_ld4_issue(tm_h + (8 * q + 4) * TG::kColsPerC, qb);
+                        tmem_wait_ld();
+                        C hv[4];
+                        tmem_unpack4(qa, hv);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) v[8 * q + i] = cmulc(hv[i], v[8 * q + i]);
+                        tmem_unpack4(qb, hv);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) v[8 * q + 4 + i] = cmulc(hv[i], v[8 * q + 4 + i]);
+                    }
                 }
             } else {
 #pragma unroll
@@ -561,6 +664,7 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
                 };
                 post(ic<0>{}); post(ic<1>{}); post(ic<2>{}); post(ic<3>{}); post(ic<4>{}); post(ic<5>{}); post(ic<6>{}); post(ic<7>{});
                 post(ic<8>{}); post(ic<9>{}); post(ic<10>{}); post(ic<11>{}); post(ic<12>{}); post(ic<13>{}); post(ic<14>{}); post(ic<15>{});
+                pp_release(1);
                 CAF_TR(c, 16);
                 bar_group(1);                 // all X4 reads of this half are done: it becomes the mailbox
 #pragma unroll
@@ -570,6 +674,7 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
                 ++posts;
                 drain_pending = true;
             } else {
+                pp_release(0);
                 const int L = FULL ? kL0 : a.L;
                 const int nout = 2 * L, skip = kM - nout;
                 T* orow = (MODE == kSurface && a.out) ? reinterpret_cast<T*>(a.out) + item * (long long)nout : nullptr;
@@ -623,24 +728,10 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
                         int oi = __shfl_xor_sync(0xffffffffu, bidx, off);
                         amax_take<T>(best, bidx, ov, oi);
                     }
-                    // red_* were last read before the group barriers of this item -> no hazard
-                    if (lane == 0) { red_val[wg] = (double)best; red_idx[wg] = (unsigned long long)bidx; }
-                    bar_group(0);
-                    if (wg == 0) {
-                        double bv = (lane < 8) ? red_val[lane] : 0.0;
-                        int bi = (lane < 8) ? (int)red_idx[lane] : 0x7fffffff;
-#pragma unroll
-                        for (int off = 4; off > 0; off >>= 1) {
-                            double ov = __shfl_xor_sync(0xffffffffu, bv, off);
-                            int oi = __shfl_xor_sync(0xffffffffu, bi, off);
-                            amax_take<double>(bv, bi, ov, oi);
-                        }
-                        if (lane == 0) {
-                            if (!(bv > 0.0)) bi = 0;   // nothing beat the initial max = 0.0 (mod.rs:143-144)
-                            if (a.row_peak_val) a.row_peak_val[item] = (T)bv;
-                            if (a.row_peak_idx) a.row_peak_idx[item] = (unsigned long long)bi;
-                        }
-                    }
+                    // per-warp maxima are parked in shared memory; one warp folds them after the NEXT group barrier
+                    // (inside the next forward transform), so no barrier is spent on the reduction
+                    if (lane == 0) { red_val[(buf & 1) * 8 + wg] = (double)best; red_idx[(buf & 1) * 8 + wg] = (unsigned long long)bidx; }
+                    peak_pending = item;
                 }
             }
         }
@@ -649,6 +740,9 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
         if (++row == rows_per_pair) { row = 0; ++pair; }
     }
     if (!tables_ready) cp_async_wait_all();
+    if constexpr (MODE == kSurface) {
+        if (r == 0) { bar_group(0); flush_peak((buf ^ 1) & 1); }   // the last row of this CTA
+    }
 
     if constexpr (kUseTmem) {
         asm volatile("tcgen05.fence::before_thread_sync;\n");

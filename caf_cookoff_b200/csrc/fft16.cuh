@@ -29,6 +29,40 @@ template <typename C> __device__ __forceinline__ C cmulc(C a, C b) {
 // a * (INV ? conj(w) : w)
 template <bool INV, typename C> __device__ __forceinline__ C ctw(C a, C w) { return INV ? cmulc(a, w) : cmul(a, w); }
 
+// a * a
+template <typename C> __device__ __forceinline__ C csq(C a) {
+    C r; r.x = a.x * a.x - a.y * a.y; r.y = (a.x + a.x) * a.y; return r;
+}
+
+// v[k] *= w^k (conjugated when INV), k = 1..15.  The powers are generated in registers (two interleaved product
+// chains, odd and even exponents, stepping by w^2: 3 values live) instead of 15 shared-memory loads: a 128-bit
+// load costs the SM's single LSU port 4 wavefront cycles, a complex product costs the four fp64 pipes 2 cycles
+// in total, and the LSU port is what the pass-to-pass exchanges need.  Rounding: <= 8 products deep, ~1e-15.
+template <bool INV, typename C>
+__device__ __forceinline__ void twiddle_powers(C (&v)[16], C w) {
+    const C w2 = csq(w);
+    C po = w, pe = w2;
+#pragma unroll
+    for (int k = 1; k < 16; k += 2) {
+        v[k] = ctw<INV>(v[k], po);
+        if (k + 1 < 16) v[k + 1] = ctw<INV>(v[k + 1], pe);
+        if (k + 2 < 16) { po = cmul(po, w2); pe = cmul(pe, w2); }
+    }
+}
+
+// v[k] *= b * rho^k (conjugated when INV), k = 0..15: two interleaved product chains of length 8
+template <bool INV, typename C>
+__device__ __forceinline__ void twiddle_geometric(C (&v)[16], C b, C rho) {
+    const C r8 = csq(csq(csq(rho)));
+    C ca = b, cb = cmul(b, r8);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        v[k] = ctw<INV>(v[k], ca);
+        v[k + 8] = ctw<INV>(v[k + 8], cb);
+        if (k < 7) { ca = cmul(ca, rho); cb = cmul(cb, rho); }
+    }
+}
+
 template <typename T, bool INV>
 __device__ __forceinline__ void radix4(cx<T>& a0, cx<T>& a1, cx<T>& a2, cx<T>& a3) {
     cx<T> t0 = cadd(a0, a2), t1 = csub(a0, a2), t2 = cadd(a1, a3), t3 = csub(a1, a3);
