@@ -91,14 +91,10 @@ struct RowArgs {
 template <typename T>
 struct SmemLayout {
     static constexpr size_t kS = sizeof(cx<T>) * 2 * kL0;        // exchange fabric [2][4096]
-    static constexpr size_t kTw1 = sizeof(cx<T>) * 16 * 256;
-    static constexpr size_t kTw2 = sizeof(cx<T>) * 256;
-    static constexpr size_t kG = sizeof(cx<T>) * 256;
     static constexpr size_t kPtab = sizeof(cx<T>) * 2 * 2 * 48;  // [2 buf][2 r][3][16]
     static constexpr size_t kRed = 16 * 8 + 16 * 8;              // argmax scratch
-    static constexpr size_t kMisc = 64;                          // tmem base, flags
-    static constexpr size_t offTw1 = kS, offTw2 = offTw1 + kTw1, offG = offTw2 + kTw2, offPtab = offG + kG,
-                            offRed = offPtab + kPtab, offMisc = offRed + kRed, kTotal = offMisc + kMisc;
+    static constexpr size_t kMisc = 64;                          // tmem base, flags, mbarriers
+    static constexpr size_t offPtab = kS, offRed = offPtab + kPtab, offMisc = offRed + kRed, kTotal = offMisc + kMisc;
 };
 
 template <typename T>
@@ -106,10 +102,8 @@ struct Ctx {
     cx<T>* S;        // exchange fabric
     cx<T>* Sr;       // this thread's pipeline half
     cx<T>* Sw;       // this warp's 256-entry region inside Sr
-    const cx<T>* tw1;
-    const cx<T>* tw2;
-    const cx<T>* g256;
     cx<T>* ptab;
+    uint32_t tm_tw;  // TMEM address of this thread's five twiddle bases: W_4096^t, W_256^h, W_4096^{k1 h}, W_256^{k1}, W_8192^{-t}
     int w, lane, r, h, t;
     long long* tr;   // CAF_TRACE: this warp's slot array for the current item (lane 0 writes)
 };
@@ -147,9 +141,28 @@ __device__ __forceinline__ void tmem_st_x8(uint32_t taddr, const uint32_t (&r)[8
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory"); }
 
+__device__ __forceinline__ void tmem_ld_x4(uint32_t taddr, uint32_t (&r)[4]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];\n"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_st_x4(uint32_t taddr, const uint32_t (&r)[4]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};\n"
+                 :: "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_x2(uint32_t taddr, uint32_t (&r)[2]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0,%1}, [%2];\n" : "=r"(r[0]), "=r"(r[1]) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_st_x2(uint32_t taddr, const uint32_t (&r)[2]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1,%2};\n" :: "r"(taddr), "r"(r[0]), "r"(r[1]) : "memory");
+}
+
 template <typename T> struct TmemGeom;
-template <> struct TmemGeom<double> { static constexpr int kColsPerC = 4, kColsPerGroup = 128, kAlloc = 512; };
-template <> struct TmemGeom<float>  { static constexpr int kColsPerC = 2, kColsPerGroup = 64,  kAlloc = 256; };
+// TMEM map of one lane quarter (the 4 warps q, q+4, q+8, q+12 share lanes 32q..32q+31), in units of one complex
+// value (kColsPerC 32-bit columns):   [0, 64)  H bins, 16 per warp        (j = warp / 4 selects the 16)
+//                                     [64, 96) needle samples, 16 per t   (warps j and j + 2 hold the same t: shared)
+//                                     [96, 128) twiddle bases, 8 slots per warp (5 used)
+template <> struct TmemGeom<double> { static constexpr int kColsPerC = 4, kAlloc = 512; };
+template <> struct TmemGeom<float>  { static constexpr int kColsPerC = 2, kAlloc = 256; };
 
 // 4 complex values <-> TMEM columns [taddr, taddr + 4*kColsPerC).  Loads are split into issue / unpack so
 // several can be in flight behind a single tcgen05.wait::ld.
@@ -187,6 +200,28 @@ __device__ __forceinline__ void tmem_st4(uint32_t taddr, const float2 (&v)[4]) {
     tmem_st_x8(taddr, r);
 }
 
+// one complex value <-> TMEM (twiddle bases); the load waits for its own completion
+__device__ __forceinline__ double2 tmem_ld1(uint32_t taddr, double) {
+    uint32_t r[4];
+    tmem_ld_x4(taddr, r);
+    tmem_wait_ld();
+    return make_double2(__hiloint2double((int)r[1], (int)r[0]), __hiloint2double((int)r[3], (int)r[2]));
+}
+__device__ __forceinline__ float2 tmem_ld1(uint32_t taddr, float) {
+    uint32_t r[2];
+    tmem_ld_x2(taddr, r);
+    tmem_wait_ld();
+    return make_float2(__uint_as_float(r[0]), __uint_as_float(r[1]));
+}
+__device__ __forceinline__ void tmem_st1(uint32_t taddr, double2 v) {
+    uint32_t r[4] = {(uint32_t)__double2loint(v.x), (uint32_t)__double2hiint(v.x), (uint32_t)__double2loint(v.y), (uint32_t)__double2hiint(v.y)};
+    tmem_st_x4(taddr, r);
+}
+__device__ __forceinline__ void tmem_st1(uint32_t taddr, float2 v) {
+    uint32_t r[2] = {__float_as_uint(v.x), __float_as_uint(v.y)};
+    tmem_st_x2(taddr, r);
+}
+
 template <typename T>
 __device__ __forceinline__ cx<T> ldg(const cx<T>* p) { return __ldg(p); }
 
@@ -221,8 +256,29 @@ __device__ __forceinline__ void bar_group(int r) { asm volatile("bar.sync %0, 25
 // butterfly blocks only while it holds the token, and does its shared-memory exchange while the other group
 // computes.  pp_acquire = bar.sync on the own barrier (256 waiters + 256 arrivals from the other group),
 // pp_release = bar.arrive on the other group's barrier.
+// Measured on B200 (round 1): the token costs slightly more than it gains (50.3 vs 49.7 us per 400 x 8192 surface)
+// because ptxas floats register arithmetic across bar.sync, so the butterflies do not stay inside the token window;
+// it is therefore compiled in only with -DCAF_PINGPONG.
+#ifdef CAF_PINGPONG
 __device__ __forceinline__ void pp_acquire(int r) { asm volatile("bar.sync %0, 512;\n" :: "r"(3 + r) : "memory"); }
 __device__ __forceinline__ void pp_release(int r) { asm volatile("bar.arrive %0, 512;\n" :: "r"(4 - r) : "memory"); }
+#else
+__device__ __forceinline__ void pp_acquire(int) {}
+__device__ __forceinline__ void pp_release(int) {}
+#endif
+// The token only helps if the butterflies really sit between acquire and release in the instruction stream.
+// Register arithmetic has no memory side effect, so the compiler is free to float it across the barriers; these
+// empty asm statements make every value of the row an input+output of the barrier point and pin the math in place.
+__device__ __forceinline__ void pin(double2 (&v)[16]) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) asm volatile("" : "+d"(v[i].x), "+d"(v[i].y));
+}
+__device__ __forceinline__ void pin(float2 (&v)[16]) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) asm volatile("" : "+f"(v[i].x), "+f"(v[i].y));
+}
+template <typename C> __device__ __forceinline__ void pp_acquire(int r, C (&v)[16]) { pin(v); pp_acquire(r); pin(v); }
+template <typename C> __device__ __forceinline__ void pp_release(int r, C (&v)[16]) { pin(v); pp_release(r); pin(v); }
 
 __device__ __forceinline__ void mbar_init(uint64_t* mb, int count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" :: "r"((uint32_t)__cvta_generic_to_shared(mb)), "r"(count) : "memory");
@@ -239,13 +295,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t* mb, int parity) {
 
 // ------------------------------------------------------------------------------------------------
 // forward: v[i] = u_r[t + 256 i]  ->  v[k3] = U_r[k1 + 16 h + 256 k3]          (xcor_rustfft.rs:59,61)
+// Token discipline: entered HOLDING the fp64 token, returns HOLDING it.  Every shared-memory load a butterfly
+// block needs (twiddle bases) is issued in the exchange phase BEFORE the token is re-acquired, so a block never
+// waits behind the other group's exchange traffic in the LSU queue.
+// The five per-thread twiddle bases live in TMEM (tcgen05.ld is not queued behind shared-memory traffic).
 // `empty_mb` (group 1 only): the mailbox barrier to wait on before the fabric half is overwritten.
+// `hook()` runs in the exchange phase after the block barriers (deferred row-peak reduction).
 // ------------------------------------------------------------------------------------------------
-template <typename T>
-__device__ __forceinline__ void forward_4096(cx<T> (&v)[16], const Ctx<T>& c, uint64_t* empty_mb, int empty_parity) {
+template <typename T, typename Hook>
+__device__ __forceinline__ void forward_4096(cx<T> (&v)[16], const Ctx<T>& c,
+                                             uint64_t* empty_mb, int empty_parity, Hook&& hook) {
+    constexpr int kC = TmemGeom<T>::kColsPerC;
     fft16<T, false>(v);
-    twiddle_powers<false>(v, c.tw1[256 + c.t]);                 // W_4096^{t k}
-    pp_release(c.r);
+    twiddle_powers<false>(v, tmem_ld1(c.tm_tw, T()));           // W_4096^{t k}
+    pp_release(c.r, v);
     CAF_TR(c, 3);
     if (empty_mb) mbar_wait(empty_mb, empty_parity);   // group 0 has drained the previous row's mailbox
     bar_group(c.r);    // every earlier reader of this half of the fabric (previous X4 / X2) is done
@@ -255,12 +318,13 @@ __device__ __forceinline__ void forward_4096(cx<T> (&v)[16], const Ctx<T>& c, ui
     bar_group(c.r);
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = c.Sw[c.h + 16 * i];
+    hook();
     CAF_TR(c, 5);
 
-    pp_acquire(c.r);
+    pp_acquire(c.r, v);
     fft16<T, false>(v);
-    twiddle_powers<false>(v, c.tw2[16 + c.h]);                  // W_256^{h k}
-    pp_release(c.r);
+    twiddle_powers<false>(v, tmem_ld1(c.tm_tw + kC, T()));      // W_256^{h k}
+    pp_release(c.r, v);
     CAF_TR(c, 6);
     __syncwarp();
 #pragma unroll
@@ -270,19 +334,21 @@ __device__ __forceinline__ void forward_4096(cx<T> (&v)[16], const Ctx<T>& c, ui
     for (int m = 0; m < 16; ++m) v[m] = c.Sw[c.h * 16 + (m ^ c.h)];
     CAF_TR(c, 7);
 
-    pp_acquire(c.r);
+    pp_acquire(c.r, v);
     fft16<T, false>(v);    // returns holding the token
     CAF_TR(c, 8);
 }
 
 // ------------------------------------------------------------------------------------------------
 // inverse: v[k3] = Y_r[k1 + 16 h + 256 k3]  ->  v[n1] = A_r[t + 256 n1]  (unnormalised, xcor_rustfft.rs:76)
+// Entered and left HOLDING the token.
 // ------------------------------------------------------------------------------------------------
 template <typename T>
 __device__ __forceinline__ void inverse_4096(cx<T> (&v)[16], const Ctx<T>& c) {
-    fft16<T, true>(v);     // entered holding the token
-    twiddle_powers<true>(v, c.tw2[16 + c.h]);                   // conj W_256^{h k}
-    pp_release(c.r);
+    constexpr int kC = TmemGeom<T>::kColsPerC;
+    fft16<T, true>(v);
+    twiddle_powers<true>(v, tmem_ld1(c.tm_tw + kC, T()));       // conj W_256^{h k}
+    pp_release(c.r, v);
     CAF_TR(c, 10);
     __syncwarp();
 #pragma unroll
@@ -292,10 +358,13 @@ __device__ __forceinline__ void inverse_4096(cx<T> (&v)[16], const Ctx<T>& c) {
     for (int m = 0; m < 16; ++m) v[m] = c.Sw[c.h * 16 + (m ^ c.h)];
     CAF_TR(c, 11);
 
-    pp_acquire(c.r);
+    pp_acquire(c.r, v);
     fft16<T, true>(v);
-    twiddle_geometric<true>(v, c.tw1[c.w * 256 + c.h], c.tw2[16 + c.w]);   // conj W_4096^{k1 (16 k + h)}
-    pp_release(c.r);
+    {
+        const cx<T> b = tmem_ld1(c.tm_tw + 2 * kC, T()), rho = tmem_ld1(c.tm_tw + 3 * kC, T());
+        twiddle_geometric<true>(v, b, rho);                     // conj W_4096^{k1 (16 k + h)}
+    }
+    pp_release(c.r, v);
     CAF_TR(c, 12);
     __syncwarp();
 #pragma unroll
@@ -306,7 +375,7 @@ __device__ __forceinline__ void inverse_4096(cx<T> (&v)[16], const Ctx<T>& c) {
     for (int k = 0; k < 16; ++k) v[k] = c.Sr[k * 256 + c.t];
     CAF_TR(c, 14);
 
-    pp_acquire(c.r);
+    pp_acquire(c.r, v);
     fft16<T, true>(v);     // returns holding the token
     CAF_TR(c, 15);
 }
@@ -342,9 +411,6 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
     using TG = TmemGeom<T>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     C* S = reinterpret_cast<C*>(smem_raw);
-    C* tw1s = reinterpret_cast<C*>(smem_raw + SL::offTw1);
-    C* tw2s = reinterpret_cast<C*>(smem_raw + SL::offTw2);
-    C* g256s = reinterpret_cast<C*>(smem_raw + SL::offG);
     C* ptab = reinterpret_cast<C*>(smem_raw + SL::offPtab);
     unsigned long long* red_idx = reinterpret_cast<unsigned long long*>(smem_raw + SL::offRed);
     double* red_val = reinterpret_cast<double*>(smem_raw + SL::offRed + 128);
@@ -363,27 +429,13 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
     c.w = 2 * (hw_warp & 7) + ((c.lane >> 3) & 1);     // k1: the 256-point sub-transform this thread works in
     c.t = 16 * c.w + c.h;
     c.S = S; c.Sr = S + c.r * kL0; c.Sw = c.Sr + c.w * 256;
-    c.tw1 = tw1s; c.tw2 = tw2s; c.g256 = g256s; c.ptab = ptab;
+    c.ptab = ptab; c.tm_tw = 0;
     const int w = c.w, lane = c.lane, r = c.r, h = c.h, t = c.t, tg = tid & 255, wg = hw_warp & 7;
 
     constexpr bool kHalfZero = (MODE == kSurface || MODE == kSpectrumHalf || MODE == kXcorHalf);
     constexpr bool kWritesH = (MODE == kSpectrumHalf || MODE == kSpectrumFull);
-    constexpr bool kUseTmem = (MODE == kSurface);
+    constexpr bool kUseTmem = (MODE == kSurface);   // H and the needle live in TMEM (the twiddle bases always do)
 
-    // ---- stage the twiddle tables in shared memory (once per CTA), asynchronously: the copies fly
-    //      while TMEM is allocated and the first operands are fetched ----
-    {
-        constexpr int kChunks1 = (int)(SL::kTw1 / 16), kChunks2 = (int)(SL::kTw2 / 16);
-        const char* g1 = reinterpret_cast<const char*>(a.tw1);
-        const char* g2 = reinterpret_cast<const char*>(a.tw2);
-        const char* g3 = reinterpret_cast<const char*>(a.g);
-        for (int i = tid; i < kChunks1; i += kThreads) cp_async16(smem_raw + SL::offTw1 + 16 * i, g1 + 16 * i);
-        for (int i = tid; i < kChunks2; i += kThreads) {
-            cp_async16(smem_raw + SL::offTw2 + 16 * i, g2 + 16 * i);
-            cp_async16(smem_raw + SL::offG + 16 * i, g3 + 16 * i);
-        }
-        asm volatile("cp.async.commit_group;\n" ::: "memory");
-    }
     if (tid == 0) {
         mbar_init(mb_full, 256);
         mbar_init(mb_empty, 256);
@@ -392,7 +444,7 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
 
     // ---- TMEM: the tensor memory of this SM becomes the per-thread operand store ----
     uint32_t tm_h = 0, tm_n = 0;
-    if (kUseTmem) {
+    {
         if (hw_warp == 0) {
             asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n"
                          :: "l"((uint64_t)__cvta_generic_to_shared(&misc[0])), "n"(TG::kAlloc));
@@ -401,11 +453,18 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
         asm volatile("tcgen05.fence::before_thread_sync;\n");
         __syncthreads();
         asm volatile("tcgen05.fence::after_thread_sync;\n");
-        const uint32_t base = misc[0] + ((uint32_t)(32 * (hw_warp & 3)) << 16) + (uint32_t)(TG::kColsPerGroup * (hw_warp >> 2));
-        tm_h = base;                              // 16 H bins
-        tm_n = base + 16 * TG::kColsPerC;         // 16 needle samples
-    } else {
-        __syncthreads();
+        const uint32_t base = misc[0] + ((uint32_t)(32 * (hw_warp & 3)) << 16);
+        const int j = hw_warp >> 2;
+        tm_h = base + (uint32_t)((16 * j) * TG::kColsPerC);                 // 16 H bins
+        tm_n = base + (uint32_t)((64 + 16 * (j & 1)) * TG::kColsPerC);      // 16 needle samples (shared by both groups)
+        c.tm_tw = base + (uint32_t)((96 + 8 * j) * TG::kColsPerC);          // 5 twiddle bases
+        // per-thread twiddle bases, once per CTA: W_4096^t, W_256^h, W_4096^{k1 h}, W_256^{k1}, W_8192^{-t}
+        tmem_st1(c.tm_tw + 0 * TG::kColsPerC, ldg<T>(a.tw1 + 256 + t));
+        tmem_st1(c.tm_tw + 1 * TG::kColsPerC, ldg<T>(a.tw2 + 16 + h));
+        tmem_st1(c.tm_tw + 2 * TG::kColsPerC, ldg<T>(a.tw1 + w * 256 + h));
+        tmem_st1(c.tm_tw + 3 * TG::kColsPerC, ldg<T>(a.tw2 + 16 + w));
+        tmem_st1(c.tm_tw + 4 * TG::kColsPerC, ldg<T>(a.g + t));
+        tmem_wait_st();
     }
 
     // phasor factor tables of this group's pipeline: ptab[buf][r][0][i] = e^{j2pi 256 i phi_r}, [1][a] = 16 a, [2][b] = b
@@ -418,17 +477,21 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
             ptab[(buf * 2 + r) * 48 + e] = mk<T>((T)p.x, (T)p.y);
         }
     };
-    // v[i] *= phasor_r(t + 256 i)
-    auto phasor_mul = [&](C (&v)[16], int buf) {
-        // phasor(t + 256 i) = [e^{j 2 pi 16 w phi} e^{j 2 pi h phi}] * (e^{j 2 pi 256 phi})^i: two product chains of 8
+    // v[i] *= phasor_r(t + 256 i) = [e^{j 2 pi 16 w phi} e^{j 2 pi h phi}] * (e^{j 2 pi 256 phi})^i: two product chains
+    // of 8.  The four table entries are fetched by phasor_load() in the exchange phase, before the token is taken.
+    struct Ph { C d1, d8, pw, ph; };
+    auto phasor_load = [&](int buf) {
         const C* pt = ptab + (buf * 2 + r) * 48;
-        const C d1 = pt[1];
-        C qa = cmul(pt[16 + w], pt[32 + h]), qb = cmul(qa, pt[8]);
+        Ph p; p.d1 = pt[1]; p.d8 = pt[8]; p.pw = pt[16 + w]; p.ph = pt[32 + h];
+        return p;
+    };
+    auto phasor_mul = [&](C (&v)[16], const Ph& p) {
+        C qa = cmul(p.pw, p.ph), qb = cmul(qa, p.d8);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             v[i] = cmul(v[i], qa);
             v[i + 8] = cmul(v[i + 8], qb);
-            if (i < 7) { qa = cmul(qa, d1); qb = cmul(qb, d1); }
+            if (i < 7) { qa = cmul(qa, p.d1); qb = cmul(qb, p.d1); }
         }
     };
     // v[i] = src[t + 256 i]  (zero beyond L)
@@ -448,7 +511,6 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
 
     int buf = 0;
     int cur_pair = -1;
-    bool tables_ready = false;
     int posts = 0;            // mailbox posts so far (group 1) / mailbox reads so far (group 0)
     bool drain_pending = false;   // group 1: a posted mailbox that group 0 may still be reading
     bool h_from_share = false;    // consumer CTA: H still has to be fetched from CTA 0's publication
@@ -507,14 +569,14 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
                     fill_ptab(buf, 0.0);
                     load_half(v, a.in2 + (long long)pair * a.L, a.L);
                 }
-                if (!tables_ready) { cp_async_wait_all(); __syncthreads(); tables_ready = true; }
-                else bar_group(r);
+                bar_group(r);
                 if (producer) {
-                    pp_acquire(r);
-                    phasor_mul(v, buf);
+                    const Ph ph0 = phasor_load(buf);
+                    pp_acquire(r, v);
+                    phasor_mul(v, ph0);
                     uint64_t* mb; int par;
                     empty_gate(mb, par);
-                    forward_4096<T>(v, c, mb, par);
+                    forward_4096<T>(v, c, mb, par, []{});
                     const T sc = (T)(1.0 / 8192.0);   // the /n of xcor_rustfft.rs:72 (n = transform length)
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
@@ -561,17 +623,25 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
                 tmem_unpack4(q2, tmp); v[8] = tmp[0]; v[9] = tmp[1]; v[10] = tmp[2]; v[11] = tmp[3];
                 tmem_unpack4(q3, tmp); v[12] = tmp[0]; v[13] = tmp[1]; v[14] = tmp[2]; v[15] = tmp[3];
             }
-            pp_acquire(r);
-            phasor_mul(v, buf);
+            {
+                const Ph ph0 = phasor_load(buf);
+                // phasors of the next row: produced here, while this group waits for the token anyway; the group
+                // barriers of this row order them before their first use
+                if ((item + 1 < hi) && (row + 1 < a.D)) fill_ptab(buf ^ 1, a.freqs[row + 1] * a.dt);
+                pp_acquire(r, v);
+                phasor_mul(v, ph0);
+            }
             CAF_TR(c, 2);
         } else if constexpr (kHalfZero) {
             bar_group(r);
             fill_ptab(buf, 0.0);
             load_half(v, a.in + (long long)pair * a.L, a.L);
-            if (!tables_ready) { cp_async_wait_all(); __syncthreads(); tables_ready = true; }
-            else bar_group(r);
-            pp_acquire(r);
-            phasor_mul(v, buf);
+            bar_group(r);
+            {
+                const Ph ph0 = phasor_load(buf);
+                pp_acquire(r, v);
+                phasor_mul(v, ph0);
+            }
         } else {
             // general 8192-sample input: explicit first radix-2 stage
             const C* src = a.in + (long long)pair * kM;
@@ -582,7 +652,6 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
                 if (r == 0) v[i] = cadd(x0, x1);
                 else v[i] = cmulc(csub(x0, x1), ldg<T>(a.g + n));   // * W_8192^{+n} = conj(g[n])
             }
-            if (!tables_ready) { cp_async_wait_all(); __syncthreads(); tables_ready = true; }
             pp_acquire(r);
         }
 
@@ -590,13 +659,8 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
         {
             uint64_t* mb; int par;
             empty_gate(mb, par);
-            forward_4096<T>(v, c, mb, par);
-        }
-        if constexpr (MODE == kSurface) flush_peak((buf ^ 1) & 1);   // previous row's maxima: two group barriers have passed
-        // phasors of the next row are produced while the fabric is quiet; the group barrier inside
-        // inverse_4096 orders them before their first use
-        if constexpr (MODE == kSurface) {
-            if ((item + 1 < hi) && (row + 1 < a.D)) fill_ptab(buf ^ 1, a.freqs[row + 1] * a.dt);
+            // the previous row's per-warp maxima are folded in the first exchange phase (two group barriers have passed)
+            forward_4096<T>(v, c, mb, par, [&] { if constexpr (MODE == kSurface) flush_peak((buf ^ 1) & 1); });
         }
 
         // standalone-xcor spectrum layout in global memory: [k3][k1][r][h]
@@ -657,14 +721,14 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
             // ---------------- final radix-2 across the pipelines:  y[n] = A + B', y[n + 4096] = A - B',
             //                  B' = B W_8192^{-n},  n = t + 256 n1,  W_8192^{-n} = g[t] W_32^{-n1} ----------------
             if (r == 1) {
-                const C gt = g256s[t];
+                const C gt = tmem_ld1(c.tm_tw + 4 * TG::kColsPerC, T());
                 auto post = [&](auto jt) {
                     constexpr int j = decltype(jt)::value;
                     v[j] = cmul(v[j], mul_w32_inv<T, j>(gt));
                 };
                 post(ic<0>{}); post(ic<1>{}); post(ic<2>{}); post(ic<3>{}); post(ic<4>{}); post(ic<5>{}); post(ic<6>{}); post(ic<7>{});
                 post(ic<8>{}); post(ic<9>{}); post(ic<10>{}); post(ic<11>{}); post(ic<12>{}); post(ic<13>{}); post(ic<14>{}); post(ic<15>{});
-                pp_release(1);
+                pp_release(1, v);
                 CAF_TR(c, 16);
                 bar_group(1);                 // all X4 reads of this half are done: it becomes the mailbox
 #pragma unroll
@@ -674,7 +738,8 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
                 ++posts;
                 drain_pending = true;
             } else {
-                pp_release(0);
+                // group 0 keeps the token through the epilogue: group 1 posted B' right after ITS last block,
+                // which precedes this one in token order, so the mailbox is normally full already
                 const int L = FULL ? kL0 : a.L;
                 const int nout = 2 * L, skip = kM - nout;
                 T* orow = (MODE == kSurface && a.out) ? reinterpret_cast<T*>(a.out) + item * (long long)nout : nullptr;
@@ -714,6 +779,7 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
                     emit(csub(v[k], Bp), n + kL0, best1, bidx1);       // lag index n + 4096
                 }
                 mbar_arrive(mb_empty);
+                pp_release(0);
                 CAF_TR(c, 18);
                 ++posts;
 
@@ -739,12 +805,11 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
         // next item
         if (++row == rows_per_pair) { row = 0; ++pair; }
     }
-    if (!tables_ready) cp_async_wait_all();
     if constexpr (MODE == kSurface) {
         if (r == 0) { bar_group(0); flush_peak((buf ^ 1) & 1); }   // the last row of this CTA
     }
 
-    if constexpr (kUseTmem) {
+    {
         asm volatile("tcgen05.fence::before_thread_sync;\n");
         __syncthreads();
         if (hw_warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" :: "r"(misc[0]), "n"(TG::kAlloc));
