@@ -124,14 +124,14 @@ class _Variant32:
 def surface_arrays(needle, haystack, freqs_hz, fs: int, *, variant=_Variant, want_surface=True,
                    handle: Optional[Handle] = None):
     """caf_b200_surface_{f64,f32}: returns (surface or None, row_peak_idx, row_peak_val, Peak)."""
-    h = handle or default_handle()
-    lib = _lib.load()
     n_ = np.ascontiguousarray(needle, dtype=variant.cdt).ravel()
     h_ = np.ascontiguousarray(haystack, dtype=variant.cdt).ravel()
     f_ = np.ascontiguousarray(freqs_hz, dtype=np.float64).ravel()
     if n_.size != h_.size:
         # the reference pads each to 2*len and Xcor::run asserts equal length (xcor_rustfft.rs:54-55)
         raise CafPanic("assertion failed: a.len() == self.n (xcor_rustfft.rs:54-55)")
+    h = handle or default_handle()
+    lib = _lib.load()
     l, d = n_.size, f_.size
     surf = np.empty((d, 2 * l), dtype=variant.rdt) if want_surface else None
     pidx = np.zeros(d, dtype=np.uint64)
@@ -146,13 +146,13 @@ def surface_arrays(needle, haystack, freqs_hz, fs: int, *, variant=_Variant, wan
 def batch_arrays(needles, haystacks, freqs_hz, fs: int, *, variant=_Variant, want_surface=False,
                  handle: Optional[Handle] = None):
     """caf_b200_batch_*: needles/haystacks [P, L].  Returns (surface[P,D,2L] or None, pidx[P,D], pval[P,D], peaks)."""
-    h = handle or default_handle()
-    lib = _lib.load()
     n_ = np.ascontiguousarray(needles, dtype=variant.cdt)
     h_ = np.ascontiguousarray(haystacks, dtype=variant.cdt)
     f_ = np.ascontiguousarray(freqs_hz, dtype=np.float64).ravel()
     if n_.shape != h_.shape or n_.ndim != 2:
         raise CafPanic("needles and haystacks must both be [P, L] (xcor_rustfft.rs:54-55)")
+    h = handle or default_handle()
+    lib = _lib.load()
     p, l = n_.shape
     d = f_.size
     surf = np.empty((p, d, 2 * l), dtype=variant.rdt) if want_surface else None
