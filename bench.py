@@ -106,6 +106,17 @@ class ClockSampler:
         return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
+def committed_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of the row kernel, per launch, from the newest committed
+    `ncu --set full` capture (profiles/rNN_traffic.json, written by scripts/summarize_ncu.py)."""
+    try:
+        pdir = os.path.join(ROOT, "profiles")
+        names = sorted(n for n in os.listdir(pdir) if n.endswith("_traffic.json"))
+        return json.load(open(os.path.join(pdir, names[-1]))).get("dram_bytes_per_launch") if names else None
+    except Exception:
+        return None
+
+
 def measured_peaks():
     try:
         return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -270,7 +281,9 @@ def run_b200(args):
         "bound": "fp64" if not f32 else "fp32", "kernel": f"caf_rows_kernel<{'float' if f32 else 'double'}, kSurface>",
         "achieved": achieved_tf, "peak": tf.value, "unit": "TFLOP/s", "frac": achieved_tf / tf.value if tf.value else None,
         "peak_source": "in-run FMA-pipe probe (caf_b200_probe_fma_tflops); MEASURED_PEAKS.json has no fp64/fp32 entry",
-        "flops_per_launch": row_flops, "kernel_ms": rows_avg_ms, "traffic": None,
+        "flops_per_launch": row_flops, "kernel_ms": rows_avg_ms,
+        "traffic": committed_traffic() if not f32 else None,
+        "traffic_note": "DRAM bytes per launch from the committed ncu capture; the 26.2 MB surface is written back from the 126 MB L2 after the kernel ends",
         "hbm": {"achieved": surf_bytes / (rows_avg_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                 "frac": surf_bytes / (rows_avg_ms * 1e-3) / 1e9 / hbm_peak,
                 "peak_source": "MEASURED_PEAKS.json (measured)" if mp else "fallback 6650 GB/s"},

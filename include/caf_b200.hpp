@@ -1,0 +1,155 @@
+// caf_b200.hpp — C++ host-side mirror of caf_rust's public API over the C ABI (caf_b200.h).
+//
+// The reference's host language is Rust and no Rust toolchain exists in this build image, so the host side above
+// the C ABI is written in C++ with the reference's names, argument order and error behaviour:
+//     trait CafSurface { caf_surface, find_peak, apply_freq_shift }     caf_rust/src/caf/mod.rs:23-66
+//     struct CafSurfaceRow { freq, xcor_mag, xcor_peak_idx, xcor_peak_val }  caf_rust/src/caf/mod.rs:17-22
+//     struct Xcor { new, run, clone }                                    caf_rust/src/caf/xcor_rustfft.rs:14-93
+//     read_file_c64 / BinaryIO::write_file_binary                        caf_rust/src/utils.rs:10-63
+// The reference panics on bad input (assert!/unwrap); here that is a thrown caf::Panic.
+// Header only; link with libcaf_b200.so.  rust/ holds the equivalent Rust shim as (uncompiled) source.
+#pragma once
+#include <complex>
+#include <cstdint>
+#include <cstdio>
+#include <fstream>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "caf_b200.h"
+
+namespace caf {
+
+using Complex64 = std::complex<double>;   // Rust's num_complex::Complex64 = Complex<f64> (utils.rs:8-9)
+using Complex32 = std::complex<float>;
+
+struct Panic : std::runtime_error { using std::runtime_error::runtime_error; };
+
+inline void check(int rc) {
+    if (rc != CAF_B200_OK) throw Panic(std::string("caf_b200 status ") + std::to_string(rc) + ": " + caf_b200_last_error());
+}
+
+// one lazily created handle per thread: the trait functions are static and must be callable from any thread
+inline caf_b200_handle thread_handle() {
+    struct Holder {
+        caf_b200_handle h = nullptr;
+        ~Holder() { if (h) caf_b200_destroy(h); }
+    };
+    thread_local Holder holder;
+    if (!holder.h) check(caf_b200_create(0, &holder.h));
+    return holder.h;
+}
+
+// mod.rs:17-22 (fields are private in the reference; accessors added so results can be inspected)
+class CafSurfaceRow {
+public:
+    double freq = 0.0;
+    std::vector<double> xcor_mag;
+    std::size_t xcor_peak_idx = 0;
+    double xcor_peak_val = 0.0;
+};
+
+struct CafB200 {
+    // mod.rs:121-166 (every strategy struct computes this)
+    static std::vector<CafSurfaceRow> caf_surface(const std::vector<Complex64>& needle, const std::vector<Complex64>& haystack,
+                                                  const std::vector<double>& freqs_hz, uint32_t fs) {
+        if (needle.size() != haystack.size()) throw Panic("assertion failed: a.len() == self.n (xcor_rustfft.rs:54-55)");
+        const std::size_t l = needle.size(), d = freqs_hz.size(), n = 2 * l;
+        std::vector<double> surface(d * n), pval(d);
+        std::vector<uint64_t> pidx(d);
+        check(caf_b200_surface_f64(thread_handle(), reinterpret_cast<const caf_c128*>(needle.data()),
+                                   reinterpret_cast<const caf_c128*>(haystack.data()), l, freqs_hz.data(), d, fs,
+                                   surface.data(), pval.data(), pidx.data(), nullptr));
+        std::vector<CafSurfaceRow> rows(d);
+        for (std::size_t r = 0; r < d; ++r) {
+            rows[r].freq = freqs_hz[r];
+            rows[r].xcor_mag.assign(surface.begin() + r * n, surface.begin() + (r + 1) * n);
+            rows[r].xcor_peak_idx = (std::size_t)pidx[r];
+            rows[r].xcor_peak_val = pval[r];
+        }
+        return rows;
+    }
+    // mod.rs:31-42: strict > from a dummy row (0.0, peak 0.0); consumes the surface like the reference
+    static std::pair<double, std::size_t> find_peak(std::vector<CafSurfaceRow> arr) {
+        double best = 0.0, f = 0.0;
+        std::size_t idx = 0;
+        for (const auto& row : arr)
+            if (row.xcor_peak_val > best) { best = row.xcor_peak_val; f = row.freq; idx = row.xcor_peak_idx; }
+        return {f, idx};
+    }
+    // caf_surface + find_peak fused on the GPU, the surface never leaves the chip
+    static std::pair<double, std::size_t> caf_peak(const std::vector<Complex64>& needle, const std::vector<Complex64>& haystack,
+                                                   const std::vector<double>& freqs_hz, uint32_t fs) {
+        if (needle.size() != haystack.size()) throw Panic("assertion failed: a.len() == self.n (xcor_rustfft.rs:54-55)");
+        caf_b200_peak pk;
+        check(caf_b200_peak_f64(thread_handle(), reinterpret_cast<const caf_c128*>(needle.data()),
+                                reinterpret_cast<const caf_c128*>(haystack.data()), needle.size(), freqs_hz.data(),
+                                freqs_hz.size(), fs, &pk));
+        return {pk.freq_hz, (std::size_t)pk.delay_idx};
+    }
+    // mod.rs:46-65
+    static std::vector<Complex64> apply_freq_shift(const std::vector<Complex64>& samples, double freq_shift, uint32_t fs) {
+        std::vector<Complex64> out(samples.size());
+        check(caf_b200_apply_freq_shift_f64(thread_handle(), reinterpret_cast<const caf_c128*>(samples.data()), samples.size(),
+                                            freq_shift, fs, reinterpret_cast<caf_c128*>(out.data())));
+        return out;
+    }
+    static std::vector<Complex64> apply_shift(const std::vector<Complex64>& s, double f, uint32_t fs) { return apply_freq_shift(s, f, fs); }
+};
+
+// the seven strategy structs of the reference (mod.rs:67,118,169,219,266,313,388): one computation, one path
+using CafFFTW = CafB200;
+using CafRustFFT = CafB200;
+using CafRustFFTRayon = CafB200;
+using CafRustFFTIter = CafB200;
+using CafRustFFTIterRayon = CafB200;
+using CafRustFFTThreads = CafB200;
+using CafRustFFTThreadpool = CafB200;
+
+// xcor_rustfft.rs:14-93
+class Xcor {
+    std::size_t n_;
+public:
+    explicit Xcor(std::size_t n) : n_(n) {}
+    static Xcor make(std::size_t n) { return Xcor(n); }       // Xcor::new
+    Xcor clone() const { return Xcor(n_); }
+    std::vector<Complex64> run(const std::vector<Complex64>& a, const std::vector<Complex64>& b) const {
+        if (a.size() != n_ || b.size() != n_) throw Panic("assertion failed: a.len() == self.n (xcor_rustfft.rs:54-55)");
+        std::vector<Complex64> out(n_);
+        check(caf_b200_xcor_f64(thread_handle(), reinterpret_cast<const caf_c128*>(a.data()),
+                                reinterpret_cast<const caf_c128*>(b.data()), n_, reinterpret_cast<caf_c128*>(out.data())));
+        return out;
+    }
+};
+
+// utils.rs:10-35: packed little-endian f32 I/Q -> Complex64
+inline std::vector<Complex64> read_file_c64(const std::string& filename) {
+    std::ifstream f(filename, std::ios::binary);
+    if (!f) throw std::runtime_error("read_file_c64: cannot open " + filename);      // io::Result Err in the reference
+    std::vector<char> buf((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+    if (buf.size() % 8) throw Panic("read_file_c64: trailing partial sample");
+    std::vector<Complex64> out(buf.size() / 8);
+    const float* p = reinterpret_cast<const float*>(buf.data());
+    for (std::size_t i = 0; i < out.size(); ++i) out[i] = Complex64((double)p[2 * i], (double)p[2 * i + 1]);
+    return out;
+}
+
+// utils.rs:39-63: raw little-endian f64 pairs (numpy complex128)
+inline void write_file_binary(const std::vector<Complex64>& v, const std::string& filename) {
+    std::ofstream f(filename, std::ios::binary);
+    if (!f) throw Panic("write_file_binary: cannot create " + filename);
+    f.write(reinterpret_cast<const char*>(v.data()), (std::streamsize)(v.size() * sizeof(Complex64)));
+}
+
+// tests/test.rs:335-352
+inline std::vector<double> gen_float_shifts(double start, double end, double step) {
+    const int s = (int)(start * 1000.0), e = (int)(end * 1000.0);
+    const std::size_t st = (std::size_t)(step * 1000.0);
+    std::vector<double> out;
+    for (int m = s; m < e; m += (int)st) out.push_back((double)m / 1e3);
+    return out;
+}
+
+}  // namespace caf

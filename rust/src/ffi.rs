@@ -1,0 +1,58 @@
+//! Hand-written extern "C" block for include/caf_b200.h (only what the crate API needs).
+#![allow(non_camel_case_types, dead_code)]
+use num_complex::Complex64;
+use std::os::raw::{c_char, c_int, c_void};
+
+#[repr(C)]
+pub struct caf_b200_handle_s { _private: [u8; 0] }
+pub type caf_b200_handle = *mut caf_b200_handle_s;
+
+#[repr(C)]
+#[derive(Clone, Copy, Default)]
+pub struct caf_b200_peak {
+    pub value: f64,
+    pub freq_hz: f64,
+    pub doppler_idx: u64,
+    pub delay_idx: u64,
+}
+
+extern "C" {
+    pub fn caf_b200_create(device: c_int, out: *mut caf_b200_handle) -> c_int;
+    pub fn caf_b200_destroy(h: caf_b200_handle) -> c_int;
+    pub fn caf_b200_last_error() -> *const c_char;
+    pub fn caf_b200_apply_freq_shift_f64(h: caf_b200_handle, input: *const Complex64, n: usize, freq_hz: f64,
+                                         fs: u32, out: *mut Complex64) -> c_int;
+    pub fn caf_b200_xcor_f64(h: caf_b200_handle, a: *const Complex64, b: *const Complex64, n: usize,
+                             out: *mut Complex64) -> c_int;
+    pub fn caf_b200_surface_f64(h: caf_b200_handle, needle: *const Complex64, haystack: *const Complex64, l: usize,
+                                freqs_hz: *const f64, d: usize, fs: u32, surface: *mut f64,
+                                row_peak_val: *mut f64, row_peak_idx: *mut u64, peak: *mut caf_b200_peak) -> c_int;
+    pub fn caf_b200_peak_f64(h: caf_b200_handle, needle: *const Complex64, haystack: *const Complex64, l: usize,
+                             freqs_hz: *const f64, d: usize, fs: u32, peak: *mut caf_b200_peak) -> c_int;
+    pub fn caf_b200_host_alloc(out: *mut *mut c_void, bytes: usize) -> c_int;
+    pub fn caf_b200_host_free(p: *mut c_void) -> c_int;
+}
+
+/// One lazily created handle per thread: the trait functions are associated functions without `self`, callable
+/// from any thread (rayon workers included), and a handle is not thread-safe.
+pub struct ThreadHandle(pub caf_b200_handle);
+impl Drop for ThreadHandle {
+    fn drop(&mut self) { unsafe { caf_b200_destroy(self.0); } }
+}
+thread_local! {
+    pub static HANDLE: ThreadHandle = {
+        let mut h: caf_b200_handle = std::ptr::null_mut();
+        let rc = unsafe { caf_b200_create(0, &mut h) };
+        if rc != 0 { panic!("caf_b200_create failed ({}): {}", rc, last_error()); }
+        ThreadHandle(h)
+    };
+}
+
+pub fn last_error() -> String {
+    unsafe { std::ffi::CStr::from_ptr(caf_b200_last_error()).to_string_lossy().into_owned() }
+}
+
+/// The reference panics where this library returns a status (xcor_rustfft.rs:54-55 assert!, unwrap()s).
+pub fn check(rc: c_int) {
+    if rc != 0 { panic!("caf_b200 status {}: {}", rc, last_error()); }
+}
