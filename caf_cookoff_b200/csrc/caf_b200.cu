@@ -196,6 +196,19 @@ int run_batch_dev(caf_b200_handle h, const caf::cx<T>* needles, const caf::cx<T>
     if (fused_peak) { a.peak = peaks; a.done_counter = h->done_counter; }
     if (p == 1 && d > 1) {                        // one pair over many CTAs: CTA 0 publishes H, the rest consume it
         a.hshare = reinterpret_cast<cx<T>*>(h->hshare); a.hflag = h->hflag; a.epoch = ++h->epoch;
+        // H_1's publisher: the lowest-index CTA other than 0 that owns the fewest rows (same split as the kernel)
+        const long long n_items = (long long)d;
+        const int occ = std::is_same<T, double>::value ? h->occ_d : h->occ_f;
+        const long long cap = (long long)h->sm_count * occ;
+        const long long grid = n_items < cap ? n_items : cap;
+        a.hprod1 = 0;
+#ifndef CAF_PINGPONG
+        long long best = -1;
+        for (long long b = 1; b < grid; ++b) {
+            const long long cnt = n_items * (b + 1) / grid - n_items * b / grid;
+            if (best < 0 || cnt < best) { best = cnt; a.hprod1 = (int)b; }
+        }
+#endif
     }
     const bool prof = h->profiling;
     if (prof) {

@@ -82,6 +82,7 @@ struct RowArgs {
     cx<T>* hshare;          // kSurface, P == 1: H published by CTA 0 for every other CTA, [16][512] per-thread order
     unsigned int* hflag;    // [2] per-group publish counters (monotonic across launches)
     unsigned int epoch;     // this launch's counter value
+    int hprod1;             // CTA that publishes H_1 (H_0 comes from CTA 0); 0 = CTA 0 publishes both
     long long* trace;       // CAF_TRACE builds only: [cta][warp][8 items][24 slots] clock64 stamps
 };
 
@@ -302,40 +303,53 @@ __device__ __forceinline__ void mbar_wait(uint64_t* mb, int parity) {
 // `empty_mb` (group 1 only): the mailbox barrier to wait on before the fabric half is overwritten.
 // `hook()` runs in the exchange phase after the block barriers (deferred row-peak reduction).
 // ------------------------------------------------------------------------------------------------
+// development experiments (never defined in the product build): drop the exchanges or the butterflies to see
+// how much of a row each side costs on its own (results are then wrong by construction)
+#ifdef CAF_EXP_NOXCHG
+#define CAF_XCHG(...) do { } while (0)
+#else
+#define CAF_XCHG(...) do { __VA_ARGS__; } while (0)
+#endif
+#ifdef CAF_EXP_NOFP
+#define CAF_FP(...) do { } while (0)
+#else
+#define CAF_FP(...) do { __VA_ARGS__; } while (0)
+#endif
+
 template <typename T, typename Hook>
 __device__ __forceinline__ void forward_4096(cx<T> (&v)[16], const Ctx<T>& c,
                                              uint64_t* empty_mb, int empty_parity, Hook&& hook) {
     constexpr int kC = TmemGeom<T>::kColsPerC;
-    fft16<T, false>(v);
-    twiddle_powers<false>(v, tmem_ld1(c.tm_tw, T()));           // W_4096^{t k}
+    CAF_FP(fft16<T, false>(v));
+    CAF_FP(twiddle_powers<false>(v, tmem_ld1(c.tm_tw, T())));           // W_4096^{t k}
     pp_release(c.r, v);
     CAF_TR(c, 3);
     if (empty_mb) mbar_wait(empty_mb, empty_parity);   // group 0 has drained the previous row's mailbox
     bar_group(c.r);    // every earlier reader of this half of the fabric (previous X4 / X2) is done
 #pragma unroll
-    for (int k = 0; k < 16; ++k) c.Sr[k * 256 + c.t] = v[k];
+    CAF_XCHG(for (int k = 0; k < 16; ++k) c.Sr[k * 256 + c.t] = v[k]);
     CAF_TR(c, 4);
     bar_group(c.r);
 #pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = c.Sw[c.h + 16 * i];
+    CAF_XCHG(for (int i = 0; i < 16; ++i) v[i] = c.Sw[c.h + 16 * i]);
     hook();
     CAF_TR(c, 5);
 
     pp_acquire(c.r, v);
-    fft16<T, false>(v);
-    twiddle_powers<false>(v, tmem_ld1(c.tm_tw + kC, T()));      // W_256^{h k}
+    CAF_FP(fft16<T, false>(v));
+    CAF_FP(twiddle_powers<false>(v, tmem_ld1(c.tm_tw + kC, T())));      // W_256^{h k}
     pp_release(c.r, v);
     CAF_TR(c, 6);
     __syncwarp();
 #pragma unroll
-    for (int k = 0; k < 16; ++k) c.Sw[k * 16 + (c.h ^ k)] = v[k];
+    CAF_XCHG(for (int k = 0; k < 16; ++k) c.Sw[k * 16 + (c.h ^ k)] = v[k]);
     __syncwarp();
 #pragma unroll
-    for (int m = 0; m < 16; ++m) v[m] = c.Sw[c.h * 16 + (m ^ c.h)];
+    CAF_XCHG(for (int m = 0; m < 16; ++m) v[m] = c.Sw[c.h * 16 + (m ^ c.h)]);
     CAF_TR(c, 7);
 
     pp_acquire(c.r, v);
-    fft16<T, false>(v);    // returns holding the token
+    CAF_FP(fft16<T, false>(v));    // returns holding the token
     CAF_TR(c, 8);
 }
 
@@ -346,37 +360,37 @@ __device__ __forceinline__ void forward_4096(cx<T> (&v)[16], const Ctx<T>& c,
 template <typename T>
 __device__ __forceinline__ void inverse_4096(cx<T> (&v)[16], const Ctx<T>& c) {
     constexpr int kC = TmemGeom<T>::kColsPerC;
-    fft16<T, true>(v);
-    twiddle_powers<true>(v, tmem_ld1(c.tm_tw + kC, T()));       // conj W_256^{h k}
+    CAF_FP(fft16<T, true>(v));
+    CAF_FP(twiddle_powers<true>(v, tmem_ld1(c.tm_tw + kC, T())));       // conj W_256^{h k}
     pp_release(c.r, v);
     CAF_TR(c, 10);
     __syncwarp();
 #pragma unroll
-    for (int k = 0; k < 16; ++k) c.Sw[k * 16 + (c.h ^ k)] = v[k];
+    CAF_XCHG(for (int k = 0; k < 16; ++k) c.Sw[k * 16 + (c.h ^ k)] = v[k]);
     __syncwarp();
 #pragma unroll
-    for (int m = 0; m < 16; ++m) v[m] = c.Sw[c.h * 16 + (m ^ c.h)];
+    CAF_XCHG(for (int m = 0; m < 16; ++m) v[m] = c.Sw[c.h * 16 + (m ^ c.h)]);
     CAF_TR(c, 11);
 
     pp_acquire(c.r, v);
-    fft16<T, true>(v);
+    CAF_FP(fft16<T, true>(v));
     {
         const cx<T> b = tmem_ld1(c.tm_tw + 2 * kC, T()), rho = tmem_ld1(c.tm_tw + 3 * kC, T());
-        twiddle_geometric<true>(v, b, rho);                     // conj W_4096^{k1 (16 k + h)}
+        CAF_FP(twiddle_geometric<true>(v, b, rho));                     // conj W_4096^{k1 (16 k + h)}
     }
     pp_release(c.r, v);
     CAF_TR(c, 12);
     __syncwarp();
 #pragma unroll
-    for (int k = 0; k < 16; ++k) c.Sw[16 * k + c.h] = v[k];
+    CAF_XCHG(for (int k = 0; k < 16; ++k) c.Sw[16 * k + c.h] = v[k]);
     CAF_TR(c, 13);
     bar_group(c.r);
 #pragma unroll
-    for (int k = 0; k < 16; ++k) v[k] = c.Sr[k * 256 + c.t];
+    CAF_XCHG(for (int k = 0; k < 16; ++k) v[k] = c.Sr[k * 256 + c.t]);
     CAF_TR(c, 14);
 
     pp_acquire(c.r, v);
-    fft16<T, true>(v);     // returns holding the token
+    CAF_FP(fft16<T, true>(v));     // returns holding the token
     CAF_TR(c, 15);
 }
 
@@ -419,6 +433,10 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
     uint64_t* mb_empty = reinterpret_cast<uint64_t*>(smem_raw + SL::offMisc + 24);
 
     const int tid = threadIdx.x;
+#ifdef CAF_TRACE
+    long long tr_g0 = 0, tr_c0 = clock64();
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tr_g0));
+#endif
     Ctx<T> c;
     // group r = tid / 256.  Inside a warp: lane = h[2:0] | sub << 3 | h[3] << 4; the warp's two sub-transforms
     // k1 = 2 * warp_in_group + sub sit in adjacent quarter-warps, so a 128-bit W_256 twiddle load (same address
@@ -435,6 +453,42 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
     constexpr bool kHalfZero = (MODE == kSurface || MODE == kSpectrumHalf || MODE == kXcorHalf);
     constexpr bool kWritesH = (MODE == kSpectrumHalf || MODE == kSpectrumFull);
     constexpr bool kUseTmem = (MODE == kSurface);   // H and the needle live in TMEM (the twiddle bases always do)
+
+    // ---- work split: contiguous ranges of (pair, row) items so a CTA changes pair as rarely as possible ----
+    const int rows_per_pair = (MODE == kSurface) ? a.D : 1;
+    const long long n_items = (long long)a.P * rows_per_pair;     // host guarantees < 2^31
+    const int lo = (int)(n_items * blockIdx.x / gridDim.x), hi = (int)(n_items * (blockIdx.x + 1) / gridDim.x);
+    int pair = lo / rows_per_pair, row = lo - pair * rows_per_pair;   // one division per CTA
+
+    int buf = 0;
+    int cur_pair = -1;
+    int posts = 0;            // mailbox posts so far (group 1) / mailbox reads so far (group 0)
+    bool drain_pending = false;   // group 1: a posted mailbox that group 0 may still be reading
+    bool h_from_share = false;    // consumer CTA: H still has to be fetched from CTA 0's publication
+    int peak_pending = -1;        // group 0: item whose per-warp maxima wait in red_* for the deferred reduction
+    C v[16];
+
+    // ---- everything the prologue needs from global memory is requested NOW, so the DRAM / L2 round trips run
+    //      behind the TMEM allocation instead of after it: the five twiddle bases, the first operand block
+    //      (haystack for a group that publishes H, else the needle) and the first doppler shift ----
+    const C tb0 = ldg<T>(a.tw1 + 256 + t), tb1 = ldg<T>(a.tw2 + 16 + h), tb2 = ldg<T>(a.tw1 + w * 256 + h),
+            tb3 = ldg<T>(a.tw2 + 16 + w), tb4 = ldg<T>(a.g + t);
+    bool preloaded = false;        // v already holds the first operand block of the first pair
+    double phi_first = 0.0;
+    if constexpr (MODE == kSurface) {
+        if (lo < hi) {
+            const bool shared_h0 = (a.hshare != nullptr);
+            const bool producer0 = !shared_h0 || (int)blockIdx.x == ((r == 0) ? 0 : a.hprod1);
+            const C* src = (producer0 ? a.in2 : a.in) + (long long)pair * a.L;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const int n = t + 256 * i;
+                v[i] = (n < a.L) ? ldg<T>(src + n) : mk<T>((T)0, (T)0);
+            }
+            preloaded = true;
+            phi_first = __ldg(a.freqs + row) * a.dt;
+        }
+    }
 
     if (tid == 0) {
         mbar_init(mb_full, 256);
@@ -459,11 +513,11 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
         tm_n = base + (uint32_t)((64 + 16 * (j & 1)) * TG::kColsPerC);      // 16 needle samples (shared by both groups)
         c.tm_tw = base + (uint32_t)((96 + 8 * j) * TG::kColsPerC);          // 5 twiddle bases
         // per-thread twiddle bases, once per CTA: W_4096^t, W_256^h, W_4096^{k1 h}, W_256^{k1}, W_8192^{-t}
-        tmem_st1(c.tm_tw + 0 * TG::kColsPerC, ldg<T>(a.tw1 + 256 + t));
-        tmem_st1(c.tm_tw + 1 * TG::kColsPerC, ldg<T>(a.tw2 + 16 + h));
-        tmem_st1(c.tm_tw + 2 * TG::kColsPerC, ldg<T>(a.tw1 + w * 256 + h));
-        tmem_st1(c.tm_tw + 3 * TG::kColsPerC, ldg<T>(a.tw2 + 16 + w));
-        tmem_st1(c.tm_tw + 4 * TG::kColsPerC, ldg<T>(a.g + t));
+        tmem_st1(c.tm_tw + 0 * TG::kColsPerC, tb0);
+        tmem_st1(c.tm_tw + 1 * TG::kColsPerC, tb1);
+        tmem_st1(c.tm_tw + 2 * TG::kColsPerC, tb2);
+        tmem_st1(c.tm_tw + 3 * TG::kColsPerC, tb3);
+        tmem_st1(c.tm_tw + 4 * TG::kColsPerC, tb4);
         tmem_wait_st();
     }
 
@@ -503,19 +557,6 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
         }
     };
 
-    // ---- work split: contiguous ranges of (pair, row) items so a CTA changes pair as rarely as possible ----
-    const int rows_per_pair = (MODE == kSurface) ? a.D : 1;
-    const long long n_items = (long long)a.P * rows_per_pair;     // host guarantees < 2^31
-    const int lo = (int)(n_items * blockIdx.x / gridDim.x), hi = (int)(n_items * (blockIdx.x + 1) / gridDim.x);
-    int pair = lo / rows_per_pair, row = lo - pair * rows_per_pair;   // one division per CTA
-
-    int buf = 0;
-    int cur_pair = -1;
-    int posts = 0;            // mailbox posts so far (group 1) / mailbox reads so far (group 0)
-    bool drain_pending = false;   // group 1: a posted mailbox that group 0 may still be reading
-    bool h_from_share = false;    // consumer CTA: H still has to be fetched from CTA 0's publication
-    int peak_pending = -1;        // group 0: item whose per-warp maxima wait in red_* for the deferred reduction
-    C v[16];
 
     // fold the 8 per-warp maxima of a finished row (parked in red_*[slot]) into its row peak: warp 0 of group 0
     auto flush_peak = [&](int slot) {
@@ -563,11 +604,17 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
                 // the others start their first row at once and pick H up just before they need it.
                 cur_pair = pair;
                 const bool shared_h = (a.hshare != nullptr);
-                const bool producer = !shared_h || blockIdx.x == 0;
+                // H_0 is published by CTA 0 and H_1 by CTA hprod1 (both own one row fewer than the critical path).
+                // In a publishing CTA the other group parks at barrier 0 so the publisher has the SM's fp64 pipes
+                // to itself and H is ready before any consumer needs it.
+                const int my_prod_cta = (r == 0) ? 0 : a.hprod1;
+                const bool producer = !shared_h || (int)blockIdx.x == my_prod_cta;
+                const bool park = shared_h && a.hprod1 != 0 && ((int)blockIdx.x == 0 || (int)blockIdx.x == a.hprod1);
                 bar_group(r);                     // nobody in this group still reads ptab[buf] of an earlier item
                 if (producer) {
                     fill_ptab(buf, 0.0);
-                    load_half(v, a.in2 + (long long)pair * a.L, a.L);
+                    if (!preloaded) load_half(v, a.in2 + (long long)pair * a.L, a.L);
+                    preloaded = false;
                 }
                 bar_group(r);
                 if (producer) {
@@ -597,7 +644,10 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
                 } else {
                     h_from_share = true;
                 }
-                load_half(v, a.in + (long long)pair * a.L, a.L);
+                if (park) __syncthreads();
+                if (!preloaded) load_half(v, a.in + (long long)pair * a.L, a.L);
+                const bool first_row_phi = preloaded || (item == lo);
+                preloaded = false;
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     C tmp[4];
@@ -607,7 +657,7 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
                 }
                 tmem_wait_st();
                 bar_group(r);                     // ptab[buf] (phi = 0) is dead from here
-                fill_ptab(buf, a.freqs[row] * a.dt);
+                fill_ptab(buf, first_row_phi ? phi_first : a.freqs[row] * a.dt);
                 bar_group(r);
             }
             CAF_TR(c, 1);
@@ -815,6 +865,13 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
         if (hw_warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" :: "r"(misc[0]), "n"(TG::kAlloc));
     }
 
+#ifdef CAF_TRACE
+    if (a.trace && (tid & 31) == 0) {
+        long long g1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g1));
+        long long* q = a.trace + (((long long)blockIdx.x * 16 + hw_warp) * 8 + 0) * 24;
+        q[20] = tr_g0; q[21] = g1; q[22] = tr_c0; q[23] = clock64();
+    }
+#endif
     // ---------------- fused find_peak (mod.rs:31-42), single pair: the last CTA to finish reduces the rows ----------------
     if constexpr (MODE == kSurface) {
         if (a.peak != nullptr && a.done_counter != nullptr) {

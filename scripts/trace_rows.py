@@ -33,3 +33,18 @@ for cta in range(ncta):
 print("row duration (warp 0) cycles: median", np.median(dur), "min", np.min(dur), "max", np.max(dur))
 pro = [buf[c, 0, 0, 1] - buf[c, 0, 0, 0] for c in range(ncta) if buf[c, 0, 0, 1] > 0]
 print("prologue (item start -> row start) cycles: median", np.median(pro))
+
+# whole-kernel view: CTA lifetimes on the global timer (ns) and on the SM clock
+g0 = buf[:, 0, 0, 20]; g1 = buf[:, 0, 0, 21]; c0 = buf[:, 0, 0, 22]; c1 = buf[:, 0, 0, 23]
+ok = g0 > 0
+base = g0[ok].min()
+print("CTA start (ns after first CTA): min %d med %d max %d" % ((g0[ok]-base).min(), np.median(g0[ok]-base), (g0[ok]-base).max()))
+print("CTA end   (ns after first CTA): min %d med %d max %d" % ((g1[ok]-base).min(), np.median(g1[ok]-base), (g1[ok]-base).max()))
+life = (c1 - c0)[ok]
+print("CTA lifetime cycles: min %d med %d max %d" % (life.min(), np.median(life), life.max()))
+first = np.array([buf[c, 0, 0, 0] - buf[c, 0, 0, 22] for c in range(ncta) if buf[c,0,0,0] > 0])
+print("setup (entry -> first item start) cycles: med %d max %d" % (np.median(first), first.max()))
+nrows = np.array([(buf[c, 0, :, 19] > 0).sum() for c in range(ncta)])
+for k in (2, 3):
+    sel = (nrows == k) & ok
+    if sel.any(): print(f"CTAs with {k} rows: n={sel.sum()} lifetime med {np.median((c1-c0)[sel]):.0f} max {(c1-c0)[sel].max()}")
