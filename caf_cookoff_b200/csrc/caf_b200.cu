@@ -64,7 +64,6 @@ struct caf_b200_handle_s {
     Tables<float> tf;
     int occ_d = 1, occ_f = 1;   // resident CTAs per SM of the surface kernel
     DevBuf needle, hay, hperm, freqs, surface, rowval, rowidx, peaks, scratch;
-    int stagger = 0;
     long long* trace = nullptr;   // CAF_TRACE builds: device buffer for phase stamps
     unsigned int* done_counter = nullptr;   // last-CTA-done ticket of the fused find_peak
     void* hshare = nullptr;                 // single-pair launches: H published by CTA 0 (8192 complex128)
@@ -157,7 +156,6 @@ caf::RowArgs<T> base_args(caf_b200_handle h) {
     Tables<T>& t = tables<T>(h);
     a.tw1 = t.tw1; a.tw2 = t.tw2; a.g = t.g;
     a.dt = 0.0; a.L = 0; a.D = 1; a.P = 1;
-    a.stagger = h->stagger;
     a.trace = h->trace;
     return a;
 }
@@ -389,7 +387,7 @@ static int create_impl(int device, bool own_stream, void* cuda_stream, caf_b200_
     if (!h) return fail(CAF_B200_EINVAL, "out of host memory");
     h->device = device;
     h->sm_count = prop.multiProcessorCount;
-    if (const char* e_ = getenv("CAF_B200_STAGGER")) h->stagger = atoi(e_);
+
     if (!own_stream) { h->stream = (cudaStream_t)cuda_stream; h->own_stream = false; }   // 0 = legacy default stream
     else {
         e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);

@@ -78,7 +78,6 @@ struct RowArgs {
     int L;                  // samples per input signal (<= 4096)
     int D;                  // doppler rows per pair
     int P;                  // pairs
-    int stagger;            // cycles group 0 idles before its first item (phase offset between the groups)
     cx<T>* hshare;          // kSurface, P == 1: H published by CTA 0 for every other CTA, [16][512] per-thread order
     unsigned int* hflag;    // [2] per-group publish counters (monotonic across launches)
     unsigned int epoch;     // this launch's counter value
@@ -225,12 +224,6 @@ __device__ __forceinline__ void tmem_st1(uint32_t taddr, float2 v) {
 
 template <typename T>
 __device__ __forceinline__ cx<T> ldg(const cx<T>* p) { return __ldg(p); }
-
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n"
-                 :: "r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
 // fractional part helper: cycles -> (cos, sin)(2 pi cycles), evaluated in fp64 for both variants
 __device__ __forceinline__ double2 unit_phasor(double n, double phi, double exact_sub) {
@@ -418,6 +411,8 @@ __device__ __forceinline__ void amax_take(T& best, int& bidx, T m, int k) {
 template <int I> using ic = std::integral_constant<int, I>;
 
 // FULL = the reference's shape, L == 4096: every one of the 8192 cells is an output cell (no index remap).
+// One CTA per SM for both precisions: two complex64 CTAs per SM fit (64 regs, 64 KB fabric) but measured slower
+// (36.9 vs 33.0 us per surface) because every CTA pays the per-launch prologue for half as many rows.
 template <typename T, int MODE, bool FULL>
 __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> a) {
     using C = cx<T>;
@@ -585,11 +580,6 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
     };
 
     if (r == 0) pp_release(0);     // group 1 computes first: hand it the token
-    if (r == 0 && a.stagger > 0 && lo < hi) {
-        // start group 0 half a pass behind group 1: from then on one group's exchange overlaps the other's math
-        const long long t0 = clock64();
-        while (clock64() - t0 < a.stagger) { }
-    }
 
     c.tr = nullptr;
     for (int item = lo; item < hi; ++item, buf ^= 1) {
