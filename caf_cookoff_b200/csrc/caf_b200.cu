@@ -16,6 +16,7 @@
 
 #include "../../include/caf_b200.h"
 #include "caf_kernels.cuh"
+#include "caf_large.cuh"
 
 namespace {
 
@@ -64,6 +65,7 @@ struct caf_b200_handle_s {
     Tables<float> tf;
     int occ_d = 1, occ_f = 1;   // resident CTAs per SM of the surface kernel
     DevBuf needle, hay, hperm, freqs, surface, rowval, rowidx, peaks, scratch;
+    DevBuf lwbuf, lhbig, lpart;             // long-row path: chunk scratch, H, partial row maxima
     long long* trace = nullptr;   // CAF_TRACE builds: device buffer for phase stamps
     unsigned int* done_counter = nullptr;   // last-CTA-done ticket of the fused find_peak
     void* hshare = nullptr;                 // single-pair launches: H published by CTA 0 (8192 complex128)
@@ -136,6 +138,8 @@ cudaError_t configure_all(int* occ) {
     if ((e = configure_kernel<T, caf::kSpectrumFull>(nullptr)) != cudaSuccess) return e;
     if ((e = configure_kernel<T, caf::kXcorFull>(nullptr)) != cudaSuccess) return e;
     if ((e = configure_kernel<T, caf::kXcorHalf>(nullptr)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(caf::caf_large_core<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<T>())) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(caf::caf_large_core<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<T>())) != cudaSuccess) return e;
     return cudaSuccess;
 }
 
@@ -160,6 +164,88 @@ caf::RowArgs<T> base_args(caf_b200_handle h) {
     return a;
 }
 
+// ---- rows longer than 8192 cells: four-step FFT (caf_large.cuh), one pair at a time, rows in L2-sized chunks ----
+template <typename T, int R>
+cudaError_t launch_large_rt(caf_b200_handle h, const caf::LargeArgs<T>& a, bool gather) {
+    dim3 grid(16, (unsigned)a.rows);
+    if (!gather) caf::caf_large_spread<T, R><<<grid, 256, 0, h->stream>>>(a);
+    else caf::caf_large_gather<T, R><<<grid, 256, 0, h->stream>>>(a);
+    h->launches++;
+    return cudaGetLastError();
+}
+template <typename T>
+cudaError_t launch_large(caf_b200_handle h, const caf::LargeArgs<T>& a, bool gather) {
+    switch (a.R) {
+        case 2: return launch_large_rt<T, 2>(h, a, gather);
+        case 4: return launch_large_rt<T, 4>(h, a, gather);
+        case 8: return launch_large_rt<T, 8>(h, a, gather);
+        case 16: return launch_large_rt<T, 16>(h, a, gather);
+        default: return cudaErrorInvalidValue;
+    }
+}
+template <typename T, bool HMODE>
+cudaError_t launch_large_core(caf_b200_handle h, const caf::LargeArgs<T>& a) {
+    const long long units = (long long)a.rows * 2 * a.R;
+    long long ctas = (units + 1) / 2;
+    if (ctas > h->sm_count) ctas = h->sm_count;
+    caf::caf_large_core<T, HMODE><<<(unsigned)ctas, caf::kThreads, smem_bytes<T>(), h->stream>>>(a);
+    h->launches++;
+    return cudaGetLastError();
+}
+
+template <typename T>
+int run_large_dev(caf_b200_handle h, const caf::cx<T>* needles, const caf::cx<T>* hays, size_t p, size_t l,
+                  const double* freqs, size_t d, uint32_t fs, T* surface, T* rowval,
+                  unsigned long long* rowidx, caf::PeakOut* peaks) {
+    using namespace caf;
+    int n = 16384;
+    while ((size_t)n < 2 * l) n *= 2;
+    const int R = n / 2 / 4096;
+    const size_t row_bytes = sizeof(cx<T>) * (size_t)n;
+    size_t chunk = (48u << 20) / row_bytes;
+    if (chunk < 1) chunk = 1;
+    if (chunk > d) chunk = d;
+    CK(h->lwbuf.ensure(row_bytes * chunk));
+    CK(h->lhbig.ensure(row_bytes));
+    CK(h->lpart.ensure((sizeof(double) + sizeof(int)) * 16 * chunk));
+    T* rv = rowval; unsigned long long* ri = rowidx;
+    if (!rv || !ri) {
+        CK(h->scratch.ensure((sizeof(T) + sizeof(unsigned long long)) * p * d + 16));
+        ri = reinterpret_cast<unsigned long long*>(h->scratch.p);
+        rv = reinterpret_cast<T*>(ri + p * d);
+    }
+    Tables<T>& t = tables<T>(h);
+    LargeArgs<T> a{};
+    a.wbuf = (cx<T>*)h->lwbuf.p; a.hbig = (cx<T>*)h->lhbig.p;
+    a.part_val = (double*)h->lpart.p; a.part_idx = (int*)((double*)h->lpart.p + 16 * chunk);
+    a.tw1 = t.tw1; a.tw2 = t.tw2; a.g = t.g;
+    a.dt = 1.0 / (double)fs; a.L = (int)l; a.N = n; a.R = R;
+    for (size_t pi = 0; pi < p; ++pi) {
+        // H = FFT(haystack)/N once per pair
+        a.in = hays + pi * l; a.freqs = nullptr; a.rows = 1; a.surface = nullptr;
+        CK(launch_large<T>(h, a, false));
+        CK((launch_large_core<T, true>(h, a)));
+        for (size_t off = 0; off < d; off += chunk) {
+            const size_t c = (d - off < chunk) ? d - off : chunk;
+            a.in = needles + pi * l; a.freqs = freqs + off; a.rows = (int)c;
+            a.surface = surface ? surface + (pi * d + off) * 2 * l : nullptr;
+            a.row_peak_val = rv + pi * d + off; a.row_peak_idx = ri + pi * d + off;
+            CK(launch_large<T>(h, a, false));
+            CK((launch_large_core<T, false>(h, a)));
+            CK(launch_large<T>(h, a, true));
+            caf_large_rowpeak<T><<<(unsigned)((c + 127) / 128), 128, 0, h->stream>>>(a);
+            h->launches++;
+            CK(cudaGetLastError());
+        }
+    }
+    if (peaks) {
+        caf_peak_kernel<T><<<(unsigned)p, 256, 0, h->stream>>>(rv, ri, freqs, (int)d, peaks);
+        h->launches++;
+        CK(cudaGetLastError());
+    }
+    return CAF_B200_OK;
+}
+
 // The whole device-side pipeline for p pairs; every pointer is device memory.
 template <typename T>
 int run_batch_dev(caf_b200_handle h, const caf::cx<T>* needles, const caf::cx<T>* hays, size_t p, size_t l,
@@ -179,6 +265,7 @@ int run_batch_dev(caf_b200_handle h, const caf::cx<T>* needles, const caf::cx<T>
         }
         return CAF_B200_OK;
     }
+    if (l > (size_t)kL0) return run_large_dev<T>(h, needles, hays, p, l, freqs, d, fs, surface, rowval, rowidx, peaks);
     // row peaks are needed internally for find_peak even when the caller does not want them
     T* rv = rowval; unsigned long long* ri = rowidx;
     if (peaks && (!rv || !ri)) {
@@ -239,8 +326,8 @@ int check_common(caf_b200_handle h, const void* needle, const void* hay, size_t 
     if (p && l && (!needle || !hay)) return fail(CAF_B200_EINVAL, "null needle/haystack");
     if (d && !freqs) return fail(CAF_B200_EINVAL, "null freqs_hz");
     if (fs == 0) return fail(CAF_B200_EINVAL, "fs must be non-zero");
-    if (l > (size_t)caf::kL0)
-        return fail(CAF_B200_EUNSUPPORTED, "l > 4096: rows longer than 8192 delay cells are not built yet");
+    if (l > 65536)
+        return fail(CAF_B200_EUNSUPPORTED, "l > 65536: rows longer than 131072 delay cells are not built yet");
     if (p > (1u << 30) || d > (1u << 30) || (double)p * (double)d > 2.0e9)
         return fail(CAF_B200_EUNSUPPORTED, "p*d too large");
     return CAF_B200_OK;
@@ -420,7 +507,7 @@ int caf_b200_destroy(caf_b200_handle h) {
     if (!h) return CAF_B200_OK;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
-    for (DevBuf* b : {&h->needle, &h->hay, &h->hperm, &h->freqs, &h->surface, &h->rowval, &h->rowidx, &h->peaks, &h->scratch})
+    for (DevBuf* b : {&h->needle, &h->hay, &h->hperm, &h->freqs, &h->surface, &h->rowval, &h->rowidx, &h->peaks, &h->scratch, &h->lwbuf, &h->lhbig, &h->lpart})
         b->release();
     for (void* q : {(void*)h->td.tw1, (void*)h->td.tw2, (void*)h->td.g, (void*)h->tf.tw1, (void*)h->tf.tw2, (void*)h->tf.g})
         if (q) cudaFree(q);

@@ -172,8 +172,8 @@ def test_length_errors_and_unsupported_sizes():
     with pytest.raises(caf.CafPanic):
         caf.CafB200.caf_surface(z, z[:15], [0.0], FS)
     with pytest.raises(caf.CafError) as e:
-        caf.CafB200.caf_surface(np.zeros(4097, complex), np.zeros(4097, complex), [0.0], FS)
-    assert e.value.status == -3      # CAF_B200_EUNSUPPORTED: longer rows are the next kernel family
+        caf.Xcor.new(5000).run(np.zeros(5000, complex), np.zeros(5000, complex))
+    assert e.value.status == -3      # CAF_B200_EUNSUPPORTED: standalone xcor is built for n = 8192 and n <= 4096
 
 
 # ---------------------------------------------------------------------------------------------------------------
