@@ -65,7 +65,7 @@ struct caf_b200_handle_s {
     Tables<float> tf;
     int occ_d = 1, occ_f = 1;   // resident CTAs per SM of the surface kernel
     DevBuf needle, hay, hperm, freqs, surface, rowval, rowidx, peaks, scratch;
-    DevBuf lwbuf, lhbig, lpart;             // long-row path: chunk scratch, H, partial row maxima
+    DevBuf lwbuf, lzbuf, lhbig, lpart;      // long-row path: chunk scratch (two levels), H, partial row maxima
     long long* trace = nullptr;   // CAF_TRACE builds: device buffer for phase stamps
     unsigned int* done_counter = nullptr;   // last-CTA-done ticket of the fused find_peak
     void* hshare = nullptr;                 // single-pair launches: H published by CTA 0 (8192 complex128)
@@ -164,33 +164,56 @@ caf::RowArgs<T> base_args(caf_b200_handle h) {
     return a;
 }
 
-// ---- rows longer than 8192 cells: four-step FFT (caf_large.cuh), one pair at a time, rows in L2-sized chunks ----
+// ---- rows longer than 8192 cells: four-/six-step FFT (caf_large.cuh), one pair at a time, rows in L2-sized chunks ----
 template <typename T, int R>
-cudaError_t launch_large_rt(caf_b200_handle h, const caf::LargeArgs<T>& a, bool gather) {
-    dim3 grid(16, (unsigned)a.rows);
-    if (!gather) caf::caf_large_spread<T, R><<<grid, 256, 0, h->stream>>>(a);
-    else caf::caf_large_gather<T, R><<<grid, 256, 0, h->stream>>>(a);
+cudaError_t launch_large_top_rt(caf_b200_handle h, const caf::LargeArgs<T>& a, bool gather) {
+    dim3 grid((unsigned)(a.inner_top / 256), (unsigned)a.rows);
+    if (!gather) caf::caf_large_spread_top<T, R><<<grid, 256, 0, h->stream>>>(a);
+    else caf::caf_large_gather_top<T, R><<<grid, 256, 0, h->stream>>>(a);
     h->launches++;
     return cudaGetLastError();
 }
 template <typename T>
-cudaError_t launch_large(caf_b200_handle h, const caf::LargeArgs<T>& a, bool gather) {
-    switch (a.R) {
-        case 2: return launch_large_rt<T, 2>(h, a, gather);
-        case 4: return launch_large_rt<T, 4>(h, a, gather);
-        case 8: return launch_large_rt<T, 8>(h, a, gather);
-        case 16: return launch_large_rt<T, 16>(h, a, gather);
+cudaError_t launch_large_top(caf_b200_handle h, const caf::LargeArgs<T>& a, bool gather) {
+    switch (a.Rtop) {
+        case 2: return launch_large_top_rt<T, 2>(h, a, gather);
+        case 4: return launch_large_top_rt<T, 4>(h, a, gather);
+        case 8: return launch_large_top_rt<T, 8>(h, a, gather);
+        case 16: return launch_large_top_rt<T, 16>(h, a, gather);
         default: return cudaErrorInvalidValue;
     }
 }
+template <typename T>
+cudaError_t launch_large_mid(caf_b200_handle h, const caf::LargeArgs<T>& a, bool gather) {
+    dim3 grid(16, (unsigned)(a.rows * 2 * a.Rtop));
+    if (!gather) caf::caf_large_spread_mid<T><<<grid, 256, 0, h->stream>>>(a);
+    else caf::caf_large_gather_mid<T><<<grid, 256, 0, h->stream>>>(a);
+    h->launches++;
+    return cudaGetLastError();
+}
 template <typename T, bool HMODE>
 cudaError_t launch_large_core(caf_b200_handle h, const caf::LargeArgs<T>& a) {
-    const long long units = (long long)a.rows * 2 * a.R;
+    const long long units = (long long)a.rows * (a.N / caf::kL0);
     long long ctas = (units + 1) / 2;
     if (ctas > h->sm_count) ctas = h->sm_count;
     caf::caf_large_core<T, HMODE><<<(unsigned)ctas, caf::kThreads, smem_bytes<T>(), h->stream>>>(a);
     h->launches++;
     return cudaGetLastError();
+}
+// forward chain (spread[s] + core) and, unless H is being built, the inverse chain (gather[s] + row peaks)
+template <typename T, bool HMODE>
+int large_chain(caf_b200_handle h, const caf::LargeArgs<T>& a) {
+    const bool two = a.inner_top != caf::kL0;
+    CK(launch_large_top<T>(h, a, false));
+    if (two) CK(launch_large_mid<T>(h, a, false));
+    CK((launch_large_core<T, HMODE>(h, a)));
+    if (HMODE) return CAF_B200_OK;
+    if (two) CK(launch_large_mid<T>(h, a, true));
+    CK(launch_large_top<T>(h, a, true));
+    caf::caf_large_rowpeak<T><<<(unsigned)((a.rows + 3) / 4), 128, 0, h->stream>>>(a);
+    h->launches++;
+    CK(cudaGetLastError());
+    return CAF_B200_OK;
 }
 
 template <typename T>
@@ -198,16 +221,20 @@ int run_large_dev(caf_b200_handle h, const caf::cx<T>* needles, const caf::cx<T>
                   const double* freqs, size_t d, uint32_t fs, T* surface, T* rowval,
                   unsigned long long* rowidx, caf::PeakOut* peaks) {
     using namespace caf;
-    int n = 16384;
+    long long n = 16384;
     while ((size_t)n < 2 * l) n *= 2;
-    const int R = n / 2 / 4096;
+    const bool two = n > 131072;
+    const int inner = two ? 65536 : kL0;
+    const int rtop = (int)(n / 2 / inner);
     const size_t row_bytes = sizeof(cx<T>) * (size_t)n;
-    size_t chunk = (48u << 20) / row_bytes;
+    size_t chunk = ((two ? 32u : 48u) << 20) / row_bytes;     // scratch stays inside the 126 MB L2
     if (chunk < 1) chunk = 1;
     if (chunk > d) chunk = d;
+    const int nparts = inner / 256;
     CK(h->lwbuf.ensure(row_bytes * chunk));
+    if (two) CK(h->lzbuf.ensure(row_bytes * chunk));
     CK(h->lhbig.ensure(row_bytes));
-    CK(h->lpart.ensure((sizeof(double) + sizeof(int)) * 16 * chunk));
+    CK(h->lpart.ensure((sizeof(double) + sizeof(int)) * (size_t)nparts * chunk));
     T* rv = rowval; unsigned long long* ri = rowidx;
     if (!rv || !ri) {
         CK(h->scratch.ensure((sizeof(T) + sizeof(unsigned long long)) * p * d + 16));
@@ -216,26 +243,22 @@ int run_large_dev(caf_b200_handle h, const caf::cx<T>* needles, const caf::cx<T>
     }
     Tables<T>& t = tables<T>(h);
     LargeArgs<T> a{};
-    a.wbuf = (cx<T>*)h->lwbuf.p; a.hbig = (cx<T>*)h->lhbig.p;
-    a.part_val = (double*)h->lpart.p; a.part_idx = (int*)((double*)h->lpart.p + 16 * chunk);
+    a.wbuf = (cx<T>*)h->lwbuf.p; a.zbuf = (cx<T>*)h->lzbuf.p; a.hbig = (cx<T>*)h->lhbig.p;
+    a.part_val = (double*)h->lpart.p; a.part_idx = (int*)((double*)h->lpart.p + (size_t)nparts * chunk);
     a.tw1 = t.tw1; a.tw2 = t.tw2; a.g = t.g;
-    a.dt = 1.0 / (double)fs; a.L = (int)l; a.N = n; a.R = R;
+    a.dt = 1.0 / (double)fs; a.L = (int)l; a.N = (int)n; a.Rtop = rtop; a.inner_top = inner;
     for (size_t pi = 0; pi < p; ++pi) {
-        // H = FFT(haystack)/N once per pair
+        // H = FFT(haystack)/N once per pair (the reference recomputes it per row, xcor_rustfft.rs:58-59)
         a.in = hays + pi * l; a.freqs = nullptr; a.rows = 1; a.surface = nullptr;
-        CK(launch_large<T>(h, a, false));
-        CK((launch_large_core<T, true>(h, a)));
+        int rc = large_chain<T, true>(h, a);
+        if (rc) return rc;
         for (size_t off = 0; off < d; off += chunk) {
             const size_t c = (d - off < chunk) ? d - off : chunk;
             a.in = needles + pi * l; a.freqs = freqs + off; a.rows = (int)c;
             a.surface = surface ? surface + (pi * d + off) * 2 * l : nullptr;
             a.row_peak_val = rv + pi * d + off; a.row_peak_idx = ri + pi * d + off;
-            CK(launch_large<T>(h, a, false));
-            CK((launch_large_core<T, false>(h, a)));
-            CK(launch_large<T>(h, a, true));
-            caf_large_rowpeak<T><<<(unsigned)((c + 127) / 128), 128, 0, h->stream>>>(a);
-            h->launches++;
-            CK(cudaGetLastError());
+            rc = large_chain<T, false>(h, a);
+            if (rc) return rc;
         }
     }
     if (peaks) {
@@ -326,8 +349,8 @@ int check_common(caf_b200_handle h, const void* needle, const void* hay, size_t 
     if (p && l && (!needle || !hay)) return fail(CAF_B200_EINVAL, "null needle/haystack");
     if (d && !freqs) return fail(CAF_B200_EINVAL, "null freqs_hz");
     if (fs == 0) return fail(CAF_B200_EINVAL, "fs must be non-zero");
-    if (l > 65536)
-        return fail(CAF_B200_EUNSUPPORTED, "l > 65536: rows longer than 131072 delay cells are not built yet");
+    if (l > (1u << 19))
+        return fail(CAF_B200_EUNSUPPORTED, "l > 2^19: rows longer than 2^20 delay cells are not built");
     if (p > (1u << 30) || d > (1u << 30) || (double)p * (double)d > 2.0e9)
         return fail(CAF_B200_EUNSUPPORTED, "p*d too large");
     return CAF_B200_OK;
@@ -507,7 +530,7 @@ int caf_b200_destroy(caf_b200_handle h) {
     if (!h) return CAF_B200_OK;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
-    for (DevBuf* b : {&h->needle, &h->hay, &h->hperm, &h->freqs, &h->surface, &h->rowval, &h->rowidx, &h->peaks, &h->scratch, &h->lwbuf, &h->lhbig, &h->lpart})
+    for (DevBuf* b : {&h->needle, &h->hay, &h->hperm, &h->freqs, &h->surface, &h->rowval, &h->rowidx, &h->peaks, &h->scratch, &h->lwbuf, &h->lzbuf, &h->lhbig, &h->lpart})
         b->release();
     for (void* q : {(void*)h->td.tw1, (void*)h->td.tw2, (void*)h->td.g, (void*)h->tf.tw1, (void*)h->tf.tw2, (void*)h->tf.g})
         if (q) cudaFree(q);

@@ -24,8 +24,8 @@
  * Sizes.  l = samples per input signal (needle and haystack must be equal length, as the reference's
  * Xcor asserts).  A surface row has n = 2*l delay cells (both inputs zero-padded at the end to 2*l,
  * mod.rs:130-131); cell k < l is lag +k, cell k > l is lag k - 2l.  Rows stay in on-chip memory for l <= 4096
- * (the reference's only shape is l = 4096); 4096 < l <= 65536 runs a four-step FFT through L2 (BASELINE config 3);
- * larger l returns CAF_B200_EUNSUPPORTED.
+ * (the reference's only shape is l = 4096); 4096 < l <= 2^19 runs a four- or six-step FFT through L2 (BASELINE
+ * configs 3 and 5); larger l returns CAF_B200_EUNSUPPORTED.
  */
 #ifndef CAF_B200_H
 #define CAF_B200_H

@@ -19,7 +19,7 @@ def _pair(l, seed=0):
     return G.as_inputs(p)
 
 
-@pytest.mark.parametrize("l", [4097, 5000, 8192, 10000, 16384, 20001, 32768, 65536])
+@pytest.mark.parametrize("l", [4097, 5000, 8192, 10000, 16384, 20001, 32768, 65536, 65537, 100000, 131072, 262144])
 def test_long_rows_match_oracle(l):
     needle, hay = _pair(l)
     shifts = np.array([-50.0, 0.0, 12.5, 68.0, 69.25, 70.5])
@@ -72,8 +72,23 @@ def test_long_row_delay_and_doppler_properties():
     assert pk.freq_hz == f0
 
 
+def test_config5_row_length_peak_only():
+    """BASELINE config 5 row length (2^20 delay cells), peak only: the surface is never materialised."""
+    p = G.pair(0, seed=1, chirp_length=1 << 19)
+    needle, hay = G.as_inputs(p)
+    step = 0.25
+    f0 = round(p.foffset_hz / step) * step
+    shifts = np.array([f0 - step, f0, f0 + step, f0 + 2 * step])
+    _, pidx, pval, pk = caf.surface_arrays(needle, hay, shifts, FS, want_surface=False)
+    _, opidx, opval = O.caf_surface(needle, hay, shifts, FS, want_surface=False)
+    assert np.array_equal(pidx, opidx)
+    assert rel_max(pval, opval) <= 1e-9
+    assert (pk.freq_hz, int(pk.delay_idx)) == O.find_peak(shifts, opidx, opval)
+    assert abs(int(pk.delay_idx) - p.lag) <= 16     # the chirp's delay-doppler ridge moves the peak a few samples
+
+
 def test_too_long_is_unsupported():
-    z = np.zeros(65537, dtype=complex)
+    z = np.zeros((1 << 19) + 1, dtype=complex)
     with pytest.raises(caf.CafError) as e:
         caf.surface_arrays(z, z, [0.0], FS)
     assert e.value.status == -3
