@@ -210,9 +210,6 @@ int large_chain(caf_b200_handle h, const caf::LargeArgs<T>& a) {
     if (HMODE) return CAF_B200_OK;
     if (two) CK(launch_large_mid<T>(h, a, true));
     CK(launch_large_top<T>(h, a, true));
-    caf::caf_large_rowpeak<T><<<(unsigned)((a.rows + 3) / 4), 128, 0, h->stream>>>(a);
-    h->launches++;
-    CK(cudaGetLastError());
     return CAF_B200_OK;
 }
 
@@ -227,14 +224,16 @@ int run_large_dev(caf_b200_handle h, const caf::cx<T>* needles, const caf::cx<T>
     const int inner = two ? 65536 : kL0;
     const int rtop = (int)(n / 2 / inner);
     const size_t row_bytes = sizeof(cx<T>) * (size_t)n;
-    size_t chunk = ((two ? 32u : 48u) << 20) / row_bytes;     // scratch stays inside the 126 MB L2
+    size_t budget_mb = two ? 48 : 72;                          // scratch (x2 for two levels) sized around the 126 MB L2; measured best
+    if (const char* e_ = getenv("CAF_B200_CHUNK_MB")) budget_mb = (size_t)atoi(e_);
+    size_t chunk = (budget_mb << 20) / row_bytes;
     if (chunk < 1) chunk = 1;
     if (chunk > d) chunk = d;
     const int nparts = inner / 256;
     CK(h->lwbuf.ensure(row_bytes * chunk));
     if (two) CK(h->lzbuf.ensure(row_bytes * chunk));
     CK(h->lhbig.ensure(row_bytes));
-    CK(h->lpart.ensure((sizeof(double) + sizeof(int)) * (size_t)nparts * chunk));
+    CK(h->lpart.ensure((sizeof(double) + sizeof(int)) * (size_t)nparts * chunk + sizeof(unsigned int) * chunk));
     T* rv = rowval; unsigned long long* ri = rowidx;
     if (!rv || !ri) {
         CK(h->scratch.ensure((sizeof(T) + sizeof(unsigned long long)) * p * d + 16));
@@ -245,6 +244,8 @@ int run_large_dev(caf_b200_handle h, const caf::cx<T>* needles, const caf::cx<T>
     LargeArgs<T> a{};
     a.wbuf = (cx<T>*)h->lwbuf.p; a.zbuf = (cx<T>*)h->lzbuf.p; a.hbig = (cx<T>*)h->lhbig.p;
     a.part_val = (double*)h->lpart.p; a.part_idx = (int*)((double*)h->lpart.p + (size_t)nparts * chunk);
+    a.row_ticket = (unsigned int*)(a.part_idx + (size_t)nparts * chunk);
+    CK(cudaMemsetAsync(a.row_ticket, 0, sizeof(unsigned int) * chunk, h->stream));   // tickets start at zero (the layout moves with the shape)
     a.tw1 = t.tw1; a.tw2 = t.tw2; a.g = t.g;
     a.dt = 1.0 / (double)fs; a.L = (int)l; a.N = (int)n; a.Rtop = rtop; a.inner_top = inner;
     for (size_t pi = 0; pi < p; ++pi) {

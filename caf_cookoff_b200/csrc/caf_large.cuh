@@ -29,6 +29,7 @@ struct LargeArgs {
     T* surface;                        // [rows][2L] or null
     double* part_val;                  // [rows][nparts] partial row maxima (one per gather_top block)
     int* part_idx;
+    unsigned int* row_ticket;          // [rows] zero-initialised tickets: the last gather block of a row folds its partials
     T* row_peak_val;                   // [rows]
     unsigned long long* row_peak_idx;  // [rows]
     const cx<T>* tw1; const cx<T>* tw2; const cx<T>* g;   // tables for the core's twiddle bases
@@ -53,10 +54,8 @@ __device__ __forceinline__ cx<T> mul_by_d(cx<T> x, double2 p) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// spread_top: one thread per (row, j), j < inner_top.  R is a template parameter so the register arrays stay static;
-// sizes below 16 run through the 16-point butterfly on a zero-padded vector (X16[s * 16/R] is the R-point DFT) — the
-// kernel is bound by its global traffic, not by flops.  Output [row][r][s][inner_top] goes to zbuf (two levels) or
-// wbuf (one level).
+// spread_top: one thread per (row, j), j < inner_top.  R is a template parameter so the register arrays stay static.
+// Output [row][r][s][inner_top] goes to zbuf (two levels) or wbuf (one level).
 // ------------------------------------------------------------------------------------------------
 template <typename T, int R>
 __global__ void __launch_bounds__(256) caf_large_spread_top(const LargeArgs<T> a) {
@@ -80,16 +79,13 @@ __global__ void __launch_bounds__(256) caf_large_spread_top(const LargeArgs<T> a
         C v[16];
         double2 p = base;
 #pragma unroll
-        for (int rho = 0; rho < 16; ++rho) {
-            if (rho < R) { v[rho] = mul_by_d<T>(x[rho], p); p = cmul_d(p, step); }
-            else v[rho] = mk<T>((T)0, (T)0);
-        }
-        fft16<T, false>(v);
+        for (int rho = 0; rho < R; ++rho) { v[rho] = mul_by_d<T>(x[rho], p); p = cmul_d(p, step); }
+        dft_small<T, R, false>(v);
         double2 tw = make_double2(1.0, 0.0);
         C* dst = out + ((size_t)(row * 2 + r) * R) * inner + j;
 #pragma unroll
         for (int s = 0; s < R; ++s) {
-            dst[(size_t)s * inner] = mul_by_d<T>(v[s * (16 / R)], tw);
+            dst[(size_t)s * inner] = mul_by_d<T>(v[s], tw);
             tw = cmul_d(tw, om);
         }
     }
@@ -227,12 +223,12 @@ __global__ void __launch_bounds__(256) caf_large_gather_top(const LargeArgs<T> a
     C a0[16], a1[16];
     const C* src = in + ((size_t)(row * 2) * R) * inner + j;
 #pragma unroll
-    for (int s = 0; s < 16; ++s) {
-        a0[s] = (s < R) ? src[(size_t)s * inner] : mk<T>((T)0, (T)0);
-        a1[s] = (s < R) ? src[(size_t)(R + s) * inner] : mk<T>((T)0, (T)0);
+    for (int s = 0; s < R; ++s) {
+        a0[s] = src[(size_t)s * inner];
+        a1[s] = src[(size_t)(R + s) * inner];
     }
-    fft16<T, true>(a0);
-    fft16<T, true>(a1);
+    dft_small<T, R, true>(a0);
+    dft_small<T, R, true>(a1);
     // W_N^{-n}, n = j + inner rho
     double2 gph = root_of_unity(j, a.N, 1.0);
     const double2 gstep = root_of_unity(inner, a.N, 1.0);
@@ -241,8 +237,8 @@ __global__ void __launch_bounds__(256) caf_large_gather_top(const LargeArgs<T> a
     int bidx = 0;
 #pragma unroll
     for (int rho = 0; rho < R; ++rho) {
-        const C A = a0[rho * (16 / R)];
-        const C B = mul_by_d<T>(a1[rho * (16 / R)], gph);
+        const C A = a0[rho];
+        const C B = mul_by_d<T>(a1[rho], gph);
         gph = cmul_d(gph, gstep);
         const long long n = (long long)j + (long long)inner * rho;
 #pragma unroll
@@ -266,33 +262,36 @@ __global__ void __launch_bounds__(256) caf_large_gather_top(const LargeArgs<T> a
     }
     if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = best; si[threadIdx.x >> 5] = bidx; }
     __syncthreads();
+    const int nparts = inner / 256;
+    __shared__ unsigned int s_last;
     if (threadIdx.x == 0) {
         for (int q = 1; q < 8; ++q) amax_take<double>(best, bidx, sv[q], si[q]);
-        const int nparts = inner / 256;
         a.part_val[(size_t)row * nparts + blockIdx.x] = best;
         a.part_idx[(size_t)row * nparts + blockIdx.x] = bidx;
+        __threadfence();
+        const unsigned int ticket = atomicAdd(a.row_ticket + row, 1u);
+        s_last = (ticket == (unsigned int)nparts - 1) ? 1u : 0u;
     }
-}
-
-// fold the block partials of every row: first strict-> maximum (mod.rs:141-153).  One warp per row.
-template <typename T>
-__global__ void __launch_bounds__(128) caf_large_rowpeak(const LargeArgs<T> a) {
-    const int row = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    if (row >= a.rows) return;
-    const int nparts = a.inner_top / 256;
-    double best = 0.0;
-    int bidx = 0;
-    for (int q = lane; q < nparts; q += 32) amax_take<double>(best, bidx, a.part_val[(size_t)row * nparts + q], a.part_idx[(size_t)row * nparts + q]);
+    __syncthreads();
+    if (s_last && threadIdx.x < 32) {
+        // the last block of this row folds the block partials: first strict-> maximum (mod.rs:141-153)
+        __threadfence();
+        double b2 = 0.0;
+        int i2 = 0;
+        for (int q = threadIdx.x; q < nparts; q += 32)
+            amax_take<double>(b2, i2, __ldcg(a.part_val + (size_t)row * nparts + q), __ldcg(a.part_idx + (size_t)row * nparts + q));
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-        double ov = __shfl_xor_sync(0xffffffffu, best, off);
-        int oi = __shfl_xor_sync(0xffffffffu, bidx, off);
-        amax_take<double>(best, bidx, ov, oi);
-    }
-    if (lane == 0) {
-        if (!(best > 0.0)) bidx = 0;
-        if (a.row_peak_val) a.row_peak_val[row] = (T)best;
-        if (a.row_peak_idx) a.row_peak_idx[row] = (unsigned long long)bidx;
+        for (int off = 16; off > 0; off >>= 1) {
+            double ov = __shfl_xor_sync(0xffffffffu, b2, off);
+            int oi = __shfl_xor_sync(0xffffffffu, i2, off);
+            amax_take<double>(b2, i2, ov, oi);
+        }
+        if (threadIdx.x == 0) {
+            if (!(b2 > 0.0)) i2 = 0;
+            if (a.row_peak_val) a.row_peak_val[row] = (T)b2;
+            if (a.row_peak_idx) a.row_peak_idx[row] = (unsigned long long)i2;
+            a.row_ticket[row] = 0u;          // self-resetting for the next chunk
+        }
     }
 }
 

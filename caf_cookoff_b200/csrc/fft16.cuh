@@ -124,4 +124,32 @@ __device__ __forceinline__ void fft16(cx<T> (&v)[16]) {
     for (int i = 0; i < 16; ++i) v[i] = o[i];
 }
 
+// In-place R-point DFT (R = 2, 4, 8 or 16) on v[0..R), natural order in and out.  Used by the long-row spread /
+// gather steps, whose radix is N / 8192.
+template <typename T, int R, bool INV>
+__device__ __forceinline__ void dft_small(cx<T> (&v)[16]) {
+    if constexpr (R == 16) {
+        fft16<T, INV>(v);
+    } else if constexpr (R == 2) {
+        const cx<T> a = v[0], b = v[1];
+        v[0] = cadd(a, b); v[1] = csub(a, b);
+    } else if constexpr (R == 4) {
+        radix4<T, INV>(v[0], v[1], v[2], v[3]);
+    } else {
+        static_assert(R == 8, "radix must be 2, 4, 8 or 16");
+        // 8 = 2 x 4: i = c + 2 a (a < 4), k = ka + 4 kb:  W8^{c ka} between the stages
+        cx<T> e0 = v[0], e1 = v[2], e2 = v[4], e3 = v[6];      // c = 0
+        cx<T> o0 = v[1], o1 = v[3], o2 = v[5], o3 = v[7];      // c = 1
+        radix4<T, INV>(e0, e1, e2, e3);
+        radix4<T, INV>(o0, o1, o2, o3);
+        o1 = mul_w16<T, 2, INV>(o1);                           // W8^1 = W16^2
+        o2 = mul_w16<T, 4, INV>(o2);                           // W8^2
+        o3 = mul_w16<T, 6, INV>(o3);                           // W8^3
+        v[0] = cadd(e0, o0); v[4] = csub(e0, o0);
+        v[1] = cadd(e1, o1); v[5] = csub(e1, o1);
+        v[2] = cadd(e2, o2); v[6] = csub(e2, o2);
+        v[3] = cadd(e3, o3); v[7] = csub(e3, o3);
+    }
+}
+
 }  // namespace caf
