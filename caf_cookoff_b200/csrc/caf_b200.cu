@@ -311,13 +311,15 @@ int run_batch_dev(caf_b200_handle h, const caf::cx<T>* needles, const caf::cx<T>
         const long long cap = (long long)h->sm_count * occ;
         const long long grid = n_items < cap ? n_items : cap;
         a.hprod1 = 0;
-#ifndef CAF_PINGPONG
-        long long best = -1;
-        for (long long b = 1; b < grid; ++b) {
-            const long long cnt = n_items * (b + 1) / grid - n_items * b / grid;
-            if (best < 0 || cnt < best) { best = cnt; a.hprod1 = (int)b; }
+        // with the fp64 token (complex128) both groups of a CTA must take the same number of turns, so CTA 0
+        // publishes both halves of H; otherwise H_1 comes from a second lightly loaded CTA
+        if (!(caf::kPingPong && std::is_same<T, double>::value)) {
+            long long best = -1;
+            for (long long b = 1; b < grid; ++b) {
+                const long long cnt = n_items * (b + 1) / grid - n_items * b / grid;
+                if (best < 0 || cnt < best) { best = cnt; a.hprod1 = (int)b; }
+            }
         }
-#endif
     }
     const bool prof = h->profiling;
     if (prof) {
@@ -601,14 +603,14 @@ int caf_b200_probe_fma_tflops(caf_b200_handle h, int is_f64, double* tflops) {
 }
 
 /* development hook (CAF_TRACE builds): copy the per-warp phase stamps of the last surface launch to `out`
- * (n_cta * 16 * 8 * 24 int64).  Allocates the trace buffer on first use; returns EUNSUPPORTED otherwise. */
+ * (n_cta * 16 * 8 * 32 int64).  Allocates the trace buffer on first use; returns EUNSUPPORTED otherwise. */
 int caf_b200_debug_trace(caf_b200_handle h, long long* out, size_t n_cta) {
 #ifdef CAF_TRACE
     if (!h) return fail(CAF_B200_EINVAL, "null handle");
-    const size_t bytes = sizeof(long long) * 512 * 16 * 8 * 24;
+    const size_t bytes = sizeof(long long) * 512 * 16 * 8 * 32;
     if (!h->trace) { CK(cudaMalloc(&h->trace, bytes)); CK(cudaMemset(h->trace, 0, bytes)); return CAF_B200_OK; }
     CK(cudaStreamSynchronize(h->stream));
-    if (out) CK(cudaMemcpy(out, h->trace, sizeof(long long) * n_cta * 16 * 8 * 24, cudaMemcpyDeviceToHost));
+    if (out) CK(cudaMemcpy(out, h->trace, sizeof(long long) * n_cta * 16 * 8 * 32, cudaMemcpyDeviceToHost));
     return CAF_B200_OK;
 #else
     (void)h; (void)out; (void)n_cta;

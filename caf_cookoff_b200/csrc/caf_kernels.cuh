@@ -82,7 +82,7 @@ struct RowArgs {
     unsigned int* hflag;    // [2] per-group publish counters (monotonic across launches)
     unsigned int epoch;     // this launch's counter value
     int hprod1;             // CTA that publishes H_1 (H_0 comes from CTA 0); 0 = CTA 0 publishes both
-    long long* trace;       // CAF_TRACE builds only: [cta][warp][8 items][24 slots] clock64 stamps
+    long long* trace;       // CAF_TRACE builds only: [cta][warp][8 items][32 slots] clock64 stamps
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -97,15 +97,74 @@ struct SmemLayout {
     static constexpr size_t offPtab = kS, offRed = offPtab + kPtab, offMisc = offRed + kRed, kTotal = offMisc + kMisc;
 };
 
+// ------------------------------------------------------------------------------------------------
+// Exchange fabric.  An element is 16 bytes (complex128, 128-bit accesses: a wavefront is a quarter-warp) or 8 bytes
+// (complex64 as float2: a wavefront is a half-warp, i.e. the lanes (h[2:0], sub) of one h[3]).  The two sub-transforms
+// of a warp sit 256 elements apart (same banks), so bit 3 of the in-region index is flipped by
+// (region parity ^ bit 4 of the index): every access pattern of X1..X4 is then conflict free for both element sizes
+// (complex64 rows: 13.0 k -> 11.0 k cycles per row on B200).
+// -DCAF_FAB_SOA keeps complex128 as two planes per pipeline (re[4096] | im[4096]) moved with 64-bit accesses.  On
+// B200 a conflict-free LDS.128 costs 8 cycles per warp (64 B/clk) against 2 x 2 cycles for two LDS.64
+// (scripts/micro/mio_cost.cu), so the planes halve the load time of every exchange -- and the row time does not move
+// (20.27 k vs 20.21 k cycles): the rows are not bound by shared-memory bandwidth.  Kept as an option, off by default.
+// ------------------------------------------------------------------------------------------------
+template <typename T> struct Fab;
+#ifdef CAF_FAB_SOA
+template <> struct Fab<double> {
+    using E = double;
+    static constexpr int kPipe = 2 * kL0;          // elements per pipeline
+    static __device__ __forceinline__ void st(E* p, int i, double2 v) { p[i] = v.x; p[kL0 + i] = v.y; }
+    static __device__ __forceinline__ double2 ld(const E* p, int i) { return make_double2(p[i], p[kL0 + i]); }
+};
+#else
+template <> struct Fab<double> {       // default: interleaved complex128, 128-bit accesses
+    using E = double2;
+    static constexpr int kPipe = kL0;
+    static __device__ __forceinline__ void st(E* p, int i, double2 v) { p[i] = v; }
+    static __device__ __forceinline__ double2 ld(const E* p, int i) { return p[i]; }
+};
+#endif
+template <> struct Fab<float> {
+    using E = float2;
+    static constexpr int kPipe = kL0;
+    static __device__ __forceinline__ void st(E* p, int i, float2 v) { p[i] = v; }
+    static __device__ __forceinline__ float2 ld(const E* p, int i) { return p[i]; }
+};
+
 template <typename T>
 struct Ctx {
-    cx<T>* S;        // exchange fabric
-    cx<T>* Sr;       // this thread's pipeline half
-    cx<T>* Sw;       // this warp's 256-entry region inside Sr
+    typename Fab<T>::E* Sr;   // this thread's pipeline half of the fabric
     cx<T>* ptab;
     uint32_t tm_tw;  // TMEM address of this thread's five twiddle bases: W_4096^t, W_256^h, W_4096^{k1 h}, W_256^{k1}, W_8192^{-t}
     int w, lane, r, h, t;
+    int wb;          // 256 w: this thread's region (sub-transform k1 = w) inside the pipeline
+    int hs[2];       // h with bit 3 flipped by (sub ^ p): in-region column for an index whose bit 4 is p
+    int hr;          // h with bit 3 flipped by (sub ^ h[0]): column base of the transposed X2/X3 reads (bit 4 = h[0])
+    uint32_t gate_scratch;   // shared-memory address of a scratch word (target of the never-taken release store)
     long long* tr;   // CAF_TRACE: this warp's slot array for the current item (lane 0 writes)
+
+    __device__ __forceinline__ void init(unsigned char* smem_raw, int tid) {
+        const int hw_warp = tid >> 5;
+        lane = tid & 31; r = tid >> 8;
+        // inside a warp: lane = h[2:0] | sub << 3 | h[3] << 4; the warp's two sub-transforms k1 = 2 * warp_in_group + sub
+        h = (lane & 7) | ((lane >> 1) & 8);
+        const int sub = (lane >> 3) & 1;
+        w = 2 * (hw_warp & 7) + sub;
+        t = 16 * w + h;
+        wb = 256 * w;
+        hs[0] = h ^ (sub << 3); hs[1] = hs[0] ^ 8;
+        hr = h ^ (((sub ^ h) & 1) << 3);
+        Sr = reinterpret_cast<typename Fab<T>::E*>(smem_raw) + r * Fab<T>::kPipe;
+        ptab = nullptr; tm_tw = 0; tr = nullptr;
+        gate_scratch = (uint32_t)__cvta_generic_to_shared(smem_raw + SmemLayout<T>::offMisc + 8);
+    }
+    // block exchange X1 / X4 / mailbox: element (region k, column t)
+    __device__ __forceinline__ int ix_block(int k) const { return k * 256 + 16 * w + hs[k & 1]; }
+    // own region, element 16 i + h
+    __device__ __forceinline__ int ix_own(int i) const { return wb + 16 * i + hs[i & 1]; }
+    // own region, 16 x 16 transpose: write (k, h ^ k), read (h, m ^ h)
+    __device__ __forceinline__ int ix_tw(int k) const { return wb + 16 * k + (hs[k & 1] ^ k); }
+    __device__ __forceinline__ int ix_tr(int m) const { return wb + 16 * h + (m ^ hr); }
 };
 
 #ifdef CAF_TRACE
@@ -213,6 +272,19 @@ __device__ __forceinline__ float2 tmem_ld1(uint32_t taddr, float) {
     tmem_wait_ld();
     return make_float2(__uint_as_float(r[0]), __uint_as_float(r[1]));
 }
+// the real part of one slot (the ping-pong gate, 1.0)
+__device__ __forceinline__ double tmem_ld_gate(uint32_t taddr, double) {
+    uint32_t r[2];
+    tmem_ld_x2(taddr, r);
+    tmem_wait_ld();
+    return __hiloint2double((int)r[1], (int)r[0]);
+}
+__device__ __forceinline__ float tmem_ld_gate(uint32_t taddr, float) {
+    uint32_t r;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];\n" : "=r"(r) : "r"(taddr) : "memory");
+    tmem_wait_ld();
+    return __uint_as_float(r);
+}
 __device__ __forceinline__ void tmem_st1(uint32_t taddr, double2 v) {
     uint32_t r[4] = {(uint32_t)__double2loint(v.x), (uint32_t)__double2hiint(v.x), (uint32_t)__double2loint(v.y), (uint32_t)__double2hiint(v.y)};
     tmem_st_x4(taddr, r);
@@ -246,33 +318,76 @@ __device__ __forceinline__ double2 unit_phasor(double n, double phi, double exac
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void bar_group(int r) { asm volatile("bar.sync %0, 256;\n" :: "r"(r + 1) : "memory"); }
 
-// Ping-pong of the fp64 pipe between the two groups (the FlashAttention-3 warpgroup schedule): a group runs its
-// butterfly blocks only while it holds the token, and does its shared-memory exchange while the other group
-// computes.  pp_acquire = bar.sync on the own barrier (256 waiters + 256 arrivals from the other group),
-// pp_release = bar.arrive on the other group's barrier.
-// Measured on B200 (round 1): the token costs slightly more than it gains (50.3 vs 49.7 us per 400 x 8192 surface)
-// because ptxas floats register arithmetic across bar.sync, so the butterflies do not stay inside the token window;
-// it is therefore compiled in only with -DCAF_PINGPONG.
-#ifdef CAF_PINGPONG
-__device__ __forceinline__ void pp_acquire(int r) { asm volatile("bar.sync %0, 512;\n" :: "r"(3 + r) : "memory"); }
-__device__ __forceinline__ void pp_release(int r) { asm volatile("bar.arrive %0, 512;\n" :: "r"(4 - r) : "memory"); }
-#else
-__device__ __forceinline__ void pp_acquire(int) {}
-__device__ __forceinline__ void pp_release(int) {}
+// Ping-pong of the fp64 pipe between the two groups (the FlashAttention-3 warpgroup schedule), -DCAF_PINGPONG=1:
+// a group runs its butterfly blocks only while it holds the token and does its shared-memory exchange while the
+// other group computes.
+//   acquire = bar.sync on the own barrier (256 waiters + 256 arrivals from the other group)
+//   release = bar.arrive on the other group's barrier
+// A barrier orders memory operations, not register arithmetic: ptxas floated two thirds of every butterfly block
+// out of its token window (SASS of the first attempt: 31 fp64 instructions left between BAR.SYNC and BAR.ARV).
+// The window is therefore closed with DATA dependencies:
+//   * acquire returns g == 1.0 read from TMEM after the barrier (tcgen05.ld is not queued behind the other
+//     group's shared-memory traffic) and the first butterfly level is computed as a +- g b (fft16_impl<GATED>), so
+//     no arithmetic of the block can start before the token is held;
+//   * release folds the bit patterns of every value of the row into one word and issues a shared-memory store
+//     predicated on that word (never true in practice, harmless if it were); bar.arrive cannot be moved above a
+//     store, so all arithmetic of the block is complete when the token is handed over.
+// Measured on B200 (scripts/trace_rows.py, scripts/quick_bench.py): the windows are then truly exclusive, and the
+// row gets SLOWER (21.1 k cycles against 20.2 k free-running; 21.9 k with CAF_PP_EARLY): with one group computing,
+// two warps per scheduler reach only ~75 % of the fp64 issue rate inside a window (exposed tcgen05.ld / barrier /
+// chain latencies that the other group's warps hide when both run free) and every hand-over leaves the pipe idle
+// for 30-400 cycles.  The free-running groups are the better schedule; the token stays in the source, off.
+#ifndef CAF_PINGPONG
+#define CAF_PINGPONG 0
 #endif
-// The token only helps if the butterflies really sit between acquire and release in the instruction stream.
-// Register arithmetic has no memory side effect, so the compiler is free to float it across the barriers; these
-// empty asm statements make every value of the row an input+output of the barrier point and pin the math in place.
-__device__ __forceinline__ void pin(double2 (&v)[16]) {
+constexpr bool kPingPong = (CAF_PINGPONG != 0);
+// Early release: the token is handed over after the butterfly of a block, so the twiddle multiplies (40 % of a
+// block) overlap the other group's start-up latency (barrier, gate load, first dependent levels).
+#ifndef CAF_PP_EARLY
+#define CAF_PP_EARLY 1
+#endif
+constexpr bool kEarlyRelease = (CAF_PP_EARLY != 0);
+
+__device__ __forceinline__ uint32_t fold_bits(const double2 (&v)[16]) {
+    uint32_t x = 0;
 #pragma unroll
-    for (int i = 0; i < 16; ++i) asm volatile("" : "+d"(v[i].x), "+d"(v[i].y));
+    for (int i = 0; i < 16; ++i) x ^= (uint32_t)__double2hiint(v[i].x) ^ (uint32_t)__double2hiint(v[i].y);
+    return x;
 }
-__device__ __forceinline__ void pin(float2 (&v)[16]) {
+__device__ __forceinline__ uint32_t fold_bits(const float2 (&v)[16]) {
+    uint32_t x = 0;
 #pragma unroll
-    for (int i = 0; i < 16; ++i) asm volatile("" : "+f"(v[i].x), "+f"(v[i].y));
+    for (int i = 0; i < 16; ++i) x ^= __float_as_uint(v[i].x) ^ __float_as_uint(v[i].y);
+    return x;
 }
-template <typename C> __device__ __forceinline__ void pp_acquire(int r, C (&v)[16]) { pin(v); pp_acquire(r); pin(v); }
-template <typename C> __device__ __forceinline__ void pp_release(int r, C (&v)[16]) { pin(v); pp_release(r); pin(v); }
+__device__ __forceinline__ uint32_t fold_bits(double a, double b) { return (uint32_t)__double2hiint(a) ^ (uint32_t)__double2hiint(b); }
+__device__ __forceinline__ uint32_t fold_bits(float a, float b) { return __float_as_uint(a) ^ __float_as_uint(b); }
+
+template <bool PP, typename T>
+__device__ __forceinline__ T pp_acquire(const Ctx<T>& c) {
+    if constexpr (PP) {
+        asm volatile("bar.sync %0, 512;\n" :: "r"(3 + c.r) : "memory");
+        return tmem_ld_gate(c.tm_tw + 5 * TmemGeom<T>::kColsPerC, T());
+    } else {
+        return (T)1;
+    }
+}
+// hand the token over once `bits` (a fold of every result of the block) exists
+template <bool PP, typename T>
+__device__ __forceinline__ void pp_release_bits(const Ctx<T>& c, uint32_t bits) {
+    if constexpr (PP) {
+        asm volatile("{\n.reg .pred p;\nsetp.eq.u32 p, %0, 0x7ff5a5a5;\n@p st.shared.u32 [%1], %0;\nbar.arrive %2, 512;\n}\n"
+                     :: "r"(bits), "r"(c.gate_scratch), "r"(4 - c.r) : "memory");
+    }
+}
+template <bool PP, typename T>
+__device__ __forceinline__ void pp_release(const Ctx<T>& c, const cx<T> (&v)[16]) {
+    if constexpr (PP) pp_release_bits<PP, T>(c, fold_bits(v));
+}
+template <bool PP>
+__device__ __forceinline__ void pp_release_plain(int r) {
+    if constexpr (PP) asm volatile("bar.arrive %0, 512;\n" :: "r"(4 - r) : "memory");
+}
 
 __device__ __forceinline__ void mbar_init(uint64_t* mb, int count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" :: "r"((uint32_t)__cvta_generic_to_shared(mb)), "r"(count) : "memory");
@@ -309,40 +424,44 @@ __device__ __forceinline__ void mbar_wait(uint64_t* mb, int parity) {
 #define CAF_FP(...) do { __VA_ARGS__; } while (0)
 #endif
 
-template <typename T, typename Hook>
+template <typename T, bool PP, typename Hook>
 __device__ __forceinline__ void forward_4096(cx<T> (&v)[16], const Ctx<T>& c,
                                              uint64_t* empty_mb, int empty_parity, Hook&& hook) {
     constexpr int kC = TmemGeom<T>::kColsPerC;
     CAF_FP(fft16<T, false>(v));
+    if (kEarlyRelease) pp_release<PP, T>(c, v);
     CAF_FP(twiddle_powers<false>(v, tmem_ld1(c.tm_tw, T())));           // W_4096^{t k}
-    pp_release(c.r, v);
+    if (!kEarlyRelease) pp_release<PP, T>(c, v);
     CAF_TR(c, 3);
     if (empty_mb) mbar_wait(empty_mb, empty_parity);   // group 0 has drained the previous row's mailbox
     bar_group(c.r);    // every earlier reader of this half of the fabric (previous X4 / X2) is done
 #pragma unroll
-    CAF_XCHG(for (int k = 0; k < 16; ++k) c.Sr[k * 256 + c.t] = v[k]);
+    CAF_XCHG(for (int k = 0; k < 16; ++k) Fab<T>::st(c.Sr, c.ix_block(k), v[k]));
     CAF_TR(c, 4);
     bar_group(c.r);
 #pragma unroll
-    CAF_XCHG(for (int i = 0; i < 16; ++i) v[i] = c.Sw[c.h + 16 * i]);
+    CAF_XCHG(for (int i = 0; i < 16; ++i) v[i] = Fab<T>::ld(c.Sr, c.ix_own(i)));
     hook();
     CAF_TR(c, 5);
 
-    pp_acquire(c.r, v);
-    CAF_FP(fft16<T, false>(v));
+    T g = pp_acquire<PP, T>(c);
+    CAF_TR(c, 25);
+    CAF_FP(fft16_impl<T, false, PP>(v, g));
+    if (kEarlyRelease) pp_release<PP, T>(c, v);
     CAF_FP(twiddle_powers<false>(v, tmem_ld1(c.tm_tw + kC, T())));      // W_256^{h k}
-    pp_release(c.r, v);
+    if (!kEarlyRelease) pp_release<PP, T>(c, v);
     CAF_TR(c, 6);
     __syncwarp();
 #pragma unroll
-    CAF_XCHG(for (int k = 0; k < 16; ++k) c.Sw[k * 16 + (c.h ^ k)] = v[k]);
+    CAF_XCHG(for (int k = 0; k < 16; ++k) Fab<T>::st(c.Sr, c.ix_tw(k), v[k]));
     __syncwarp();
 #pragma unroll
-    CAF_XCHG(for (int m = 0; m < 16; ++m) v[m] = c.Sw[c.h * 16 + (m ^ c.h)]);
+    CAF_XCHG(for (int m = 0; m < 16; ++m) v[m] = Fab<T>::ld(c.Sr, c.ix_tr(m)));
     CAF_TR(c, 7);
 
-    pp_acquire(c.r, v);
-    CAF_FP(fft16<T, false>(v));    // returns holding the token
+    g = pp_acquire<PP, T>(c);
+    CAF_TR(c, 26);
+    CAF_FP(fft16_impl<T, false, PP>(v, g));    // returns holding the token
     CAF_TR(c, 8);
 }
 
@@ -350,40 +469,44 @@ __device__ __forceinline__ void forward_4096(cx<T> (&v)[16], const Ctx<T>& c,
 // inverse: v[k3] = Y_r[k1 + 16 h + 256 k3]  ->  v[n1] = A_r[t + 256 n1]  (unnormalised, xcor_rustfft.rs:76)
 // Entered and left HOLDING the token.
 // ------------------------------------------------------------------------------------------------
-template <typename T>
+template <typename T, bool PP>
 __device__ __forceinline__ void inverse_4096(cx<T> (&v)[16], const Ctx<T>& c) {
     constexpr int kC = TmemGeom<T>::kColsPerC;
     CAF_FP(fft16<T, true>(v));
+    if (kEarlyRelease) pp_release<PP, T>(c, v);
     CAF_FP(twiddle_powers<true>(v, tmem_ld1(c.tm_tw + kC, T())));       // conj W_256^{h k}
-    pp_release(c.r, v);
+    if (!kEarlyRelease) pp_release<PP, T>(c, v);
     CAF_TR(c, 10);
     __syncwarp();
 #pragma unroll
-    CAF_XCHG(for (int k = 0; k < 16; ++k) c.Sw[k * 16 + (c.h ^ k)] = v[k]);
+    CAF_XCHG(for (int k = 0; k < 16; ++k) Fab<T>::st(c.Sr, c.ix_tw(k), v[k]));
     __syncwarp();
 #pragma unroll
-    CAF_XCHG(for (int m = 0; m < 16; ++m) v[m] = c.Sw[c.h * 16 + (m ^ c.h)]);
+    CAF_XCHG(for (int m = 0; m < 16; ++m) v[m] = Fab<T>::ld(c.Sr, c.ix_tr(m)));
     CAF_TR(c, 11);
 
-    pp_acquire(c.r, v);
-    CAF_FP(fft16<T, true>(v));
+    T g = pp_acquire<PP, T>(c);
+    CAF_TR(c, 27);
+    CAF_FP(fft16_impl<T, true, PP>(v, g));
+    if (kEarlyRelease) pp_release<PP, T>(c, v);
     {
         const cx<T> b = tmem_ld1(c.tm_tw + 2 * kC, T()), rho = tmem_ld1(c.tm_tw + 3 * kC, T());
         CAF_FP(twiddle_geometric<true>(v, b, rho));                     // conj W_4096^{k1 (16 k + h)}
     }
-    pp_release(c.r, v);
+    if (!kEarlyRelease) pp_release<PP, T>(c, v);
     CAF_TR(c, 12);
     __syncwarp();
 #pragma unroll
-    CAF_XCHG(for (int k = 0; k < 16; ++k) c.Sw[16 * k + c.h] = v[k]);
+    CAF_XCHG(for (int k = 0; k < 16; ++k) Fab<T>::st(c.Sr, c.ix_own(k), v[k]));
     CAF_TR(c, 13);
     bar_group(c.r);
 #pragma unroll
-    CAF_XCHG(for (int k = 0; k < 16; ++k) v[k] = c.Sr[k * 256 + c.t]);
+    CAF_XCHG(for (int k = 0; k < 16; ++k) v[k] = Fab<T>::ld(c.Sr, c.ix_block(k)));
     CAF_TR(c, 14);
 
-    pp_acquire(c.r, v);
-    CAF_FP(fft16<T, true>(v));     // returns holding the token
+    g = pp_acquire<PP, T>(c);
+    CAF_TR(c, 28);
+    CAF_FP(fft16_impl<T, true, PP>(v, g));     // returns holding the token
     CAF_TR(c, 15);
 }
 
@@ -419,7 +542,6 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
     using SL = SmemLayout<T>;
     using TG = TmemGeom<T>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    C* S = reinterpret_cast<C*>(smem_raw);
     C* ptab = reinterpret_cast<C*>(smem_raw + SL::offPtab);
     unsigned long long* red_idx = reinterpret_cast<unsigned long long*>(smem_raw + SL::offRed);
     double* red_val = reinterpret_cast<double*>(smem_raw + SL::offRed + 128);
@@ -433,21 +555,17 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tr_g0));
 #endif
     Ctx<T> c;
-    // group r = tid / 256.  Inside a warp: lane = h[2:0] | sub << 3 | h[3] << 4; the warp's two sub-transforms
-    // k1 = 2 * warp_in_group + sub sit in adjacent quarter-warps, so a 128-bit W_256 twiddle load (same address
-    // for both) costs 2 shared-memory wavefronts instead of 4.
+    // group r = tid / 256; the thread map and the fabric indexing live in Ctx::init
     const int hw_warp = tid >> 5;
-    c.lane = tid & 31; c.r = tid >> 8;
-    c.h = (c.lane & 7) | ((c.lane >> 1) & 8);
-    c.w = 2 * (hw_warp & 7) + ((c.lane >> 3) & 1);     // k1: the 256-point sub-transform this thread works in
-    c.t = 16 * c.w + c.h;
-    c.S = S; c.Sr = S + c.r * kL0; c.Sw = c.Sr + c.w * 256;
-    c.ptab = ptab; c.tm_tw = 0;
+    c.init(smem_raw, tid);
+    c.ptab = ptab;
     const int w = c.w, lane = c.lane, r = c.r, h = c.h, t = c.t, tg = tid & 255, wg = hw_warp & 7;
 
     constexpr bool kHalfZero = (MODE == kSurface || MODE == kSpectrumHalf || MODE == kXcorHalf);
     constexpr bool kWritesH = (MODE == kSpectrumHalf || MODE == kSpectrumFull);
     constexpr bool kUseTmem = (MODE == kSurface);   // H and the needle live in TMEM (the twiddle bases always do)
+    // the fp64 token: surface rows in complex128 (the complex64 rows are not fp32-pipe bound)
+    constexpr bool PP = kPingPong && MODE == kSurface && std::is_same<T, double>::value;
 
     // ---- work split: contiguous ranges of (pair, row) items so a CTA changes pair as rarely as possible ----
     const int rows_per_pair = (MODE == kSurface) ? a.D : 1;
@@ -513,6 +631,7 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
         tmem_st1(c.tm_tw + 2 * TG::kColsPerC, tb2);
         tmem_st1(c.tm_tw + 3 * TG::kColsPerC, tb3);
         tmem_st1(c.tm_tw + 4 * TG::kColsPerC, tb4);
+        tmem_st1(c.tm_tw + 5 * TG::kColsPerC, mk<T>((T)1, (T)0));           // the ping-pong gate
         tmem_wait_st();
     }
 
@@ -534,8 +653,9 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
         Ph p; p.d1 = pt[1]; p.d8 = pt[8]; p.pw = pt[16 + w]; p.ph = pt[32 + h];
         return p;
     };
-    auto phasor_mul = [&](C (&v)[16], const Ph& p) {
-        C qa = cmul(p.pw, p.ph), qb = cmul(qa, p.d8);
+    // g: the token gate (1.0); scaling the leading factor by it makes the whole phasor block depend on the acquire
+    auto phasor_mul = [&](C (&v)[16], const Ph& p, T g) {
+        C qa = cmul(mk<T>(p.pw.x * g, p.pw.y * g), p.ph), qb = cmul(qa, p.d8);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             v[i] = cmul(v[i], qa);
@@ -579,12 +699,12 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
         else { mb = nullptr; par = 0; }
     };
 
-    if (r == 0) pp_release(0);     // group 1 computes first: hand it the token
+    if (r == 0) pp_release_plain<PP>(0);     // group 1 computes first: hand it the token
 
     c.tr = nullptr;
     for (int item = lo; item < hi; ++item, buf ^= 1) {
 #ifdef CAF_TRACE
-        c.tr = (a.trace && item - lo < 8) ? a.trace + ((((long long)blockIdx.x * 16 + hw_warp) * 8 + (item - lo)) * 24) : nullptr;
+        c.tr = (a.trace && item - lo < 8) ? a.trace + ((((long long)blockIdx.x * 16 + hw_warp) * 8 + (item - lo)) * 32) : nullptr;
 #endif
         CAF_TR(c, 0);
         if constexpr (MODE == kSurface) {
@@ -609,11 +729,11 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
                 bar_group(r);
                 if (producer) {
                     const Ph ph0 = phasor_load(buf);
-                    pp_acquire(r, v);
-                    phasor_mul(v, ph0);
+                    const T g0 = pp_acquire<PP, T>(c);
+                    phasor_mul(v, ph0, g0);
                     uint64_t* mb; int par;
                     empty_gate(mb, par);
-                    forward_4096<T>(v, c, mb, par, []{});
+                    forward_4096<T, PP>(v, c, mb, par, []{});
                     const T sc = (T)(1.0 / 8192.0);   // the /n of xcor_rustfft.rs:72 (n = transform length)
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
@@ -625,7 +745,7 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
                         }
                         tmem_st4(tm_h + 4 * q * TG::kColsPerC, tmp);
                     }
-                    pp_release(r);
+                    pp_release<PP, T>(c, v);
                     if (shared_h) {
                         __threadfence();
                         bar_group(r);
@@ -668,8 +788,9 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
                 // phasors of the next row: produced here, while this group waits for the token anyway; the group
                 // barriers of this row order them before their first use
                 if ((item + 1 < hi) && (row + 1 < a.D)) fill_ptab(buf ^ 1, a.freqs[row + 1] * a.dt);
-                pp_acquire(r, v);
-                phasor_mul(v, ph0);
+                const T g0 = pp_acquire<PP, T>(c);
+                CAF_TR(c, 24);
+                phasor_mul(v, ph0, g0);
             }
             CAF_TR(c, 2);
         } else if constexpr (kHalfZero) {
@@ -679,8 +800,7 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
             bar_group(r);
             {
                 const Ph ph0 = phasor_load(buf);
-                pp_acquire(r, v);
-                phasor_mul(v, ph0);
+                phasor_mul(v, ph0, (T)1);
             }
         } else {
             // general 8192-sample input: explicit first radix-2 stage
@@ -692,7 +812,6 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
                 if (r == 0) v[i] = cadd(x0, x1);
                 else v[i] = cmulc(csub(x0, x1), ldg<T>(a.g + n));   // * W_8192^{+n} = conj(g[n])
             }
-            pp_acquire(r);
         }
 
         // ---------------- forward transform ----------------
@@ -700,7 +819,7 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
             uint64_t* mb; int par;
             empty_gate(mb, par);
             // the previous row's per-warp maxima are folded in the first exchange phase (two group barriers have passed)
-            forward_4096<T>(v, c, mb, par, [&] { if constexpr (MODE == kSurface) flush_peak((buf ^ 1) & 1); });
+            forward_4096<T, PP>(v, c, mb, par, [&] { if constexpr (MODE == kSurface) flush_peak((buf ^ 1) & 1); });
         }
 
         // standalone-xcor spectrum layout in global memory: [k3][k1][r][h]
@@ -709,7 +828,6 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
             const T sc = (T)(1.0 / 8192.0);
 #pragma unroll
             for (int k = 0; k < 16; ++k) hp[((k * 16 + w) * 2 + r) * 16 + h] = mk<T>(v[k].x * sc, v[k].y * sc);
-            pp_release(r);
         } else {
             // ---------------- H * conj(X)  (xcor_rustfft.rs:64-73) ----------------
             if constexpr (kUseTmem) {
@@ -756,10 +874,11 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
 
             CAF_TR(c, 9);
             // ---------------- inverse transform ----------------
-            inverse_4096<T>(v, c);   // v[n1] = A_r[t + 256 n1]
+            inverse_4096<T, PP>(v, c);   // v[n1] = A_r[t + 256 n1]
 
             // ---------------- final radix-2 across the pipelines:  y[n] = A + B', y[n + 4096] = A - B',
             //                  B' = B W_8192^{-n},  n = t + 256 n1,  W_8192^{-n} = g[t] W_32^{-n1} ----------------
+            if (kEarlyRelease) pp_release<PP, T>(c, v);     // the last butterfly is done: the radix-2 / epilogue tail overlaps
             if (r == 1) {
                 const C gt = tmem_ld1(c.tm_tw + 4 * TG::kColsPerC, T());
                 auto post = [&](auto jt) {
@@ -768,11 +887,11 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
                 };
                 post(ic<0>{}); post(ic<1>{}); post(ic<2>{}); post(ic<3>{}); post(ic<4>{}); post(ic<5>{}); post(ic<6>{}); post(ic<7>{});
                 post(ic<8>{}); post(ic<9>{}); post(ic<10>{}); post(ic<11>{}); post(ic<12>{}); post(ic<13>{}); post(ic<14>{}); post(ic<15>{});
-                pp_release(1, v);
+                if (!kEarlyRelease) pp_release<PP, T>(c, v);
                 CAF_TR(c, 16);
                 bar_group(1);                 // all X4 reads of this half are done: it becomes the mailbox
 #pragma unroll
-                for (int k = 0; k < 16; ++k) c.Sr[k * 256 + t] = v[k];
+                for (int k = 0; k < 16; ++k) Fab<T>::st(c.Sr, c.ix_block(k), v[k]);
                 mbar_arrive(mb_full);
                 CAF_TR(c, 17);
                 ++posts;
@@ -810,16 +929,16 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
                 CAF_TR(c, 16);
                 mbar_wait(mb_full, posts & 1);
                 CAF_TR(c, 17);
-                const C* mail = S + kL0;
+                const typename Fab<T>::E* mail = c.Sr + Fab<T>::kPipe;   // group 1's half (same t, same columns)
 #pragma unroll
                 for (int k = 0; k < 16; ++k) {
-                    const C Bp = mail[k * 256 + t];
+                    const C Bp = Fab<T>::ld(mail, c.ix_block(k));
                     const int n = t + 256 * k;
                     emit(cadd(v[k], Bp), n, best0, bidx0);             // lag index n
                     emit(csub(v[k], Bp), n + kL0, best1, bidx1);       // lag index n + 4096
                 }
                 mbar_arrive(mb_empty);
-                pp_release(0);
+                if (!kEarlyRelease) pp_release_bits<PP, T>(c, fold_bits(best0, best1));
                 CAF_TR(c, 18);
                 ++posts;
 
@@ -858,7 +977,7 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
 #ifdef CAF_TRACE
     if (a.trace && (tid & 31) == 0) {
         long long g1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g1));
-        long long* q = a.trace + (((long long)blockIdx.x * 16 + hw_warp) * 8 + 0) * 24;
+        long long* q = a.trace + (((long long)blockIdx.x * 16 + hw_warp) * 8 + 0) * 32;
         q[20] = tr_g0; q[21] = g1; q[22] = tr_c0; q[23] = clock64();
     }
 #endif

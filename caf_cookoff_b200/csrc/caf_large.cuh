@@ -122,17 +122,11 @@ __global__ void __launch_bounds__(kThreads, 1) caf_large_core(const LargeArgs<T>
     using SL = SmemLayout<T>;
     using TG = TmemGeom<T>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    C* S = reinterpret_cast<C*>(smem_raw);
     uint32_t* misc = reinterpret_cast<uint32_t*>(smem_raw + SL::offMisc);
 
     const int tid = threadIdx.x, hw_warp = tid >> 5;
     Ctx<T> c;
-    c.lane = tid & 31; c.r = tid >> 8;                    // c.r = warp group (selects the fabric half and the barrier)
-    c.h = (c.lane & 7) | ((c.lane >> 1) & 8);
-    c.w = 2 * (hw_warp & 7) + ((c.lane >> 3) & 1);
-    c.t = 16 * c.w + c.h;
-    c.S = S; c.Sr = S + c.r * kL0; c.Sw = c.Sr + c.w * 256;
-    c.ptab = nullptr; c.tr = nullptr;
+    c.init(smem_raw, tid);                                // c.r = warp group (selects the fabric half and the barrier)
     const int t = c.t, tg = tid & 255;
 
     const C tb0 = ldg<T>(a.tw1 + 256 + t), tb1 = ldg<T>(a.tw2 + 16 + c.h), tb2 = ldg<T>(a.tw1 + c.w * 256 + c.h),
@@ -164,7 +158,7 @@ __global__ void __launch_bounds__(kThreads, 1) caf_large_core(const LargeArgs<T>
         C* buf = a.wbuf + (size_t)u * kL0;
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] = buf[t + 256 * i];
-        forward_4096<T>(v, c, nullptr, 0, [] {});
+        forward_4096<T, false>(v, c, nullptr, 0, [] {});
         C* hp = a.hbig + ((size_t)hu * 16) * 256 + tg;
         if (HMODE) {
 #pragma unroll
@@ -172,7 +166,7 @@ __global__ void __launch_bounds__(kThreads, 1) caf_large_core(const LargeArgs<T>
         } else {
 #pragma unroll
             for (int k = 0; k < 16; ++k) v[k] = cmulc(ldg<T>(hp + k * 256), v[k]);       // H conj(X), xcor_rustfft.rs:64-73
-            inverse_4096<T>(v, c);                                                       // v[n1] at m = t + 256 n1
+            inverse_4096<T, false>(v, c);                                                       // v[n1] at m = t + 256 n1
             // conj(W_tot^{m s}) = e^{+2 pi j (t + 256 n1) s / tot}
             const double2 b = root_of_unity((long long)t * s, tot, 1.0), rho = root_of_unity(256LL * s, tot, 1.0);
             twiddle_geometric<false>(v, mk<T>((T)b.x, (T)b.y), mk<T>((T)rho.x, (T)rho.y));

@@ -15,7 +15,7 @@ __global__ void __launch_bounds__(512, 1) k(unsigned long long* sink, int iters)
     if (MODE == 0 || MODE == 5) idx = threadIdx.x;                                  // distinct 16 B per lane
     if (MODE == 1) idx = w * 32 + ((lane & 7) | ((lane >> 1) & 8));                 // adjacent quarter-warps share
     if (MODE == 2) idx = w * 32;                                                    // warp broadcast
-    if (MODE == 3 || MODE == 4 || MODE == 6 || MODE == 7) idx = threadIdx.x;
+    if (MODE == 3 || MODE == 4 || MODE >= 6) idx = threadIdx.x;
     unsigned long long acc = threadIdx.x;
     uint32_t tb = 0, tbase = 0;
     if (MODE == 7) {
@@ -35,6 +35,10 @@ __global__ void __launch_bounds__(512, 1) k(unsigned long long* sink, int iters)
             if (MODE == 3) { acc += reinterpret_cast<unsigned long long*>(smraw)[e]; }
             if (MODE == 4) { acc += reinterpret_cast<unsigned*>(smraw)[e]; }
             if (MODE == 5) { s128[e] = make_uint4((unsigned)acc, u, it, lane); }
+            if (MODE == 8) { reinterpret_cast<unsigned long long*>(smraw)[e] = acc + u; }
+            if (MODE == 9) { acc += reinterpret_cast<unsigned long long*>(smraw)[e] ^ reinterpret_cast<unsigned long long*>(smraw)[e + 5120]; }
+            if (MODE == 10) { reinterpret_cast<unsigned long long*>(smraw)[e] = acc + u; reinterpret_cast<unsigned long long*>(smraw)[e + 5120] = acc ^ u; }
+            if (MODE == 11) { reinterpret_cast<unsigned*>(smraw)[e] = (unsigned)acc + u; }
             if (MODE == 6) { acc += __shfl_xor_sync(0xffffffffu, (unsigned)acc, (u & 15) + 1); }
             if (MODE == 7) {
                 uint32_t r[16];
@@ -45,7 +49,7 @@ __global__ void __launch_bounds__(512, 1) k(unsigned long long* sink, int iters)
                 acc += r[0] ^ r[15];
             }
         }
-        if (MODE == 5) __syncwarp();
+        if (MODE == 5 || MODE == 8 || MODE == 10 || MODE == 11) __syncwarp();
     }
     sink[blockIdx.x * 512 + threadIdx.x] = acc + (MODE == 5 ? s128[idx].x : 0);
     if (MODE == 7) { __syncthreads(); if (w == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" :: "r"(tbase)); }
@@ -72,5 +76,9 @@ int main() {
     run<5>("STS.128 distinct", d);
     run<6>("SHFL.32 (dependent chain per warp)", d);
     run<7>("LDTM.x16 + wait each", d);
+    run<8>("STS.64 distinct", d);
+    run<9>("2 x LDS.64 distinct (SoA complex128)", d);
+    run<10>("2 x STS.64 distinct (SoA complex128)", d);
+    run<11>("STS.32 distinct", d);
     return 0;
 }
