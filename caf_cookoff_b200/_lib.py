@@ -94,6 +94,8 @@ SYMBOLS = {
     "caf_b200_batch_f32": (_int, _batch),
     "caf_b200_batch_f64_dev": (_int, _batch),
     "caf_b200_batch_f32_dev": (_int, _batch),
+    "caf_b200_surface_layout_f64": (_int, [_vp, _vp, _vp, _sz, _vp, _sz, _u32, _int, _vp, _vp]),
+    "caf_b200_surface_layout_f32": (_int, [_vp, _vp, _vp, _sz, _vp, _sz, _u32, _int, _vp, _vp]),
     "caf_b200_peak_pack": (None, [_PK, C.c_uint64, C.POINTER(C.c_uint64)]),
     "caf_b200_peak_resolve": (None, [C.POINTER(C.c_uint64), _sz, _PK]),
 }

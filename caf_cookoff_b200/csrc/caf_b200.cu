@@ -64,7 +64,7 @@ struct caf_b200_handle_s {
     Tables<double> td;
     Tables<float> tf;
     int occ_d = 1, occ_f = 1;   // resident CTAs per SM of the surface kernel
-    DevBuf needle, hay, hperm, freqs, surface, rowval, rowidx, peaks, scratch;
+    DevBuf needle, hay, hperm, freqs, surface, rowval, rowidx, peaks, scratch, layout;
     DevBuf lwbuf, lzbuf, lhbig, lpart;      // long-row path: chunk scratch (two levels), H, partial row maxima
     long long* trace = nullptr;   // CAF_TRACE builds: device buffer for phase stamps
     unsigned int* done_counter = nullptr;   // last-CTA-done ticket of the fused find_peak
@@ -411,6 +411,53 @@ int run_batch_host(caf_b200_handle h, const caf::cx<T>* needles, const caf::cx<T
     return CAF_B200_OK;
 }
 
+// Sibling layouts (caf_layout_kernel): the surface is computed in the Rust layout on the device, converted there,
+// and only the converted array crosses PCIe.
+template <typename T>
+int run_layout_host(caf_b200_handle h, const caf::cx<T>* needle, const caf::cx<T>* hay, size_t l, const double* freqs,
+                    size_t d, uint32_t fs, int layout, T* out, caf_b200_peak* peak) {
+    using namespace caf;
+    int rc = check_common<T>(h, needle, hay, 1, l, freqs, d, fs);
+    if (rc) return rc;
+    if (layout != CAF_B200_LAYOUT_PYTHON && layout != CAF_B200_LAYOUT_GO)
+        return fail(CAF_B200_EINVAL, "layout must be CAF_B200_LAYOUT_PYTHON or CAF_B200_LAYOUT_GO");
+    if (l > (1u << 26)) return fail(CAF_B200_EUNSUPPORTED, "l too large");
+    CK(cudaSetDevice(h->device));
+    const size_t W = (layout == CAF_B200_LAYOUT_PYTHON) ? l : 2 * l;
+    const int lag0 = (layout == CAF_B200_LAYOUT_PYTHON) ? (int)(l / 2) : (int)l;
+    if (peak) { peak->value = 0.0; peak->freq_hz = 0.0; peak->doppler_idx = ~0ull; peak->delay_idx = 0; }
+    if (l == 0 || d == 0) return CAF_B200_OK;
+    cudaStream_t s = h->stream;
+    CK(h->needle.ensure(sizeof(cx<T>) * l));
+    CK(h->hay.ensure(sizeof(cx<T>) * l));
+    CK(h->freqs.ensure(sizeof(double) * d));
+    CK(cudaMemcpyAsync(h->needle.p, needle, sizeof(cx<T>) * l, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(h->hay.p, hay, sizeof(cx<T>) * l, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(h->freqs.p, freqs, sizeof(double) * d, cudaMemcpyHostToDevice, s));
+    CK(h->surface.ensure(sizeof(T) * d * 2 * l));
+    CK(h->layout.ensure(sizeof(T) * d * W));
+    CK(h->rowval.ensure(sizeof(T) * d));
+    CK(h->rowidx.ensure(sizeof(unsigned long long) * d));
+    CK(h->peaks.ensure(sizeof(PeakOut)));
+    rc = run_batch_dev<T>(h, (const cx<T>*)h->needle.p, (const cx<T>*)h->hay.p, 1, l, (const double*)h->freqs.p, d, fs,
+                          (T*)h->surface.p, nullptr, nullptr, nullptr);
+    if (rc) return rc;
+    caf_layout_kernel<T><<<(unsigned)d, 256, 0, s>>>((const T*)h->surface.p, (T*)h->layout.p, (int)l, (int)W, lag0,
+                                                     (T*)h->rowval.p, (unsigned long long*)h->rowidx.p);
+    h->launches++;
+    CK(cudaGetLastError());
+    caf_peak_kernel<T><<<1, 256, 0, s>>>((const T*)h->rowval.p, (const unsigned long long*)h->rowidx.p,
+                                         (const double*)h->freqs.p, (int)d, (PeakOut*)h->peaks.p);
+    h->launches++;
+    CK(cudaGetLastError());
+    if (out) CK(cudaMemcpyAsync(out, h->layout.p, sizeof(T) * d * W, cudaMemcpyDeviceToHost, s));
+    PeakOut pk;
+    CK(cudaMemcpyAsync(&pk, h->peaks.p, sizeof(PeakOut), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (peak) to_public(pk, peak);
+    return CAF_B200_OK;
+}
+
 template <typename T>
 int run_shift(caf_b200_handle h, const caf::cx<T>* in, size_t n, double f, uint32_t fs, caf::cx<T>* out) {
     using namespace caf;
@@ -533,7 +580,7 @@ int caf_b200_destroy(caf_b200_handle h) {
     if (!h) return CAF_B200_OK;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
-    for (DevBuf* b : {&h->needle, &h->hay, &h->hperm, &h->freqs, &h->surface, &h->rowval, &h->rowidx, &h->peaks, &h->scratch, &h->lwbuf, &h->lzbuf, &h->lhbig, &h->lpart})
+    for (DevBuf* b : {&h->needle, &h->hay, &h->hperm, &h->freqs, &h->surface, &h->rowval, &h->rowidx, &h->peaks, &h->scratch, &h->layout, &h->lwbuf, &h->lzbuf, &h->lhbig, &h->lpart})
         b->release();
     for (void* q : {(void*)h->td.tw1, (void*)h->td.tw2, (void*)h->td.g, (void*)h->tf.tw1, (void*)h->tf.tw2, (void*)h->tf.g})
         if (q) cudaFree(q);
@@ -678,6 +725,15 @@ int caf_b200_peak_f32(caf_b200_handle h, const caf_c64* needle, const caf_c64* h
                       size_t d, uint32_t fs, caf_b200_peak* peak) {
     if (!peak) return fail(CAF_B200_EINVAL, "null peak");
     return caf_b200_batch_f32(h, needle, hay, 1, l, freqs, d, fs, nullptr, nullptr, nullptr, peak);
+}
+
+int caf_b200_surface_layout_f64(caf_b200_handle h, const caf_c128* needle, const caf_c128* hay, size_t l,
+                                const double* freqs, size_t d, uint32_t fs, int layout, double* out, caf_b200_peak* peak) {
+    return run_layout_host<double>(h, (const double2*)needle, (const double2*)hay, l, freqs, d, fs, layout, out, peak);
+}
+int caf_b200_surface_layout_f32(caf_b200_handle h, const caf_c64* needle, const caf_c64* hay, size_t l,
+                                const double* freqs, size_t d, uint32_t fs, int layout, float* out, caf_b200_peak* peak) {
+    return run_layout_host<float>(h, (const float2*)needle, (const float2*)hay, l, freqs, d, fs, layout, out, peak);
 }
 
 static_assert(sizeof(caf_b200_peak) == sizeof(caf::PeakOut), "peak layouts must match");

@@ -1062,6 +1062,50 @@ __global__ void __launch_bounds__(256) caf_peak_kernel(const T* __restrict__ row
 }
 
 // ---------------------------------------------------------------------------------------------
+// Sibling-program layouts of one surface.  The Go and Python programs of the reference
+// compute the same correlation with the operands swapped and store |.| instead of |.|^2:
+//     Python  caf_python/caf.py:12-13,145   row = |correlate(shifted, haystack, 'same')|: L columns, column j = lag L/2 - j
+//     Go      caf_go/caf.go:93-116, main.go:35  banana padded in FRONT: 2L columns, column k = lag L - k (mod 2L)
+// with "lag" in the Rust sense (mod.rs:139: haystack delayed by tau peaks at tau).  One block per row:
+//     out[row][j] = sqrt(rust[row][(lag0 - j) mod 2L]),  j < W
+// plus the row maximum in COLUMN order (first strict-> maximum, caf.go:217-226 / np.argmax), so the peak of the
+// converted surface is the sibling program's own answer even on ties.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) caf_layout_kernel(const T* __restrict__ rust, T* __restrict__ out, int L, int W,
+                                                         int lag0, T* __restrict__ row_val,
+                                                         unsigned long long* __restrict__ row_idx) {
+    __shared__ double sv[8];
+    __shared__ int si[8];
+    const long long row = blockIdx.x;
+    const T* src = rust + row * 2LL * L;
+    T* dst = out + row * (long long)W;
+    double best = 0.0;
+    int bidx = 0x7fffffff;
+    for (int j = threadIdx.x; j < W; j += blockDim.x) {
+        int k = lag0 - j;
+        if (k < 0) k += 2 * L;
+        const T m = sqrt(src[k]);
+        dst[j] = m;
+        if ((double)m > best) { best = (double)m; bidx = j; }     // j ascending per thread: first maximum kept
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        double ov = __shfl_xor_sync(0xffffffffu, best, off);
+        int oi = __shfl_xor_sync(0xffffffffu, bidx, off);
+        amax_take<double>(best, bidx, ov, oi);
+    }
+    if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = best; si[threadIdx.x >> 5] = bidx; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int q = 1; q < 8; ++q) amax_take<double>(best, bidx, sv[q], si[q]);
+        if (!(best > 0.0)) bidx = 0;
+        row_val[row] = (T)best;
+        row_idx[row] = (unsigned long long)bidx;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Standalone apply_freq_shift (mod.rs:46-65): y[n] = x[n] e^{+j 2 pi f n / fs}.  Phase in fp64.
 // ---------------------------------------------------------------------------------------------
 template <typename T>

@@ -142,6 +142,25 @@ int caf_b200_batch_f32_dev(caf_b200_handle h, const caf_c64* needles, const caf_
                            size_t l, const double* freqs_hz, size_t d, uint32_t fs,
                            float* surface, float* row_peak_val, uint64_t* row_peak_idx, caf_b200_peak* peaks);
 
+/* ---- the sibling programs' layouts of the same surface -------------------
+ * The reference's Go and Python programs compute this correlation with the operands swapped and keep the
+ * magnitude |xcor| (cmplx.Abs, np.abs) where the Rust crate keeps |xcor|^2 (norm_sqr):
+ *   CAF_B200_LAYOUT_PYTHON  caf_python/caf.py:12-13,101-122  amb_surf: out is d x l, row =
+ *                           |scipy.signal.correlate(shifted, haystack, 'same')|, column j holds Rust lag l/2 - j;
+ *                           caf.py:145 reports tau = l//2 - argmax column.
+ *   CAF_B200_LAYOUT_GO      caf_go/caf.go:93-116,162-173  amb_surf: out is d x 2l (banana zero-padded in FRONT),
+ *                           column k holds Rust lag l - k (mod 2l); main.go:35 reports len - tdx.
+ * The surface is computed once on the GPU (Rust layout, |.|^2) and converted there; `out` may be NULL.
+ * peak: the sibling's 2-D argmax (first strict-> maximum in row-major order, caf.go:217-226 / np.argmax):
+ * value = |xcor|, freq_hz, doppler_idx = row, delay_idx = COLUMN of the converted surface. */
+typedef enum { CAF_B200_LAYOUT_RUST = 0, CAF_B200_LAYOUT_PYTHON = 1, CAF_B200_LAYOUT_GO = 2 } caf_b200_layout;
+int caf_b200_surface_layout_f64(caf_b200_handle h, const caf_c128* needle, const caf_c128* haystack, size_t l,
+                                const double* freqs_hz, size_t d, uint32_t fs, int layout,
+                                double* out, caf_b200_peak* peak);
+int caf_b200_surface_layout_f32(caf_b200_handle h, const caf_c64* needle, const caf_c64* haystack, size_t l,
+                                const double* freqs_hz, size_t d, uint32_t fs, int layout,
+                                float* out, caf_b200_peak* peak);
+
 /* ---- multi-GPU peak reduction (doppler rows or pairs sharded across ranks) ----
  * Each rank computes the peak of its shard, packs it with its GLOBAL first-row offset into 4 uint64
  * words, the caller all-gathers (or all-reduces a zero-initialised 4*world buffer with SUM/MAX) the

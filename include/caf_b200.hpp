@@ -124,6 +124,32 @@ public:
     }
 };
 
+// The Go program of the reference (caf_go/caf.go) from the same kernels: amb_surf (caf.go:162-173) returns
+// [][]float64 of 2L columns, |xcor|, column k = Rust lag L - k; find_2d_peak (caf.go:217-226) is the first
+// strict-> maximum in row-major order; main.go:35 reports len(apple) - tdx.
+struct GoSibling {
+    static std::vector<std::vector<double>> amb_surf(const std::vector<Complex64>& needle, const std::vector<Complex64>& haystack,
+                                                     const std::vector<double>& freqs_hz, double samp_rate) {
+        if (needle.size() != haystack.size()) throw Panic("input arrays should be same size (caf.go:97-99)");
+        const std::size_t l = needle.size(), d = freqs_hz.size(), w = 2 * l;
+        std::vector<double> flat(d * w);
+        check(caf_b200_surface_layout_f64(thread_handle(), reinterpret_cast<const caf_c128*>(needle.data()),
+                                          reinterpret_cast<const caf_c128*>(haystack.data()), l, freqs_hz.data(), d,
+                                          (uint32_t)(samp_rate + 0.5), CAF_B200_LAYOUT_GO, flat.data(), nullptr));
+        std::vector<std::vector<double>> surf(d);
+        for (std::size_t r = 0; r < d; ++r) surf[r].assign(flat.begin() + r * w, flat.begin() + (r + 1) * w);
+        return surf;
+    }
+    struct Peak2d { int fdx, tdx; double max; };
+    static Peak2d find_2d_peak(const std::vector<std::vector<double>>& surf) {
+        Peak2d p{0, 0, 0.0};
+        for (std::size_t i = 0; i < surf.size(); ++i)
+            for (std::size_t j = 0; j < surf[i].size(); ++j)
+                if (surf[i][j] > p.max) p = Peak2d{(int)i, (int)j, surf[i][j]};
+        return p;
+    }
+};
+
 // utils.rs:10-35: packed little-endian f32 I/Q -> Complex64
 inline std::vector<Complex64> read_file_c64(const std::string& filename) {
     std::ifstream f(filename, std::ios::binary);

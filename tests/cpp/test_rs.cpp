@@ -54,6 +54,16 @@ int main(int argc, char** argv) {
         auto [f, idx] = CafB200::caf_peak(needle, hay, shifts, 48000);
         std::printf("Frequency offset: %.1fHz\nTime offset: %zu samples (%.3fms)\n", f, idx, (double)idx / 48.0);
         ASSERT_EQ(f, 69.0); ASSERT_EQ(idx, (std::size_t)202);
+        // main.go:13-35 equivalent on the chirp_4 pair: "caf result: 70 samples 83 hz"
+        {
+            auto apple = read_file_c64(dir + "/chirp_4_raw.c64");
+            auto banana = read_file_c64(dir + "/chirp_4_T+70samp_F+82.89Hz.c64"); banana.resize(4096);
+            std::vector<double> fz; for (double x = 80.0; x < 86.0; x += .5) fz.push_back(x);
+            auto surf = GoSibling::amb_surf(apple, banana, fz, 48000);
+            auto pk = GoSibling::find_2d_peak(surf);
+            std::printf("caf result: %d samples %g hz @ amb = %g\n", (int)apple.size() - pk.tdx, fz[pk.fdx], pk.max);
+            ASSERT_EQ((int)apple.size() - pk.tdx, 70); ASSERT_EQ(fz[pk.fdx], 83.0);
+        }
     } catch (const std::exception& e) {
         std::printf("EXCEPTION: %s\n", e.what());
         return 2;
