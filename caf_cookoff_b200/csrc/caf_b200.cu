@@ -75,6 +75,8 @@ struct caf_b200_handle_s {
     size_t h_peaks_cap = 0;
     bool profiling = false;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // around spectrum | rows | peak
+    cudaStream_t copy_stream = nullptr;     // host calls: D2H of the head rows while the rest is computed
+    cudaEvent_t ev_head = nullptr, ev_copy = nullptr;
     bool ev_valid = false;
 };
 
@@ -398,10 +400,39 @@ int run_batch_host(caf_b200_handle h, const caf::cx<T>* needles, const caf::cx<T
             h->h_peaks_cap = sizeof(PeakOut) * p;
         }
     }
-    rc = run_batch_dev<T>(h, (const cx<T>*)h->needle.p, (const cx<T>*)h->hay.p, p, l, (const double*)h->freqs.p, d,
-                          fs, d_surface, d_rv, d_ri, d_pk);
-    if (rc) return rc;
-    if (d_surface) CK(cudaMemcpyAsync(surface, d_surface, sizeof(T) * rows * n, cudaMemcpyDeviceToHost, s));
+    // One pair with the surface wanted on the host: the D2H copy (26 MB at PCIe speed, ~0.5 ms) dwarfs the kernels
+    // (~50 us), so the rows are issued as a short head (one wave of CTAs) and the rest; the head's cells start
+    // crossing PCIe on a second stream while the rest is still being computed.  find_peak then runs as its own
+    // small kernel over all row peaks.  CAF_B200_PIPELINE=0 in the environment keeps the single-launch path.
+    static const bool allow_pipeline = [] { const char* e = getenv("CAF_B200_PIPELINE"); return !(e && e[0] == '0'); }();
+    const size_t d0 = (size_t)h->sm_count;
+    if (allow_pipeline && d_surface && p == 1 && l <= (size_t)kL0 && d >= 2 * d0 && d_rv && d_ri) {
+        if (!h->copy_stream) CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+        if (!h->ev_head) CK(cudaEventCreateWithFlags(&h->ev_head, cudaEventDisableTiming));
+        if (!h->ev_copy) CK(cudaEventCreateWithFlags(&h->ev_copy, cudaEventDisableTiming));
+        const double* fq = (const double*)h->freqs.p;
+        rc = run_batch_dev<T>(h, (const cx<T>*)h->needle.p, (const cx<T>*)h->hay.p, 1, l, fq, d0, fs, d_surface, d_rv, d_ri, nullptr);
+        if (rc) return rc;
+        CK(cudaEventRecord(h->ev_head, s));
+        CK(cudaStreamWaitEvent(h->copy_stream, h->ev_head, 0));
+        CK(cudaMemcpyAsync(surface, d_surface, sizeof(T) * d0 * n, cudaMemcpyDeviceToHost, h->copy_stream));
+        CK(cudaEventRecord(h->ev_copy, h->copy_stream));
+        rc = run_batch_dev<T>(h, (const cx<T>*)h->needle.p, (const cx<T>*)h->hay.p, 1, l, fq + d0, d - d0, fs,
+                              d_surface + d0 * n, d_rv + d0, d_ri + d0, nullptr);
+        if (rc) return rc;
+        if (d_pk) {
+            caf_peak_kernel<T><<<1, 256, 0, s>>>(d_rv, d_ri, fq, (int)d, d_pk);
+            h->launches++;
+            CK(cudaGetLastError());
+        }
+        CK(cudaMemcpyAsync(surface + d0 * n, d_surface + d0 * n, sizeof(T) * (d - d0) * n, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamWaitEvent(s, h->ev_copy, 0));
+    } else {
+        rc = run_batch_dev<T>(h, (const cx<T>*)h->needle.p, (const cx<T>*)h->hay.p, p, l, (const double*)h->freqs.p, d,
+                              fs, d_surface, d_rv, d_ri, d_pk);
+        if (rc) return rc;
+        if (d_surface) CK(cudaMemcpyAsync(surface, d_surface, sizeof(T) * rows * n, cudaMemcpyDeviceToHost, s));
+    }
     if (rowval && rows) CK(cudaMemcpyAsync(rowval, d_rv, sizeof(T) * rows, cudaMemcpyDeviceToHost, s));
     if (rowidx && rows) CK(cudaMemcpyAsync(rowidx, d_ri, sizeof(uint64_t) * rows, cudaMemcpyDeviceToHost, s));
     if (peaks) CK(cudaMemcpyAsync(h->h_peaks, d_pk, sizeof(PeakOut) * p, cudaMemcpyDeviceToHost, s));
@@ -589,6 +620,9 @@ int caf_b200_destroy(caf_b200_handle h) {
     if (h->hshare) cudaFree(h->hshare);
     if (h->hflag) cudaFree(h->hflag);
     for (auto& e : h->ev) if (e) cudaEventDestroy(e);
+    if (h->ev_head) cudaEventDestroy(h->ev_head);
+    if (h->ev_copy) cudaEventDestroy(h->ev_copy);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return CAF_B200_OK;

@@ -86,3 +86,27 @@ if os.environ.get("CAF_TRACE_TOKEN"):
     ev.sort()
     t0 = ev[0][0]
     for a_, r_, nm, it, acq in ev: print(f"{nm} item {it} acquire {acq}: [{a_ - t0:7d}, {r_ - t0:7d})  len {r_ - a_}")
+
+# how many of the 16 warps are inside a butterfly block at any time (steady-state rows): 0 = fp64 pipe idle
+if os.environ.get("CAF_TRACE_OCC"):
+    comp = ((1, 2), (2, 3), (5, 6), (7, 8), (8, 9), (9, 10), (11, 12), (14, 15), (15, 16), (17, 18))
+    hist = np.zeros(17)
+    for cta in range(ncta):
+        a0, a1 = buf[cta, 0, 1, 1], buf[cta, 0, 2, 1]       # row start of item 1 .. row start of item 2 (warp 0)
+        if a0 <= 0 or a1 <= 0: continue
+        n = int(a1 - a0)
+        occ = np.zeros(n + 1, dtype=np.int32)
+        for wp in range(16):
+            for it in (0, 1, 2):
+                for s0, s1 in comp:
+                    b0, b1 = buf[cta, wp, it, s0], buf[cta, wp, it, s1]
+                    if b0 <= 0 or b1 <= 0: continue
+                    lo_, hi_ = int(max(b0 - a0, 0)), int(min(b1 - a0, n))
+                    if hi_ > lo_:
+                        occ[lo_] += 1; occ[hi_] -= 1
+        occ = np.cumsum(occ)[:n]
+        hist += np.bincount(occ, minlength=17)[:17]
+    hist /= hist.sum()
+    print("fraction of row time with k warps inside a butterfly block:")
+    print("  k=0 %.3f | 1-4 %.3f | 5-8 %.3f | 9-12 %.3f | 13-16 %.3f" % (hist[0], hist[1:5].sum(), hist[5:9].sum(), hist[9:13].sum(), hist[13:].sum()))
+    print("  mean warps computing %.2f" % (np.arange(17) * hist).sum())
