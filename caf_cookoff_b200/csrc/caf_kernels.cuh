@@ -409,7 +409,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t* mb, int parity) {
 // waits behind the other group's exchange traffic in the LSU queue.
 // The five per-thread twiddle bases live in TMEM (tcgen05.ld is not queued behind shared-memory traffic).
 // `empty_mb` (group 1 only): the mailbox barrier to wait on before the fabric half is overwritten.
-// `hook()` runs in the exchange phase after the block barriers (deferred row-peak reduction).
+// `hook()` runs in the exchange phase after the block barriers (deferred row-peak reduction), `hook3()` before the
+// last butterfly (a consumer CTA polls the H publication flag there, one pass ahead of its first use).
 // ------------------------------------------------------------------------------------------------
 // development experiments (never defined in the product build): drop the exchanges or the butterflies to see
 // how much of a row each side costs on its own (results are then wrong by construction)
@@ -424,9 +425,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* mb, int parity) {
 #define CAF_FP(...) do { __VA_ARGS__; } while (0)
 #endif
 
-template <typename T, bool PP, typename Hook>
+template <typename T, bool PP, typename Hook, typename Hook3>
 __device__ __forceinline__ void forward_4096(cx<T> (&v)[16], const Ctx<T>& c,
-                                             uint64_t* empty_mb, int empty_parity, Hook&& hook) {
+                                             uint64_t* empty_mb, int empty_parity, Hook&& hook, Hook3&& hook3) {
     constexpr int kC = TmemGeom<T>::kColsPerC;
     CAF_FP(fft16<T, false>(v));
     if (kEarlyRelease) pp_release<PP, T>(c, v);
@@ -457,6 +458,7 @@ __device__ __forceinline__ void forward_4096(cx<T> (&v)[16], const Ctx<T>& c,
     __syncwarp();
 #pragma unroll
     CAF_XCHG(for (int m = 0; m < 16; ++m) v[m] = Fab<T>::ld(c.Sr, c.ix_tr(m)));
+    hook3();
     CAF_TR(c, 7);
 
     g = pp_acquire<PP, T>(c);
@@ -728,12 +730,17 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
                 }
                 bar_group(r);
                 if (producer) {
+#ifdef CAF_TRACE
+                    long long* tr_row = c.tr;        // the H transform of a producer is stamped into item slot 7
+                    if (a.trace && item == lo) c.tr = a.trace + ((((long long)blockIdx.x * 16 + hw_warp) * 8 + 7) * 32);
+#endif
+                    CAF_TR(c, 0);
                     const Ph ph0 = phasor_load(buf);
                     const T g0 = pp_acquire<PP, T>(c);
                     phasor_mul(v, ph0, g0);
                     uint64_t* mb; int par;
                     empty_gate(mb, par);
-                    forward_4096<T, PP>(v, c, mb, par, []{});
+                    forward_4096<T, PP>(v, c, mb, par, []{}, []{});
                     const T sc = (T)(1.0 / 8192.0);   // the /n of xcor_rustfft.rs:72 (n = transform length)
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
@@ -751,6 +758,10 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
                         bar_group(r);
                         if (tg == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;\n" :: "l"(a.hflag + r), "r"(a.epoch) : "memory");
                     }
+                    CAF_TR(c, 9);
+#ifdef CAF_TRACE
+                    c.tr = tr_row;
+#endif
                 } else {
                     h_from_share = true;
                 }
@@ -819,7 +830,19 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
             uint64_t* mb; int par;
             empty_gate(mb, par);
             // the previous row's per-warp maxima are folded in the first exchange phase (two group barriers have passed)
-            forward_4096<T, PP>(v, c, mb, par, [&] { if constexpr (MODE == kSurface) flush_peak((buf ^ 1) & 1); });
+            forward_4096<T, PP>(v, c, mb, par, [&] { if constexpr (MODE == kSurface) flush_peak((buf ^ 1) & 1); },
+                                [&] {
+                                    // first row of a consumer CTA: wait for H's publication here, while the last
+                                    // butterfly is still ahead, so the L2 round trip of the flag is off the critical path
+                                    if constexpr (kUseTmem) {
+                                        if (h_from_share && tg == 0) {
+                                            unsigned int seen;
+                                            do {
+                                                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(seen) : "l"(a.hflag + r) : "memory");
+                                            } while ((int)(seen - a.epoch) < 0);
+                                        }
+                                    }
+                                });
         }
 
         // standalone-xcor spectrum layout in global memory: [k3][k1][r][h]
@@ -832,24 +855,24 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
             // ---------------- H * conj(X)  (xcor_rustfft.rs:64-73) ----------------
             if constexpr (kUseTmem) {
                 if (h_from_share) {
-                    // first row of a consumer CTA: H arrives from CTA 0 through L2; keep it in TMEM for later rows
+                    // first row of a consumer CTA: H arrives from the publishing CTA through L2 (flag seen in hook3) and
+                    // is kept in TMEM for the later rows.  The spectrum is parked in this warp's own fabric region for
+                    // a moment so that all 16 loads of H are in flight at once: one L2 round trip instead of four.
                     h_from_share = false;
-                    if (tg == 0) {
-                        unsigned int seen;
-                        do {
-                            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(seen) : "l"(a.hflag + r) : "memory");
-                        } while ((int)(seen - a.epoch) < 0);
-                    }
                     bar_group(r);
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) Fab<T>::st(c.Sr, c.ix_own(k), v[k]);
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) v[k] = __ldcg(a.hshare + k * kThreads + tid);
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
                         C hv[4];
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) hv[i] = __ldcg(a.hshare + (4 * q + i) * kThreads + tid);
+                        for (int i = 0; i < 4; ++i) hv[i] = v[4 * q + i];
                         tmem_st4(tm_h + 4 * q * TG::kColsPerC, hv);
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) v[4 * q + i] = cmulc(hv[i], v[4 * q + i]);
                     }
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) v[k] = cmulc(v[k], Fab<T>::ld(c.Sr, c.ix_own(k)));
                     tmem_wait_st();
                 } else {
 #pragma unroll

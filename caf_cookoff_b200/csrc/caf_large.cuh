@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(kThreads, 1) caf_large_core(const LargeArgs<T>
         C* buf = a.wbuf + (size_t)u * kL0;
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] = buf[t + 256 * i];
-        forward_4096<T, false>(v, c, nullptr, 0, [] {});
+        forward_4096<T, false>(v, c, nullptr, 0, [] {}, [] {});
         C* hp = a.hbig + ((size_t)hu * 16) * 256 + tg;
         if (HMODE) {
 #pragma unroll

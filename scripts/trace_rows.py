@@ -110,3 +110,16 @@ if os.environ.get("CAF_TRACE_OCC"):
     print("fraction of row time with k warps inside a butterfly block:")
     print("  k=0 %.3f | 1-4 %.3f | 5-8 %.3f | 9-12 %.3f | 13-16 %.3f" % (hist[0], hist[1:5].sum(), hist[5:9].sum(), hist[9:13].sum(), hist[13:].sum()))
     print("  mean warps computing %.2f" % (np.arange(17) * hist).sum())
+
+# H producers (CTA 0 group 0, CTA hprod1 group 1): the haystack transform is stamped into item slot 7
+if os.environ.get("CAF_TRACE_H"):
+    for cta in range(ncta):
+        for wp in (0, 8):
+            if buf[cta, wp, 7, 0] > 0:
+                c0_ = buf[cta, 0, 0, 22]
+                st = [int(buf[cta, wp, 7, s_] - c0_) if buf[cta, wp, 7, s_] > 0 else -1 for s_ in (0, 3, 4, 5, 6, 7, 8, 9)]
+                print(f"H producer CTA {cta} warp {wp}: cycles since CTA entry: start {st[0]} f1 {st[1]} X1w {st[2]} X1r {st[3]} f2 {st[4]} X2 {st[5]} f3 {st[6]} published {st[7]}")
+    # consumers: when did H arrive (slot 9 of item 0) relative to CTA entry
+    arr = [int(buf[c_, 0, 0, 9] - buf[c_, 0, 0, 22]) for c_ in range(ncta) if buf[c_, 0, 0, 9] > 0 and buf[c_, 0, 7, 0] == 0]
+    f3 = [int(buf[c_, 0, 0, 8] - buf[c_, 0, 0, 22]) for c_ in range(ncta) if buf[c_, 0, 0, 9] > 0 and buf[c_, 0, 7, 0] == 0]
+    print("consumers (G0): f3 done at median %d, H multiplied at median %d cycles after CTA entry" % (np.median(f3), np.median(arr)))
