@@ -20,7 +20,7 @@ HEADER = os.path.join(_ROOT, "include", "caf_b200.h")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
-    "-Xcompiler", "-fPIC", "-shared",
+    "-Xcompiler", "-fPIC", "-shared", "-ldl",
 ]
 
 
@@ -96,6 +96,14 @@ SYMBOLS = {
     "caf_b200_batch_f32_dev": (_int, _batch),
     "caf_b200_surface_layout_f64": (_int, [_vp, _vp, _vp, _sz, _vp, _sz, _u32, _int, _vp, _vp]),
     "caf_b200_surface_layout_f32": (_int, [_vp, _vp, _vp, _sz, _vp, _sz, _u32, _int, _vp, _vp]),
+    "caf_b200_comm_unique_id": (_int, [_vp]),
+    "caf_b200_comm_create": (_int, [_vp, _int, _int, _vp, C.POINTER(_vp)]),
+    "caf_b200_comm_adopt": (_int, [_vp, _vp, _int, _int, C.POINTER(_vp)]),
+    "caf_b200_comm_destroy": (_int, [_vp]),
+    "caf_b200_comm_shard": (_int, [_vp, _sz, C.POINTER(_sz), C.POINTER(_sz)]),
+    "caf_b200_peak_allgather_dev": (_int, [_vp, _vp, _vp, C.c_uint64, _PK]),
+    "caf_b200_surface_sharded_f64": (_int, [_vp, _vp, _vp, _vp, _sz, _vp, _sz, _u32, _vp, _PK]),
+    "caf_b200_surface_sharded_f32": (_int, [_vp, _vp, _vp, _vp, _sz, _vp, _sz, _u32, _vp, _PK]),
     "caf_b200_peak_pack": (None, [_PK, C.c_uint64, C.POINTER(C.c_uint64)]),
     "caf_b200_peak_resolve": (None, [C.POINTER(C.c_uint64), _sz, _PK]),
 }
@@ -103,10 +111,29 @@ SYMBOLS = {
 _lib = None
 
 
+def _prefer_bundled_nccl():
+    """The library dlopen()s libnccl.so.2 lazily (caf_b200_comm_*).  In a Python process that may later import torch,
+    the copy loaded first wins for everybody (same soname), and torch needs ITS bundled NCCL: point the library at
+    that copy unless the caller chose one (CAF_B200_NCCL_LIB).  A process without the wheel uses the system NCCL."""
+    if os.environ.get("CAF_B200_NCCL_LIB"):
+        return
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("nvidia.nccl")
+        for base in (list(spec.submodule_search_locations or []) if spec else []):
+            cand = os.path.join(base, "lib", "libnccl.so.2")
+            if os.path.exists(cand):
+                os.environ["CAF_B200_NCCL_LIB"] = cand
+                return
+    except Exception:
+        pass
+
+
 def load():
     """dlopen the in-tree library and type every entry point.  Raises if it has not been built."""
     global _lib
     if _lib is None:
+        _prefer_bundled_nccl()
         if not os.path.exists(SO_PATH):
             raise RuntimeError(
                 f"{SO_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "

@@ -13,6 +13,7 @@
 #include <vector>
 
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include "../../include/caf_b200.h"
 #include "caf_kernels.cuh"
@@ -54,6 +55,59 @@ struct DevBuf {
 template <typename T> struct Tables { caf::cx<T>* tw1 = nullptr; caf::cx<T>* tw2 = nullptr; caf::cx<T>* g = nullptr; };
 
 }  // namespace
+
+// ---- NCCL, bound at run time --------------------------------------------------------------------------------
+// The library has no link-time NCCL dependency: libnccl.so.2 is dlopen()ed on first use (inside a torch process
+// that is the copy torch already loaded, otherwise the system one).  Only the handful of entry points the peak
+// exchange needs are bound; the types below are NCCL's stable 2.x ABI (nccl.h: ncclUniqueId is 128 opaque bytes,
+// ncclUint64 == 5, ncclSuccess == 0).
+namespace {
+struct NcclUniqueId { char internal[CAF_B200_NCCL_ID_BYTES]; };
+struct NcclApi {
+    void* lib = nullptr;
+    int (*GetUniqueId)(NcclUniqueId*) = nullptr;
+    int (*CommInitRank)(void**, int, NcclUniqueId, int) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    std::string why;
+    bool ok() const { return lib && GetUniqueId && CommInitRank && CommDestroy && AllGather && GetErrorString; }
+};
+NcclApi& nccl_api() {
+    static NcclApi api = [] {
+        NcclApi a;
+        // a copy the process already holds (torch's) wins; then the caller's choice; then the system library
+        a.lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+        const char* names[] = {getenv("CAF_B200_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+        for (const char* n : names) {
+            if (a.lib) break;
+            if (!n || !*n) continue;
+            a.lib = dlopen(n, RTLD_NOW | RTLD_LOCAL);
+            if (!a.lib) a.why = dlerror();
+        }
+        if (!a.lib) return a;
+        a.GetUniqueId = (int (*)(NcclUniqueId*))dlsym(a.lib, "ncclGetUniqueId");
+        a.CommInitRank = (int (*)(void**, int, NcclUniqueId, int))dlsym(a.lib, "ncclCommInitRank");
+        a.CommDestroy = (int (*)(void*))dlsym(a.lib, "ncclCommDestroy");
+        a.AllGather = (int (*)(const void*, void*, size_t, int, void*, cudaStream_t))dlsym(a.lib, "ncclAllGather");
+        a.GetErrorString = (const char* (*)(int))dlsym(a.lib, "ncclGetErrorString");
+        if (!a.ok()) a.why = "libnccl is missing one of ncclGetUniqueId/CommInitRank/CommDestroy/AllGather/GetErrorString";
+        return a;
+    }();
+    return api;
+}
+constexpr int kNcclUint64 = 5;
+}  // namespace
+
+struct caf_b200_comm_s {
+    caf_b200_handle h = nullptr;
+    void* comm = nullptr;       // ncclComm_t
+    bool own = false;
+    int world = 1, rank = 0;
+    unsigned long long* send = nullptr;   // device: 4 words
+    unsigned long long* recv = nullptr;   // device: 4 * world words
+    unsigned long long* host = nullptr;   // pinned: 4 * world words
+};
 
 struct caf_b200_handle_s {
     int device = 0;
@@ -793,6 +847,130 @@ int caf_b200_batch_f32_dev(caf_b200_handle h, const caf_c64* needles, const caf_
 
 // ---- multi-GPU peak words: [0] = bits(value), [1] = global doppler row (UINT64_MAX if none),
 //      [2] = delay index, [3] = bits(freq_hz) ----
+#define CKN(call)                                                                                   \
+    do {                                                                                            \
+        int e_ = (call);                                                                            \
+        if (e_ != 0) return fail(CAF_B200_ENCCL, std::string(#call " failed: ") + nccl_api().GetErrorString(e_)); \
+    } while (0)
+
+int caf_b200_comm_unique_id(unsigned char id[CAF_B200_NCCL_ID_BYTES]) {
+    if (!id) return fail(CAF_B200_EINVAL, "null id");
+    NcclApi& n = nccl_api();
+    if (!n.ok()) return fail(CAF_B200_ENCCL, "NCCL is not available: " + n.why);
+    NcclUniqueId u;
+    CKN(n.GetUniqueId(&u));
+    std::memcpy(id, u.internal, CAF_B200_NCCL_ID_BYTES);
+    return CAF_B200_OK;
+}
+
+static int comm_finish(caf_b200_comm c, caf_b200_comm* out) {
+    cudaError_t e;
+    if ((e = cudaMalloc(&c->send, 8 * 4)) != cudaSuccess || (e = cudaMalloc(&c->recv, 8 * 4 * (size_t)c->world)) != cudaSuccess ||
+        (e = cudaMallocHost(&c->host, 8 * 4 * (size_t)c->world)) != cudaSuccess) {
+        caf_b200_comm_destroy(c);
+        return fail(CAF_B200_ECUDA, std::string("communicator buffers: ") + cudaGetErrorString(e));
+    }
+    *out = c;
+    return CAF_B200_OK;
+}
+
+int caf_b200_comm_create(caf_b200_handle h, int world, int rank, const unsigned char id[CAF_B200_NCCL_ID_BYTES],
+                         caf_b200_comm* out) {
+    if (!h || !out || !id) return fail(CAF_B200_EINVAL, "null argument");
+    if (world < 1 || rank < 0 || rank >= world) return fail(CAF_B200_EINVAL, "bad world / rank");
+    NcclApi& n = nccl_api();
+    if (!n.ok()) return fail(CAF_B200_ENCCL, "NCCL is not available: " + n.why);
+    CK(cudaSetDevice(h->device));
+    caf_b200_comm c = new (std::nothrow) caf_b200_comm_s();
+    if (!c) return fail(CAF_B200_EINVAL, "out of memory");
+    c->h = h; c->world = world; c->rank = rank; c->own = true;
+    NcclUniqueId u;
+    std::memcpy(u.internal, id, CAF_B200_NCCL_ID_BYTES);
+    int e = n.CommInitRank(&c->comm, world, u, rank);
+    if (e != 0) { delete c; return fail(CAF_B200_ENCCL, std::string("ncclCommInitRank failed: ") + n.GetErrorString(e)); }
+    return comm_finish(c, out);
+}
+
+int caf_b200_comm_adopt(caf_b200_handle h, void* nccl_comm, int world, int rank, caf_b200_comm* out) {
+    if (!h || !out || !nccl_comm) return fail(CAF_B200_EINVAL, "null argument");
+    if (world < 1 || rank < 0 || rank >= world) return fail(CAF_B200_EINVAL, "bad world / rank");
+    NcclApi& n = nccl_api();
+    if (!n.ok()) return fail(CAF_B200_ENCCL, "NCCL is not available: " + n.why);
+    CK(cudaSetDevice(h->device));
+    caf_b200_comm c = new (std::nothrow) caf_b200_comm_s();
+    if (!c) return fail(CAF_B200_EINVAL, "out of memory");
+    c->h = h; c->world = world; c->rank = rank; c->own = false; c->comm = nccl_comm;
+    return comm_finish(c, out);
+}
+
+int caf_b200_comm_destroy(caf_b200_comm c) {
+    if (!c) return CAF_B200_OK;
+    if (c->h) cudaSetDevice(c->h->device);
+    if (c->send) cudaFree(c->send);
+    if (c->recv) cudaFree(c->recv);
+    if (c->host) cudaFreeHost(c->host);
+    if (c->own && c->comm && nccl_api().ok()) nccl_api().CommDestroy(c->comm);
+    delete c;
+    return CAF_B200_OK;
+}
+
+int caf_b200_comm_shard(caf_b200_comm c, size_t n, size_t* lo, size_t* hi) {
+    if (!c || !lo || !hi) return fail(CAF_B200_EINVAL, "null argument");
+    *lo = n * (size_t)c->rank / (size_t)c->world;
+    *hi = n * ((size_t)c->rank + 1) / (size_t)c->world;
+    return CAF_B200_OK;
+}
+
+int caf_b200_peak_allgather_dev(caf_b200_handle h, caf_b200_comm c, const caf_b200_peak* local_dev,
+                                uint64_t global_row_offset, caf_b200_peak* out) {
+    if (!h || !c || !local_dev || !out) return fail(CAF_B200_EINVAL, "null argument");
+    if (c->h != h) return fail(CAF_B200_EINVAL, "communicator belongs to another handle");
+    CK(cudaSetDevice(h->device));
+    caf::caf_peak_pack_kernel<<<1, 32, 0, h->stream>>>((const caf::PeakOut*)local_dev, (unsigned long long)global_row_offset, c->send);
+    h->launches++;
+    CK(cudaGetLastError());
+    CKN(nccl_api().AllGather(c->send, c->recv, 4, kNcclUint64, c->comm, h->stream));
+    CK(cudaMemcpyAsync(c->host, c->recv, 8 * 4 * (size_t)c->world, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    caf_b200_peak_resolve((const uint64_t*)c->host, (size_t)c->world, out);
+    return CAF_B200_OK;
+}
+
+extern "C++" {
+namespace {
+// rows [lo, hi) of the doppler grid on this rank, then find_peak across ranks
+template <typename T>
+int run_sharded(caf_b200_handle h, caf_b200_comm c, const caf::cx<T>* needle, const caf::cx<T>* hay, size_t l,
+                const double* freqs, size_t d, uint32_t fs, T* surface_local, caf_b200_peak* peak) {
+    if (!c) return fail(CAF_B200_EINVAL, "null communicator");
+    if (!peak) return fail(CAF_B200_EINVAL, "null peak");
+    size_t lo = 0, hi = 0;
+    caf_b200_comm_shard(c, d, &lo, &hi);
+    caf_b200_peak local;
+    int rc = run_batch_host<T>(h, needle, hay, 1, l, freqs ? freqs + lo : freqs, hi - lo, fs, surface_local, nullptr, nullptr, &local);
+    if (rc) return rc;
+    // the local peak is on the host here (run_batch_host staged it); it is tiny, so the exchange re-uploads the words
+    uint64_t words[4];
+    caf_b200_peak_pack(&local, lo, words);
+    CK(cudaMemcpyAsync(c->send, words, sizeof words, cudaMemcpyHostToDevice, h->stream));
+    CKN(nccl_api().AllGather(c->send, c->recv, 4, kNcclUint64, c->comm, h->stream));
+    CK(cudaMemcpyAsync(c->host, c->recv, 8 * 4 * (size_t)c->world, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    caf_b200_peak_resolve((const uint64_t*)c->host, (size_t)c->world, peak);
+    return CAF_B200_OK;
+}
+}  // namespace
+}  // extern "C++"
+
+int caf_b200_surface_sharded_f64(caf_b200_handle h, caf_b200_comm c, const caf_c128* needle, const caf_c128* hay, size_t l,
+                                 const double* freqs, size_t d, uint32_t fs, double* surface_local, caf_b200_peak* peak) {
+    return run_sharded<double>(h, c, (const double2*)needle, (const double2*)hay, l, freqs, d, fs, surface_local, peak);
+}
+int caf_b200_surface_sharded_f32(caf_b200_handle h, caf_b200_comm c, const caf_c64* needle, const caf_c64* hay, size_t l,
+                                 const double* freqs, size_t d, uint32_t fs, float* surface_local, caf_b200_peak* peak) {
+    return run_sharded<float>(h, c, (const float2*)needle, (const float2*)hay, l, freqs, d, fs, surface_local, peak);
+}
+
 void caf_b200_peak_pack(const caf_b200_peak* local, uint64_t global_row_offset, uint64_t words[4]) {
     double v = local->value, f = local->freq_hz;
     std::memcpy(&words[0], &v, 8);

@@ -1084,6 +1084,18 @@ __global__ void __launch_bounds__(256) caf_peak_kernel(const T* __restrict__ row
     }
 }
 
+// caf_b200_peak_pack on the device: [value bits, global doppler row (or ~0), delay, freq bits] for the NCCL all-gather
+__global__ void caf_peak_pack_kernel(const PeakOut* __restrict__ local, unsigned long long global_row_offset,
+                                     unsigned long long* __restrict__ words) {
+    if (threadIdx.x == 0) {
+        const PeakOut p = *local;
+        words[0] = (unsigned long long)__double_as_longlong(p.value);
+        words[1] = (p.doppler_idx == ~0ull) ? ~0ull : p.doppler_idx + global_row_offset;
+        words[2] = p.delay_idx;
+        words[3] = (unsigned long long)__double_as_longlong(p.freq_hz);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Sibling-program layouts of one surface.  The Go and Python programs of the reference
 // compute the same correlation with the operands swapped and store |.| instead of |.|^2:

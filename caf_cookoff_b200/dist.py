@@ -13,7 +13,7 @@ from typing import Tuple
 import numpy as np
 
 from . import _lib
-from .api import peak_pack, peak_resolve
+from .api import _check, peak_pack, peak_resolve
 
 
 def shard_bounds(n: int, world: int, rank: int) -> Tuple[int, int]:
@@ -35,3 +35,75 @@ def exchange_peak(local: _lib.Peak, global_row_offset: int, device=None, group=N
     out = torch.empty(world * 4, dtype=torch.int64, device=t.device)
     dist.all_gather_into_tensor(out, t, group=group)
     return peak_resolve(out.cpu().numpy().view(np.uint64).reshape(world, 4))
+
+
+class Comm:
+    """The library's own NCCL communicator (caf_b200_comm_*): what a caller without torch.distributed (the Rust
+    shim) uses.  The 128-byte NCCL id travels out of band; here through a small file any rank can read."""
+
+    def __init__(self, handle, world: int, rank: int, id_path: str, timeout_s: float = 120.0):
+        import ctypes as C
+        import os
+        import time
+        self._lib = _lib.load()
+        self.world, self.rank, self.handle = world, rank, handle
+        buf = (C.c_ubyte * 128)()
+        if rank == 0:
+            _check(self._lib.caf_b200_comm_unique_id(C.cast(buf, C.c_void_p)))
+            tmp = id_path + ".tmp"
+            with open(tmp, "wb") as f:
+                f.write(bytes(buf))
+            os.replace(tmp, id_path)                      # atomic publish
+        else:
+            t_end = time.time() + timeout_s
+            while not os.path.exists(id_path):
+                if time.time() > t_end:
+                    raise TimeoutError(f"rank {rank}: no NCCL id at {id_path}")
+                time.sleep(0.01)
+            C.memmove(buf, open(id_path, "rb").read(128), 128)
+        self._c = C.c_void_p()
+        _check(self._lib.caf_b200_comm_create(handle.raw, world, rank, C.cast(buf, C.c_void_p), C.byref(self._c)))
+
+    @property
+    def raw(self):
+        return self._c
+
+    def shard(self, n: int) -> Tuple[int, int]:
+        import ctypes as C
+        lo, hi = C.c_size_t(), C.c_size_t()
+        _check(self._lib.caf_b200_comm_shard(self._c, n, C.byref(lo), C.byref(hi)))
+        return lo.value, hi.value
+
+    def peak_allgather_dev(self, local_peak_dev_ptr: int, global_row_offset: int) -> _lib.Peak:
+        import ctypes as C
+        out = _lib.Peak()
+        _check(self._lib.caf_b200_peak_allgather_dev(self.handle.raw, self._c, C.c_void_p(local_peak_dev_ptr),
+                                                     int(global_row_offset), C.byref(out)))
+        return out
+
+    def surface_sharded(self, needle, haystack, freqs_hz, fs: int, want_surface: bool = True):
+        """caf_b200_surface_sharded_f64: (local rows [hi-lo, 2L] or None, global Peak)."""
+        import ctypes as C
+        n_ = np.ascontiguousarray(needle, dtype=np.complex128).ravel()
+        h_ = np.ascontiguousarray(haystack, dtype=np.complex128).ravel()
+        f_ = np.ascontiguousarray(freqs_hz, dtype=np.float64).ravel()
+        lo, hi = self.shard(f_.size)
+        surf = np.empty((hi - lo, 2 * n_.size), dtype=np.float64) if want_surface else None
+        pk = _lib.Peak()
+        _check(self._lib.caf_b200_surface_sharded_f64(
+            self.handle.raw, self._c, n_.ctypes.data_as(C.c_void_p), h_.ctypes.data_as(C.c_void_p), n_.size,
+            f_.ctypes.data_as(C.c_void_p), f_.size, int(fs), None if surf is None else surf.ctypes.data_as(C.c_void_p),
+            C.byref(pk)))
+        return surf, pk
+
+    def close(self):
+        if self._c:
+            self._lib.caf_b200_comm_destroy(self._c)
+            import ctypes as C
+            self._c = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -48,7 +48,8 @@ typedef enum {
     CAF_B200_ELENGTH = -2,       /* needle.len() != haystack.len()  (xcor_rustfft.rs:54-55 assert) */
     CAF_B200_EUNSUPPORTED = -3,  /* size outside what this build implements */
     CAF_B200_ECUDA = -4,         /* CUDA runtime error (message in last_error) */
-    CAF_B200_ENODEVICE = -5      /* no usable sm_100 GPU — there is no CPU fallback */
+    CAF_B200_ENODEVICE = -5,     /* no usable sm_100 GPU — there is no CPU fallback */
+    CAF_B200_ENCCL = -6          /* NCCL missing or an NCCL call failed (message in last_error) */
 } caf_b200_status;
 
 /* Result of CafSurface::find_peak (mod.rs:31-42).  When no row beats the dummy 0.0 row (empty or
@@ -168,6 +169,37 @@ int caf_b200_surface_layout_f32(caf_b200_handle h, const caf_c64* needle, const 
  * doppler row).  Pure host helpers; no GPU work. */
 void caf_b200_peak_pack(const caf_b200_peak* local, uint64_t global_row_offset, uint64_t words[4]);
 void caf_b200_peak_resolve(const uint64_t* words, size_t world, caf_b200_peak* out);
+
+/* ---- the same exchange inside the library: NCCL over NVLink, one process per GPU ---------------------
+ * For callers without their own collective layer (the Rust shim).  libnccl.so.2 is dlopen()ed on first use —
+ * no link-time dependency; CAF_B200_ENCCL if it cannot be found.  Rank 0 obtains an id with
+ * caf_b200_comm_unique_id and hands the 128 bytes to the other ranks out of band (file, env, MPI, socket);
+ * every rank then calls caf_b200_comm_create (collective, = ncclCommInitRank on the handle's device).
+ * caf_b200_comm_adopt wraps an ncclComm_t the caller already owns (not destroyed with the communicator). */
+#define CAF_B200_NCCL_ID_BYTES 128
+typedef struct caf_b200_comm_s* caf_b200_comm;
+int caf_b200_comm_unique_id(unsigned char id[CAF_B200_NCCL_ID_BYTES]);
+int caf_b200_comm_create(caf_b200_handle h, int world, int rank, const unsigned char id[CAF_B200_NCCL_ID_BYTES],
+                         caf_b200_comm* out);
+int caf_b200_comm_adopt(caf_b200_handle h, void* nccl_comm, int world, int rank, caf_b200_comm* out);
+int caf_b200_comm_destroy(caf_b200_comm c);
+/* contiguous block [lo, hi) of n doppler rows (or pairs) owned by this rank */
+int caf_b200_comm_shard(caf_b200_comm c, size_t n, size_t* lo, size_t* hi);
+/* find_peak across ranks: local_peak_dev is the DEVICE peak a *_dev call of this rank produced for its shard
+ * (rows global_row_offset ...); it is packed on the device, all-gathered (32 bytes per rank, ncclAllGather on
+ * the handle's stream) and resolved with find_peak's tie-break.  Every rank gets the same `out` (host). */
+int caf_b200_peak_allgather_dev(caf_b200_handle h, caf_b200_comm c, const caf_b200_peak* local_peak_dev,
+                                uint64_t global_row_offset, caf_b200_peak* out);
+/* CafSurface::caf_surface + find_peak with the doppler ROWS sharded across the communicator (mod.rs:185 par_iter
+ * over rows, one GPU per block of rows): every rank passes the SAME host inputs and the full grid; rank r computes
+ * rows [lo, hi) = caf_b200_comm_shard(d), writes them to surface_local ((hi-lo) x 2l, or NULL) and receives the
+ * global peak (doppler_idx is the global row). */
+int caf_b200_surface_sharded_f64(caf_b200_handle h, caf_b200_comm c, const caf_c128* needle, const caf_c128* haystack,
+                                 size_t l, const double* freqs_hz, size_t d, uint32_t fs,
+                                 double* surface_local, caf_b200_peak* peak);
+int caf_b200_surface_sharded_f32(caf_b200_handle h, caf_b200_comm c, const caf_c64* needle, const caf_c64* haystack,
+                                 size_t l, const double* freqs_hz, size_t d, uint32_t fs,
+                                 float* surface_local, caf_b200_peak* peak);
 
 #ifdef __cplusplus
 }

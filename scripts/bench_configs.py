@@ -23,6 +23,9 @@ def main():
     ap.add_argument("--rows", type=int, default=0, help="doppler rows (configs 3/5) or pairs (config 4); 0 = the BASELINE size")
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=1)
+    ap.add_argument("--exchange", choices=["abi", "torch"], default="abi",
+                    help="peak exchange of configs 3/5: the library's own NCCL communicator (caf_b200_peak_allgather_dev) "
+                         "or torch.distributed.all_gather_into_tensor")
     args = ap.parse_args()
     import torch, torch.distributed as dist
     from caf_cookoff_b200 import Handle, _lib, generate as G, dist as cdist, bench_shifts, read_file_c64
@@ -35,6 +38,15 @@ def main():
     stream = torch.cuda.Stream(device=dev); torch.cuda.set_stream(stream)
     h = Handle(local, stream=stream.cuda_stream); lib = _lib.load()
     FS = 48000
+    comm = None
+    if args.exchange == "abi" and args.config in (3, 5):
+        import tempfile
+        id_path = os.path.join(tempfile.gettempdir(), "caf_nccl_id_%s_%s" % (os.environ.get("MASTER_PORT", "0"), os.environ.get("TORCHELASTIC_RUN_ID", "x")))
+        if rank == 0 and os.path.exists(id_path):
+            os.remove(id_path)
+        if world > 1:
+            dist.barrier()
+        comm = cdist.Comm(h, world, rank, id_path)
     if args.config in (3, 5):
         L = 32768 if args.config == 3 else 1 << 19
         D = args.rows or (4096 if args.config == 3 else 16384)
@@ -54,6 +66,10 @@ def main():
             rc = lib.caf_b200_batch_f64_dev(h.raw, nd.data_ptr(), hd.data_ptr(), 1, L, fd.data_ptr(), d_loc, FS,
                                             surf.data_ptr() if want_surface else None, rv.data_ptr(), ri.data_ptr(), pk.data_ptr())
             assert rc == 0, lib.caf_b200_last_error()
+            if comm is not None:
+                # pack on the device, ncclAllGather of 32 B per rank on the handle's stream, resolve: all inside the library
+                result["peak"] = comm.peak_allgather_dev(pk.data_ptr(), lo)
+                return
             w = pk.clone()                                   # [value bits, freq bits, doppler_idx, delay_idx]
             # pack: caf_b200_peak_pack layout = [value bits, global row, delay, freq bits]
             words = torch.stack([w[0], torch.where(w[2] == -1, w[2], w[2] + lo), w[3], w[1]])
@@ -108,8 +124,13 @@ def main():
     line = {"workload": what, "n_gpus": world, "ms_per_step": ms, "cells_per_s": cells / (ms * 1e-3), "steps": args.steps}
     if args.config in (3, 5):
         from caf_cookoff_b200 import api
-        w = result["words"].cpu().numpy().view(np.uint64).reshape(-1, 4)
-        g = api.peak_resolve(w)
+        if comm is not None:
+            g = result["peak"]
+            line["exchange"] = "caf_b200_peak_allgather_dev (library-owned NCCL communicator)"
+        else:
+            w = result["words"].cpu().numpy().view(np.uint64).reshape(-1, 4)
+            g = api.peak_resolve(w)
+            line["exchange"] = "torch.distributed all_gather_into_tensor"
         n_ = 2 * L
         line.update({"peak": {"freq_hz": g.freq_hz, "delay_idx": int(g.delay_idx), "doppler_idx": int(g.doppler_idx), "value": g.value},
                      "algorithmic_tflops": D * (10.0 * n_ * np.log2(n_) + 15.0 * n_) / (ms * 1e-3) / 1e12})

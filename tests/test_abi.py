@@ -88,3 +88,19 @@ def test_peak_pack_resolve_is_find_peak_over_shards():
     # order of the shards must not matter
     out2 = api.peak_resolve(words[::-1].copy())
     assert (out2.doppler_idx, out2.delay_idx) == (101, 11)
+
+
+def test_nccl_is_bound_at_run_time_and_id_works_without_a_gpu():
+    """caf_b200_comm_*: libnccl is dlopen()ed lazily (no link-time dependency) and an id can be minted on the CPU."""
+    import shutil, subprocess
+    lib = _lib.load()
+    buf = (C.c_ubyte * 128)()
+    rc = lib.caf_b200_comm_unique_id(C.cast(buf, C.c_void_p))
+    assert rc == 0, lib.caf_b200_last_error()
+    assert any(bytes(buf))
+    out = C.c_void_p()
+    assert lib.caf_b200_comm_create(None, 2, 0, C.cast(buf, C.c_void_p), C.byref(out)) == -1     # EINVAL: null handle
+    ldd = shutil.which("ldd")
+    if ldd:
+        deps = subprocess.run([ldd, _lib.SO_PATH], capture_output=True, text=True).stdout
+        assert "nccl" not in deps and "torch" not in deps, deps
