@@ -96,3 +96,50 @@ impl Xcor {
         out
     }
 }
+
+/// One process per GPU: rank `rank` of `world` computes its block of doppler rows and every rank gets the global
+/// `find_peak` answer (one 32-byte NCCL all-gather inside the library).  `id` is the 128-byte NCCL id rank 0 made with
+/// `nccl_unique_id()` and handed to the other ranks out of band.  This is mod.rs:185's `par_iter` over rows with GPUs
+/// in place of rayon workers.
+pub struct ShardedCaf { comm: ffi::caf_b200_comm }
+pub fn nccl_unique_id() -> [u8; ffi::CAF_B200_NCCL_ID_BYTES] {
+    let mut id = [0u8; ffi::CAF_B200_NCCL_ID_BYTES];
+    ffi::check(unsafe { ffi::caf_b200_comm_unique_id(id.as_mut_ptr()) });
+    id
+}
+impl ShardedCaf {
+    pub fn new(world: usize, rank: usize, id: &[u8; ffi::CAF_B200_NCCL_ID_BYTES]) -> Self {
+        let mut comm: ffi::caf_b200_comm = std::ptr::null_mut();
+        ffi::HANDLE.with(|h| ffi::check(unsafe { ffi::caf_b200_comm_create(h.0, world as i32, rank as i32, id.as_ptr(), &mut comm) }));
+        ShardedCaf { comm }
+    }
+    /// (rows [lo, hi) of the surface owned by this rank, global (freq, delay) peak)
+    pub fn caf_surface_peak(&self, needle: &[Complex64], haystack: &[Complex64], freqs_hz: &[f64], fs: u32)
+                            -> (Vec<f64>, (usize, usize), (f64, usize)) {
+        assert!(needle.len() == haystack.len());
+        let (mut lo, mut hi) = (0usize, 0usize);
+        ffi::check(unsafe { ffi::caf_b200_comm_shard(self.comm, freqs_hz.len(), &mut lo, &mut hi) });
+        let mut local = vec![0f64; (hi - lo) * 2 * needle.len()];
+        let mut pk = ffi::caf_b200_peak::default();
+        ffi::HANDLE.with(|h| ffi::check(unsafe {
+            ffi::caf_b200_surface_sharded_f64(h.0, self.comm, needle.as_ptr(), haystack.as_ptr(), needle.len(),
+                                              freqs_hz.as_ptr(), freqs_hz.len(), fs, local.as_mut_ptr(), &mut pk)
+        }));
+        (local, (lo, hi), (pk.freq_hz, pk.delay_idx as usize))
+    }
+}
+impl Drop for ShardedCaf {
+    fn drop(&mut self) { unsafe { ffi::caf_b200_comm_destroy(self.comm); } }
+}
+
+/// The Go program's surface (caf_go/caf.go:162-173): [d][2l] of |xcor|, column k = lag l - k.
+pub fn go_amb_surf(needle: &[Complex64], haystack: &[Complex64], freqs_hz: &[f64], samp_rate: f64) -> Vec<Vec<f64>> {
+    assert!(needle.len() == haystack.len());
+    let (l, d) = (needle.len(), freqs_hz.len());
+    let mut flat = vec![0f64; d * 2 * l];
+    ffi::HANDLE.with(|h| ffi::check(unsafe {
+        ffi::caf_b200_surface_layout_f64(h.0, needle.as_ptr(), haystack.as_ptr(), l, freqs_hz.as_ptr(), d,
+                                         samp_rate.round() as u32, 2, flat.as_mut_ptr(), std::ptr::null_mut())
+    }));
+    flat.chunks(2 * l).map(|r| r.to_vec()).collect()
+}

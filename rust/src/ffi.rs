@@ -31,7 +31,24 @@ extern "C" {
                              freqs_hz: *const f64, d: usize, fs: u32, peak: *mut caf_b200_peak) -> c_int;
     pub fn caf_b200_host_alloc(out: *mut *mut c_void, bytes: usize) -> c_int;
     pub fn caf_b200_host_free(p: *mut c_void) -> c_int;
+    // sibling layouts (caf_go / caf_python conventions): layout 1 = Python [d][l], 2 = Go [d][2l], |xcor|
+    pub fn caf_b200_surface_layout_f64(h: caf_b200_handle, needle: *const Complex64, haystack: *const Complex64, l: usize,
+                                       freqs_hz: *const f64, d: usize, fs: u32, layout: c_int, out: *mut f64,
+                                       peak: *mut caf_b200_peak) -> c_int;
+    // multi-GPU: the library's own NCCL communicator (libnccl is dlopen()ed by the library, nothing to link here)
+    pub fn caf_b200_comm_unique_id(id: *mut u8) -> c_int;
+    pub fn caf_b200_comm_create(h: caf_b200_handle, world: c_int, rank: c_int, id: *const u8, out: *mut caf_b200_comm) -> c_int;
+    pub fn caf_b200_comm_destroy(c: caf_b200_comm) -> c_int;
+    pub fn caf_b200_comm_shard(c: caf_b200_comm, n: usize, lo: *mut usize, hi: *mut usize) -> c_int;
+    pub fn caf_b200_surface_sharded_f64(h: caf_b200_handle, c: caf_b200_comm, needle: *const Complex64,
+                                        haystack: *const Complex64, l: usize, freqs_hz: *const f64, d: usize, fs: u32,
+                                        surface_local: *mut f64, peak: *mut caf_b200_peak) -> c_int;
 }
+
+#[repr(C)]
+pub struct caf_b200_comm_s { _private: [u8; 0] }
+pub type caf_b200_comm = *mut caf_b200_comm_s;
+pub const CAF_B200_NCCL_ID_BYTES: usize = 128;
 
 /// One lazily created handle per thread: the trait functions are associated functions without `self`, callable
 /// from any thread (rayon workers included), and a handle is not thread-safe.
