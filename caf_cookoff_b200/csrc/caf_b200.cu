@@ -129,6 +129,7 @@ struct caf_b200_handle_s {
     size_t h_peaks_cap = 0;
     bool profiling = false;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // around spectrum | rows | peak
+    int max_clusters[2][3] = {{0, 0, 0}, {0, 0, 0}};   // resident clusters of caf_cluster_rows_kernel<T, R>
     cudaStream_t copy_stream = nullptr;     // host calls: D2H of the head rows while the rest is computed
     cudaEvent_t ev_head = nullptr, ev_copy = nullptr;
     bool ev_valid = false;
@@ -196,6 +197,9 @@ cudaError_t configure_all(int* occ) {
     if ((e = configure_kernel<T, caf::kXcorHalf>(nullptr)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(caf::caf_large_core<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<T>())) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(caf::caf_large_core<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<T>())) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(caf::caf_cluster_rows_kernel<T, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<T>())) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(caf::caf_cluster_rows_kernel<T, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<T>())) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(caf::caf_cluster_rows_kernel<T, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<T>())) != cudaSuccess) return e;
     return cudaSuccess;
 }
 
@@ -256,6 +260,39 @@ cudaError_t launch_large_core(caf_b200_handle h, const caf::LargeArgs<T>& a) {
     h->launches++;
     return cudaGetLastError();
 }
+// rows of 16 384 .. 65 536 cells: one cluster of R CTAs per row, transposes through distributed shared memory
+template <typename T, int R>
+cudaError_t launch_cluster_rows_rt(caf_b200_handle h, const caf::LargeArgs<T>& a) {
+    auto k = caf::caf_cluster_rows_kernel<T, R>;
+    cudaLaunchConfig_t cfg{};
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = R; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cfg.blockDim = dim3(caf::kThreads); cfg.dynamicSmemBytes = smem_bytes<T>(); cfg.stream = h->stream;
+    int& cached = h->max_clusters[std::is_same<T, double>::value ? 0 : 1][R == 2 ? 0 : R == 4 ? 1 : 2];
+    if (cached == 0) {
+        cfg.gridDim = dim3((unsigned)(R * (h->sm_count / R)));
+        int ncl = 0;
+        cudaError_t e = cudaOccupancyMaxActiveClusters(&ncl, k, &cfg);
+        if (e != cudaSuccess) return e;
+        cached = ncl < 1 ? 1 : ncl;
+    }
+    const int ncl = a.rows < cached ? a.rows : cached;
+    cfg.gridDim = dim3((unsigned)(ncl * R));
+    h->launches++;
+    return cudaLaunchKernelEx(&cfg, k, a);
+}
+template <typename T>
+cudaError_t launch_cluster_rows(caf_b200_handle h, const caf::LargeArgs<T>& a) {
+    switch (a.Rtop) {
+        case 2: return launch_cluster_rows_rt<T, 2>(h, a);
+        case 4: return launch_cluster_rows_rt<T, 4>(h, a);
+        case 8: return launch_cluster_rows_rt<T, 8>(h, a);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
 // forward chain (spread[s] + core) and, unless H is being built, the inverse chain (gather[s] + row peaks)
 template <typename T, bool HMODE>
 int large_chain(caf_b200_handle h, const caf::LargeArgs<T>& a) {
@@ -285,11 +322,20 @@ int run_large_dev(caf_b200_handle h, const caf::cx<T>* needles, const caf::cx<T>
     size_t chunk = (budget_mb << 20) / row_bytes;
     if (chunk < 1) chunk = 1;
     if (chunk > d) chunk = d;
-    const int nparts = inner / 256;
+    // One level and at most 8 units per pipeline can also run as one cluster of R CTAs per row with both transposes in
+    // distributed shared memory (caf_cluster_rows_kernel).  Measured on B200 it LOSES to the chain through L2 (config 3:
+    // 6.8 ms against 6.0 ms): only 15 clusters of 8 CTAs are resident (120 of 148 SMs), remote shared-memory stores
+    // drain at ~15 B/clk per SM, and the phases of a row are serialised by cluster barriers.  It is therefore opt-in:
+    // CAF_B200_CLUSTER=1 in the environment (read per call).
+    const char* cl_env = getenv("CAF_B200_CLUSTER");
+    const bool cluster = cl_env && cl_env[0] == '1' && !two && rtop <= 8;
+    if (cluster) chunk = 1;                                    // scratch is only needed for the one H transform
+    const int nparts = cluster ? rtop : inner / 256;
+    const size_t peak_rows = cluster ? d : chunk;
     CK(h->lwbuf.ensure(row_bytes * chunk));
     if (two) CK(h->lzbuf.ensure(row_bytes * chunk));
     CK(h->lhbig.ensure(row_bytes));
-    CK(h->lpart.ensure((sizeof(double) + sizeof(int)) * (size_t)nparts * chunk + sizeof(unsigned int) * chunk));
+    CK(h->lpart.ensure((sizeof(double) + sizeof(int)) * (size_t)nparts * peak_rows + sizeof(unsigned int) * peak_rows));
     T* rv = rowval; unsigned long long* ri = rowidx;
     if (!rv || !ri) {
         CK(h->scratch.ensure((sizeof(T) + sizeof(unsigned long long)) * p * d + 16));
@@ -299,16 +345,24 @@ int run_large_dev(caf_b200_handle h, const caf::cx<T>* needles, const caf::cx<T>
     Tables<T>& t = tables<T>(h);
     LargeArgs<T> a{};
     a.wbuf = (cx<T>*)h->lwbuf.p; a.zbuf = (cx<T>*)h->lzbuf.p; a.hbig = (cx<T>*)h->lhbig.p;
-    a.part_val = (double*)h->lpart.p; a.part_idx = (int*)((double*)h->lpart.p + (size_t)nparts * chunk);
-    a.row_ticket = (unsigned int*)(a.part_idx + (size_t)nparts * chunk);
-    CK(cudaMemsetAsync(a.row_ticket, 0, sizeof(unsigned int) * chunk, h->stream));   // tickets start at zero (the layout moves with the shape)
+    a.part_val = (double*)h->lpart.p; a.part_idx = (int*)((double*)h->lpart.p + (size_t)nparts * peak_rows);
+    a.row_ticket = (unsigned int*)(a.part_idx + (size_t)nparts * peak_rows);
+    CK(cudaMemsetAsync(a.row_ticket, 0, sizeof(unsigned int) * peak_rows, h->stream));   // tickets start at zero (the layout moves with the shape)
     a.tw1 = t.tw1; a.tw2 = t.tw2; a.g = t.g;
     a.dt = 1.0 / (double)fs; a.L = (int)l; a.N = (int)n; a.Rtop = rtop; a.inner_top = inner;
+    a.trace = h->trace;
     for (size_t pi = 0; pi < p; ++pi) {
         // H = FFT(haystack)/N once per pair (the reference recomputes it per row, xcor_rustfft.rs:58-59)
         a.in = hays + pi * l; a.freqs = nullptr; a.rows = 1; a.surface = nullptr;
         int rc = large_chain<T, true>(h, a);
         if (rc) return rc;
+        if (cluster) {
+            a.in = needles + pi * l; a.freqs = freqs; a.rows = (int)d;
+            a.surface = surface ? surface + (pi * d) * 2 * l : nullptr;
+            a.row_peak_val = rv + pi * d; a.row_peak_idx = ri + pi * d;
+            CK(launch_cluster_rows<T>(h, a));
+            continue;
+        }
         for (size_t off = 0; off < d; off += chunk) {
             const size_t c = (d - off < chunk) ? d - off : chunk;
             a.in = needles + pi * l; a.freqs = freqs + off; a.rows = (int)c;
