@@ -253,9 +253,13 @@ cudaError_t launch_large_mid(caf_b200_handle h, const caf::LargeArgs<T>& a, bool
 }
 template <typename T, bool HMODE>
 cudaError_t launch_large_core(caf_b200_handle h, const caf::LargeArgs<T>& a) {
-    const long long units = (long long)a.rows * (a.N / caf::kL0);
-    long long ctas = (units + 1) / 2;
-    if (ctas > h->sm_count) ctas = h->sm_count;
+    // one warp group per (row, position) unit, at most two groups per SM; whole sets of positions only (the kernel keeps a
+    // group on one position of the row so that its H stays in TMEM)
+    const long long upr = a.N / caf::kL0;
+    const long long units = (long long)a.rows * upr;
+    long long groups = units < 2LL * h->sm_count ? units : 2LL * h->sm_count;
+    if (groups > upr) groups = groups / upr * upr;
+    long long ctas = (groups + 1) / 2;
     caf::caf_large_core<T, HMODE><<<(unsigned)ctas, caf::kThreads, smem_bytes<T>(), h->stream>>>(a);
     h->launches++;
     return cudaGetLastError();

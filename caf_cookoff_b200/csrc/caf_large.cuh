@@ -151,26 +151,60 @@ __global__ void __launch_bounds__(kThreads, 1) caf_large_core(const LargeArgs<T>
     const int units_per_row = a.N / kL0 / 2 * 2;          // 2 pipelines x N/2/4096
     const int tot = (a.inner_top == kL0) ? a.N / 2 : 65536;   // length of the innermost factored array
     const int Rin = tot / kL0;
-    const long long n_units = (long long)a.rows * units_per_row;
     const T scale = (T)(1.0 / (double)a.N);              // the /n of xcor_rustfft.rs:72
+    // Every warp group keeps ONE position hu inside the row for the whole launch and walks down the rows, so its 4096
+    // bins of H (TMEM) and the roots of its conjugate inner twiddle (TMEM) are fetched once instead of once per unit:
+    // that is a third of the kernel's L2 reads and two sincospi per thread and unit.  Groups beyond the last full set
+    // of positions stay idle (296 groups, 16 positions for config 3: 288 work).
+    const int n_groups = 2 * gridDim.x, g = 2 * blockIdx.x + c.r;
+    const int sets = n_groups / units_per_row;           // >= 1: the host launches at least one group per position
+    const bool active = g < sets * units_per_row;
+    const int hu = g % units_per_row, s = hu % Rin;
+    const uint32_t tm_h = misc[0] + ((uint32_t)(32 * (hw_warp & 3)) << 16) + (uint32_t)((16 * (hw_warp >> 2)) * TG::kColsPerC);
+    C* hp = a.hbig + ((size_t)hu * 16) * 256 + tg;
+    if (active && !HMODE) {
+        // conj(W_tot^{m s}) = e^{+2 pi j (t + 256 n1) s / tot}: base and ratio
+        const double2 b = root_of_unity((long long)t * s, tot, 1.0), rho = root_of_unity(256LL * s, tot, 1.0);
+        tmem_st1(c.tm_tw + 5 * TG::kColsPerC, mk<T>((T)b.x, (T)b.y));
+        tmem_st1(c.tm_tw + 6 * TG::kColsPerC, mk<T>((T)rho.x, (T)rho.y));
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+            C tmp[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) tmp[i] = ldg<T>(hp + (4 * q4 + i) * 256);
+            tmem_st4(tm_h + 4 * q4 * TG::kColsPerC, tmp);
+        }
+        tmem_wait_st();
+    }
     C v[16];
-    for (long long u = 2LL * blockIdx.x + c.r; u < n_units; u += 2LL * gridDim.x) {
-        const int s = (int)(u % Rin), hu = (int)(u % units_per_row);
-        C* buf = a.wbuf + (size_t)u * kL0;
+    for (long long row = active ? g / units_per_row : a.rows; row < a.rows; row += sets) {
+        C* buf = a.wbuf + ((size_t)row * units_per_row + hu) * kL0;
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] = buf[t + 256 * i];
         forward_4096<T, false>(v, c, nullptr, 0, [] {}, [] {});
-        C* hp = a.hbig + ((size_t)hu * 16) * 256 + tg;
         if (HMODE) {
 #pragma unroll
             for (int k = 0; k < 16; ++k) hp[k * 256] = mk<T>(v[k].x * scale, v[k].y * scale);
         } else {
 #pragma unroll
-            for (int k = 0; k < 16; ++k) v[k] = cmulc(ldg<T>(hp + k * 256), v[k]);       // H conj(X), xcor_rustfft.rs:64-73
+            for (int q = 0; q < 2; ++q) {                                                       // H conj(X), xcor_rustfft.rs:64-73
+                typename raw4_of<T>::type qa, qb;
+                tmem_ld4_issue(tm_h + (8 * q) * TG::kColsPerC, qa);
+                tmem_ld4_issue(tm_h + (8 * q + 4) * TG::kColsPerC, qb);
+                tmem_wait_ld();
+                C hv[4];
+                tmem_unpack4(qa, hv);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) v[8 * q + i] = cmulc(hv[i], v[8 * q + i]);
+                tmem_unpack4(qb, hv);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) v[8 * q + 4 + i] = cmulc(hv[i], v[8 * q + 4 + i]);
+            }
             inverse_4096<T, false>(v, c);                                                       // v[n1] at m = t + 256 n1
-            // conj(W_tot^{m s}) = e^{+2 pi j (t + 256 n1) s / tot}
-            const double2 b = root_of_unity((long long)t * s, tot, 1.0), rho = root_of_unity(256LL * s, tot, 1.0);
-            twiddle_geometric<false>(v, mk<T>((T)b.x, (T)b.y), mk<T>((T)rho.x, (T)rho.y));
+            {
+                const C b = tmem_ld1(c.tm_tw + 5 * TG::kColsPerC, T()), rho = tmem_ld1(c.tm_tw + 6 * TG::kColsPerC, T());
+                twiddle_geometric<false>(v, b, rho);
+            }
 #pragma unroll
             for (int k = 0; k < 16; ++k) buf[t + 256 * k] = v[k];
         }
