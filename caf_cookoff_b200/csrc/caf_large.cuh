@@ -61,9 +61,13 @@ __device__ __forceinline__ cx<T> mul_by_d(cx<T> x, double2 p) {
 template <typename T, int R>
 __global__ void __launch_bounds__(256) caf_large_spread_top(const LargeArgs<T> a) {
     using C = cx<T>;
+    __shared__ double2 s_step[2];
     const int j = blockIdx.x * 256 + threadIdx.x, row = blockIdx.y;
     const int inner = a.inner_top, Lp = a.N / 2;
     const double phi = a.freqs ? a.freqs[row] * a.dt : 0.0;
+    // the phasor step over one block of `inner` samples is the same for every column of the row: two threads compute it
+    if (threadIdx.x < 2)
+        s_step[threadIdx.x] = unit_phasor((double)inner, phi, (double)threadIdx.x * (double)inner / (double)a.N);
     C* out = (inner == 4096) ? a.wbuf : a.zbuf;
     C x[R];
 #pragma unroll
@@ -71,12 +75,17 @@ __global__ void __launch_bounds__(256) caf_large_spread_top(const LargeArgs<T> a
         const long long n = (long long)j + (long long)inner * rho;
         x[rho] = (n < a.L) ? __ldg(a.in + n) : mk<T>((T)0, (T)0);
     }
-    const double2 om = root_of_unity(j, Lp, -1.0);                       // W_{N/2}^{j}
+    // two sincospi per thread instead of five: g = W_N^{j} gives both the radix-2 split of pipeline 1 (e^{-j 2 pi j/N}) and,
+    // squared, the outer twiddle W_{N/2}^{j}; the doppler phasor e^{j 2 pi j phi} is shared by the two pipelines
+    const double2 g = root_of_unity(j, a.N, -1.0);
+    const double2 om = cmul_d(g, g);                                     // W_{N/2}^{j}
+    const double2 base0 = unit_phasor((double)j, phi, 0.0);
+    __syncthreads();
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
         // phasor e^{j 2 pi n (f/fs - r/N)}, n = j + inner rho: base * step^rho, products kept in fp64 for both variants
-        const double2 base = unit_phasor((double)j, phi, (double)r * (double)j / (double)a.N);
-        const double2 step = unit_phasor((double)inner, phi, (double)r * (double)inner / (double)a.N);
+        const double2 base = r ? cmul_d(base0, g) : base0;
+        const double2 step = s_step[r];
         C v[16];
         double2 p = base;
 #pragma unroll
@@ -94,7 +103,7 @@ __global__ void __launch_bounds__(256) caf_large_spread_top(const LargeArgs<T> a
 
 // spread_mid: zbuf [unit][65536] -> wbuf [unit][16][4096], unit = (row, r, s_top); one thread per (unit, m)
 template <typename T>
-__global__ void __launch_bounds__(256) caf_large_spread_mid(const LargeArgs<T> a) {
+__global__ void __launch_bounds__(256, 3) caf_large_spread_mid(const LargeArgs<T> a) {
     using C = cx<T>;
     const int m = blockIdx.x * 256 + threadIdx.x;
     const size_t unit = blockIdx.y;
@@ -217,7 +226,7 @@ __global__ void __launch_bounds__(kThreads, 1) caf_large_core(const LargeArgs<T>
 // gather_mid: wbuf [unit][16][4096] -> zbuf [unit][65536]: inverse 16-point DFT across s, then the conjugate twiddle
 // of the TOP level, conj(W_{N/2}^{j s_top}), j = m + 4096 rho, so that gather_top is a plain inverse DFT.
 template <typename T>
-__global__ void __launch_bounds__(256) caf_large_gather_mid(const LargeArgs<T> a) {
+__global__ void __launch_bounds__(256, 3) caf_large_gather_mid(const LargeArgs<T> a) {
     using C = cx<T>;
     const int m = blockIdx.x * 256 + threadIdx.x;
     const size_t unit = blockIdx.y;
@@ -240,8 +249,9 @@ __global__ void __launch_bounds__(256) caf_large_gather_mid(const LargeArgs<T> a
 // ------------------------------------------------------------------------------------------------
 // gather_top: one thread per (row, j): inverse R-point DFT across s for both pipelines, radix-2 combine, |.|^2, argmax
 // ------------------------------------------------------------------------------------------------
+// (three blocks per SM for R <= 8: the kernel waits on its 2R loads, more warps in flight hide them)
 template <typename T, int R>
-__global__ void __launch_bounds__(256) caf_large_gather_top(const LargeArgs<T> a) {
+__global__ void __launch_bounds__(256, R <= 8 ? 3 : 1) caf_large_gather_top(const LargeArgs<T> a) {
     using C = cx<T>;
     __shared__ double sv[8];
     __shared__ int si[8];
@@ -260,7 +270,10 @@ __global__ void __launch_bounds__(256) caf_large_gather_top(const LargeArgs<T> a
     dft_small<T, R, true>(a1);
     // W_N^{-n}, n = j + inner rho
     double2 gph = root_of_unity(j, a.N, 1.0);
-    const double2 gstep = root_of_unity(inner, a.N, 1.0);
+    __shared__ double2 s_gstep;                                          // e^{+2 pi j inner / N}: one sincospi per block
+    if (threadIdx.x == 0) s_gstep = root_of_unity(inner, a.N, 1.0);
+    __syncthreads();
+    const double2 gstep = s_gstep;
     T* orow = a.surface ? a.surface + (size_t)row * nout : nullptr;
     double best = 0.0;
     int bidx = 0;
