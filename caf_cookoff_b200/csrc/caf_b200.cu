@@ -321,9 +321,24 @@ int run_large_dev(caf_b200_handle h, const caf::cx<T>* needles, const caf::cx<T>
     const int inner = two ? 65536 : kL0;
     const int rtop = (int)(n / 2 / inner);
     const size_t row_bytes = sizeof(cx<T>) * (size_t)n;
-    size_t budget_mb = two ? 48 : 72;                          // scratch (x2 for two levels) sized around the 126 MB L2; measured best
+    // Rows are processed in chunks whose scratch (one buffer, two for two levels) is bounded by a budget.  Round 1 first
+    // sized the chunks to stay inside the 126 MB L2; measured with the final kernels the opposite holds -- the streaming
+    // spread / gather kernels run as fast out of HBM, and every extra chunk costs launches, a TMEM/H prologue per core
+    // launch and a partly filled last pass (config 3: 72 MB chunks 5.54 ms, 432 MB 4.70 ms, one chunk 4.23 ms; config 5
+    // rows: 48 MB 34.3 us, 4 GB 27.3 us per row).  Default budget 6 GB per buffer; CAF_B200_CHUNK_MB overrides.
+    size_t budget_mb = 6144;
     if (const char* e_ = getenv("CAF_B200_CHUNK_MB")) budget_mb = (size_t)atoi(e_);
     size_t chunk = (budget_mb << 20) / row_bytes;
+    if (chunk < 1) chunk = 1;
+    if (chunk < d) {
+        // equal chunks, each a whole number of "sets" of rows (groups / positions): the core keeps every warp group on one
+        // position of the row, so such a chunk leaves no group idle in its last pass
+        const size_t upr = (size_t)(n / kL0), groups = 2 * (size_t)h->sm_count;
+        const size_t sets = groups >= upr ? groups / upr : 1;
+        const size_t nch = (d + chunk - 1) / chunk;
+        chunk = (d + nch - 1) / nch;
+        chunk = (chunk + sets - 1) / sets * sets;
+    }
     if (chunk < 1) chunk = 1;
     if (chunk > d) chunk = d;
     // One level and at most 8 units per pipeline can also run as one cluster of R CTAs per row with both transposes in
