@@ -197,6 +197,8 @@ cudaError_t configure_all(int* occ) {
     if ((e = configure_kernel<T, caf::kXcorHalf>(nullptr)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(caf::caf_large_core<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<T>())) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(caf::caf_large_core<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<T>())) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(caf::caf_large_spread2<T, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(caf::cx<T>) * 4096))) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(caf::caf_large_gather2<T, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(caf::cx<T>) * 4096))) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(caf::caf_cluster_rows_kernel<T, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<T>())) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(caf::caf_cluster_rows_kernel<T, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<T>())) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(caf::caf_cluster_rows_kernel<T, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<T>())) != cudaSuccess) return e;
@@ -251,6 +253,25 @@ cudaError_t launch_large_mid(caf_b200_handle h, const caf::LargeArgs<T>& a, bool
     h->launches++;
     return cudaGetLastError();
 }
+// two-level rows: fused spread (top + mid) and gather (mid + top), 16 innermost positions per block
+template <typename T, int RT>
+cudaError_t launch_large_fused_rt(caf_b200_handle h, const caf::LargeArgs<T>& a, bool gather) {
+    dim3 grid((unsigned)(caf::kL0 / 16), (unsigned)a.rows);
+    const size_t smem = sizeof(caf::cx<T>) * 2 * RT * 16 * 16;
+    if (!gather) caf::caf_large_spread2<T, RT><<<grid, 256, smem, h->stream>>>(a);
+    else caf::caf_large_gather2<T, RT><<<grid, 256, smem, h->stream>>>(a);
+    h->launches++;
+    return cudaGetLastError();
+}
+template <typename T>
+cudaError_t launch_large_fused(caf_b200_handle h, const caf::LargeArgs<T>& a, bool gather) {
+    switch (a.Rtop) {
+        case 2: return launch_large_fused_rt<T, 2>(h, a, gather);
+        case 4: return launch_large_fused_rt<T, 4>(h, a, gather);
+        case 8: return launch_large_fused_rt<T, 8>(h, a, gather);
+        default: return cudaErrorInvalidValue;
+    }
+}
 template <typename T, bool HMODE>
 cudaError_t launch_large_core(caf_b200_handle h, const caf::LargeArgs<T>& a) {
     // one warp group per (row, position) unit, at most two groups per SM; whole sets of positions only (the kernel keeps a
@@ -301,12 +322,21 @@ cudaError_t launch_cluster_rows(caf_b200_handle h, const caf::LargeArgs<T>& a) {
 template <typename T, bool HMODE>
 int large_chain(caf_b200_handle h, const caf::LargeArgs<T>& a) {
     const bool two = a.inner_top != caf::kL0;
-    CK(launch_large_top<T>(h, a, false));
-    if (two) CK(launch_large_mid<T>(h, a, false));
+    // two levels: the fused kernels (three passes over memory) unless CAF_B200_FUSED2=0 asks for the five-pass chain
+    const char* f2 = getenv("CAF_B200_FUSED2");
+    const bool fused = two && !(f2 && f2[0] == '0');
+    if (fused) CK(launch_large_fused<T>(h, a, false));
+    else {
+        CK(launch_large_top<T>(h, a, false));
+        if (two) CK(launch_large_mid<T>(h, a, false));
+    }
     CK((launch_large_core<T, HMODE>(h, a)));
     if (HMODE) return CAF_B200_OK;
-    if (two) CK(launch_large_mid<T>(h, a, true));
-    CK(launch_large_top<T>(h, a, true));
+    if (fused) CK(launch_large_fused<T>(h, a, true));
+    else {
+        if (two) CK(launch_large_mid<T>(h, a, true));
+        CK(launch_large_top<T>(h, a, true));
+    }
     return CAF_B200_OK;
 }
 
@@ -352,7 +382,10 @@ int run_large_dev(caf_b200_handle h, const caf::cx<T>* needles, const caf::cx<T>
     const int nparts = cluster ? rtop : inner / 256;
     const size_t peak_rows = cluster ? d : chunk;
     CK(h->lwbuf.ensure(row_bytes * chunk));
-    if (two) CK(h->lzbuf.ensure(row_bytes * chunk));
+    {
+        const char* f2 = getenv("CAF_B200_FUSED2");
+        if (two && f2 && f2[0] == '0') CK(h->lzbuf.ensure(row_bytes * chunk));   // only the five-pass chain needs the second buffer
+    }
     CK(h->lhbig.ensure(row_bytes));
     CK(h->lpart.ensure((sizeof(double) + sizeof(int)) * (size_t)nparts * peak_rows + sizeof(unsigned int) * peak_rows));
     T* rv = rowval; unsigned long long* ri = rowidx;

@@ -337,6 +337,188 @@ __global__ void __launch_bounds__(256, R <= 8 ? 3 : 1) caf_large_gather_top(cons
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Two-level rows (N > 131 072), fused: spread_top + spread_mid in one kernel and gather_mid + gather_top in one, so a
+// row makes three passes over memory (spread2 writes, core reads + writes, gather2 reads) instead of five -- these
+// kernels stream 16 MB per row and pipeline and run at HBM speed, so the passes are the time.
+// A block owns 16 consecutive innermost positions m and all K = 16 RT samples m + 4096 k behind them, for both
+// pipelines: 256 (m, k_mid) columns for the RT-point stage, 2 RT 16 (pipeline, s_top, m) columns for the 16-point
+// stage, exchanged through a 2 x RT x 16 x 16 tile in shared memory (64 KB for complex128).
+// The arithmetic is exactly that of the two-kernel chain above.
+// ------------------------------------------------------------------------------------------------
+template <typename T, int RT>
+__global__ void __launch_bounds__(256, 3) caf_large_spread2(const LargeArgs<T> a) {
+    using C = cx<T>;
+    extern __shared__ __align__(16) unsigned char smem_raw2[];
+    C* tile = reinterpret_cast<C*>(smem_raw2);                       // [r][s_top][k_mid][jj]
+    __shared__ double2 s_step[2];
+    const int tid = threadIdx.x, jj = tid & 15, row = blockIdx.y;
+    const int m = blockIdx.x * 16 + jj;
+    const int Lp = a.N / 2;
+    const double phi = a.freqs ? a.freqs[row] * a.dt : 0.0;
+    if (tid < 2) s_step[tid] = unit_phasor(65536.0, phi, (double)tid * 65536.0 / (double)a.N);
+    {
+        // ---- stage 1: column (m, k_mid): RT-point DFT over the top blocks, for both pipelines ----
+        const int k_mid = tid >> 4;
+        const int j = m + 4096 * k_mid;                              // position inside the 65 536-long top-level array
+        C x[RT];
+#pragma unroll
+        for (int rho = 0; rho < RT; ++rho) {
+            const long long n = (long long)j + 65536LL * rho;
+            x[rho] = (n < a.L) ? __ldg(a.in + n) : mk<T>((T)0, (T)0);
+        }
+        const double2 g = root_of_unity(j, a.N, -1.0);               // e^{-j 2 pi j/N}: pipeline 1's split, and sqrt of the twiddle
+        const double2 om = cmul_d(g, g);                             // W_{N/2}^{j}
+        const double2 base0 = unit_phasor((double)j, phi, 0.0);
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const double2 step = s_step[r];
+            double2 p = r ? cmul_d(base0, g) : base0;
+            C v[16];
+#pragma unroll
+            for (int rho = 0; rho < RT; ++rho) { v[rho] = mul_by_d<T>(x[rho], p); p = cmul_d(p, step); }
+            dft_small<T, RT, false>(v);
+            double2 tw = make_double2(1.0, 0.0);
+#pragma unroll
+            for (int s_ = 0; s_ < RT; ++s_) {
+                tile[((r * RT + s_) * 16 + k_mid) * 16 + jj] = mul_by_d<T>(v[s_], tw);
+                tw = cmul_d(tw, om);
+            }
+        }
+    }
+    __syncthreads();
+    {
+        // ---- stage 2: column (r, s_top, m): 16-point DFT over k_mid, twiddle W_65536^{m s_mid} ----
+        const int col = tid >> 4;                                    // r * RT + s_top
+        if (col < 2 * RT) {
+            C v[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) v[k] = tile[(col * 16 + k) * 16 + jj];
+            fft16<T, false>(v);
+            const double2 om2 = root_of_unity(m, 65536, -1.0);
+            double2 tw = make_double2(1.0, 0.0);
+            C* dst = a.wbuf + ((size_t)(row * 2 * RT + col) * 16) * kL0 + m;
+#pragma unroll
+            for (int s_ = 0; s_ < 16; ++s_) {
+                dst[(size_t)s_ * kL0] = mul_by_d<T>(v[s_], tw);
+                tw = cmul_d(tw, om2);
+            }
+        }
+    }
+}
+
+template <typename T, int RT>
+__global__ void __launch_bounds__(256, 3) caf_large_gather2(const LargeArgs<T> a) {
+    using C = cx<T>;
+    extern __shared__ __align__(16) unsigned char smem_raw2[];
+    C* tile = reinterpret_cast<C*>(smem_raw2);                       // [r][s_top][k_mid][jj]
+    __shared__ double sv[8];
+    __shared__ int si[8];
+    __shared__ double2 s_gstep;
+    __shared__ unsigned int s_last;
+    const int tid = threadIdx.x, jj = tid & 15, row = blockIdx.y;
+    const int m = blockIdx.x * 16 + jj;
+    const int Lp = a.N / 2, L = a.L;
+    if (tid == 0) s_gstep = root_of_unity(65536, a.N, 1.0);
+    {
+        // ---- stage A: column (r, s_top, m): inverse 16-point DFT over s_mid, conjugate top-level twiddle ----
+        const int col = tid >> 4;
+        if (col < 2 * RT) {
+            const int s_top = col % RT;
+            const C* src = a.wbuf + ((size_t)(row * 2 * RT + col) * 16) * kL0 + m;
+            C v[16];
+#pragma unroll
+            for (int s_ = 0; s_ < 16; ++s_) v[s_] = src[(size_t)s_ * kL0];
+            fft16<T, true>(v);
+            double2 tw = root_of_unity((long long)m * s_top, Lp, 1.0);
+            const double2 step = root_of_unity(4096LL * s_top, Lp, 1.0);
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                tile[(col * 16 + k) * 16 + jj] = mul_by_d<T>(v[k], tw);
+                tw = cmul_d(tw, step);
+            }
+        }
+    }
+    __syncthreads();
+    double best = 0.0;
+    int bidx = 0;
+    {
+        // ---- stage B: column (m, k_mid): inverse RT-point DFT of both pipelines, radix-2 across them, |.|^2, argmax ----
+        const int k_mid = tid >> 4;
+        const int j = m + 4096 * k_mid;
+        const long long nout = 2LL * L, skip = (long long)a.N - nout;
+        C a0[16], a1[16];
+#pragma unroll
+        for (int s_ = 0; s_ < RT; ++s_) {
+            a0[s_] = tile[((0 * RT + s_) * 16 + k_mid) * 16 + jj];
+            a1[s_] = tile[((1 * RT + s_) * 16 + k_mid) * 16 + jj];
+        }
+        dft_small<T, RT, true>(a0);
+        dft_small<T, RT, true>(a1);
+        double2 gph = root_of_unity(j, a.N, 1.0);                    // W_N^{-n}, n = j + 65536 rho
+        const double2 gstep = s_gstep;
+        T* orow = a.surface ? a.surface + (size_t)row * nout : nullptr;
+#pragma unroll
+        for (int rho = 0; rho < RT; ++rho) {
+            const C A = a0[rho];
+            const C B = mul_by_d<T>(a1[rho], gph);
+            gph = cmul_d(gph, gstep);
+            const long long n = (long long)j + 65536LL * rho;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const C y = half ? csub(A, B) : cadd(A, B);
+                const long long kp = n + (long long)half * Lp;
+                const T mag = y.x * y.x + y.y * y.y;                 // norm_sqr, mod.rs:147
+                long long k = -1;
+                if (kp <= L) k = kp; else if (kp > (long long)a.N - L) k = kp - skip;   // the reference's 2L-cell layout
+                if (k >= 0 && k < nout) {
+                    if (orow) orow[k] = mag;
+                    amax_take<double>(best, bidx, (double)mag, (int)k);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        double ov = __shfl_xor_sync(0xffffffffu, best, off);
+        int oi = __shfl_xor_sync(0xffffffffu, bidx, off);
+        amax_take<double>(best, bidx, ov, oi);
+    }
+    if ((tid & 31) == 0) { sv[tid >> 5] = best; si[tid >> 5] = bidx; }
+    __syncthreads();
+    const int nparts = kL0 / 16;                                     // blocks per row
+    if (tid == 0) {
+        for (int q = 1; q < 8; ++q) amax_take<double>(best, bidx, sv[q], si[q]);
+        a.part_val[(size_t)row * nparts + blockIdx.x] = best;
+        a.part_idx[(size_t)row * nparts + blockIdx.x] = bidx;
+        __threadfence();
+        const unsigned int ticket = atomicAdd(a.row_ticket + row, 1u);
+        s_last = (ticket == (unsigned int)nparts - 1) ? 1u : 0u;
+    }
+    __syncthreads();
+    if (s_last && tid < 32) {
+        // the last block of this row folds the block partials: first strict-> maximum (mod.rs:141-153)
+        __threadfence();
+        double b2 = 0.0;
+        int i2 = 0;
+        for (int q = tid; q < nparts; q += 32)
+            amax_take<double>(b2, i2, __ldcg(a.part_val + (size_t)row * nparts + q), __ldcg(a.part_idx + (size_t)row * nparts + q));
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            double ov = __shfl_xor_sync(0xffffffffu, b2, off);
+            int oi = __shfl_xor_sync(0xffffffffu, i2, off);
+            amax_take<double>(b2, i2, ov, oi);
+        }
+        if (tid == 0) {
+            if (!(b2 > 0.0)) i2 = 0;
+            if (a.row_peak_val) a.row_peak_val[row] = (T)b2;
+            if (a.row_peak_idx) a.row_peak_idx[row] = (unsigned long long)i2;
+            a.row_ticket[row] = 0u;          // self-resetting for the next chunk
+        }
+    }
+}
+
 // ================================================================================================
 // Cluster-fused long rows (16 384 <= N <= 65 536, i.e. R = N/8192 = 2, 4 or 8 units per pipeline; BASELINE config 3).
 //
