@@ -346,17 +346,35 @@ __global__ void __launch_bounds__(256, R <= 8 ? 3 : 1) caf_large_gather_top(cons
 // stage, exchanged through a 2 x RT x 16 x 16 tile in shared memory (64 KB for complex128).
 // The arithmetic is exactly that of the two-kernel chain above.
 // ------------------------------------------------------------------------------------------------
+// (z^e for a small run-time exponent e < 32, by squaring: the fused kernels derive every root they need from a
+//  handful of per-block sincospi results instead of three per thread)
+__device__ __forceinline__ double2 cpow_small(double2 z, int e) {
+    double2 p = make_double2(1.0, 0.0);
+#pragma unroll
+    for (int bit = 0; bit < 5; ++bit) {
+        if (e & (1 << bit)) p = cmul_d(p, z);
+        z = cmul_d(z, z);
+    }
+    return p;
+}
+
 template <typename T, int RT>
 __global__ void __launch_bounds__(256, 3) caf_large_spread2(const LargeArgs<T> a) {
     using C = cx<T>;
     extern __shared__ __align__(16) unsigned char smem_raw2[];
     C* tile = reinterpret_cast<C*>(smem_raw2);                       // [r][s_top][k_mid][jj]
-    __shared__ double2 s_step[2];
+    // per-block tables (66 sincospi per block instead of three per thread):
+    //   s_g[jj]  = e^{-j 2 pi m/N}           s_k[k] = e^{-j 2 pi 4096 k/N}         (row independent)
+    //   s_em[jj] = e^{+j 2 pi m phi}         s_ek[k] = e^{+j 2 pi 4096 k phi}      s_step[r] = phasor step over 65 536 samples
+    __shared__ double2 s_g[16], s_k[16], s_em[16], s_ek[16], s_step[2];
     const int tid = threadIdx.x, jj = tid & 15, row = blockIdx.y;
     const int m = blockIdx.x * 16 + jj;
-    const int Lp = a.N / 2;
     const double phi = a.freqs ? a.freqs[row] * a.dt : 0.0;
-    if (tid < 2) s_step[tid] = unit_phasor(65536.0, phi, (double)tid * 65536.0 / (double)a.N);
+    if (tid < 16) s_g[tid] = root_of_unity(blockIdx.x * 16 + tid, a.N, -1.0);
+    else if (tid < 32) s_k[tid - 16] = root_of_unity(4096LL * (tid - 16), a.N, -1.0);
+    else if (tid < 48) s_em[tid - 32] = unit_phasor((double)(blockIdx.x * 16 + tid - 32), phi, 0.0);
+    else if (tid < 64) s_ek[tid - 48] = unit_phasor(4096.0 * (tid - 48), phi, 0.0);
+    else if (tid < 66) s_step[tid - 64] = unit_phasor(65536.0, phi, (double)(tid - 64) * 65536.0 / (double)a.N);
     {
         // ---- stage 1: column (m, k_mid): RT-point DFT over the top blocks, for both pipelines ----
         const int k_mid = tid >> 4;
@@ -367,10 +385,10 @@ __global__ void __launch_bounds__(256, 3) caf_large_spread2(const LargeArgs<T> a
             const long long n = (long long)j + 65536LL * rho;
             x[rho] = (n < a.L) ? __ldg(a.in + n) : mk<T>((T)0, (T)0);
         }
-        const double2 g = root_of_unity(j, a.N, -1.0);               // e^{-j 2 pi j/N}: pipeline 1's split, and sqrt of the twiddle
-        const double2 om = cmul_d(g, g);                             // W_{N/2}^{j}
-        const double2 base0 = unit_phasor((double)j, phi, 0.0);
         __syncthreads();
+        const double2 g = cmul_d(s_g[jj], s_k[k_mid]);               // e^{-j 2 pi j/N}: pipeline 1's split, and sqrt of the twiddle
+        const double2 om = cmul_d(g, g);                             // W_{N/2}^{j}
+        const double2 base0 = cmul_d(s_em[jj], s_ek[k_mid]);         // e^{+j 2 pi j phi}
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
             const double2 step = s_step[r];
@@ -396,7 +414,7 @@ __global__ void __launch_bounds__(256, 3) caf_large_spread2(const LargeArgs<T> a
 #pragma unroll
             for (int k = 0; k < 16; ++k) v[k] = tile[(col * 16 + k) * 16 + jj];
             fft16<T, false>(v);
-            const double2 om2 = root_of_unity(m, 65536, -1.0);
+            const double2 om2 = cpow_small(s_g[jj], 2 * RT);         // e^{-j 2 pi m/65536} = (e^{-j 2 pi m/N})^{N/65536}, N = 2 RT 65536
             double2 tw = make_double2(1.0, 0.0);
             C* dst = a.wbuf + ((size_t)(row * 2 * RT + col) * 16) * kL0 + m;
 #pragma unroll
@@ -415,24 +433,32 @@ __global__ void __launch_bounds__(256, 3) caf_large_gather2(const LargeArgs<T> a
     C* tile = reinterpret_cast<C*>(smem_raw2);                       // [r][s_top][k_mid][jj]
     __shared__ double sv[8];
     __shared__ int si[8];
-    __shared__ double2 s_gstep;
+    // per-block tables: s_g[jj] = e^{+j 2 pi m/N}, s_k[k] = e^{+j 2 pi 4096 k/N}, s_gstep = e^{+j 2 pi 65536/N}
+    __shared__ double2 s_g[16], s_k[16], s_gstep;
     __shared__ unsigned int s_last;
     const int tid = threadIdx.x, jj = tid & 15, row = blockIdx.y;
     const int m = blockIdx.x * 16 + jj;
     const int Lp = a.N / 2, L = a.L;
-    if (tid == 0) s_gstep = root_of_unity(65536, a.N, 1.0);
+    if (tid < 16) s_g[tid] = root_of_unity(blockIdx.x * 16 + tid, a.N, 1.0);
+    else if (tid < 32) s_k[tid - 16] = root_of_unity(4096LL * (tid - 16), a.N, 1.0);
+    else if (tid == 32) s_gstep = root_of_unity(65536, a.N, 1.0);
     {
         // ---- stage A: column (r, s_top, m): inverse 16-point DFT over s_mid, conjugate top-level twiddle ----
         const int col = tid >> 4;
+        C v[16];
+        const C* src = a.wbuf + ((size_t)(row * 2 * RT + (col < 2 * RT ? col : 0)) * 16) * kL0 + m;
         if (col < 2 * RT) {
-            const int s_top = col % RT;
-            const C* src = a.wbuf + ((size_t)(row * 2 * RT + col) * 16) * kL0 + m;
-            C v[16];
 #pragma unroll
             for (int s_ = 0; s_ < 16; ++s_) v[s_] = src[(size_t)s_ * kL0];
+        }
+        __syncthreads();                                             // the tables
+        if (col < 2 * RT) {
+            const int s_top = col % RT;
             fft16<T, true>(v);
-            double2 tw = root_of_unity((long long)m * s_top, Lp, 1.0);
-            const double2 step = root_of_unity(4096LL * s_top, Lp, 1.0);
+            // conj(W_{N/2}^{(m + 4096 k) s_top}) = (g_m^2)^{s_top} * ((g_4096^2)^{s_top})^k
+            const double2 gm = s_g[jj], g1 = s_k[1];
+            double2 tw = cpow_small(cmul_d(gm, gm), s_top);
+            const double2 step = cpow_small(cmul_d(g1, g1), s_top);
 #pragma unroll
             for (int k = 0; k < 16; ++k) {
                 tile[(col * 16 + k) * 16 + jj] = mul_by_d<T>(v[k], tw);
@@ -456,7 +482,7 @@ __global__ void __launch_bounds__(256, 3) caf_large_gather2(const LargeArgs<T> a
         }
         dft_small<T, RT, true>(a0);
         dft_small<T, RT, true>(a1);
-        double2 gph = root_of_unity(j, a.N, 1.0);                    // W_N^{-n}, n = j + 65536 rho
+        double2 gph = cmul_d(s_g[jj], s_k[k_mid]);                   // W_N^{-n}, n = j + 65536 rho
         const double2 gstep = s_gstep;
         T* orow = a.surface ? a.surface + (size_t)row * nout : nullptr;
 #pragma unroll
