@@ -357,7 +357,7 @@ int run_large_dev(caf_b200_handle h, const caf::cx<T>* needles, const caf::cx<T>
     // launch and a partly filled last pass (config 3: 72 MB chunks 5.54 ms, 432 MB 4.70 ms, one chunk 4.23 ms; config 5
     // rows: 48 MB 34.3 us, 4 GB 27.3 us per row).  Default budget 6 GB per buffer; CAF_B200_CHUNK_MB overrides.
     size_t budget_mb = 6144;
-    if (const char* e_ = getenv("CAF_B200_CHUNK_MB")) budget_mb = (size_t)atoi(e_);
+    if (const char* e_ = getenv("CAF_B200_CHUNK_MB")) { const long v_ = atol(e_); if (v_ > 0) budget_mb = (size_t)v_; }
     size_t chunk = (budget_mb << 20) / row_bytes;
     if (chunk < 1) chunk = 1;
     if (chunk < d) {

@@ -21,6 +21,13 @@
  *    not thread-safe; distinct handles are independent.
  *  - there is NO CPU fallback: if no sm_100 device is usable, create() fails.
  *
+ * Environment (development / measurement switches, read by the library; none is needed for normal use):
+ *    CAF_B200_CHUNK_MB=<n>   scratch budget per buffer for rows longer than 8192 cells (default 6144)
+ *    CAF_B200_FUSED2=0       two-level rows: the five-pass spread/gather chain instead of the fused kernels
+ *    CAF_B200_CLUSTER=1      one-level long rows: the cluster / distributed-shared-memory kernel (measured slower)
+ *    CAF_B200_PIPELINE=0     host surface calls: one launch + one D2H copy instead of head/rest overlap
+ *    CAF_B200_NCCL_LIB=<so>  which libnccl to dlopen for caf_b200_comm_* (default: the loaded one, then libnccl.so.2)
+ *
  * Sizes.  l = samples per input signal (needle and haystack must be equal length, as the reference's
  * Xcor asserts).  A surface row has n = 2*l delay cells (both inputs zero-padded at the end to 2*l,
  * mod.rs:130-131); cell k < l is lag +k, cell k > l is lag k - 2l.  Rows stay in on-chip memory for l <= 4096
