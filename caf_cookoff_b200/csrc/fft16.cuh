@@ -18,6 +18,12 @@ template <typename T> using cx = typename cx_of<T>::type;
 template <typename T> __device__ __forceinline__ cx<T> mk(T x, T y) { cx<T> r; r.x = x; r.y = y; return r; }
 template <typename C> __device__ __forceinline__ C cadd(C a, C b) { C r; r.x = a.x + b.x; r.y = a.y + b.y; return r; }
 template <typename C> __device__ __forceinline__ C csub(C a, C b) { C r; r.x = a.x - b.x; r.y = a.y - b.y; return r; }
+#ifndef CAF_NO_F32X2
+// sm_100 packed fp32: one FADD2 / FFMA2 per complex add / subtract -- same rounding as the scalar pair; the complex64
+// rows are issue bound (11.07 k -> 10.75 k cycles per row)
+template <> __device__ __forceinline__ float2 cadd<float2>(float2 a, float2 b) { return __fadd2_rn(a, b); }
+template <> __device__ __forceinline__ float2 csub<float2>(float2 a, float2 b) { return __ffma2_rn(b, make_float2(-1.0f, -1.0f), a); }
+#endif
 // a * b
 template <typename C> __device__ __forceinline__ C cmul(C a, C b) {
     C r; r.x = a.x * b.x - a.y * b.y; r.y = a.x * b.y + a.y * b.x; return r;
