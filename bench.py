@@ -35,6 +35,27 @@ L = 4096
 N = 2 * L
 
 
+_JSON_FD = None
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries print there too (NCCL's version banner on the first
+    communicator), so fd 1 is pointed at stderr for the whole run and the JSON line goes to the saved descriptor."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def algorithmic_flops(d: int, n: int) -> float:
     """per row 10 N log2 N + 15 N; plus 5 N log2 N once per pair for FFT(s1)."""
     lg = np.log2(n)
@@ -106,6 +127,24 @@ class ClockSampler:
         return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
+def bind_to_gpu_cpus(index: int):
+    """One process per GPU: run (and first-touch the pinned host buffers) on the CPUs NVML reports as local to this
+    GPU, so the 26 MB D2H copy of every e2e step does not cross the socket interconnect.  Best effort."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 def committed_traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum of the row kernel, per launch, from the newest committed
     `ncu --set full` capture (profiles/rNN_traffic.json, written by scripts/summarize_ncu.py)."""
@@ -168,7 +207,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_b200(args):
@@ -185,6 +224,8 @@ def run_b200(args):
         raise SystemExit("bench.py needs a B200: torch.cuda.is_available() is False and there is no CPU path")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    all_cpus = os.sched_getaffinity(0)
+    numa = bind_to_gpu_cpus(local)       # pinned staging buffers then live on the socket the GPU hangs off
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -329,7 +370,8 @@ def run_b200(args):
     # ---- CPU baseline beside it (rank 0, N = 1 only) ----------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cores = os.cpu_count() or 1
+        os.sched_setaffinity(0, all_cpus)          # the CPU baseline gets every host core again
+        cores = len(all_cpus) or 1
         med, reps = cpu_baseline_run(needle, hay, freqs, args.cpu_budget_s, cores)
         cpu = {"value": cells_step / med, "unit": "cells/s", "ms_per_surface": med * 1e3, "cores": cores, "kind": "port",
                "sample": f"{reps} whole 400x8192 surfaces (median), oracle port of CafRustFFTThreadpool, {cores} threads"}
@@ -345,13 +387,14 @@ def run_b200(args):
                        "utils/generate.py seed-0 pairs (rank r uses chirp_r), fs=48000",
                        "doppler_rows": D, "delay_cells": N, "pairs_per_step_per_gpu": 1,
                        "l2": "flushed between timed steps (256 MiB overwrite); each step timed with its own CUDA event pair",
-                       "parallelism": f"pairs sharded x{world}, no data-path collective"},
+                       "parallelism": f"pairs sharded x{world}, no data-path collective",
+                       "host_cpus_bound_to_gpu": numa},
             "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
             "clocks": sampler.summary(),
             "check": {"peak_freq_hz": peak_freq, "peak_delay": peak_delay},
             "step_ms_min_med_max": [float(per_step.min()), float(np.median(per_step)), float(per_step.max())],
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -366,6 +409,7 @@ def main():
     ap.add_argument("--cpu-budget-s", type=float, default=3.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    claim_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:
