@@ -175,3 +175,22 @@ def test_cuda_shift_and_xcor_values():
     r = Xcor.new(2 * L).run(np.concatenate([b, z]), np.concatenate([a, z]))
     j = np.arange(L)
     assert rel_max(np.abs(r[(L // 2 - j) % (2 * L)]), G["xcor_abs_same"]) <= 1e-9
+
+
+@pytest.mark.gpu
+def test_cuda_sibling_layouts_on_long_rows():
+    """Rows longer than 8192 cells (the four-step path) through the same layout conversion."""
+    from caf_cookoff_b200 import generate as Gen, surface_layout
+    needle, hay = Gen.as_inputs(Gen.pair(0, seed=0, chirp_length=5000))
+    shifts = np.array([-3.0, 68.0, 69.25])
+    from oracle import np_oracle as NO
+    surf, _, _ = NO.caf_surface(needle, hay, shifts, FS, direct_phasor=True)
+    py, pkp = surface_layout(needle, hay, shifts, FS, 1)
+    go, pkg = surface_layout(needle, hay, shifts, FS, 2)
+    assert py.shape == (3, 5000) and go.shape == (3, 10000)
+    assert rel_max(py, rust_to_python(surf, 5000)) <= 1e-9
+    assert rel_max(go, rust_to_go(surf, 5000)) <= 1e-9
+    fm, tm = np.unravel_index(rust_to_python(surf, 5000).argmax(), (3, 5000))
+    assert (int(pkp.doppler_idx), int(pkp.delay_idx)) == (fm, tm)
+    fm, tm = np.unravel_index(rust_to_go(surf, 5000).argmax(), (3, 10000))
+    assert (int(pkg.doppler_idx), int(pkg.delay_idx)) == (fm, tm)
