@@ -358,26 +358,26 @@ __device__ __forceinline__ double2 cpow_small(double2 z, int e) {
     return p;
 }
 
-template <typename T, int RT>
-__global__ void __launch_bounds__(256, 3) caf_large_spread2(const LargeArgs<T> a) {
+template <typename T, int RT, int J>
+__global__ void __launch_bounds__(16 * J, J == 16 ? 3 : J == 8 ? 6 : 1) caf_large_spread2(const LargeArgs<T> a) {
     using C = cx<T>;
     extern __shared__ __align__(16) unsigned char smem_raw2[];
     C* tile = reinterpret_cast<C*>(smem_raw2);                       // [r][s_top][k_mid][jj]
     // per-block tables (66 sincospi per block instead of three per thread):
     //   s_g[jj]  = e^{-j 2 pi m/N}           s_k[k] = e^{-j 2 pi 4096 k/N}         (row independent)
     //   s_em[jj] = e^{+j 2 pi m phi}         s_ek[k] = e^{+j 2 pi 4096 k phi}      s_step[r] = phasor step over 65 536 samples
-    __shared__ double2 s_g[16], s_k[16], s_em[16], s_ek[16], s_step[2];
-    const int tid = threadIdx.x, jj = tid & 15, row = blockIdx.y;
-    const int m = blockIdx.x * 16 + jj;
+    __shared__ double2 s_g[J], s_k[16], s_em[J], s_ek[16], s_step[2];
+    const int tid = threadIdx.x, jj = tid % J, row = blockIdx.y;
+    const int m = blockIdx.x * J + jj;
     const double phi = a.freqs ? a.freqs[row] * a.dt : 0.0;
-    if (tid < 16) s_g[tid] = root_of_unity(blockIdx.x * 16 + tid, a.N, -1.0);
-    else if (tid < 32) s_k[tid - 16] = root_of_unity(4096LL * (tid - 16), a.N, -1.0);
-    else if (tid < 48) s_em[tid - 32] = unit_phasor((double)(blockIdx.x * 16 + tid - 32), phi, 0.0);
-    else if (tid < 64) s_ek[tid - 48] = unit_phasor(4096.0 * (tid - 48), phi, 0.0);
-    else if (tid < 66) s_step[tid - 64] = unit_phasor(65536.0, phi, (double)(tid - 64) * 65536.0 / (double)a.N);
+    if (tid < J) s_g[tid] = root_of_unity(blockIdx.x * J + tid, a.N, -1.0);
+    else if (tid < J + 16) s_k[tid - J] = root_of_unity(4096LL * (tid - J), a.N, -1.0);
+    else if (tid < 2 * J + 16) s_em[tid - J - 16] = unit_phasor((double)(blockIdx.x * J + tid - J - 16), phi, 0.0);
+    else if (tid < 2 * J + 32) s_ek[tid - 2 * J - 16] = unit_phasor(4096.0 * (tid - 2 * J - 16), phi, 0.0);
+    else if (tid < 2 * J + 34) s_step[tid - 2 * J - 32] = unit_phasor(65536.0, phi, (double)(tid - 2 * J - 32) * 65536.0 / (double)a.N);
     {
         // ---- stage 1: column (m, k_mid): RT-point DFT over the top blocks, for both pipelines ----
-        const int k_mid = tid >> 4;
+        const int k_mid = tid / J;
         const int j = m + 4096 * k_mid;                              // position inside the 65 536-long top-level array
         C x[RT];
 #pragma unroll
@@ -400,7 +400,7 @@ __global__ void __launch_bounds__(256, 3) caf_large_spread2(const LargeArgs<T> a
             double2 tw = make_double2(1.0, 0.0);
 #pragma unroll
             for (int s_ = 0; s_ < RT; ++s_) {
-                tile[((r * RT + s_) * 16 + k_mid) * 16 + jj] = mul_by_d<T>(v[s_], tw);
+                tile[((r * RT + s_) * 16 + k_mid) * J + jj] = mul_by_d<T>(v[s_], tw);
                 tw = cmul_d(tw, om);
             }
         }
@@ -408,11 +408,11 @@ __global__ void __launch_bounds__(256, 3) caf_large_spread2(const LargeArgs<T> a
     __syncthreads();
     {
         // ---- stage 2: column (r, s_top, m): 16-point DFT over k_mid, twiddle W_65536^{m s_mid} ----
-        const int col = tid >> 4;                                    // r * RT + s_top
+        const int col = tid / J;                                    // r * RT + s_top
         if (col < 2 * RT) {
             C v[16];
 #pragma unroll
-            for (int k = 0; k < 16; ++k) v[k] = tile[(col * 16 + k) * 16 + jj];
+            for (int k = 0; k < 16; ++k) v[k] = tile[(col * 16 + k) * J + jj];
             fft16<T, false>(v);
             const double2 om2 = cpow_small(s_g[jj], 2 * RT);         // e^{-j 2 pi m/65536} = (e^{-j 2 pi m/N})^{N/65536}, N = 2 RT 65536
             double2 tw = make_double2(1.0, 0.0);
@@ -426,25 +426,25 @@ __global__ void __launch_bounds__(256, 3) caf_large_spread2(const LargeArgs<T> a
     }
 }
 
-template <typename T, int RT>
-__global__ void __launch_bounds__(256, 3) caf_large_gather2(const LargeArgs<T> a) {
+template <typename T, int RT, int J>
+__global__ void __launch_bounds__(16 * J, J == 16 ? 3 : J == 8 ? 6 : 1) caf_large_gather2(const LargeArgs<T> a) {
     using C = cx<T>;
     extern __shared__ __align__(16) unsigned char smem_raw2[];
     C* tile = reinterpret_cast<C*>(smem_raw2);                       // [r][s_top][k_mid][jj]
-    __shared__ double sv[8];
-    __shared__ int si[8];
+    __shared__ double sv[16];
+    __shared__ int si[16];
     // per-block tables: s_g[jj] = e^{+j 2 pi m/N}, s_k[k] = e^{+j 2 pi 4096 k/N}, s_gstep = e^{+j 2 pi 65536/N}
-    __shared__ double2 s_g[16], s_k[16], s_gstep;
+    __shared__ double2 s_g[J], s_k[16], s_gstep;
     __shared__ unsigned int s_last;
-    const int tid = threadIdx.x, jj = tid & 15, row = blockIdx.y;
-    const int m = blockIdx.x * 16 + jj;
+    const int tid = threadIdx.x, jj = tid % J, row = blockIdx.y;
+    const int m = blockIdx.x * J + jj;
     const int Lp = a.N / 2, L = a.L;
-    if (tid < 16) s_g[tid] = root_of_unity(blockIdx.x * 16 + tid, a.N, 1.0);
-    else if (tid < 32) s_k[tid - 16] = root_of_unity(4096LL * (tid - 16), a.N, 1.0);
-    else if (tid == 32) s_gstep = root_of_unity(65536, a.N, 1.0);
+    if (tid < J) s_g[tid] = root_of_unity(blockIdx.x * J + tid, a.N, 1.0);
+    else if (tid < J + 16) s_k[tid - J] = root_of_unity(4096LL * (tid - J), a.N, 1.0);
+    else if (tid == J + 16) s_gstep = root_of_unity(65536, a.N, 1.0);
     {
         // ---- stage A: column (r, s_top, m): inverse 16-point DFT over s_mid, conjugate top-level twiddle ----
-        const int col = tid >> 4;
+        const int col = tid / J;
         C v[16];
         const C* src = a.wbuf + ((size_t)(row * 2 * RT + (col < 2 * RT ? col : 0)) * 16) * kL0 + m;
         if (col < 2 * RT) {
@@ -461,7 +461,7 @@ __global__ void __launch_bounds__(256, 3) caf_large_gather2(const LargeArgs<T> a
             const double2 step = cpow_small(cmul_d(g1, g1), s_top);
 #pragma unroll
             for (int k = 0; k < 16; ++k) {
-                tile[(col * 16 + k) * 16 + jj] = mul_by_d<T>(v[k], tw);
+                tile[(col * 16 + k) * J + jj] = mul_by_d<T>(v[k], tw);
                 tw = cmul_d(tw, step);
             }
         }
@@ -471,14 +471,14 @@ __global__ void __launch_bounds__(256, 3) caf_large_gather2(const LargeArgs<T> a
     int bidx = 0;
     {
         // ---- stage B: column (m, k_mid): inverse RT-point DFT of both pipelines, radix-2 across them, |.|^2, argmax ----
-        const int k_mid = tid >> 4;
+        const int k_mid = tid / J;
         const int j = m + 4096 * k_mid;
         const long long nout = 2LL * L, skip = (long long)a.N - nout;
         C a0[16], a1[16];
 #pragma unroll
         for (int s_ = 0; s_ < RT; ++s_) {
-            a0[s_] = tile[((0 * RT + s_) * 16 + k_mid) * 16 + jj];
-            a1[s_] = tile[((1 * RT + s_) * 16 + k_mid) * 16 + jj];
+            a0[s_] = tile[((0 * RT + s_) * 16 + k_mid) * J + jj];
+            a1[s_] = tile[((1 * RT + s_) * 16 + k_mid) * J + jj];
         }
         dft_small<T, RT, true>(a0);
         dft_small<T, RT, true>(a1);
@@ -513,9 +513,9 @@ __global__ void __launch_bounds__(256, 3) caf_large_gather2(const LargeArgs<T> a
     }
     if ((tid & 31) == 0) { sv[tid >> 5] = best; si[tid >> 5] = bidx; }
     __syncthreads();
-    const int nparts = kL0 / 16;                                     // blocks per row
+    const int nparts = kL0 / J;                                      // blocks per row
     if (tid == 0) {
-        for (int q = 1; q < 8; ++q) amax_take<double>(best, bidx, sv[q], si[q]);
+        for (int q = 1; q < (16 * J) / 32; ++q) amax_take<double>(best, bidx, sv[q], si[q]);
         a.part_val[(size_t)row * nparts + blockIdx.x] = best;
         a.part_idx[(size_t)row * nparts + blockIdx.x] = bidx;
         __threadfence();
