@@ -33,6 +33,10 @@ sys.path.insert(0, ROOT)
 FS = 48000
 L = 4096
 N = 2 * L
+# the reference's published figure for exactly this metric (one 400 x 8192 fp64 surface +
+# find_peak, README.md:36, rust RustFFT + threadpool on an R9-3900X, 12C/24T): 28 ms = 117.0 Mcell/s.  Other hardware.
+PUBLISHED_CELLS_PER_S = 400 * N / 28e-3
+PUBLISHED_NOTE = "BASELINE.md: rust RustFFT + threadpool, 28 ms per surface on an R9-3900X (README.md:36)"
 
 
 _JSON_FD = None
@@ -200,7 +204,8 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": "CAF cells/s (400x8192 fp64 surface + peak)", "value": value, "unit": "cells/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": value / PUBLISHED_CELLS_PER_S,
+        "vs_baseline_note": PUBLISHED_NOTE, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "cfg1: 400 doppler x 8192 delay fp64 CAF surface + peak, chirp_0 pair (seed 0), fs=48000"},
         "cpu_baseline": {"value": value, "unit": "cells/s", "cores": threads, "kind": "port",
                          "sample": f"{args.steps} whole surfaces, oracle port of CafRustFFTThreadpool (3 FFTs/row), {threads} threads"},
@@ -381,7 +386,9 @@ def run_b200(args):
             "metric": "CAF cells/s (400x8192 %s surface + peak)" % ("fp32" if f32 else "fp64"),
             "value": value, "unit": "cells/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": total_ms_max / args.steps, "ms_per_surface": total_ms_max / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None if f32 else value / PUBLISHED_CELLS_PER_S,
+            "vs_baseline_note": "no published complex64 figure" if f32 else PUBLISHED_NOTE,
             "dtype": "f32" if f32 else "f64", "data": "synthetic",
             "config": {"workload": ("cfg2" if f32 else "cfg1") + ": 400 doppler x 8192 delay CAF surface + peak per step per GPU, "
                        "utils/generate.py seed-0 pairs (rank r uses chirp_r), fs=48000",
