@@ -372,6 +372,31 @@ def run_b200(args):
            "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
            "peak": [pk_h.freq_hz, int(pk_h.delay_idx)]}
 
+    # ---- the same call without the surface crossing PCIe: caf_b200_peak_* (what caf_bench.rs's closure observes:
+    #      find_peak(caf_surface(..)) returns (freq, delay); CafSurfaceRow's fields are private, mod.rs:17-22) --------
+    peak_fn = getattr(lib, f"caf_b200_peak_{sfx}")
+    pk2 = _lib.Peak()
+
+    def step_peak():
+        rc = peak_fn(h.raw, needle_h.data_ptr(), hay_h.data_ptr(), L, freqs_h.data_ptr(), D, FS,
+                     C.cast(C.byref(pk2), C.c_void_p))
+        if rc != 0:
+            raise RuntimeError(lib.caf_b200_last_error().decode())
+
+    for _ in range(3):
+        step_peak()
+    barrier()
+    evs = timed_pass(step_peak, e2e_steps)
+    barrier()
+    pk_ms = float(sum(a.elapsed_time(b) for a, b in evs))
+    t = torch.tensor([pk_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_peak = {"value": world * cells_step * e2e_steps / (float(t.item()) * 1e-3), "unit": "cells/s",
+                "ms_per_step": float(t.item()) / e2e_steps, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 32,
+                "peak": [pk2.freq_hz, int(pk2.delay_idx)],
+                "note": "host inputs in, (freq, delay) out: the surface stays on the GPU (caf_b200_peak_*)"}
+
     # ---- CPU baseline beside it (rank 0, N = 1 only) ----------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -396,7 +421,7 @@ def run_b200(args):
                        "l2": "flushed between timed steps (256 MiB overwrite); each step timed with its own CUDA event pair",
                        "parallelism": f"pairs sharded x{world}, no data-path collective",
                        "host_cpus_bound_to_gpu": numa},
-            "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+            "e2e": e2e, "e2e_peak_only": e2e_peak, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
             "clocks": sampler.summary(),
             "check": {"peak_freq_hz": peak_freq, "peak_delay": peak_delay},
             "step_ms_min_med_max": [float(per_step.min()), float(np.median(per_step)), float(per_step.max())],
