@@ -1,0 +1,25 @@
+"""Small end-to-end pass over every kernel family for compute-sanitizer (memcheck / racecheck):
+   compute-sanitizer --tool memcheck python scripts/sanitize_check.py"""
+import os, sys
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from caf_cookoff_b200 import (CafB200, Xcor, batch_arrays, generate as G, read_file_c64, surface_arrays, surface_layout, api)
+D = os.path.join(ROOT, "tests/golden/data/")
+needle = read_file_c64(D + "chirp_0_raw.c64"); hay = read_file_c64(D + "chirp_0_T+202samp_F+69.25Hz.c64")[:4096]
+f = np.array([68.5, 69.0, 69.25, 70.0, -3.0])
+s, pi, pv, pk = surface_arrays(needle, hay, f, 48000); print("rows", pk.freq_hz, pk.delay_idx)
+surface_arrays(needle, hay, np.linspace(-100, 100, 300, endpoint=False), 48000)           # pipelined host path, 2-3 rows per CTA
+surface_arrays(needle[:1000], hay[:1000], f, 48000)
+surface_arrays(needle, hay, f, 48000, variant=api._Variant32)
+batch_arrays(np.stack([needle, needle]), np.stack([hay, hay]), f, 48000)
+CafB200.apply_freq_shift(needle[:777], 12.5, 48000)
+Xcor.new(8192).run(np.concatenate([needle, needle]), np.concatenate([hay, hay])); Xcor.new(1000).run(needle[:1000], hay[:1000])
+surface_layout(needle, hay, f, 48000, 1); surface_layout(needle, hay, f, 48000, 2)
+for l in (5000, 20001):                                                                   # one level, R = 2 and 8
+    n2, h2 = G.as_inputs(G.pair(0, seed=0, chirp_length=l))
+    surface_arrays(n2, h2, f[:3], 48000)
+    os.environ["CAF_B200_CLUSTER"] = "1"; surface_arrays(n2, h2, f[:3], 48000); del os.environ["CAF_B200_CLUSTER"]
+n3, h3 = G.as_inputs(G.pair(0, seed=0, chirp_length=100000))                              # two levels, fused kernels
+_, pi3, _, pk3 = surface_arrays(n3, h3, f[:2], 48000, want_surface=False); print("two-level", pk3.freq_hz, pk3.delay_idx)
+print("sanitize pass done")
