@@ -80,6 +80,17 @@ def test_long_rows_fp32():
     assert int(pidx[2]) == int(opidx[2])
 
 
+def test_two_level_rows_fp32():
+    """complex64 through the fused two-level kernels (N = 2^18: top radix 2, middle radix 16)."""
+    needle, hay = _pair(100000)
+    shifts = np.array([0.0, 69.25])
+    surf, pidx, pval, pk = caf.surface_arrays(needle, hay, shifts, FS, variant=api._Variant32)
+    osurf, opidx, _ = NO.caf_surface(needle, hay, shifts, FS, direct_phasor=True)
+    assert surf.dtype == np.float32 and surf.shape == (2, 200000)
+    assert rel_max(surf.astype(np.float64), osurf) <= 1e-4
+    assert int(pidx[1]) == int(opidx[1])
+
+
 def test_long_row_delay_and_doppler_properties():
     """The generator puts s1 `lag` samples and `foffset` Hz away from s0: the peak must land there."""
     p = G.pair(0, seed=3, chirp_length=65536)
