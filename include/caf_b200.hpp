@@ -150,6 +150,42 @@ struct GoSibling {
     }
 };
 
+// Doppler rows sharded over one process per GPU (mod.rs:185's par_iter with GPUs for workers): the library's own NCCL
+// communicator.  Rank 0 makes the 128-byte id (ShardedCaf::unique_id) and hands it to the other ranks out of band.
+class ShardedCaf {
+    caf_b200_comm comm_ = nullptr;
+public:
+    static std::vector<unsigned char> unique_id() {
+        std::vector<unsigned char> id(CAF_B200_NCCL_ID_BYTES);
+        check(caf_b200_comm_unique_id(id.data()));
+        return id;
+    }
+    ShardedCaf(int world, int rank, const std::vector<unsigned char>& id) {
+        if (id.size() != CAF_B200_NCCL_ID_BYTES) throw Panic("NCCL id must be 128 bytes");
+        check(caf_b200_comm_create(thread_handle(), world, rank, id.data(), &comm_));
+    }
+    ShardedCaf(const ShardedCaf&) = delete;
+    ShardedCaf& operator=(const ShardedCaf&) = delete;
+    ~ShardedCaf() { if (comm_) caf_b200_comm_destroy(comm_); }
+    std::pair<std::size_t, std::size_t> shard(std::size_t n) const {
+        std::size_t lo = 0, hi = 0;
+        check(caf_b200_comm_shard(comm_, n, &lo, &hi));
+        return {lo, hi};
+    }
+    // this rank's rows [lo, hi) of the surface (row-major, 2l cells each) and the GLOBAL find_peak answer
+    std::pair<std::vector<double>, std::pair<double, std::size_t>> caf_surface_peak(
+        const std::vector<Complex64>& needle, const std::vector<Complex64>& haystack, const std::vector<double>& freqs_hz, uint32_t fs) const {
+        if (needle.size() != haystack.size()) throw Panic("assertion failed: a.len() == self.n (xcor_rustfft.rs:54-55)");
+        const auto [lo, hi] = shard(freqs_hz.size());
+        std::vector<double> rows((hi - lo) * 2 * needle.size());
+        caf_b200_peak pk;
+        check(caf_b200_surface_sharded_f64(thread_handle(), comm_, reinterpret_cast<const caf_c128*>(needle.data()),
+                                           reinterpret_cast<const caf_c128*>(haystack.data()), needle.size(), freqs_hz.data(),
+                                           freqs_hz.size(), fs, rows.data(), &pk));
+        return {std::move(rows), {pk.freq_hz, (std::size_t)pk.delay_idx}};
+    }
+};
+
 // utils.rs:10-35: packed little-endian f32 I/Q -> Complex64
 inline std::vector<Complex64> read_file_c64(const std::string& filename) {
     std::ifstream f(filename, std::ios::binary);
