@@ -275,27 +275,36 @@ __global__ void __launch_bounds__(256, R <= 8 ? 3 : 1) caf_large_gather_top(cons
     __syncthreads();
     const double2 gstep = s_gstep;
     T* orow = a.surface ? a.surface + (size_t)row * nout : nullptr;
-    double best = 0.0;
-    int bidx = 0;
+    // two running maxima: the cells of the lower half (n) and of the upper half (n + N/2) are each visited in ascending
+    // order, so a strict > keeps the first maximum (mod.rs:148); every upper index is above every lower one
+    const bool full = (nout == (long long)a.N);              // L = N/2: every cell is an output cell, no index remap
+    const int iL = (int)L, iN = a.N, iskip = (int)skip;
+    T best0 = (T)0, best1 = (T)0;
+    int bidx0 = 0, bidx1 = 0;
 #pragma unroll
     for (int rho = 0; rho < R; ++rho) {
         const C A = a0[rho];
         const C B = mul_by_d<T>(a1[rho], gph);
         gph = cmul_d(gph, gstep);
-        const long long n = (long long)j + (long long)inner * rho;
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            const C y = half ? csub(A, B) : cadd(A, B);
-            const long long kp = n + (long long)half * Lp;
-            const T mag = y.x * y.x + y.y * y.y;                        // norm_sqr, mod.rs:147
-            long long k = -1;
-            if (kp <= L) k = kp; else if (kp > (long long)a.N - L) k = kp - skip;   // the reference's 2L-cell layout
-            if (k >= 0 && k < nout) {
-                if (orow) orow[k] = mag;
-                amax_take<double>(best, bidx, (double)mag, (int)k);
-            }
+        const int n = j + inner * rho;
+        const C y0 = cadd(A, B), y1 = csub(A, B);
+        const T m0 = y0.x * y0.x + y0.y * y0.y, m1 = y1.x * y1.x + y1.y * y1.y;      // norm_sqr, mod.rs:147
+        if (full) {
+            if (orow) { orow[n] = m0; orow[n + Lp] = m1; }
+            if (m0 > best0) { best0 = m0; bidx0 = n; }
+            if (m1 > best1) { best1 = m1; bidx1 = n + Lp; }
+        } else {
+            // the reference's 2L-cell layout: cell kp <= L stays, kp > N - L moves down by N - 2L, the rest is padding
+            const int kp1 = n + Lp;
+            if (n <= iL) { if (orow) orow[n] = m0; if (m0 > best0) { best0 = m0; bidx0 = n; } }
+            else if (n > iN - iL) { if (orow) orow[n - iskip] = m0; if (m0 > best0) { best0 = m0; bidx0 = n - iskip; } }
+            if (kp1 <= iL) { if (orow) orow[kp1] = m1; if (m1 > best1) { best1 = m1; bidx1 = kp1; } }
+            else if (kp1 > iN - iL) { if (orow) orow[kp1 - iskip] = m1; if (m1 > best1) { best1 = m1; bidx1 = kp1 - iskip; } }
         }
     }
+    double best = (double)best0;
+    int bidx = bidx0;
+    if (best1 > best0) { best = (double)best1; bidx = bidx1; }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
         double ov = __shfl_xor_sync(0xffffffffu, best, off);
@@ -485,25 +494,34 @@ __global__ void __launch_bounds__(16 * J, J == 16 ? 3 : J == 8 ? 6 : 1) caf_larg
         double2 gph = cmul_d(s_g[jj], s_k[k_mid]);                   // W_N^{-n}, n = j + 65536 rho
         const double2 gstep = s_gstep;
         T* orow = a.surface ? a.surface + (size_t)row * nout : nullptr;
+        // two running maxima (lower half n, upper half n + N/2), each visited in ascending order: strict > keeps the first
+        const bool full = (nout == (long long)a.N);          // L = N/2: every cell is an output cell, no index remap
+        const int iL = (int)L, iN = a.N, iskip = (int)skip;
+        T best0 = (T)0, best1 = (T)0;
+        int bidx0 = 0, bidx1 = 0;
 #pragma unroll
         for (int rho = 0; rho < RT; ++rho) {
             const C A = a0[rho];
             const C B = mul_by_d<T>(a1[rho], gph);
             gph = cmul_d(gph, gstep);
-            const long long n = (long long)j + 65536LL * rho;
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                const C y = half ? csub(A, B) : cadd(A, B);
-                const long long kp = n + (long long)half * Lp;
-                const T mag = y.x * y.x + y.y * y.y;                 // norm_sqr, mod.rs:147
-                long long k = -1;
-                if (kp <= L) k = kp; else if (kp > (long long)a.N - L) k = kp - skip;   // the reference's 2L-cell layout
-                if (k >= 0 && k < nout) {
-                    if (orow) orow[k] = mag;
-                    amax_take<double>(best, bidx, (double)mag, (int)k);
-                }
+            const int n = j + 65536 * rho;
+            const C y0 = cadd(A, B), y1 = csub(A, B);
+            const T m0 = y0.x * y0.x + y0.y * y0.y, m1 = y1.x * y1.x + y1.y * y1.y;  // norm_sqr, mod.rs:147
+            if (full) {
+                if (orow) { orow[n] = m0; orow[n + Lp] = m1; }
+                if (m0 > best0) { best0 = m0; bidx0 = n; }
+                if (m1 > best1) { best1 = m1; bidx1 = n + Lp; }
+            } else {
+                // the reference's 2L-cell layout: cell kp <= L stays, kp > N - L moves down by N - 2L, the rest is padding
+                const int kp1 = n + Lp;
+                if (n <= iL) { if (orow) orow[n] = m0; if (m0 > best0) { best0 = m0; bidx0 = n; } }
+                else if (n > iN - iL) { if (orow) orow[n - iskip] = m0; if (m0 > best0) { best0 = m0; bidx0 = n - iskip; } }
+                if (kp1 <= iL) { if (orow) orow[kp1] = m1; if (m1 > best1) { best1 = m1; bidx1 = kp1; } }
+                else if (kp1 > iN - iL) { if (orow) orow[kp1 - iskip] = m1; if (m1 > best1) { best1 = m1; bidx1 = kp1 - iskip; } }
             }
         }
+        best = (double)best0; bidx = bidx0;
+        if (best1 > best0) { best = (double)best1; bidx = bidx1; }
     }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
