@@ -48,6 +48,27 @@ if len(src) > 2:
     for r in data:
         for i, x in stalls: tot[x] += int(r[i] or 0)
     lines.append("== warp-state samples over the whole kernel: " + ", ".join(f"{k[6:]} {v}" for k, v in tot.most_common(9)))
+    # row loop vs everything else: an instruction of the loop runs once per (row, warp) -- 400 rows x 8 or 16 warps --
+    # while set-up / prologue / tail code runs once per warp and CTA
+    import re
+    def fl(x):
+        try: return float(x)
+        except ValueError: return 0.0
+    loop = [r for r in data if fl(r[iexe]) >= 3000]
+    rest = [r for r in data if fl(r[iexe]) < 3000]
+    for name, part in (("row loop", loop), ("set-up, prologue, H exchange, tail", rest)):
+        c = collections.Counter()
+        for r in part:
+            for i, x in stalls: c[x] += int(r[i] or 0)
+        n = sum(int(r[isamp] or 0) for r in part); t = sum(c.values()) or 1
+        lines.append(f"== {name}: {n} samples ({100.0 * n / max(1, sum(int(r[isamp] or 0) for r in data)):.0f} % of the kernel): "
+                     + ", ".join(f"{k[6:]} {100.0 * v / t:.0f}%" for k, v in c.most_common(9)))
+    ops = collections.Counter()
+    for r in loop:
+        m = re.match(r"\s*(@!?U?P\d+\s+)?([A-Z0-9_]+)", r[isrc])
+        if m: ops[m.group(2)] += fl(r[iexe])
+    lines.append("== row loop, instructions per warp and row (executions / 6400): "
+                 + ", ".join(f"{k} {v / 6400:.0f}" for k, v in ops.most_common(12)))
     lines.append("== top instructions by samples (samples, executions, SASS, top stall)")
     for r in sorted(data, key=lambda r: -int(r[isamp] or 0))[:15]:
         st = sorted(((x, int(r[i] or 0)) for i, x in stalls), key=lambda t: -t[1])[0]
