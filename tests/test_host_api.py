@@ -62,3 +62,43 @@ def test_length_mismatch_panics_before_any_gpu_work():
         caf.Xcor.new(8).run(np.zeros(8, complex), np.zeros(7, complex))
     with pytest.raises(caf.CafPanic):
         caf.CafRustFFTIter.caf_surface(np.zeros(0, complex), np.zeros(0, complex), [1.0], 48000)  # xcor_mag[0]
+
+
+def test_peak_pack_resolve_matches_find_peak_model():
+    """caf_b200_peak_pack / _resolve (pure host helpers) against a direct model of find_peak (mod.rs:31-42) over the
+    concatenated rows of all ranks: strict > from a dummy 0.0 row, so the first row holding the maximum wins, a rank
+    whose shard found nothing contributes nothing, and an all-zero surface resolves to the dummy row."""
+    from hypothesis import given, settings, strategies as st
+    from caf_cookoff_b200 import _lib, api
+
+    vals = st.sampled_from([0.0, 1.0, 2.5, 2.5, 7.0, 7.0, 1e-300, 3.0])
+
+    @settings(max_examples=200, deadline=None)
+    @given(st.lists(st.lists(st.tuples(vals, st.integers(0, 8191)), min_size=0, max_size=5), min_size=1, max_size=8))
+    def check(shards):
+        words, rows, off = [], [], 0
+        for shard in shards:
+            # this rank's own find_peak over its rows
+            best, brow, bdelay = 0.0, None, 0
+            for r, (v, dly) in enumerate(shard):
+                rows.append((v, dly))
+                if v > best:
+                    best, brow, bdelay = v, r, dly
+            pk = _lib.Peak()
+            if brow is None:
+                pk.value, pk.freq_hz, pk.doppler_idx, pk.delay_idx = 0.0, 0.0, api.UINT64_MAX, 0
+            else:
+                pk.value, pk.freq_hz, pk.doppler_idx, pk.delay_idx = best, float(off + brow), brow, bdelay
+            words.append(api.peak_pack(pk, off))
+            off += len(shard)
+        got = api.peak_resolve(np.stack(words))
+        best, brow = 0.0, None
+        for r, (v, dly) in enumerate(rows):
+            if v > best:
+                best, brow = v, r
+        if brow is None:
+            assert got.doppler_idx == api.UINT64_MAX and got.value == 0.0 and got.delay_idx == 0
+        else:
+            assert (got.value, int(got.doppler_idx), int(got.delay_idx), got.freq_hz) == (best, brow, rows[brow][1], float(brow))
+
+    check()
