@@ -335,6 +335,20 @@ def run_b200(args):
                 "peak_source": "MEASURED_PEAKS.json (measured)" if mp else "fallback 6650 GB/s"},
         "step_share": {"spectrum_ms": float(np.mean(spec_ms)), "rows_ms": rows_avg_ms, "peak_ms": float(np.mean(peak_ms))},
     }
+    # the other roofline the north star names: shared memory.  A row moves every value of its two pipelines through the
+    # exchange fabric 4 times each way plus the radix-2 mailbox: 72 stores and 72 loads of one complex value per thread
+    # (DESIGN.md section 3); nominal peak 128 B/clk per SM at the SM clock.
+    try:
+        sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
+        sm_hz = 1e6 * float(sampler.max_mhz or (mp or {}).get("sm_max_mhz", 1965.0))
+        smem_bytes_row = 512 * 144 * (8 if f32 else 16)
+        smem_achieved = D * smem_bytes_row / (rows_avg_ms * 1e-3) / 1e12
+        smem_peak = sm_count * 128.0 * sm_hz / 1e12
+        roofline["smem"] = {"achieved": smem_achieved, "peak": smem_peak, "unit": "TB/s", "frac": smem_achieved / smem_peak,
+                            "bytes_per_row": smem_bytes_row,
+                            "note": "nominal 128 B/clk/SM; measured LDS.128 runs at 64 B/clk, STS.128 at 112 (scripts/micro/mio_cost.cu)"}
+    except Exception as e:      # never let the extra figure break the bench line
+        roofline["smem"] = {"error": repr(e)}
 
     # ---- e2e: the host-pointer C ABI with pinned host buffers, H2D + D2H inside the timed region ----------
     needle_h = torch.from_numpy(needle.astype(cdt)).pin_memory()
