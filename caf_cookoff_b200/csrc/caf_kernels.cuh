@@ -1045,6 +1045,12 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
             }
         }
     }
+#ifdef CAF_TRACE
+    if (a.trace && tid == 0) {   // the very end of this CTA, after the fused find_peak tail
+        long long g2; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g2));
+        a.trace[(((long long)blockIdx.x * 16 + 0) * 8 + 0) * 32 + 29] = g2;
+    }
+#endif
 }
 
 // ---------------------------------------------------------------------------------------------
