@@ -167,6 +167,29 @@ def test_all_zero_and_empty_inputs():
         caf.CafRustFFTIterRayon.caf_surface(z[:0], z[:0], [1.0], FS)
 
 
+@pytest.mark.parametrize("l", [1000, 4096, 5000])
+def test_nan_sample_never_wins(l):
+    """One NaN sample reaches every cell of every row through the transforms.  `val > max` is false for NaN, so each
+    row keeps xcor_peak_idx = 0, xcor_peak_val = 0.0 (mod.rs:143-150) and find_peak returns its dummy row
+    (mod.rs:32-41) -- on short rows, on ragged lengths and on the long-row kernels alike."""
+    rng = np.random.default_rng(l)
+    needle = rng.standard_normal(l) + 1j * rng.standard_normal(l)
+    hay = rng.standard_normal(l) + 1j * rng.standard_normal(l)
+    freqs = np.array([-3.0, 0.0, 7.5])
+    for poisoned in ("needle", "haystack"):
+        n2, h2 = needle.copy(), hay.copy()
+        (n2 if poisoned == "needle" else h2)[l // 3] = complex(np.nan, 0.0)
+        surf, pidx, pval, pk = caf.surface_arrays(n2, h2, freqs, FS)
+        assert np.isnan(surf).all()
+        assert list(pidx) == [0, 0, 0] and list(pval) == [0.0, 0.0, 0.0]
+        assert (pk.value, pk.freq_hz, int(pk.delay_idx), int(pk.doppler_idx)) == (0.0, 0.0, 0, api.UINT64_MAX)
+        if l == 4096:   # (the oracle's O(n^2) long-double DFT for other lengths is x87 code: minutes on NaN operands)
+            osurf, opidx, opval = O.caf_surface(n2, h2, freqs, FS)
+            assert np.isnan(osurf).all() and list(opidx) == [0, 0, 0] and list(opval) == [0.0, 0.0, 0.0]
+            assert O.find_peak(freqs, opidx, opval) == (0.0, 0)
+        assert caf.CafB200.find_peak(caf.CafB200.caf_surface(n2, h2, freqs, FS)) == (0.0, 0)
+
+
 def test_length_errors_and_unsupported_sizes():
     z = np.zeros(16, dtype=complex)
     with pytest.raises(caf.CafPanic):
