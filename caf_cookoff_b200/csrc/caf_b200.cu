@@ -229,6 +229,7 @@ template <typename T, int R>
 cudaError_t launch_large_top_rt(caf_b200_handle h, const caf::LargeArgs<T>& a, bool gather) {
     dim3 grid((unsigned)(a.inner_top / 256), (unsigned)a.rows);
     if (!gather) caf::caf_large_spread_top<T, R><<<grid, 256, 0, h->stream>>>(a);
+    else if (a.cplx) caf::caf_large_gather_top<T, R, true><<<grid, 256, 0, h->stream>>>(a);
     else caf::caf_large_gather_top<T, R><<<grid, 256, 0, h->stream>>>(a);
     h->launches++;
     return cudaGetLastError();
@@ -261,9 +262,11 @@ cudaError_t launch_large_fused_rt(caf_b200_handle h, const caf::LargeArgs<T>& a,
         cudaError_t e;
         if ((e = cudaFuncSetAttribute(caf::caf_large_spread2<T, RT, J>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
         if ((e = cudaFuncSetAttribute(caf::caf_large_gather2<T, RT, J>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(caf::caf_large_gather2<T, RT, J, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
         configured = true;
     }
     if (!gather) caf::caf_large_spread2<T, RT, J><<<grid, 16 * J, smem, h->stream>>>(a);
+    else if (a.cplx) caf::caf_large_gather2<T, RT, J, true><<<grid, 16 * J, smem, h->stream>>>(a);
     else caf::caf_large_gather2<T, RT, J><<<grid, 16 * J, smem, h->stream>>>(a);
     h->launches++;
     return cudaGetLastError();
@@ -350,7 +353,7 @@ int large_chain(caf_b200_handle h, const caf::LargeArgs<T>& a) {
 template <typename T>
 int run_large_dev(caf_b200_handle h, const caf::cx<T>* needles, const caf::cx<T>* hays, size_t p, size_t l,
                   const double* freqs, size_t d, uint32_t fs, T* surface, T* rowval,
-                  unsigned long long* rowidx, caf::PeakOut* peaks) {
+                  unsigned long long* rowidx, caf::PeakOut* peaks, caf::cx<T>* cplx = nullptr) {
     using namespace caf;
     long long n = 16384;
     while ((size_t)n < 2 * l) n *= 2;
@@ -384,7 +387,7 @@ int run_large_dev(caf_b200_handle h, const caf::cx<T>* needles, const caf::cx<T>
     // drain at ~15 B/clk per SM, and the phases of a row are serialised by cluster barriers.  It is therefore opt-in:
     // CAF_B200_CLUSTER=1 in the environment (read per call).
     const char* cl_env = getenv("CAF_B200_CLUSTER");
-    const bool cluster = cl_env && cl_env[0] == '1' && !two && rtop <= 8;
+    const bool cluster = cl_env && cl_env[0] == '1' && !two && rtop <= 8 && !cplx;
     if (cluster) chunk = 1;                                    // scratch is only needed for the one H transform
     const int nparts = cluster ? rtop : inner / 256;
     const size_t peak_rows = cluster ? d : chunk;
@@ -426,6 +429,7 @@ int run_large_dev(caf_b200_handle h, const caf::cx<T>* needles, const caf::cx<T>
             const size_t c = (d - off < chunk) ? d - off : chunk;
             a.in = needles + pi * l; a.freqs = freqs + off; a.rows = (int)c;
             a.surface = surface ? surface + (pi * d + off) * 2 * l : nullptr;
+            a.cplx = cplx ? cplx + (pi * d + off) * (size_t)n : nullptr;
             a.row_peak_val = rv + pi * d + off; a.row_peak_idx = ri + pi * d + off;
             rc = large_chain<T, false>(h, a);
             if (rc) return rc;
@@ -686,11 +690,32 @@ int run_xcor(caf_b200_handle h, const caf::cx<T>* a_, const caf::cx<T>* b_, size
     if (!h) return fail(CAF_B200_EINVAL, "null handle");
     if (n && (!a_ || !b_ || !out)) return fail(CAF_B200_EINVAL, "null operand");
     if (n == 0) return CAF_B200_OK;
-    if (!(n == (size_t)kM || n <= (size_t)kL0))
-        return fail(CAF_B200_EUNSUPPORTED, "xcor: n must be 8192 or <= 4096 in this build");
+    if (n > (1u << 19))
+        return fail(CAF_B200_EUNSUPPORTED, "xcor: n > 2^19 (rows longer than 2^20 cells are not built)");
     CK(cudaSetDevice(h->device));
     cudaStream_t s = h->stream;
     CK(h->needle.ensure(sizeof(cx<T>) * n)); CK(h->hay.ensure(sizeof(cx<T>) * n));
+    if (n > (size_t)kL0 && n != (size_t)kM) {
+        // any other length: the linear correlation of the two n-sample signals through the long-row kernels (one row,
+        // no doppler shift, complex cells kept), folded to the circular one: c[k] = R(k) + R(k - n)
+        size_t big_n = 16384;
+        while (big_n < 2 * n) big_n *= 2;
+        CK(h->layout.ensure(sizeof(cx<T>) * (big_n + n)));
+        CK(h->freqs.ensure(sizeof(double)));
+        CK(cudaMemsetAsync(h->freqs.p, 0, sizeof(double), s));           // one row at 0.0 Hz: the phasor is exactly 1
+        CK(cudaMemcpyAsync(h->hay.p, a_, sizeof(cx<T>) * n, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(h->needle.p, b_, sizeof(cx<T>) * n, cudaMemcpyHostToDevice, s));
+        cx<T>* y = (cx<T>*)h->layout.p;
+        int rc = run_large_dev<T>(h, (const cx<T>*)h->needle.p, (const cx<T>*)h->hay.p, 1, n, (const double*)h->freqs.p, 1, 1u,
+                                  nullptr, nullptr, nullptr, nullptr, y);
+        if (rc) return rc;
+        caf_fold_circular_kernel<T><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(y, y + big_n, (int)n, (int)big_n);
+        h->launches++;
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(out, y + big_n, sizeof(cx<T>) * n, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        return CAF_B200_OK;
+    }
     CK(h->hperm.ensure(sizeof(cx<T>) * kM)); CK(h->scratch.ensure(sizeof(cx<T>) * (kM + n)));
     CK(cudaMemcpyAsync(h->hay.p, a_, sizeof(cx<T>) * n, cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(h->needle.p, b_, sizeof(cx<T>) * n, cudaMemcpyHostToDevice, s));
@@ -709,7 +734,7 @@ int run_xcor(caf_b200_handle h, const caf::cx<T>* a_, const caf::cx<T>* b_, size
         a.in = (const cx<T>*)h->needle.p; a.out = y;
         CK((launch_rows<T, kXcorHalf>(h, a, 1)));
         res = y + kM;
-        caf_fold_circular_kernel<T><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(y, res, (int)n);
+        caf_fold_circular_kernel<T><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(y, res, (int)n, kM);
         h->launches++;
         CK(cudaGetLastError());
     }

@@ -1160,14 +1160,14 @@ __global__ void caf_apply_shift_kernel(const cx<T>* __restrict__ in, cx<T>* __re
     }
 }
 
-// Circular correlation of length n < 8192 from the linear one computed with L = n:
-//   c[k] = R(k) + R(k - n) = y[k] + y[8192 - n + k]   (y = 8192-point row, complex)
+// Circular correlation of length n from the linear one computed with L = n in a row of big_n >= 2n cells:
+//   c[k] = R(k) + R(k - n) = y[k] + y[big_n - n + k]   (y = the complex row; big_n = 8192 for n <= 4096)
 template <typename T>
-__global__ void caf_fold_circular_kernel(const cx<T>* __restrict__ y, cx<T>* __restrict__ out, int n) {
+__global__ void caf_fold_circular_kernel(const cx<T>* __restrict__ y, cx<T>* __restrict__ out, int n, int big_n) {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k < n) {
         cx<T> a = y[k];
-        cx<T> b = (k == 0) ? mk<T>((T)0, (T)0) : y[kM - n + k];
+        cx<T> b = (k == 0) ? mk<T>((T)0, (T)0) : y[big_n - n + k];
         out[k] = cadd(a, b);
     }
 }

@@ -27,6 +27,7 @@ struct LargeArgs {
     cx<T>* wbuf;                       // [units][4096] scratch around the core (units = rows * 2 * N/8192)
     cx<T>* hbig;                       // [N/8192 * 2][16][256]  H in the core's per-thread order
     T* surface;                        // [rows][2L] or null
+    cx<T>* cplx;                       // standalone Xcor (xcor_rustfft.rs:51-78): [rows][N] complex cells before |.|^2, or null
     double* part_val;                  // [rows][nparts] partial row maxima (one per gather_top block)
     int* part_idx;
     unsigned int* row_ticket;          // [rows] zero-initialised tickets: the last gather block of a row folds its partials
@@ -250,7 +251,9 @@ __global__ void __launch_bounds__(256, 3) caf_large_gather_mid(const LargeArgs<T
 // gather_top: one thread per (row, j): inverse R-point DFT across s for both pipelines, radix-2 combine, |.|^2, argmax
 // ------------------------------------------------------------------------------------------------
 // (three blocks per SM for R <= 8: the kernel waits on its 2R loads, more warps in flight hide them)
-template <typename T, int R>
+// CPLX: the standalone-Xcor instantiation, which also keeps the complex cells (a.cplx); the surface kernels are
+// compiled without it so their code is untouched.
+template <typename T, int R, bool CPLX = false>
 __global__ void __launch_bounds__(256, R <= 8 ? 3 : 1) caf_large_gather_top(const LargeArgs<T> a) {
     using C = cx<T>;
     __shared__ double sv[8];
@@ -288,6 +291,7 @@ __global__ void __launch_bounds__(256, R <= 8 ? 3 : 1) caf_large_gather_top(cons
         gph = cmul_d(gph, gstep);
         const int n = j + inner * rho;
         const C y0 = cadd(A, B), y1 = csub(A, B);
+        if constexpr (CPLX) { C* oc = a.cplx + (size_t)row * (size_t)a.N; oc[n] = y0; oc[n + Lp] = y1; }
         const T m0 = y0.x * y0.x + y0.y * y0.y, m1 = y1.x * y1.x + y1.y * y1.y;      // norm_sqr, mod.rs:147
         if (full) {
             if (orow) { orow[n] = m0; orow[n + Lp] = m1; }
@@ -435,7 +439,7 @@ __global__ void __launch_bounds__(16 * J, J == 16 ? 3 : J == 8 ? 6 : 1) caf_larg
     }
 }
 
-template <typename T, int RT, int J>
+template <typename T, int RT, int J, bool CPLX = false>
 __global__ void __launch_bounds__(16 * J, J == 16 ? 3 : J == 8 ? 6 : 1) caf_large_gather2(const LargeArgs<T> a) {
     using C = cx<T>;
     extern __shared__ __align__(16) unsigned char smem_raw2[];
@@ -506,6 +510,7 @@ __global__ void __launch_bounds__(16 * J, J == 16 ? 3 : J == 8 ? 6 : 1) caf_larg
             gph = cmul_d(gph, gstep);
             const int n = j + 65536 * rho;
             const C y0 = cadd(A, B), y1 = csub(A, B);
+            if constexpr (CPLX) { C* oc = a.cplx + (size_t)row * (size_t)a.N; oc[n] = y0; oc[n + Lp] = y1; }
             const T m0 = y0.x * y0.x + y0.y * y0.y, m1 = y1.x * y1.x + y1.y * y1.y;  // norm_sqr, mod.rs:147
             if (full) {
                 if (orow) { orow[n] = m0; orow[n + Lp] = m1; }

@@ -110,7 +110,8 @@ int caf_b200_apply_shift_f32(caf_b200_handle h, const caf_c64* in, size_t n, dou
 
 /* ---- Xcor::run (xcor_rustfft.rs:51-78 / xcor_fftw.rs:51-78) ----------------------------------------
  * out = IFFT( FFT(a) * conj(FFT(b)) / n ), unnormalised transforms: the length-n CIRCULAR correlation
- * out[k] = sum_m a[(m+k) mod n] conj(b[m]).  n == 8192 or n <= 4096 in this build. */
+ * out[k] = sum_m a[(m+k) mod n] conj(b[m]).  Any n <= 2^19 (n <= 4096 and n == 8192 stay
+ * on chip; other lengths run one row of the long-row kernels and fold the linear correlation). */
 int caf_b200_xcor_f64(caf_b200_handle h, const caf_c128* a, const caf_c128* b, size_t n, caf_c128* out);
 int caf_b200_xcor_f32(caf_b200_handle h, const caf_c64* a, const caf_c64* b, size_t n, caf_c64* out);
 

@@ -194,9 +194,10 @@ def test_length_errors_and_unsupported_sizes():
     z = np.zeros(16, dtype=complex)
     with pytest.raises(caf.CafPanic):
         caf.CafB200.caf_surface(z, z[:15], [0.0], FS)
+    big = (1 << 19) + 1
     with pytest.raises(caf.CafError) as e:
-        caf.Xcor.new(5000).run(np.zeros(5000, complex), np.zeros(5000, complex))
-    assert e.value.status == -3      # CAF_B200_EUNSUPPORTED: standalone xcor is built for n = 8192 and n <= 4096
+        caf.Xcor.new(big).run(np.zeros(big, complex), np.zeros(big, complex))
+    assert e.value.status == -3      # CAF_B200_EUNSUPPORTED: rows longer than 2^20 cells are not built
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -220,6 +221,24 @@ def test_apply_freq_shift_f32():
     got = caf.CafB200F32.apply_freq_shift(x, -31.5, FS)
     assert got.dtype == np.complex64
     assert rel_max(got.astype(np.complex128), O.apply_freq_shift(x, -31.5, FS)) <= 1e-6
+
+
+@pytest.mark.parametrize("n", [4097, 5000, 16384, 70001, 1 << 19])
+def test_xcor_any_length(n):
+    """Xcor::new(n) plans any n (RustFFT): lengths other than 8192 and <= 4096 go through one row of the long-row kernels
+    (complex cells) and a fold of the linear correlation.  Checked against numpy's FFT form of xcor_rustfft.rs:58-76
+    (the C oracle's DFT for non-power-of-two n is O(n^2)) and, for the power of two, against the C oracle."""
+    rng = np.random.default_rng(n)
+    a = rng.normal(size=n) + 1j * rng.normal(size=n)
+    b = rng.normal(size=n) + 1j * rng.normal(size=n)
+    want = np.fft.ifft(np.fft.fft(a) * np.conj(np.fft.fft(b)) / n) * n
+    got = caf.Xcor.new(n).run(a, b)
+    assert got.shape == (n,) and rel_max(got, want) <= 1e-12
+    if n == 16384:
+        assert rel_max(got, O.xcor(a, b)) <= 1e-12
+    if n == 5000:      # the complex64 twin
+        got32 = api.XcorF32.new(n).run(a.astype(np.complex64), b.astype(np.complex64))
+        assert rel_max(got32.astype(np.complex128), want) <= 1e-5
 
 
 @pytest.mark.parametrize("n", [1, 2, 37, 1000, 4096, 8192])
