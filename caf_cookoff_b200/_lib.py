@@ -42,11 +42,15 @@ def build(force: bool = False, verbose: bool = False) -> str:
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         raise RuntimeError("nvcc not found: cannot build libcaf_b200.so (no prebuilt fallback exists)")
+    tmp = SO_PATH + ".tmp%d.so" % os.getpid()   # link next to the target, then rename: nobody sees a half-written library
     cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + [
-        "-o", SO_PATH, os.path.join(CSRC, "caf_b200.cu")]
+        "-o", tmp, os.path.join(CSRC, "caf_b200.cu")]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
+        if os.path.exists(tmp):
+            os.remove(tmp)
         raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    os.replace(tmp, SO_PATH)
     if verbose:
         print(res.stderr)
     return SO_PATH

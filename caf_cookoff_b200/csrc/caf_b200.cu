@@ -186,9 +186,24 @@ cudaError_t configure_kernel(int* occ_out) {
     return cudaSuccess;
 }
 
+// fused two-level kernels: tile of 2 * RT * 16 * J cells in dynamic shared memory.  Function attributes are per
+// device, so this runs for every handle (create_impl), not once per process.
+constexpr int kFusedJ = 16;
+template <typename T, int RT>
+cudaError_t configure_fused() {
+    const int smem = (int)(sizeof(caf::cx<T>) * 2 * RT * 16 * kFusedJ);
+    cudaError_t e;
+    if ((e = cudaFuncSetAttribute(caf::caf_large_spread2<T, RT, kFusedJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(caf::caf_large_gather2<T, RT, kFusedJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return e;
+    return cudaFuncSetAttribute(caf::caf_large_gather2<T, RT, kFusedJ, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+}
+
 template <typename T>
 cudaError_t configure_all(int* occ) {
     cudaError_t e;
+    if ((e = configure_fused<T, 2>()) != cudaSuccess) return e;
+    if ((e = configure_fused<T, 4>()) != cudaSuccess) return e;
+    if ((e = configure_fused<T, 8>()) != cudaSuccess) return e;
     if ((e = configure_kernel<T, caf::kSurface, true>(occ)) != cudaSuccess) return e;
     if ((e = configure_kernel<T, caf::kSurface, false>(nullptr)) != cudaSuccess) return e;
     if ((e = configure_kernel<T, caf::kSpectrumHalf>(nullptr)) != cudaSuccess) return e;
@@ -257,14 +272,6 @@ template <typename T, int RT, int J>
 cudaError_t launch_large_fused_rt(caf_b200_handle h, const caf::LargeArgs<T>& a, bool gather) {
     dim3 grid((unsigned)(caf::kL0 / J), (unsigned)a.rows);
     const size_t smem = sizeof(caf::cx<T>) * 2 * RT * 16 * J;
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e;
-        if ((e = cudaFuncSetAttribute(caf::caf_large_spread2<T, RT, J>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-        if ((e = cudaFuncSetAttribute(caf::caf_large_gather2<T, RT, J>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-        if ((e = cudaFuncSetAttribute(caf::caf_large_gather2<T, RT, J, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-        configured = true;
-    }
     if (!gather) caf::caf_large_spread2<T, RT, J><<<grid, 16 * J, smem, h->stream>>>(a);
     else if (a.cplx) caf::caf_large_gather2<T, RT, J, true><<<grid, 16 * J, smem, h->stream>>>(a);
     else caf::caf_large_gather2<T, RT, J><<<grid, 16 * J, smem, h->stream>>>(a);
@@ -276,9 +283,9 @@ cudaError_t launch_large_fused(caf_b200_handle h, const caf::LargeArgs<T>& a, bo
     // 16 positions per block (256-byte runs, 64 KB tile, three blocks per SM) measured best: 32 positions (one block per
     // SM) 44.2 ms against 40.9 ms on 2048 config-5 rows, 8 positions the same as 16
     switch (a.Rtop) {
-        case 2: return launch_large_fused_rt<T, 2, 16>(h, a, gather);
-        case 4: return launch_large_fused_rt<T, 4, 16>(h, a, gather);
-        case 8: return launch_large_fused_rt<T, 8, 16>(h, a, gather);
+        case 2: return launch_large_fused_rt<T, 2, kFusedJ>(h, a, gather);
+        case 4: return launch_large_fused_rt<T, 4, kFusedJ>(h, a, gather);
+        case 8: return launch_large_fused_rt<T, 8, kFusedJ>(h, a, gather);
         default: return cudaErrorInvalidValue;
     }
 }
