@@ -578,6 +578,12 @@ int run_batch_host(caf_b200_handle h, const caf::cx<T>* needles, const caf::cx<T
             h->h_peaks_cap = sizeof(PeakOut) * p;
         }
     }
+    // Experiment for round 2 (unmeasured, off unless CAF_B200_PEAK_ZEROCOPY=1): the kernels store the peaks straight into
+    // the pinned staging buffer (cudaMallocHost memory is device-addressable under unified addressing), which removes
+    // the 32-byte D2H copy and its DMA set-up from the peak-only call.
+    static const bool zc_env = [] { const char* e = getenv("CAF_B200_PEAK_ZEROCOPY"); return e && e[0] == '1'; }();
+    const bool peak_zero_copy = zc_env && peaks;
+    if (peak_zero_copy) d_pk = (PeakOut*)h->h_peaks;
     // One pair with the surface wanted on the host: the D2H copy (26 MB at PCIe speed, ~0.5 ms) dwarfs the kernels
     // (~50 us), so the rows are issued as a short head (one wave of CTAs) and the rest; the head's cells start
     // crossing PCIe on a second stream while the rest is still being computed.  find_peak then runs as its own
@@ -613,7 +619,7 @@ int run_batch_host(caf_b200_handle h, const caf::cx<T>* needles, const caf::cx<T
     }
     if (rowval && rows) CK(cudaMemcpyAsync(rowval, d_rv, sizeof(T) * rows, cudaMemcpyDeviceToHost, s));
     if (rowidx && rows) CK(cudaMemcpyAsync(rowidx, d_ri, sizeof(uint64_t) * rows, cudaMemcpyDeviceToHost, s));
-    if (peaks) CK(cudaMemcpyAsync(h->h_peaks, d_pk, sizeof(PeakOut) * p, cudaMemcpyDeviceToHost, s));
+    if (peaks && !peak_zero_copy) CK(cudaMemcpyAsync(h->h_peaks, d_pk, sizeof(PeakOut) * p, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     if (peaks)
         for (size_t i = 0; i < p; ++i) to_public(reinterpret_cast<PeakOut*>(h->h_peaks)[i], &peaks[i]);
