@@ -595,6 +595,11 @@ int run_batch_host(caf_b200_handle h, const caf::cx<T>* needles, const caf::cx<T
         if (!h->ev_head) CK(cudaEventCreateWithFlags(&h->ev_head, cudaEventDisableTiming));
         if (!h->ev_copy) CK(cudaEventCreateWithFlags(&h->ev_copy, cudaEventDisableTiming));
         const double* fq = (const double*)h->freqs.p;
+        // an error return below must not leave the head's DMA into the caller's buffer in flight
+        struct Drain {
+            cudaStream_t a, b; bool armed = true;
+            ~Drain() { if (armed) { cudaStreamSynchronize(a); cudaStreamSynchronize(b); } }
+        } drain{h->copy_stream, s};
         rc = run_batch_dev<T>(h, (const cx<T>*)h->needle.p, (const cx<T>*)h->hay.p, 1, l, fq, d0, fs, d_surface, d_rv, d_ri, nullptr);
         if (rc) return rc;
         CK(cudaEventRecord(h->ev_head, s));
@@ -611,6 +616,7 @@ int run_batch_host(caf_b200_handle h, const caf::cx<T>* needles, const caf::cx<T
         }
         CK(cudaMemcpyAsync(surface + d0 * n, d_surface + d0 * n, sizeof(T) * (d - d0) * n, cudaMemcpyDeviceToHost, s));
         CK(cudaStreamWaitEvent(s, h->ev_copy, 0));
+        drain.armed = false;      // from here on the final synchronise of s covers both streams
     } else {
         rc = run_batch_dev<T>(h, (const cx<T>*)h->needle.p, (const cx<T>*)h->hay.p, p, l, (const double*)h->freqs.p, d,
                               fs, d_surface, d_rv, d_ri, d_pk);
