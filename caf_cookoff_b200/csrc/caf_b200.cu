@@ -781,7 +781,7 @@ static int create_impl(int device, bool own_stream, void* cuda_stream, caf_b200_
     if (device < 0 || device >= ndev) return fail(CAF_B200_EINVAL, "device index out of range");
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device));
-    if (prop.major != 10)
+    if (prop.major != 10 || prop.minor != 0)   // sm_100a SASS is arch-specific: it does not load on sm_103 or sm_120 either
         return fail(CAF_B200_ENODEVICE, std::string("device is sm_") + std::to_string(prop.major * 10 + prop.minor) +
                                             ", this library carries sm_100a code only (no fallback)");
     CK(cudaSetDevice(device));
