@@ -464,7 +464,7 @@ int run_batch_dev(caf_b200_handle h, const caf::cx<T>* needles, const caf::cx<T>
         if (peaks) {
             std::vector<PeakOut> z(p);
             for (auto& q : z) { q.value = 0.0; q.freq_hz = 0.0; q.doppler_idx = ~0ull; q.delay_idx = 0; }
-            CK(cudaMemcpyAsync(peaks, z.data(), sizeof(PeakOut) * p, cudaMemcpyHostToDevice, h->stream));
+            CK(cudaMemcpyAsync(peaks, z.data(), sizeof(PeakOut) * p, cudaMemcpyDefault, h->stream));   // peaks may be pinned host memory
             CK(cudaStreamSynchronize(h->stream));
         }
         return CAF_B200_OK;
@@ -578,11 +578,12 @@ int run_batch_host(caf_b200_handle h, const caf::cx<T>* needles, const caf::cx<T
             h->h_peaks_cap = sizeof(PeakOut) * p;
         }
     }
-    // Experiment for round 2 (unmeasured, off unless CAF_B200_PEAK_ZEROCOPY=1): the kernels store the peaks straight into
-    // the pinned staging buffer (cudaMallocHost memory is device-addressable under unified addressing), which removes
-    // the 32-byte D2H copy and its DMA set-up from the peak-only call.
-    static const bool zc_env = [] { const char* e = getenv("CAF_B200_PEAK_ZEROCOPY"); return e && e[0] == '1'; }();
-    const bool peak_zero_copy = zc_env && peaks;
+    // A single pair's peak is stored by the kernel straight into the pinned staging buffer (cudaMallocHost memory is
+    // device-addressable under unified addressing): no 32-byte D2H copy and no DMA set-up on the call's tail.  Measured
+    // on B200, two A/B pairs on one box: peak-only call 82.3 / 82.8 us -> 74.5 / 77.9 us, surface call 550 / 549 us ->
+    // 541 / 542 us.  CAF_B200_PEAK_ZEROCOPY=0 keeps the copy; batches (p > 1) always use it.
+    static const bool zc_env = [] { const char* e = getenv("CAF_B200_PEAK_ZEROCOPY"); return !(e && e[0] == '0'); }();
+    const bool peak_zero_copy = zc_env && peaks && p == 1;
     if (peak_zero_copy) d_pk = (PeakOut*)h->h_peaks;
     // One pair with the surface wanted on the host: the D2H copy (26 MB at PCIe speed, ~0.5 ms) dwarfs the kernels
     // (~50 us), so the rows are issued as a short head (one wave of CTAs) and the rest; the head's cells start

@@ -26,7 +26,7 @@
  *    CAF_B200_FUSED2=0       two-level rows: the five-pass spread/gather chain instead of the fused kernels
  *    CAF_B200_CLUSTER=1      one-level long rows: the cluster / distributed-shared-memory kernel (measured slower)
  *    CAF_B200_PIPELINE=0     host surface calls: one launch + one D2H copy instead of head/rest overlap
- *    CAF_B200_PEAK_ZEROCOPY=1  host calls: kernels store the peaks straight into pinned host memory (experiment, unmeasured)
+ *    CAF_B200_PEAK_ZEROCOPY=0  single-pair host calls: copy the peak back instead of storing it into pinned host memory
  *    CAF_B200_NCCL_LIB=<so>  which libnccl to dlopen for caf_b200_comm_* (default: the loaded one, then libnccl.so.2)
  *
  * Sizes.  l = samples per input signal (needle and haystack must be equal length, as the reference's
