@@ -128,6 +128,35 @@ def test_random_inputs_and_odd_grid():
     assert (pk.freq_hz, int(pk.delay_idx)) == O.find_peak(shifts, opidx, opval) == (12.3, 37)
 
 
+def test_doppler_beyond_nyquist_and_extreme_sample_rates():
+    """`fs` is any u32 and `freq_shift` any f64 (mod.rs:46-65): shifts at and beyond fs/2 alias, fs = 1 and fs = 2^32 - 1
+    are legal.  The kernel reduces the phase n*f/fs exactly; the reference rounds 2*pi*f*(1/fs) once and accumulates
+    it, so the two drift apart by ~n*eps*|f/fs| -- far inside 1e-9 for the values here."""
+    rng = np.random.default_rng(77)
+    l = 4096
+    needle = rng.normal(size=l) + 1j * rng.normal(size=l)
+    hay = np.roll(needle, 37) * np.exp(2j * np.pi * 12.3 * np.arange(l) / FS)
+    aliases = [12.3, 12.3 + FS, 12.3 - FS]
+    shifts = np.array(aliases + [FS / 2.0, 30000.0, float(FS), -95987.7])
+    surf, pidx, pval, pk = caf.surface_arrays(needle, hay, shifts, FS)
+    osurf, opidx, opval = O.caf_surface(needle, hay, shifts, FS)
+    assert rel_max(surf, osurf) <= TOL64
+    assert np.array_equal(pidx, opidx)
+    assert int(pk.delay_idx) == 37 and pk.freq_hz in aliases + [-95987.7]      # the aliased rows tie to rounding
+    assert rel_max(surf[1], surf[0]) <= TOL64 and rel_max(surf[2], surf[0]) <= TOL64
+    assert rel_max(surf[5], O.caf_surface(needle, hay, np.array([0.0]), FS)[0][0]) <= TOL64   # f = fs is no shift
+    for fs, grid in ((1, [0.0, 0.25, -0.5, 0.125]), (4294967295, [1.0e6, -2.5e8, 3.0e9])):
+        x = rng.normal(size=1000) + 1j * rng.normal(size=1000)
+        y = np.roll(x, 5) * np.exp(2j * np.pi * grid[1] * np.arange(1000) / fs)
+        g = np.array(grid)
+        s2, i2, v2, p2 = caf.surface_arrays(x, y, g, fs)
+        o2, oi2, ov2 = O.caf_surface(x, y, g, fs)
+        assert rel_max(s2, o2) <= TOL64
+        assert np.array_equal(i2, oi2)
+        assert (p2.freq_hz, int(p2.delay_idx)) == O.find_peak(g, oi2, ov2) == (grid[1], 5)
+        assert rel_max(caf.CafB200.apply_freq_shift(x, grid[1], fs), O.apply_freq_shift(x, grid[1], fs)) <= 1e-10
+
+
 def test_ties_first_row_wins_and_argmax_is_first_maximum(chirp0):
     """mod.rs:37 keeps the first maximal row (strict >): identical rows are bitwise identical on the GPU, so the
     first of them must win.  mod.rs:148 keeps the first maximal cell of a row: the reported index must be the first
