@@ -157,6 +157,23 @@ def test_doppler_beyond_nyquist_and_extreme_sample_rates():
         assert rel_max(caf.CafB200.apply_freq_shift(x, grid[1], fs), O.apply_freq_shift(x, grid[1], fs)) <= 1e-10
 
 
+def test_non_finite_doppler_rows_never_win(chirp0):
+    """A NaN or infinite `freq_shift` makes the reference's phasor NaN (from_polar, mod.rs:55-60): every cell of that
+    row is NaN, no cell passes the strict `>` (mod.rs:148-151), the row keeps (0, 0.0) and find_peak skips it."""
+    needle, hay = chirp0
+    shifts = np.array([np.nan, 69.0, np.inf, -np.inf, 69.25])
+    surf, pidx, pval, pk = caf.surface_arrays(needle, hay, shifts, FS)
+    osurf, opidx, opval = O.caf_surface(needle, hay, shifts, FS)
+    for r in (0, 2, 3):
+        assert np.isnan(osurf[r]).all() and (int(opidx[r]), float(opval[r])) == (0, 0.0)
+        assert np.isnan(surf[r]).all() and (int(pidx[r]), float(pval[r])) == (0, 0.0)
+    for r in (1, 4):
+        assert rel_max(surf[r], osurf[r]) <= TOL64 and pidx[r] == opidx[r]
+    assert (pk.freq_hz, int(pk.delay_idx), int(pk.doppler_idx)) == (69.25, 202, 4) == O.find_peak(shifts, opidx, opval) + (4,)
+    assert caf.CafB200.caf_peak(needle, hay, shifts, FS) == (69.25, 202)
+    assert caf.CafB200.caf_peak(needle, hay, np.array([np.nan, np.inf]), FS) == (0.0, 0)     # nothing beats the dummy row
+
+
 def test_ties_first_row_wins_and_argmax_is_first_maximum(chirp0):
     """mod.rs:37 keeps the first maximal row (strict >): identical rows are bitwise identical on the GPU, so the
     first of them must win.  mod.rs:148 keeps the first maximal cell of a row: the reported index must be the first

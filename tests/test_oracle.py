@@ -155,3 +155,14 @@ def test_read_file_c64_widening():
     x = O.read_file_c64(path)
     assert x.dtype == np.complex128 and x.size == 4096
     assert np.array_equal(x, raw.astype(np.complex128))
+
+
+def test_non_finite_doppler_rows_never_win(chirp0):
+    """from_polar(1, NaN) poisons the whole row (mod.rs:55-60); NaN never passes the strict > (mod.rs:148-151, 36-40)."""
+    needle, hay = chirp0
+    shifts = np.array([np.nan, 69.0, np.inf, -np.inf, 69.25])
+    surf, pidx, pval = O.caf_surface(needle, hay, shifts, 48000)
+    for r in (0, 2, 3):
+        assert np.isnan(surf[r]).all() and (int(pidx[r]), float(pval[r])) == (0, 0.0)
+    assert O.find_peak(shifts, pidx, pval) == (69.25, 202)
+    assert O.find_peak(shifts[[0, 2]], pidx[[0, 2]], pval[[0, 2]]) == (0.0, 0)
