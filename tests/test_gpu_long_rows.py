@@ -123,3 +123,24 @@ def test_too_long_is_unsupported():
     with pytest.raises(caf.CafError) as e:
         caf.surface_arrays(z, z, [0.0], FS)
     assert e.value.status == -3
+
+
+@pytest.mark.parametrize("l", [8192, 131072])
+def test_long_rows_beyond_nyquist_and_non_finite_doppler(l):
+    """The long-row kernels have their own phasor (caf_large_spread_top / caf_large_spread2): shifts beyond fs/2 alias,
+    a NaN or infinite shift poisons its row and never wins (mod.rs:55-60, 148-151) — one- and two-level rows."""
+    needle, hay = _pair(l)
+    shifts = np.array([69.25, 69.25 + FS, np.nan, 69.25 - 2 * FS, np.inf, FS / 2.0])
+    surf, pidx, pval, pk = caf.surface_arrays(needle, hay, shifts, FS)
+    osurf, opidx, opval = O.caf_surface(needle, hay, shifts, FS)
+    for r in (2, 4):
+        assert np.isnan(osurf[r]).all() and np.isnan(surf[r]).all()
+        assert (int(pidx[r]), float(pval[r])) == (0, 0.0) == (int(opidx[r]), float(opval[r]))
+    fin = [0, 1, 3, 5]
+    assert rel_max(surf[fin], osurf[fin]) <= 1e-9
+    pk_rows = [0, 1, 3]          # the fs/2 row holds rounding noise only (1e-9 of the maximum): its argmax is not defined
+    assert np.array_equal(pidx[pk_rows].astype(np.int64), np.asarray(opidx)[pk_rows].astype(np.int64))
+    assert rel_max(surf[1], surf[0]) <= 1e-9 and rel_max(surf[3], surf[0]) <= 1e-9
+    assert int(pk.delay_idx) == int(opidx[0]) and pk.freq_hz in (69.25, 69.25 + FS, 69.25 - 2 * FS)
+    _, _, _, pk2 = caf.surface_arrays(needle, hay, shifts, FS, want_surface=False)
+    assert (pk2.freq_hz, int(pk2.delay_idx), int(pk2.doppler_idx)) == (pk.freq_hz, int(pk.delay_idx), int(pk.doppler_idx))
