@@ -174,6 +174,30 @@ def test_non_finite_doppler_rows_never_win(chirp0):
     assert caf.CafB200.caf_peak(needle, hay, np.array([np.nan, np.inf]), FS) == (0.0, 0)     # nothing beats the dummy row
 
 
+def test_non_finite_and_aliased_doppler_in_complex64_and_in_batches(chirp0):
+    """The same two edge cases through the complex64 rows (phase still fp64) and through the batch path, whose
+    find_peak is a separate kernel over the row peaks."""
+    needle, hay = chirp0
+    shifts = np.array([np.nan, 69.0, np.inf, 69.25 + FS, 69.25])
+    osurf, opidx, opval = O.caf_surface(needle, hay, shifts, FS)
+    surf, pidx, pval, pk = caf.surface_arrays(needle, hay, shifts, FS, variant=api._Variant32)
+    for r in (0, 2):
+        assert np.isnan(surf[r]).all() and (int(pidx[r]), float(pval[r])) == (0, 0.0)
+    fin = [1, 3, 4]
+    assert rel_max(surf[fin].astype(np.float64), osurf[fin]) <= TOL32
+    assert np.array_equal(pidx[fin], opidx[fin])
+    assert int(pk.delay_idx) == 202 and pk.freq_hz in (69.25, 69.25 + FS)
+    ns, hs = _pairs(3)
+    bs, bi, bv, peaks = caf.batch_arrays(ns, hs, shifts, FS, want_surface=True)
+    for i in range(3):
+        o, oi, ov = O.caf_surface(ns[i], hs[i], shifts, FS)
+        assert np.isnan(bs[i][0]).all() and np.isnan(bs[i][2]).all()
+        assert rel_max(bs[i][fin], o[fin]) <= TOL64
+        assert np.array_equal(bi[i], oi) and bv[i][0] == 0.0 and bv[i][2] == 0.0
+        assert int(peaks[i].delay_idx) == O.find_peak(shifts, oi, ov)[1]
+        assert int(peaks[i].doppler_idx) in (1, 3, 4)
+
+
 def test_ties_first_row_wins_and_argmax_is_first_maximum(chirp0):
     """mod.rs:37 keeps the first maximal row (strict >): identical rows are bitwise identical on the GPU, so the
     first of them must win.  mod.rs:148 keeps the first maximal cell of a row: the reported index must be the first
