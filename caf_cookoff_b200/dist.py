@@ -37,6 +37,44 @@ def exchange_peak(local: _lib.Peak, global_row_offset: int, device=None, group=N
     return peak_resolve(out.cpu().numpy().view(np.uint64).reshape(world, 4))
 
 
+def gather_pair_peaks(local_peaks, n_pairs: int, device=None, group=None) -> np.ndarray:
+    """Pairs sharded across ranks (BASELINE config 4): rank r holds the peaks of pairs shard_bounds(n_pairs, world, r),
+    as an array of caf_b200_peak records viewed as uint64 [p_local, 4] (value bits, freq bits, doppler_idx,
+    delay_idx).  ONE all_gather of the padded blocks (32 bytes per pair) gives every rank all n_pairs records in pair
+    order.  Pairs are independent, so unlike exchange_peak nothing is resolved: this is a pure gather."""
+    import torch
+    import torch.distributed as dist
+    loc = np.ascontiguousarray(local_peaks).view(np.uint64).reshape(-1, 4)
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        if loc.shape[0] != n_pairs:
+            raise ValueError(f"one rank must hold all {n_pairs} pairs, got {loc.shape[0]}")
+        return loc.copy()
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    lo, hi = shard_bounds(n_pairs, world, rank)
+    if loc.shape[0] != hi - lo:
+        raise ValueError(f"rank {rank} owns pairs [{lo}, {hi}) but passed {loc.shape[0]} peaks")
+    width = max(b - a for a, b in (shard_bounds(n_pairs, world, r) for r in range(world)))
+    block = np.zeros((width, 4), dtype=np.uint64)
+    block[: hi - lo] = loc
+    t = torch.from_numpy(block.view(np.int64))
+    if device is not None:
+        t = t.to(device)
+    out = torch.empty((world * width, 4), dtype=torch.int64, device=t.device)      # blocks concatenated along dim 0
+    dist.all_gather_into_tensor(out, t, group=group)
+    allw = out.cpu().numpy().view(np.uint64).reshape(world, width, 4)
+    parts = []
+    for r in range(world):
+        a, b = shard_bounds(n_pairs, world, r)
+        parts.append(allw[r, : b - a])
+    return np.concatenate(parts, axis=0) if parts else np.zeros((0, 4), dtype=np.uint64)
+
+
+def peaks_as_tuples(words: np.ndarray):
+    """[(freq_hz, delay_idx)] per pair from gather_pair_peaks' uint64 records: what find_peak returns (mod.rs:31-42)."""
+    w = np.ascontiguousarray(words, dtype=np.uint64).reshape(-1, 4)
+    return [(float(w[i, 1:2].view(np.float64)[0]), int(w[i, 3])) for i in range(w.shape[0])]
+
+
 class Comm:
     """The library's own NCCL communicator (caf_b200_comm_*): what a caller without torch.distributed (the Rust
     shim) uses.  The 128-byte NCCL id travels out of band; here through a small file any rank can read."""

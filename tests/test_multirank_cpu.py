@@ -69,3 +69,69 @@ def test_shard_bounds_cover_everything():
             assert b[0][0] == 0 and b[-1][1] == n
             assert all(b[i][1] == b[i + 1][0] for i in range(world - 1))
             assert max(hi - lo for lo, hi in b) - min(hi - lo for lo, hi in b) <= 1
+
+
+def _pair_worker(rank, world, port, n_pairs, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    import torch.distributed as dist
+    from caf_cookoff_b200 import dist as cdist
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        lo, hi = cdist.shard_bounds(n_pairs, world, rank)
+        local = _pair_peak_words(range(lo, hi))
+        allw = cdist.gather_pair_peaks(local, n_pairs)
+        q.put((rank, lo, hi, allw.tobytes()))
+    finally:
+        dist.destroy_process_group()
+
+
+def _pair_peak_words(indices):
+    """caf_b200_peak records (value, freq_hz, doppler_idx, delay_idx as 4 x 8 bytes) of the seed-0 chirp pairs,
+    from the CPU oracle (the N > 1 host logic is what is under test; there is no GPU here)."""
+    from oracle import oracle as O
+    data = os.path.join(ROOT, "tests", "golden", "data")
+    names = sorted(os.listdir(data))
+    shifts = O.gen_float_shifts(-100.0, 100.0, 5.0)
+    rows = []
+    for i in indices:
+        needle = O.read_file_c64(os.path.join(data, f"chirp_{i}_raw.c64"))
+        hay = O.read_file_c64(os.path.join(data, [n for n in names if n.startswith(f"chirp_{i}_T")][0]))[:needle.size]
+        _, pidx, pval = O.caf_surface(needle, hay, shifts, 48000, want_surface=False)
+        best = int(np.argmax(pval))
+        rec = np.zeros(4, dtype=np.uint64)
+        rec[0:1] = np.array([pval[best]]).view(np.uint64)
+        rec[1:2] = np.array([shifts[best]]).view(np.uint64)
+        rec[2], rec[3] = best, int(pidx[best])
+        rows.append(rec)
+    return np.stack(rows) if rows else np.zeros((0, 4), dtype=np.uint64)
+
+
+@pytest.mark.parametrize("world,n_pairs", [(2, 10), (3, 7)])
+def test_pair_sharded_peaks_gather(world, n_pairs):
+    """BASELINE config 4's N > 1 path: pairs sharded (evenly and unevenly), one all_gather of 32-byte records, every
+    rank ends with all peaks in pair order — identical to the unsharded computation."""
+    import torch.multiprocessing as mp
+    from caf_cookoff_b200 import dist as cdist
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 30100 + (os.getpid() % 500) + world
+    procs = [ctx.Process(target=_pair_worker, args=(r, world, port, n_pairs, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=180) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    want = _pair_peak_words(range(n_pairs))
+    assert [r[1:3] for r in res] == [cdist.shard_bounds(n_pairs, world, r) for r in range(world)]
+    for r in res:
+        got = np.frombuffer(r[3], dtype=np.uint64).reshape(-1, 4)
+        assert np.array_equal(got, want)
+    tuples = cdist.peaks_as_tuples(want)
+    assert len(tuples) == n_pairs and tuples[0][1] == 202        # chirp_0: delay 202 (test.rs)
+    # world size 1 (no process group): the local block is the answer
+    assert np.array_equal(cdist.gather_pair_peaks(want, n_pairs), want)
+    with pytest.raises(ValueError):
+        cdist.gather_pair_peaks(want[:-1], n_pairs)
