@@ -78,3 +78,20 @@ def test_cli_prints_what_main_rs_prints(tmp_path):
     assert res.returncode == 0 and res.stdout.startswith("caf result: 70 samples 83 hz")
     res = subprocess.run([CLI, a4, b4, "--layout", "python"], capture_output=True, text=True, timeout=120)
     assert res.returncode == 0 and res.stdout.startswith("amb_surf (400, 4096) float64 -> 70 83")
+
+
+def test_native_programs_fail_loudly_without_a_gpu():
+    """CPU box only: the CLI and the C++ restatement of test.rs stop with the library's ENODEVICE message and a
+    non-zero exit code — neither has (or falls back to) a CPU path."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present; the failure path is exercised on the CPU-only box")
+    _build()
+    _build_cli()
+    a, b = os.path.join(DATA, "chirp_0_raw.c64"), os.path.join(DATA, "chirp_0_T+202samp_F+69.25Hz.c64")
+    res = subprocess.run([CLI, a, b], capture_output=True, text=True, timeout=120)
+    assert res.returncode == 1 and res.stdout == ""
+    assert "status -5" in res.stderr and "no CPU fallback" in res.stderr
+    res = subprocess.run([BIN, DATA], capture_output=True, text=True, timeout=120)
+    assert res.returncode != 0 and "all tests passed" not in res.stdout
+    assert "no CPU fallback" in res.stdout + res.stderr
