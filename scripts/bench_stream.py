@@ -20,6 +20,83 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
+def measure(lib, h, stream, dev, *, pairs=320, surfaces=8, steps=300, warmup=40, f32=False):
+    """Run the rotation on an existing handle / stream and return the result dict (bench.py calls this too)."""
+    import ctypes as C
+    import numpy as np
+    import torch
+    from caf_cookoff_b200 import bench_shifts, generate as G
+
+    L, N, FS = 4096, 8192, 48000
+    cdt, trdt, sfx = (np.complex64, torch.float32, "f32") if f32 else (np.complex128, torch.float64, "f64")
+    freqs = bench_shifts()
+    D = freqs.size
+
+    # distinct seeded pairs, exactly as utils/generate.py draws them
+    needles = np.empty((pairs, L), dtype=cdt)
+    hays = np.empty((pairs, L), dtype=cdt)
+    planted = []
+    i = 0
+    seed = 0
+    while i < pairs:                            # ten pairs per seed, as utils/generate.py writes them
+        for p in G.pairs(seed=seed, count=min(10, pairs - i)):
+            n_, h_ = G.as_inputs(p)
+            needles[i], hays[i] = n_.astype(cdt), h_[:L].astype(cdt)
+            planted.append((p.lag, p.foffset_hz))
+            i += 1
+        seed += 1
+    nd = torch.from_numpy(needles).to(dev)
+    hd = torch.from_numpy(hays).to(dev)
+    fd = torch.from_numpy(freqs).to(dev)
+    surfs = [torch.empty((D, N), dtype=trdt, device=dev) for _ in range(surfaces)]
+    rv = torch.empty((pairs, D), dtype=trdt, device=dev)
+    ri = torch.empty((pairs, D), dtype=torch.int64, device=dev)
+    pk = torch.zeros((pairs, 4), dtype=torch.int64, device=dev)
+    fn = getattr(lib, f"caf_b200_batch_{sfx}_dev")
+
+    def step(k):
+        i = k % pairs
+        rc = fn(h.raw, nd[i].data_ptr(), hd[i].data_ptr(), 1, L, fd.data_ptr(), D, FS,
+                surfs[k % surfaces].data_ptr(), rv[i].data_ptr(), ri[i].data_ptr(), pk[i].data_ptr())
+        assert rc == 0, lib.caf_b200_last_error().decode()
+
+    for k in range(warmup):
+        step(k)
+    torch.cuda.synchronize()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    launches0 = lib.caf_b200_launch_count(h.raw)
+    e0.record(stream)
+    for k in range(warmup, warmup + steps):
+        step(k)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) * 1e3 / steps
+    launches = lib.caf_b200_launch_count(h.raw) - launches0
+
+    # every pair that ran: the peak sits on the planted lag, at the grid point nearest the planted offset
+    w = pk.cpu().numpy()
+    ran = sorted({k % pairs for k in range(warmup + steps)})
+    bad = []
+    for i in ran:
+        f = float(w[i].view(np.float64)[1])
+        lag = int(w[i].view(np.uint64)[3])
+        want_lag, want_f = planted[i]
+        if lag != want_lag % N or abs(f - want_f) > 0.5:
+            bad.append((i, f, lag, want_f, want_lag))
+    tf = C.c_double()
+    assert lib.caf_b200_probe_fma_tflops(h.raw, 0 if f32 else 1, C.byref(tf)) == 0
+    flops = D * (10.0 * N * np.log2(N) + 15.0 * N)
+    return {
+        "method": "working set > L2, one event pair around K back-to-back launches",
+        "dtype": sfx, "us_per_surface": us, "cells_per_s": D * N / (us * 1e-6), "steps": steps, "warmup": warmup,
+        "pairs": pairs, "surface_buffers": surfaces,
+        "working_set_mb": (pairs * 2 * L * needles.itemsize + surfaces * D * N * surfs[0].element_size()) / 1e6,
+        "gpu_launches": int(launches), "tflops": flops / (us * 1e-6) / 1e12, "peak_tflops": tf.value,
+        "frac": flops / (us * 1e-6) / 1e12 / tf.value, "pairs_checked": len(ran), "peaks_off": bad[:5],
+    }
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--steps", type=int, default=400)
@@ -29,86 +106,18 @@ def main():
     ap.add_argument("--f32", action="store_true")
     args = ap.parse_args()
 
-    import ctypes as C
-    import numpy as np
     import torch
-    from caf_cookoff_b200 import Handle, _lib, bench_shifts, generate as G
+    from caf_cookoff_b200 import Handle, _lib
 
-    L, N, FS = 4096, 8192, 48000
-    cdt, trdt, sfx = (np.complex64, torch.float32, "f32") if args.f32 else (np.complex128, torch.float64, "f64")
     dev = torch.device("cuda", 0)
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
     lib = _lib.load()
     h = Handle(0, stream=stream.cuda_stream)
-    freqs = bench_shifts()
-    D = freqs.size
-
-    # distinct seeded pairs, exactly as utils/generate.py draws them
-    needles = np.empty((args.pairs, L), dtype=cdt)
-    hays = np.empty((args.pairs, L), dtype=cdt)
-    planted = []
-    i = 0
-    seed = 0
-    while i < args.pairs:                       # ten pairs per seed, as utils/generate.py writes them
-        for p in G.pairs(seed=seed, count=min(10, args.pairs - i)):
-            n_, h_ = G.as_inputs(p)
-            needles[i], hays[i] = n_.astype(cdt), h_[:L].astype(cdt)
-            planted.append((p.lag, p.foffset_hz))
-            i += 1
-        seed += 1
-    nd = torch.from_numpy(needles).to(dev)
-    hd = torch.from_numpy(hays).to(dev)
-    fd = torch.from_numpy(freqs).to(dev)
-    surfs = [torch.empty((D, N), dtype=trdt, device=dev) for _ in range(args.surfaces)]
-    rv = torch.empty((args.pairs, D), dtype=trdt, device=dev)
-    ri = torch.empty((args.pairs, D), dtype=torch.int64, device=dev)
-    pk = torch.zeros((args.pairs, 4), dtype=torch.int64, device=dev)
-    fn = getattr(lib, f"caf_b200_batch_{sfx}_dev")
-
-    def step(k):
-        i = k % args.pairs
-        rc = fn(h.raw, nd[i].data_ptr(), hd[i].data_ptr(), 1, L, fd.data_ptr(), D, FS,
-                surfs[k % args.surfaces].data_ptr(), rv[i].data_ptr(), ri[i].data_ptr(), pk[i].data_ptr())
-        assert rc == 0, lib.caf_b200_last_error().decode()
-
-    for k in range(args.warmup):
-        step(k)
-    torch.cuda.synchronize()
-    e0 = torch.cuda.Event(enable_timing=True)
-    e1 = torch.cuda.Event(enable_timing=True)
-    launches0 = lib.caf_b200_launch_count(h.raw)
-    e0.record(stream)
-    for k in range(args.warmup, args.warmup + args.steps):
-        step(k)
-    e1.record(stream)
-    torch.cuda.synchronize()
-    us = e0.elapsed_time(e1) * 1e3 / args.steps
-    launches = lib.caf_b200_launch_count(h.raw) - launches0
-
-    # every pair that ran: the peak sits on the planted lag, at the grid point nearest the planted offset
-    w = pk.cpu().numpy()
-    ran = sorted({k % args.pairs for k in range(args.warmup + args.steps)})
-    bad = []
-    for i in ran:
-        f = float(w[i].view(np.float64)[1])
-        lag = int(w[i].view(np.uint64)[3])
-        want_lag, want_f = planted[i]
-        if lag != want_lag % N or abs(f - want_f) > 0.5:
-            bad.append((i, f, lag, want_f, want_lag))
-    tf = C.c_double()
-    assert lib.caf_b200_probe_fma_tflops(h.raw, 0 if args.f32 else 1, C.byref(tf)) == 0
-    flops = D * (10.0 * N * np.log2(N) + 15.0 * N)
-    line = {
-        "method": "working set > L2, one event pair around K back-to-back launches",
-        "dtype": sfx, "us_per_surface": us, "cells_per_s": D * N / (us * 1e-6), "steps": args.steps, "warmup": args.warmup,
-        "pairs": args.pairs, "surface_buffers": args.surfaces,
-        "working_set_mb": (args.pairs * 2 * L * needles.itemsize + args.surfaces * D * N * surfs[0].element_size()) / 1e6,
-        "gpu_launches": int(launches), "tflops": flops / (us * 1e-6) / 1e12, "peak_tflops": tf.value,
-        "frac": flops / (us * 1e-6) / 1e12 / tf.value, "pairs_checked": len(ran), "peaks_off": bad[:5],
-    }
+    line = measure(lib, h, stream, dev, pairs=args.pairs, surfaces=args.surfaces, steps=args.steps,
+                   warmup=args.warmup, f32=args.f32)
     print(json.dumps(line))
-    if bad:
+    if line["peaks_off"]:
         sys.exit(1)
 
 
