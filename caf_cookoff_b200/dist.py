@@ -69,6 +69,43 @@ def gather_pair_peaks(local_peaks, n_pairs: int, device=None, group=None) -> np.
     return np.concatenate(parts, axis=0) if parts else np.zeros((0, 4), dtype=np.uint64)
 
 
+def gather_surface(local_rows, n_rows: int, group=None):
+    """The full surface, only when asked for (the path itself never needs it): rank r holds rows
+    shard_bounds(n_rows, world, r) of the doppler grid as [hi - lo, 2L] (a numpy array, or a torch tensor — a CUDA
+    tensor under NCCL, so the rows travel GPU to GPU over NVLink); ONE all_gather of the padded blocks gives every rank
+    the [n_rows, 2L] surface in freqs_hz order, exactly the Vec<CafSurfaceRow> order of the ordered strategies
+    (mod.rs:135-162).  Uneven shards are padded to the widest block and trimmed after the exchange."""
+    import torch
+    import torch.distributed as dist
+    is_np = isinstance(local_rows, np.ndarray)
+    t = torch.from_numpy(np.ascontiguousarray(local_rows)) if is_np else local_rows.contiguous()
+    if t.dim() != 2:
+        raise ValueError("local_rows must be [rows, 2L]")
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        if t.shape[0] != n_rows:
+            raise ValueError(f"one rank must hold all {n_rows} rows, got {t.shape[0]}")
+        return local_rows
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    lo, hi = shard_bounds(n_rows, world, rank)
+    if t.shape[0] != hi - lo:
+        raise ValueError(f"rank {rank} owns rows [{lo}, {hi}) but passed {t.shape[0]}")
+    bounds = [shard_bounds(n_rows, world, r) for r in range(world)]
+    width = max(b - a for a, b in bounds)
+    cols = t.shape[1]
+    if hi - lo == width:
+        block = t
+    else:
+        block = torch.zeros((width, cols), dtype=t.dtype, device=t.device)
+        block[: hi - lo] = t
+    out = torch.empty((world * width, cols), dtype=t.dtype, device=t.device)
+    dist.all_gather_into_tensor(out, block, group=group)
+    if all(b - a == width for a, b in bounds):
+        full = out
+    else:
+        full = torch.cat([out[r * width: r * width + (b - a)] for r, (a, b) in enumerate(bounds)], dim=0)
+    return full.numpy() if is_np else full
+
+
 def peaks_as_tuples(words: np.ndarray):
     """[(freq_hz, delay_idx)] per pair from gather_pair_peaks' uint64 records: what find_peak returns (mod.rs:31-42)."""
     w = np.ascontiguousarray(words, dtype=np.uint64).reshape(-1, 4)

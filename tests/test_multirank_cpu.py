@@ -135,3 +135,63 @@ def test_pair_sharded_peaks_gather(world, n_pairs):
     assert np.array_equal(cdist.gather_pair_peaks(want, n_pairs), want)
     with pytest.raises(ValueError):
         cdist.gather_pair_peaks(want[:-1], n_pairs)
+
+
+def _surface_worker(rank, world, port, n_rows, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    import torch
+    import torch.distributed as dist
+    from caf_cookoff_b200 import dist as cdist
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        needle, hay, shifts = _small_case(n_rows)
+        lo, hi = cdist.shard_bounds(n_rows, world, rank)
+        from oracle import oracle as O
+        local, _, _ = O.caf_surface(needle, hay, shifts[lo:hi], 48000)
+        local = np.asarray(local).reshape(hi - lo, 2 * needle.size)
+        full_np = cdist.gather_surface(local, n_rows)
+        full_t = cdist.gather_surface(torch.from_numpy(local.copy()), n_rows)          # tensor in, tensor out
+        assert isinstance(full_np, np.ndarray) and isinstance(full_t, torch.Tensor)
+        assert np.array_equal(full_t.numpy(), full_np)
+        q.put((rank, full_np.tobytes()))
+    finally:
+        dist.destroy_process_group()
+
+
+def _small_case(n_rows):
+    from oracle import oracle as O
+    data = os.path.join(ROOT, "tests", "golden", "data")
+    needle = O.read_file_c64(os.path.join(data, "chirp_0_raw.c64"))[:512]
+    hay = O.read_file_c64(os.path.join(data, "chirp_0_T+202samp_F+69.25Hz.c64"))[:512]
+    shifts = np.linspace(60.0, 75.0, n_rows)
+    return needle, hay, shifts
+
+
+@pytest.mark.parametrize("world,n_rows", [(2, 8), (3, 7)])
+def test_row_sharded_surface_gather(world, n_rows):
+    """'The full surface is gathered only when requested': rows sharded evenly and unevenly, one all_gather of the
+    padded blocks, every rank ends with the unsharded surface bit for bit, in freqs_hz order."""
+    import torch.multiprocessing as mp
+    from caf_cookoff_b200 import dist as cdist
+    from oracle import oracle as O
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 30700 + (os.getpid() % 500) + world
+    procs = [ctx.Process(target=_surface_worker, args=(r, world, port, n_rows, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=180) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    needle, hay, shifts = _small_case(n_rows)
+    want, _, _ = O.caf_surface(needle, hay, shifts, 48000)
+    want = np.asarray(want).reshape(n_rows, 1024)
+    for r in res:
+        assert np.array_equal(np.frombuffer(r[1], dtype=np.float64).reshape(n_rows, 1024), want)
+    # no process group: the local block is the surface
+    assert cdist.gather_surface(want, n_rows) is want
+    with pytest.raises(ValueError):
+        cdist.gather_surface(want[:-1], n_rows)
