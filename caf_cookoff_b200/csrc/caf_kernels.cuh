@@ -1109,7 +1109,7 @@ __global__ void caf_peak_pack_kernel(const PeakOut* __restrict__ local, unsigned
 //     Go      caf_go/caf.go:93-116, main.go:35  banana padded in FRONT: 2L columns, column k = lag L - k (mod 2L)
 // with "lag" in the Rust sense (mod.rs:139: haystack delayed by tau peaks at tau).  One block per row:
 //     out[row][j] = sqrt(rust[row][(lag0 - j) mod 2L]),  j < W
-// plus the row maximum in COLUMN order (first strict-> maximum, caf.go:217-226 / np.argmax), so the peak of the
+// plus the row maximum in COLUMN order (first strict-> maximum, caf.go:183-195 / np.argmax), so the peak of the
 // converted surface is the sibling program's own answer even on ties.
 // ---------------------------------------------------------------------------------------------
 template <typename T>

@@ -11,7 +11,7 @@ oracle of this repository; this module reproduces what the other two return, fro
     Go      /root/reference/caf_go/caf.go, main.go
         apply_fdoa(ray, fdoa, samp_rate)                 caf.go:118-126
         amb_surf(needle, haystack, freqs_hz, samp_rate)  caf.go:162-173  -> [D][2L] |IFFT(FFT(a|0) conj(FFT(0|b)))|
-        find_2d_peak(surf) -> (fdx, tdx, max)            caf.go:217-226  first strict-> maximum, row-major
+        find_2d_peak(surf) -> (fdx, tdx, max)            caf.go:183-195  first strict-> maximum, row-major
         main.go:35 reports len(apple) - tdx samples
         dump_surf(path, surf)                            caf.go:14-29    row-major little-endian float64
 
@@ -88,7 +88,7 @@ class GoSibling:
 
     @staticmethod
     def find_2d_peak(needle, haystack, freqs_hz, samp_rate: float) -> Tuple[int, int, float]:
-        """(fdx, tdx, max) of caf.go:217-226 without moving the surface to the host; (0, 0, 0.0) when nothing is > 0."""
+        """(fdx, tdx, max) of caf.go:183-195 without moving the surface to the host; (0, 0, 0.0) when nothing is > 0."""
         _, pk = surface_layout(needle, haystack, freqs_hz, samp_rate, LAYOUT_GO, want_surface=False)
         if pk.doppler_idx == (1 << 64) - 1:
             return 0, 0, 0.0

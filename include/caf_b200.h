@@ -161,7 +161,7 @@ int caf_b200_batch_f32_dev(caf_b200_handle h, const caf_c64* needles, const caf_
  *   CAF_B200_LAYOUT_GO      caf_go/caf.go:93-116,162-173  amb_surf: out is d x 2l (banana zero-padded in FRONT),
  *                           column k holds Rust lag l - k (mod 2l); main.go:35 reports len - tdx.
  * The surface is computed once on the GPU (Rust layout, |.|^2) and converted there; `out` may be NULL.
- * peak: the sibling's 2-D argmax (first strict-> maximum in row-major order, caf.go:217-226 / np.argmax):
+ * peak: the sibling's 2-D argmax (first strict-> maximum in row-major order, caf.go:183-195 / np.argmax):
  * value = |xcor|, freq_hz, doppler_idx = row, delay_idx = COLUMN of the converted surface. */
 typedef enum { CAF_B200_LAYOUT_RUST = 0, CAF_B200_LAYOUT_PYTHON = 1, CAF_B200_LAYOUT_GO = 2 } caf_b200_layout;
 int caf_b200_surface_layout_f64(caf_b200_handle h, const caf_c128* needle, const caf_c128* haystack, size_t l,

@@ -125,7 +125,7 @@ public:
 };
 
 // The Go program of the reference (caf_go/caf.go) from the same kernels: amb_surf (caf.go:162-173) returns
-// [][]float64 of 2L columns, |xcor|, column k = Rust lag L - k; find_2d_peak (caf.go:217-226) is the first
+// [][]float64 of 2L columns, |xcor|, column k = Rust lag L - k; find_2d_peak (caf.go:183-195) is the first
 // strict-> maximum in row-major order; main.go:35 reports len(apple) - tdx.
 struct GoSibling {
     static std::vector<std::vector<double>> amb_surf(const std::vector<Complex64>& needle, const std::vector<Complex64>& haystack,
