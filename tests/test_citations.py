@@ -10,7 +10,13 @@ from conftest import ROOT
 REF = "/root/reference"
 DOCS = ["include/caf_b200.h", "include/caf_b200.hpp", "oracle/caf_oracle.c", "oracle/np_oracle.py", "oracle/oracle.py",
         "DESIGN.md", "INTEGRATION.md", "caf_cookoff_b200/api.py", "caf_cookoff_b200/io.py", "caf_cookoff_b200/generate.py",
-        "caf_cookoff_b200/siblings.py", "caf_cookoff_b200/dist.py", "tools/caf_cli.cpp", "rust/src/caf/mod.rs"]
+        "caf_cookoff_b200/siblings.py", "caf_cookoff_b200/dist.py", "tools/caf_cli.cpp", "rust/src/caf/mod.rs",
+        "rust/src/ffi.rs", "rust/src/utils.rs", "rust/src/lib.rs", "rust/Cargo.toml", "bench.py", "README.md",
+        "__graft_entry__.py", "tests/cpp/test_rs.cpp", "caf_cookoff_b200/_lib.py",
+        "caf_cookoff_b200/csrc/caf_b200.cu", "caf_cookoff_b200/csrc/caf_kernels.cuh",
+        "caf_cookoff_b200/csrc/caf_large.cuh", "caf_cookoff_b200/csrc/fft16.cuh"]
+DOCS += sorted(os.path.relpath(p, ROOT) for p in __import__("glob").glob(os.path.join(ROOT, "tests", "*.py")))
+DOCS += sorted(os.path.relpath(p, ROOT) for p in __import__("glob").glob(os.path.join(ROOT, "scripts", "*.py")))
 CITE = re.compile(r"((?:[\w.]+/)*[\w.]+\.(?:rs|go|py|md|toml|lock)):(\d+)(?:-(\d+))?")
 
 
