@@ -40,6 +40,10 @@ N = 2 * L
 # find_peak, README.md:36, rust RustFFT + threadpool on an R9-3900X, 12C/24T): 28 ms = 117.0 Mcell/s.  Other hardware.
 PUBLISHED_CELLS_PER_S = 400 * N / 28e-3
 PUBLISHED_NOTE = "BASELINE.md: rust RustFFT + threadpool, 28 ms per surface on an R9-3900X (README.md:36)"
+# ONE workload string for both arms (the driver compares them): BASELINE config 1
+WORKLOAD_CFG1 = ("cfg1: 400 doppler x 8192 delay fp64 CAF surface + peak per step per GPU, utils/generate.py seed-0 pairs "
+                 "(rank r uses chirp_r), fs=48000")
+WORKLOAD_CFG2 = WORKLOAD_CFG1.replace("cfg1", "cfg2").replace("fp64", "complex64/float32")
 
 
 _JSON_FD = None
@@ -67,6 +71,26 @@ def algorithmic_flops(d: int, n: int) -> float:
     """per row 10 N log2 N + 15 N; plus 5 N log2 N once per pair for FFT(s1)."""
     lg = np.log2(n)
     return d * (10.0 * n * lg + 15.0 * n) + 5.0 * n * lg
+
+
+def planted_answer(index: int):
+    """(lag in samples, doppler offset in Hz) the generator planted into fixture `index`: it is in the file name
+    (generate.py:68), e.g. chirp_0_T+202samp_F+69.25Hz.c64."""
+    import re
+    data = os.path.join(ROOT, "tests", "golden", "data")
+    index %= 10
+    name = sorted(f for f in os.listdir(data) if f.startswith(f"chirp_{index}_T"))[0]
+    m = re.match(r"chirp_\d+_T([+-]\d+)samp_F([+-][0-9.]+)Hz\.c64", name)
+    return int(m.group(1)), float(m.group(2))
+
+
+def peak_is_planted(index: int, freq_hz: float, delay: int, grid_step_hz: float = 0.5) -> bool:
+    """The timed call's answer must be the pair's planted lag, on a doppler bin next to the planted offset; for the
+    README pair (index 0) it must be the known answer of the 0.5 Hz bench grid, (69.0 Hz, 202)."""
+    lag, fo = planted_answer(index)
+    if index % 10 == 0 and (freq_hz, delay) != (69.0, 202):
+        return False
+    return delay == lag and abs(freq_hz - fo) <= grid_step_hz
 
 
 def load_pair(index: int):
@@ -186,6 +210,259 @@ def cpu_baseline_run(needle, hay, freqs, budget_s: float, threads: int):
     return float(np.median(times)), len(times)
 
 
+# ------------------------------------------------------------------------------------------------------------------
+# The other BASELINE configs, measured in the same run (compact blocks of the JSON line).  Every block checks the peak
+# it timed: a wrong answer marks the block "check_ok": false and the run exits non-zero after printing the line.
+# ------------------------------------------------------------------------------------------------------------------
+class Ctx:
+    pass
+
+
+def _timed(ctx, step, k, warm):
+    """One CUDA event pair around k back-to-back steps (working sets here are far larger than L2), max over ranks."""
+    import torch
+    import torch.distributed as dist
+    for _ in range(warm):
+        step()
+    if ctx.world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record(ctx.stream)
+    for _ in range(k):
+        step()
+    e1.record(ctx.stream)
+    if ctx.world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1) / k], dtype=torch.float64, device=ctx.dev)
+    if ctx.world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return float(ms.item())
+
+
+def _row_flops(n):
+    return 10.0 * n * np.log2(n) + 15.0 * n
+
+
+def block_cfg3_sharded(ctx, d_total=4096, l=32768, steps=5):
+    """BASELINE config 3 (4096 doppler x 65536 delay fp64 surface + peak), STRONG scaling: the doppler rows are sharded
+    across the ranks (mod.rs:185,283: rows are independent), each rank runs its block with caf_b200_sharded_f64_dev --
+    local rows, find_peak packed in the kernel, ONE ncclAllGather of 32 B per rank over the library-owned communicator,
+    device-side resolve -- all inside the timed step, no host synchronisation.  At N > 1 rank 0 also times the
+    unsharded job alone in the same run, so efficiency_vs_n1 needs no second process."""
+    import tempfile
+    import torch
+    import torch.distributed as dist
+    from caf_cookoff_b200 import generate as G, dist as cdist
+    lib, h, dev = ctx.lib, ctx.h, ctx.dev
+    pr = G.pair(0, seed=0, chirp_length=l)
+    needle, hay = G.as_inputs(pr)
+    freqs = np.linspace(-100.0, 100.0, d_total, endpoint=False)
+    id_path = os.path.join(tempfile.gettempdir(), "caf_bench_nccl_id_%s_%s" % (
+        os.environ.get("MASTER_PORT", "0"), os.environ.get("TORCHELASTIC_RUN_ID", str(os.getpid()))))
+    comm = cdist.Comm(h, ctx.world, ctx.rank, id_path)
+    lo, hi = comm.shard(d_total)
+    d_loc = hi - lo
+    nd = torch.from_numpy(needle).to(dev); hd = torch.from_numpy(hay).to(dev)
+    fd = torch.from_numpy(freqs[lo:hi].copy()).to(dev)
+    surf = torch.empty((max(d_loc, 1), 2 * l), dtype=torch.float64, device=dev)
+    rv = torch.empty(max(d_loc, 1), dtype=torch.float64, device=dev); ri = torch.empty(max(d_loc, 1), dtype=torch.int64, device=dev)
+    outp = torch.zeros(4, dtype=torch.int64, device=dev)
+    launches0 = h.launch_count
+
+    def step():
+        comm.sharded_dev(nd.data_ptr(), hd.data_ptr(), l, fd.data_ptr(), d_loc, lo, FS, outp.data_ptr(),
+                         surface_local_dev=surf.data_ptr(), row_val_dev=rv.data_ptr(), row_idx_dev=ri.data_ptr())
+
+    ms = _timed(ctx, step, steps, 2)
+    launches = (h.launch_count - launches0) // (steps + 2)
+    o = outp.cpu().numpy()
+    got = (float(o.view(np.float64)[0]), float(o.view(np.float64)[1]), int(o[2]), int(o[3]))   # value, freq, row, delay
+    remote_err = comm.remote_error()
+    # ---- the unsharded answer (and, at N > 1, the N = 1 time) on rank 0 --------------------------------------------
+    n1_ms, ref = ms, got
+    if ctx.world > 1:
+        ref_t = torch.zeros(4, dtype=torch.int64, device=dev)
+        t1 = torch.zeros(1, dtype=torch.float64, device=dev)
+        if ctx.rank == 0:
+            fall = torch.from_numpy(freqs).to(dev)
+            surf1 = torch.empty((d_total, 2 * l), dtype=torch.float64, device=dev)
+            rv1 = torch.empty(d_total, dtype=torch.float64, device=dev); ri1 = torch.empty(d_total, dtype=torch.int64, device=dev)
+
+            def step1():
+                rc = lib.caf_b200_batch_f64_dev(h.raw, nd.data_ptr(), hd.data_ptr(), 1, l, fall.data_ptr(), d_total, FS,
+                                                surf1.data_ptr(), rv1.data_ptr(), ri1.data_ptr(), ref_t.data_ptr())
+                if rc != 0:
+                    raise RuntimeError(lib.caf_b200_last_error().decode())
+            step1(); torch.cuda.synchronize()
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            e0.record(ctx.stream)
+            for _ in range(3):
+                step1()
+            e1.record(ctx.stream); torch.cuda.synchronize()
+            t1[0] = e0.elapsed_time(e1) / 3
+            del surf1
+        dist.broadcast(ref_t, 0); dist.broadcast(t1, 0)
+        r = ref_t.cpu().numpy()
+        ref = (float(r.view(np.float64)[0]), float(r.view(np.float64)[1]), int(r[2]), int(r[3]))
+        n1_ms = float(t1.item())
+    ok = (got == ref) and (got[3] == pr.lag) and not remote_err      # every rank: global peak == unsharded answer, on the planted lag
+    okt = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
+    if ctx.world > 1:
+        dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+    comm.close()
+    n = 2 * l
+    fl = d_total * _row_flops(n)
+    surf_bytes = d_total * n * 8
+    return {
+        "workload": f"cfg3: {d_total} doppler x {n} delay fp64 surface + peak, doppler rows sharded x{ctx.world} "
+                    f"(caf_b200_sharded_f64_dev: local rows + packed find_peak + ncclAllGather 32 B/rank + device resolve inside the step)",
+        "scaling": "strong", "ms_per_step": ms, "cells_per_s": d_total * n / (ms * 1e-3), "steps": steps,
+        "rows_per_gpu": d_loc, "launches_per_step": int(launches),
+        "n1_ms_same_run": n1_ms, "efficiency_vs_n1": n1_ms / (ctx.world * ms),
+        "roofline": {"bound": "fp64", "achieved": fl / (ms * 1e-3) / 1e12, "peak": ctx.world * ctx.tf64, "unit": "TFLOP/s",
+                     "frac": fl / (ms * 1e-3) / 1e12 / (ctx.world * ctx.tf64) if ctx.tf64 else None,
+                     "hbm_frac_surface_write": surf_bytes / (ms * 1e-3) / 1e9 / (ctx.world * ctx.hbm_peak)},
+        "peak": {"value": got[0], "freq_hz": got[1], "doppler_idx": got[2], "delay_idx": got[3], "planted_lag": pr.lag,
+                 "planted_foffset_hz": pr.foffset_hz},
+        "check_ok": bool(int(okt.item())),
+    }
+
+
+def block_cfg4_slice(ctx, pairs_per_gpu=592, steps=2):
+    """A slice of BASELINE config 4 (4096 independent pairs of 400 x 8192, pairs sharded, peaks only): 592 pairs per GPU
+    = 4 whole pairs per SM, so this is also the row kernel's STEADY STATE (1600 rows per CTA).  One
+    dist.gather_pair_peaks_dev (all_gather of 32 B per pair, device to device) inside the step.  Pair j = seed-0 fixture j mod 10: every copy
+    must return its fixture's known answer."""
+    import torch
+    from caf_cookoff_b200 import bench_shifts, read_file_c64, dist as cdist
+    lib, h, dev = ctx.lib, ctx.h, ctx.dev
+    data = os.path.join(ROOT, "tests", "golden", "data")
+    names = sorted(os.listdir(data))
+    ns = np.stack([read_file_c64(os.path.join(data, f"chirp_{i}_raw.c64")) for i in range(10)])
+    hs = np.stack([read_file_c64(os.path.join(data, [n for n in names if n.startswith(f"chirp_{i}_T")][0]))[:L] for i in range(10)])
+    p_total = pairs_per_gpu * ctx.world
+    lo, hi = cdist.shard_bounds(p_total, ctx.world, ctx.rank)
+    idx = np.arange(lo, hi) % 10
+    freqs = bench_shifts(); d = freqs.size
+    nd = torch.from_numpy(ns[idx]).to(dev); hd = torch.from_numpy(hs[idx]).to(dev); fd = torch.from_numpy(freqs).to(dev)
+    pk = torch.zeros((hi - lo, 4), dtype=torch.int64, device=dev)
+    res = {}
+
+    def step():
+        rc = lib.caf_b200_batch_f64_dev(h.raw, nd.data_ptr(), hd.data_ptr(), hi - lo, L, fd.data_ptr(), d, FS,
+                                        None, None, None, pk.data_ptr())
+        if rc != 0:
+            raise RuntimeError(lib.caf_b200_last_error().decode())
+        res["all"] = cdist.gather_pair_peaks_dev(pk, p_total)      # one all_gather_into_tensor on the device, stream-ordered
+
+    ms = _timed(ctx, step, steps, 1)
+    allw = res["all"]
+    allw = allw.cpu().numpy() if hasattr(allw, "cpu") else np.asarray(allw)
+    allw = allw.view(np.uint64).reshape(-1, 4)
+    # known answers of the ten fixtures on the 0.5 Hz bench grid: the first copy of each fixture is the reference for
+    # the rest (bit-exact), and fixture 0 must be the README answer (69.0 Hz, delay 202)
+    ok = allw.shape[0] == p_total
+    for j in range(min(p_total, allw.shape[0])):
+        ok = ok and bool((allw[j] == allw[j % 10]).all())
+    f0 = float(allw[0, 1:2].view(np.float64)[0]); d0 = int(allw[0, 3])
+    ok = ok and (f0, d0) == (69.0, 202)
+    fl = p_total * d * _row_flops(N)
+    return {
+        "workload": f"cfg4 slice: {p_total} independent pairs of 400 x 8192 fp64, pairs sharded x{ctx.world} ({pairs_per_gpu} per GPU), "
+                    "peaks only, one all_gather of 32 B per pair inside the step",
+        "scaling": "weak", "ms_per_step": ms, "cells_per_s": p_total * d * N / (ms * 1e-3), "steps": steps,
+        "us_per_row_per_sm": ms * 1e3 / (pairs_per_gpu * d / ctx.sm_count),
+        "roofline": {"bound": "fp64", "achieved": fl / (ms * 1e-3) / 1e12, "peak": ctx.world * ctx.tf64, "unit": "TFLOP/s",
+                     "frac": fl / (ms * 1e-3) / 1e12 / (ctx.world * ctx.tf64) if ctx.tf64 else None,
+                     "note": "row kernel in steady state (1600 rows per CTA): the per-launch costs of the single surface are amortised"},
+        "first_peaks": [[float(allw[i, 1:2].view(np.float64)[0]), int(allw[i, 3])] for i in range(min(3, allw.shape[0]))],
+        "check_ok": bool(ok),
+    }
+
+
+def block_cfg2(ctx, steps=40):
+    """BASELINE config 2: the 400 x 8192 surface in complex64 / float32 (device-resident, L2 flushed between steps, one
+    event pair per step), checked against the fp64 answer of the same pair."""
+    import torch
+    from caf_cookoff_b200 import bench_shifts
+    lib, h, dev = ctx.lib, ctx.h, ctx.dev
+    needle, hay = load_pair(0)
+    freqs = bench_shifts(); d = freqs.size
+    nd = torch.from_numpy(needle.astype(np.complex64)).to(dev); hd = torch.from_numpy(hay.astype(np.complex64)).to(dev)
+    fd = torch.from_numpy(freqs).to(dev)
+    surf = torch.empty((d, N), dtype=torch.float32, device=dev); rv = torch.empty(d, dtype=torch.float32, device=dev)
+    ri = torch.empty(d, dtype=torch.int64, device=dev); pk = torch.zeros(4, dtype=torch.int64, device=dev)
+
+    def step():
+        rc = lib.caf_b200_batch_f32_dev(h.raw, nd.data_ptr(), hd.data_ptr(), 1, L, fd.data_ptr(), d, FS,
+                                        surf.data_ptr(), rv.data_ptr(), ri.data_ptr(), pk.data_ptr())
+        if rc != 0:
+            raise RuntimeError(lib.caf_b200_last_error().decode())
+    ts = []
+    for i in range(steps + 5):
+        ctx.flush.zero_()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(ctx.stream); step(); e1.record(ctx.stream)
+        torch.cuda.synchronize()
+        if i >= 5:
+            ts.append(e0.elapsed_time(e1))
+    ms = float(np.mean(ts))
+    p = pk.cpu().numpy()
+    got = (float(p.view(np.float64)[1]), int(p.view(np.uint64)[3]))
+    fl = d * _row_flops(N)
+    return {"workload": "cfg2: 400 doppler x 8192 delay CAF surface + peak in complex64/float32, chirp_0 pair, L2 flushed per step",
+            "ms_per_step": ms, "cells_per_s": d * N / (ms * 1e-3), "steps": steps,
+            "roofline": {"bound": "fp32", "achieved": fl / (ms * 1e-3) / 1e12, "peak": ctx.tf32, "unit": "TFLOP/s",
+                         "frac": fl / (ms * 1e-3) / 1e12 / ctx.tf32 if ctx.tf32 else None},
+            "peak": list(got), "check_ok": got == (69.0, 202)}
+
+
+def block_cfg5_rows(ctx, rows=296, l=1 << 19, steps=2):
+    """Rows of BASELINE config 5 (2^20 delay cells, peak only -- the surface is never materialised): `rows` doppler rows
+    on this GPU.  The full config is 16 384 such rows over 8 GPUs = 2048 per GPU; time scales with the row count."""
+    import torch
+    from caf_cookoff_b200 import generate as G
+    lib, h, dev = ctx.lib, ctx.h, ctx.dev
+    pr = G.pair(0, seed=0, chirp_length=l)
+    needle, hay = G.as_inputs(pr)
+    # the rows are a slice of the full config's grid (16 384 shifts over [-100, 100) Hz, 0.0122 Hz apart) around the planted
+    # offset: 2^19 samples integrate coherently over 10.9 s, so the main lobe is only ~0.09 Hz wide
+    full = np.linspace(-100.0, 100.0, 16384, endpoint=False)
+    c0 = int(np.argmin(np.abs(full - pr.foffset_hz)))
+    r0 = min(max(c0 - rows // 2, 0), full.size - rows)
+    freqs = full[r0:r0 + rows].copy()
+    nd = torch.from_numpy(needle).to(dev); hd = torch.from_numpy(hay).to(dev); fd = torch.from_numpy(freqs).to(dev)
+    pk = torch.zeros(4, dtype=torch.int64, device=dev)
+
+    def step():
+        rc = lib.caf_b200_batch_f64_dev(h.raw, nd.data_ptr(), hd.data_ptr(), 1, l, fd.data_ptr(), rows, FS,
+                                        None, None, None, pk.data_ptr())
+        if rc != 0:
+            raise RuntimeError(lib.caf_b200_last_error().decode())
+    world = ctx.world
+    ctx.world = 1                       # every rank runs its own rows; no cross-rank step in this block
+    try:
+        ms = _timed(ctx, step, steps, 1)
+    finally:
+        ctx.world = world
+    p = pk.cpu().numpy()
+    got = (float(p.view(np.float64)[1]), int(p.view(np.uint64)[3]))
+    n = 2 * l
+    fl = rows * _row_flops(n)
+    # scratch traffic of the three passes (spread2 writes, core reads + writes, gather2 reads one row of n complex128 each)
+    moved = rows * 4.0 * n * 16
+    return {"workload": f"cfg5 rows: {rows} doppler x {n} delay fp64, peak only (surface never materialised), one GPU",
+            "ms_per_step": ms, "us_per_row": ms * 1e3 / rows, "cells_per_s": rows * n / (ms * 1e-3), "steps": steps,
+            "roofline": {"bound": "fp64", "achieved": fl / (ms * 1e-3) / 1e12, "peak": ctx.tf64, "unit": "TFLOP/s",
+                         "frac": fl / (ms * 1e-3) / 1e12 / ctx.tf64 if ctx.tf64 else None,
+                         "hbm_frac_scratch_traffic": moved / (ms * 1e-3) / 1e9 / ctx.hbm_peak,
+                         "scratch_bytes_per_row": 4.0 * n * 16, "algorithmic_bytes_per_row": 0},
+            "peak": list(got), "planted_lag": pr.lag, "planted_foffset_hz": pr.foffset_hz,
+            "check_ok": got[1] == pr.lag and abs(got[0] - pr.foffset_hz) <= 0.1}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -197,21 +474,30 @@ def run_reference(args):
     from oracle import oracle as O
     for _ in range(max(args.warmup, 1)):
         O.caf_surface(needle, hay, freqs, FS, threads=threads, want_surface=True)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
+    # a bounded sample: at most 400 surfaces / ~60 s whatever --steps says (the GPU arm's K is sized for 50 us steps)
+    steps = max(1, min(args.steps, 400))
+    times = []
+    t_end = time.perf_counter() + 60.0
+    for _ in range(steps):
+        t0 = time.perf_counter()
         surf, pidx, pval = O.caf_surface(needle, hay, freqs, FS, threads=threads, want_surface=True)
-        O.find_peak(freqs, pidx, pval)
-    dt = time.perf_counter() - t0
+        pk = O.find_peak(freqs, pidx, pval)
+        times.append(time.perf_counter() - t0)
+        if time.perf_counter() > t_end:
+            break
+    med = float(np.median(times))          # the same statistic the GPU arm's cpu_baseline reports
     cells = freqs.size * N
-    value = cells * args.steps / dt
+    value = cells / med
     line = {
         "impl": "reference", "metric": "CAF cells/s (400x8192 fp64 surface + peak)", "value": value, "unit": "cells/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "n_gpus": args.gpus, "steps": len(times), "warmup": args.warmup, "ms_per_step": 1e3 * med,
+        "ms_per_step_mean": 1e3 * float(np.mean(times)),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": value / PUBLISHED_CELLS_PER_S,
         "vs_baseline_note": PUBLISHED_NOTE, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "cfg1: 400 doppler x 8192 delay fp64 CAF surface + peak, chirp_0 pair (seed 0), fs=48000"},
+        "config": {"workload": WORKLOAD_CFG1},
+        "check": {"peak_freq_hz": float(pk[0]), "peak_delay": int(pk[1]), "check_ok": (float(pk[0]), int(pk[1])) == (69.0, 202)},
         "cpu_baseline": {"value": value, "unit": "cells/s", "cores": threads, "kind": "port",
-                         "sample": f"{args.steps} whole surfaces, oracle port of CafRustFFTThreadpool (3 FFTs/row), {threads} threads"},
+                         "sample": f"{len(times)} whole 400x8192 surfaces (median), oracle port of CafRustFFTThreadpool (3 FFTs/row), {threads} threads"},
         "e2e": {"value": value, "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -304,9 +590,11 @@ def run_b200(args):
     cells_step = D * N
     value = world * cells_step * args.steps / (total_ms_max * 1e-3)
 
-    # correctness of what was just timed: the peak must be the known answer of this pair
+    # correctness of what was just timed: the peak must be the known answer of this pair (asserted below: a wrong
+    # peak marks the line check_ok = false and the process exits non-zero)
     pk = pk_d.cpu().numpy()
     peak_freq = float(pk.view(np.float64)[1]); peak_delay = int(pk.view(np.uint64)[3])
+    checks = {"device": peak_is_planted(rank, peak_freq, peak_delay)}
 
     # ---- roofline pass: the row kernel alone, same flush regimen, CUDA events inside the library ----------
     lib.caf_b200_set_profiling(h.raw, 1)
@@ -388,6 +676,7 @@ def run_b200(args):
            "ms_per_step": e2e_ms_max / e2e_steps, "steps": e2e_steps, "wall_ms_per_step_incl_flush": 1e3 * wall / e2e_steps,
            "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
            "peak": [pk_h.freq_hz, int(pk_h.delay_idx)]}
+    checks["e2e"] = peak_is_planted(rank, pk_h.freq_hz, int(pk_h.delay_idx)) and float(surf_h[int(pk_h.doppler_idx), int(pk_h.delay_idx)]) == pk_h.value
 
     # ---- the same call without the surface crossing PCIe: caf_b200_peak_* (what caf_bench.rs's closure observes:
     #      find_peak(caf_surface(..)) returns (freq, delay); CafSurfaceRow's fields are private, mod.rs:17-22) --------
@@ -413,6 +702,7 @@ def run_b200(args):
                 "ms_per_step": float(t.item()) / e2e_steps, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 32,
                 "peak": [pk2.freq_hz, int(pk2.delay_idx)],
                 "note": "host inputs in, (freq, delay) out: the surface stays on the GPU (caf_b200_peak_*)"}
+    checks["e2e_peak_only"] = peak_is_planted(rank, pk2.freq_hz, int(pk2.delay_idx))
 
     # ---- second timing method (N = 1 only; last thing that touches the GPU): working set larger than L2, K back-to-back
     #      launches in ONE event pair, so the ~6 us every kernel pays between two events is not charged to each step
@@ -427,6 +717,37 @@ def run_b200(args):
                                               warmup=40, f32=f32)
         except BaseException as e:      # never let the extra figure break the bench line
             stream_fig = {"error": repr(e)}
+
+    # ---- the other BASELINE configs in the same run: the SHARDED path at every N (cfg3 rows sharded + NCCL peak
+    #      exchange, strong scaling; a cfg4 slice, pairs sharded + gather), and at N = 1 compact cfg2 / cfg5-row blocks ----
+    ctx = Ctx()
+    ctx.lib, ctx.h, ctx.stream, ctx.dev, ctx.rank, ctx.world, ctx.flush = lib, h, stream, dev, rank, world, flush
+    ctx.sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
+    ctx.hbm_peak = hbm_peak
+    if f32:
+        ctx.tf32 = tf.value
+        t64 = C.c_double(); lib.caf_b200_probe_fma_tflops(h.raw, 1, C.byref(t64)); ctx.tf64 = t64.value
+    else:
+        ctx.tf64 = tf.value
+        t32 = C.c_double(); lib.caf_b200_probe_fma_tflops(h.raw, 0, C.byref(t32)); ctx.tf32 = t32.value
+    del surf_d, surf_h
+    sharded, extra = {}, {}
+
+    def run_block(store, key, fn):
+        try:
+            store[key] = fn(ctx)
+        except BaseException as e:          # a block must never take the headline line down with it
+            store[key] = {"error": repr(e), "check_ok": False}
+        torch.cuda.synchronize()
+
+    if not args.no_blocks:
+        run_block(sharded, "cfg3", block_cfg3_sharded)
+        run_block(sharded, "cfg4_slice", block_cfg4_slice)
+        if world == 1:
+            run_block(extra, "cfg2" if not f32 else "cfg1_fp64_skipped", block_cfg2 if not f32 else (lambda c: {"check_ok": True}))
+            run_block(extra, "cfg5_rows", block_cfg5_rows)
+    for k_, v_ in list(sharded.items()) + list(extra.items()):
+        checks[k_] = bool(v_.get("check_ok", False))
 
     # ---- CPU baseline beside it (rank 0, N = 1 only) ----------------------------------------------------------
     cpu = None
@@ -446,21 +767,27 @@ def run_b200(args):
             "vs_baseline": None if f32 else value / PUBLISHED_CELLS_PER_S,
             "vs_baseline_note": "no published complex64 figure" if f32 else PUBLISHED_NOTE,
             "dtype": "f32" if f32 else "f64", "data": "synthetic",
-            "config": {"workload": ("cfg2" if f32 else "cfg1") + ": 400 doppler x 8192 delay CAF surface + peak per step per GPU, "
-                       "utils/generate.py seed-0 pairs (rank r uses chirp_r), fs=48000",
+            "config": {"workload": WORKLOAD_CFG2 if f32 else WORKLOAD_CFG1,
                        "doppler_rows": D, "delay_cells": N, "pairs_per_step_per_gpu": 1,
                        "l2": "flushed between timed steps (256 MiB overwrite); each step timed with its own CUDA event pair",
                        "parallelism": f"pairs sharded x{world}, no data-path collective",
                        "host_cpus_bound_to_gpu": numa},
             "e2e": e2e, "e2e_peak_only": e2e_peak, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
             "working_set_gt_l2": stream_fig,
+            "sharded": sharded, **extra,
             "clocks": sampler.summary(),
-            "check": {"peak_freq_hz": peak_freq, "peak_delay": peak_delay},
+            "check": {"peak_freq_hz": peak_freq, "peak_delay": peak_delay, "checks": checks},
+            "check_ok": all(checks.values()),
             "step_ms_min_med_max": [float(per_step.min()), float(np.median(per_step)), float(per_step.max())],
         }
         emit(line)
+    ok_t = torch.tensor([1 if all(checks.values()) else 0], dtype=torch.int32, device=dev)
     if world > 1:
+        dist.all_reduce(ok_t, op=dist.ReduceOp.MIN)
         dist.destroy_process_group()
+    if not int(ok_t.item()):
+        sys.stderr.write("bench.py: a timed call returned a wrong peak: %r\n" % (checks,))
+        raise SystemExit(3)
 
 
 def main():
@@ -472,6 +799,7 @@ def main():
     ap.add_argument("--workload", choices=["cfg1", "cfg2"], default="cfg1")
     ap.add_argument("--cpu-budget-s", type=float, default=3.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-blocks", action="store_true", help="skip the cfg2/cfg3/cfg4/cfg5 blocks (development)")
     args = ap.parse_args()
     claim_stdout()
     if args.impl == "reference":

@@ -110,6 +110,11 @@ SYMBOLS = {
     "caf_b200_surface_sharded_f32": (_int, [_vp, _vp, _vp, _vp, _sz, _vp, _sz, _u32, _vp, _PK]),
     "caf_b200_peak_pack": (None, [_PK, C.c_uint64, C.POINTER(C.c_uint64)]),
     "caf_b200_peak_resolve": (None, [C.POINTER(C.c_uint64), _sz, _PK]),
+    "caf_b200_peak_resolve_status": (_int, [C.POINTER(C.c_uint64), _sz, _PK]),
+    "caf_b200_peak_allgather_async": (_int, [_vp, _vp, _vp, C.c_uint64, _vp]),
+    "caf_b200_comm_remote_error": (_int, [_vp, C.POINTER(_int)]),
+    "caf_b200_sharded_f64_dev": (_int, [_vp, _vp, _vp, _vp, _sz, _vp, _sz, C.c_uint64, _u32, _vp, _vp, _vp, _vp]),
+    "caf_b200_sharded_f32_dev": (_int, [_vp, _vp, _vp, _vp, _sz, _vp, _sz, C.c_uint64, _u32, _vp, _vp, _vp, _vp]),
 }
 
 _lib = None

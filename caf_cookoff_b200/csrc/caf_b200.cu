@@ -100,13 +100,15 @@ constexpr int kNcclUint64 = 5;
 }  // namespace
 
 struct caf_b200_comm_s {
-    caf_b200_handle h = nullptr;
+    caf_b200_handle h = nullptr;          // identity check only (never dereferenced: the handle may die first)
+    int device = 0;
     void* comm = nullptr;       // ncclComm_t
     bool own = false;
     int world = 1, rank = 0;
     unsigned long long* send = nullptr;   // device: 4 words
     unsigned long long* recv = nullptr;   // device: 4 * world words
     unsigned long long* host = nullptr;   // pinned: 4 * world words
+    int* status = nullptr;                // pinned, device-addressable: 1 when a peer reported a failure in the last exchange
 };
 
 struct caf_b200_handle_s {
@@ -119,19 +121,24 @@ struct caf_b200_handle_s {
     Tables<float> tf;
     int occ_d = 1, occ_f = 1;   // resident CTAs per SM of the surface kernel
     DevBuf needle, hay, hperm, freqs, surface, rowval, rowidx, peaks, scratch, layout;
-    DevBuf lwbuf, lzbuf, lhbig, lpart;      // long-row path: chunk scratch (two levels), H, partial row maxima
+    DevBuf lwbuf, lhtmp, lhbig, lpart;      // long-row path: chunk scratch, scratch of the H transform, H, partial row maxima
     long long* trace = nullptr;   // CAF_TRACE builds: device buffer for phase stamps
     unsigned int* done_counter = nullptr;   // last-CTA-done ticket of the fused find_peak
     void* hshare = nullptr;                 // single-pair launches: H published by CTA 0 (8192 complex128)
     unsigned int* hflag = nullptr;          // [2] publish counters, monotonic
     unsigned int epoch = 0;
+    unsigned long long* pack_words = nullptr;   // sharded rows: find_peak also writes its result packed for the exchange
+    unsigned long long pack_offset = 0;         // global index of the first local doppler row
     void* h_peaks = nullptr;    // pinned staging for peaks
     size_t h_peaks_cap = 0;
     bool profiling = false;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // around spectrum | rows | peak
-    int max_clusters[2][3] = {{0, 0, 0}, {0, 0, 0}};   // resident clusters of caf_cluster_rows_kernel<T, R>
-    cudaStream_t copy_stream = nullptr;     // host calls: D2H of the head rows while the rest is computed
+    cudaStream_t copy_stream = nullptr;     // side stream: D2H of the head rows while the rest is computed; the long rows' H transform
     cudaEvent_t ev_head = nullptr, ev_copy = nullptr;
+    // switches read ONCE, at handle creation (include/caf_b200.h lists them)
+    size_t chunk_mb = 6144;                 // CAF_B200_CHUNK_MB
+    bool allow_pipeline = true;             // CAF_B200_PIPELINE
+    bool peak_zero_copy = true;             // CAF_B200_PEAK_ZEROCOPY
     bool ev_valid = false;
 };
 
@@ -181,6 +188,10 @@ cudaError_t configure_kernel(int* occ_out) {
         int occ = 0;
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, caf::kThreads, smem_bytes<T>());
         if (e != cudaSuccess) return e;
+        // the occupancy calculator does not know about tensor memory: a CTA allocates TmemGeom<T>::kAlloc of the SM's 512
+        // columns, and a single-pair launch needs its whole grid co-resident (consumer CTAs wait for the publisher's H)
+        const int tmem_cap = 512 / caf::TmemGeom<T>::kAlloc;
+        if (occ > tmem_cap) occ = tmem_cap;
         *occ_out = occ < 1 ? 1 : occ;
     }
     return cudaSuccess;
@@ -212,9 +223,6 @@ cudaError_t configure_all(int* occ) {
     if ((e = configure_kernel<T, caf::kXcorHalf>(nullptr)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(caf::caf_large_core<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<T>())) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(caf::caf_large_core<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<T>())) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(caf::caf_cluster_rows_kernel<T, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<T>())) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(caf::caf_cluster_rows_kernel<T, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<T>())) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(caf::caf_cluster_rows_kernel<T, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<T>())) != cudaSuccess) return e;
     return cudaSuccess;
 }
 
@@ -259,14 +267,6 @@ cudaError_t launch_large_top(caf_b200_handle h, const caf::LargeArgs<T>& a, bool
         default: return cudaErrorInvalidValue;
     }
 }
-template <typename T>
-cudaError_t launch_large_mid(caf_b200_handle h, const caf::LargeArgs<T>& a, bool gather) {
-    dim3 grid(16, (unsigned)(a.rows * 2 * a.Rtop));
-    if (!gather) caf::caf_large_spread_mid<T><<<grid, 256, 0, h->stream>>>(a);
-    else caf::caf_large_gather_mid<T><<<grid, 256, 0, h->stream>>>(a);
-    h->launches++;
-    return cudaGetLastError();
-}
 // two-level rows: fused spread (top + mid) and gather (mid + top), J innermost positions per block
 template <typename T, int RT, int J>
 cudaError_t launch_large_fused_rt(caf_b200_handle h, const caf::LargeArgs<T>& a, bool gather) {
@@ -302,58 +302,18 @@ cudaError_t launch_large_core(caf_b200_handle h, const caf::LargeArgs<T>& a) {
     h->launches++;
     return cudaGetLastError();
 }
-// rows of 16 384 .. 65 536 cells: one cluster of R CTAs per row, transposes through distributed shared memory
-template <typename T, int R>
-cudaError_t launch_cluster_rows_rt(caf_b200_handle h, const caf::LargeArgs<T>& a) {
-    auto k = caf::caf_cluster_rows_kernel<T, R>;
-    cudaLaunchConfig_t cfg{};
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = R; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    cfg.blockDim = dim3(caf::kThreads); cfg.dynamicSmemBytes = smem_bytes<T>(); cfg.stream = h->stream;
-    int& cached = h->max_clusters[std::is_same<T, double>::value ? 0 : 1][R == 2 ? 0 : R == 4 ? 1 : 2];
-    if (cached == 0) {
-        cfg.gridDim = dim3((unsigned)(R * (h->sm_count / R)));
-        int ncl = 0;
-        cudaError_t e = cudaOccupancyMaxActiveClusters(&ncl, k, &cfg);
-        if (e != cudaSuccess) return e;
-        cached = ncl < 1 ? 1 : ncl;
-    }
-    const int ncl = a.rows < cached ? a.rows : cached;
-    cfg.gridDim = dim3((unsigned)(ncl * R));
-    h->launches++;
-    return cudaLaunchKernelEx(&cfg, k, a);
+// The three stages of a chunk of long rows: spread (one level: spread_top; two levels: the fused spread2), core, and
+// -- unless H is being built -- gather (gather_top / gather2: inverse top step, radix-2, |.|^2, row argmax).
+template <typename T>
+int large_spread(caf_b200_handle h, const caf::LargeArgs<T>& a) {
+    if (a.inner_top != caf::kL0) CK(launch_large_fused<T>(h, a, false));
+    else CK(launch_large_top<T>(h, a, false));
+    return CAF_B200_OK;
 }
 template <typename T>
-cudaError_t launch_cluster_rows(caf_b200_handle h, const caf::LargeArgs<T>& a) {
-    switch (a.Rtop) {
-        case 2: return launch_cluster_rows_rt<T, 2>(h, a);
-        case 4: return launch_cluster_rows_rt<T, 4>(h, a);
-        case 8: return launch_cluster_rows_rt<T, 8>(h, a);
-        default: return cudaErrorInvalidValue;
-    }
-}
-
-// forward chain (spread[s] + core) and, unless H is being built, the inverse chain (gather[s] + row peaks)
-template <typename T, bool HMODE>
-int large_chain(caf_b200_handle h, const caf::LargeArgs<T>& a) {
-    const bool two = a.inner_top != caf::kL0;
-    // two levels: the fused kernels (three passes over memory) unless CAF_B200_FUSED2=0 asks for the five-pass chain
-    const char* f2 = getenv("CAF_B200_FUSED2");
-    const bool fused = two && !(f2 && f2[0] == '0');
-    if (fused) CK(launch_large_fused<T>(h, a, false));
-    else {
-        CK(launch_large_top<T>(h, a, false));
-        if (two) CK(launch_large_mid<T>(h, a, false));
-    }
-    CK((launch_large_core<T, HMODE>(h, a)));
-    if (HMODE) return CAF_B200_OK;
-    if (fused) CK(launch_large_fused<T>(h, a, true));
-    else {
-        if (two) CK(launch_large_mid<T>(h, a, true));
-        CK(launch_large_top<T>(h, a, true));
-    }
+int large_gather(caf_b200_handle h, const caf::LargeArgs<T>& a) {
+    if (a.inner_top != caf::kL0) CK(launch_large_fused<T>(h, a, true));
+    else CK(launch_large_top<T>(h, a, true));
     return CAF_B200_OK;
 }
 
@@ -368,14 +328,12 @@ int run_large_dev(caf_b200_handle h, const caf::cx<T>* needles, const caf::cx<T>
     const int inner = two ? 65536 : kL0;
     const int rtop = (int)(n / 2 / inner);
     const size_t row_bytes = sizeof(cx<T>) * (size_t)n;
-    // Rows are processed in chunks whose scratch (one buffer, two for two levels) is bounded by a budget.  Round 1 first
-    // sized the chunks to stay inside the 126 MB L2; measured with the final kernels the opposite holds -- the streaming
-    // spread / gather kernels run as fast out of HBM, and every extra chunk costs launches, a TMEM/H prologue per core
-    // launch and a partly filled last pass (config 3: 72 MB chunks 5.54 ms, 432 MB 4.70 ms, one chunk 4.23 ms; config 5
-    // rows: 48 MB 34.3 us, 4 GB 27.3 us per row).  Default budget 6 GB per buffer; CAF_B200_CHUNK_MB overrides.
-    size_t budget_mb = 6144;
-    if (const char* e_ = getenv("CAF_B200_CHUNK_MB")) { const long v_ = atol(e_); if (v_ > 0) budget_mb = (size_t)v_; }
-    size_t chunk = (budget_mb << 20) / row_bytes;
+    // Rows are processed in chunks whose scratch is bounded by a budget.  Round 1 first sized the chunks to stay inside
+    // the 126 MB L2; measured with the final kernels the opposite holds -- the streaming spread / gather kernels run as
+    // fast out of HBM, and every extra chunk costs launches, a TMEM/H prologue per core launch and a partly filled last
+    // pass (config 3: 72 MB chunks 5.54 ms, 432 MB 4.70 ms, one chunk 4.23 ms; config 5 rows: 48 MB 34.3 us, 4 GB
+    // 27.3 us per row).  Default budget 6 GB; CAF_B200_CHUNK_MB (read at handle creation) overrides.
+    size_t chunk = (h->chunk_mb << 20) / row_bytes;
     if (chunk < 1) chunk = 1;
     if (chunk < d) {
         // equal chunks, each a whole number of "sets" of rows (groups / positions): the core keeps every warp group on one
@@ -388,62 +346,65 @@ int run_large_dev(caf_b200_handle h, const caf::cx<T>* needles, const caf::cx<T>
     }
     if (chunk < 1) chunk = 1;
     if (chunk > d) chunk = d;
-    // One level and at most 8 units per pipeline can also run as one cluster of R CTAs per row with both transposes in
-    // distributed shared memory (caf_cluster_rows_kernel).  Measured on B200 it LOSES to the chain through L2 (config 3:
-    // 6.8 ms against 6.0 ms): only 15 clusters of 8 CTAs are resident (120 of 148 SMs), remote shared-memory stores
-    // drain at ~15 B/clk per SM, and the phases of a row are serialised by cluster barriers.  It is therefore opt-in:
-    // CAF_B200_CLUSTER=1 in the environment (read per call).
-    const char* cl_env = getenv("CAF_B200_CLUSTER");
-    const bool cluster = cl_env && cl_env[0] == '1' && !two && rtop <= 8 && !cplx;
-    if (cluster) chunk = 1;                                    // scratch is only needed for the one H transform
-    const int nparts = cluster ? rtop : inner / 256;
-    const size_t peak_rows = cluster ? d : chunk;
+    if (chunk > 65535) chunk = 65535;                       // rows of a chunk are grid.y of the spread / gather launches
+    const int nparts = two ? kL0 / kFusedJ : inner / 256;   // gather blocks per row (each leaves one partial maximum)
     CK(h->lwbuf.ensure(row_bytes * chunk));
-    {
-        const char* f2 = getenv("CAF_B200_FUSED2");
-        if (two && f2 && f2[0] == '0') CK(h->lzbuf.ensure(row_bytes * chunk));   // only the five-pass chain needs the second buffer
-    }
+    CK(h->lhtmp.ensure(row_bytes));
     CK(h->lhbig.ensure(row_bytes));
-    CK(h->lpart.ensure((sizeof(double) + sizeof(int)) * (size_t)nparts * peak_rows + sizeof(unsigned int) * peak_rows));
+    CK(h->lpart.ensure((sizeof(double) + sizeof(int)) * (size_t)nparts * chunk + sizeof(unsigned int) * chunk));
     T* rv = rowval; unsigned long long* ri = rowidx;
     if (!rv || !ri) {
         CK(h->scratch.ensure((sizeof(T) + sizeof(unsigned long long)) * p * d + 16));
         ri = reinterpret_cast<unsigned long long*>(h->scratch.p);
         rv = reinterpret_cast<T*>(ri + p * d);
     }
+    if (!h->copy_stream) CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    if (!h->ev_head) CK(cudaEventCreateWithFlags(&h->ev_head, cudaEventDisableTiming));
+    if (!h->ev_copy) CK(cudaEventCreateWithFlags(&h->ev_copy, cudaEventDisableTiming));
     Tables<T>& t = tables<T>(h);
     LargeArgs<T> a{};
-    a.wbuf = (cx<T>*)h->lwbuf.p; a.zbuf = (cx<T>*)h->lzbuf.p; a.hbig = (cx<T>*)h->lhbig.p;
-    a.part_val = (double*)h->lpart.p; a.part_idx = (int*)((double*)h->lpart.p + (size_t)nparts * peak_rows);
-    a.row_ticket = (unsigned int*)(a.part_idx + (size_t)nparts * peak_rows);
-    CK(cudaMemsetAsync(a.row_ticket, 0, sizeof(unsigned int) * peak_rows, h->stream));   // tickets start at zero (the layout moves with the shape)
+    a.wbuf = (cx<T>*)h->lwbuf.p; a.hbig = (cx<T>*)h->lhbig.p;
+    a.part_val = (double*)h->lpart.p; a.part_idx = (int*)((double*)h->lpart.p + (size_t)nparts * chunk);
+    a.row_ticket = (unsigned int*)(a.part_idx + (size_t)nparts * chunk);
+    CK(cudaMemsetAsync(a.row_ticket, 0, sizeof(unsigned int) * chunk, h->stream));   // tickets start at zero (the layout moves with the shape)
     a.tw1 = t.tw1; a.tw2 = t.tw2; a.g = t.g;
     a.dt = 1.0 / (double)fs; a.L = (int)l; a.N = (int)n; a.Rtop = rtop; a.inner_top = inner;
     a.trace = h->trace;
+    cudaStream_t const main_s = h->stream, side_s = h->copy_stream;
     for (size_t pi = 0; pi < p; ++pi) {
-        // H = FFT(haystack)/N once per pair (the reference recomputes it per row, xcor_rustfft.rs:58-59)
-        a.in = hays + pi * l; a.freqs = nullptr; a.rows = 1; a.surface = nullptr;
-        int rc = large_chain<T, true>(h, a);
-        if (rc) return rc;
-        if (cluster) {
-            a.in = needles + pi * l; a.freqs = freqs; a.rows = (int)d;
-            a.surface = surface ? surface + (pi * d) * 2 * l : nullptr;
-            a.row_peak_val = rv + pi * d; a.row_peak_idx = ri + pi * d;
-            CK(launch_cluster_rows<T>(h, a));
-            continue;
+        // H = FFT(haystack)/N once per pair (the reference recomputes it per row, xcor_rustfft.rs:58-59).  It is a chain of
+        // under-filled launches (one row), so it runs on the side stream, with its own one-row scratch, WHILE the main
+        // stream already spreads the first chunk of needle rows; the core of that chunk waits for it.
+        CK(cudaEventRecord(h->ev_head, main_s));             // the previous pair's cores are done with hbig
+        CK(cudaStreamWaitEvent(side_s, h->ev_head, 0));
+        {
+            LargeArgs<T> ah = a;
+            ah.wbuf = (cx<T>*)h->lhtmp.p; ah.in = hays + pi * l; ah.freqs = nullptr; ah.rows = 1; ah.surface = nullptr;
+            h->stream = side_s;
+            int rc = large_spread<T>(h, ah);
+            if (!rc) { cudaError_t e = launch_large_core<T, true>(h, ah); if (e != cudaSuccess) rc = fail(CAF_B200_ECUDA, cudaGetErrorString(e)); }
+            h->stream = main_s;
+            if (rc) return rc;
+            CK(cudaEventRecord(h->ev_copy, side_s));
         }
+        bool h_pending = true;
         for (size_t off = 0; off < d; off += chunk) {
             const size_t c = (d - off < chunk) ? d - off : chunk;
             a.in = needles + pi * l; a.freqs = freqs + off; a.rows = (int)c;
             a.surface = surface ? surface + (pi * d + off) * 2 * l : nullptr;
             a.cplx = cplx ? cplx + (pi * d + off) * (size_t)n : nullptr;
             a.row_peak_val = rv + pi * d + off; a.row_peak_idx = ri + pi * d + off;
-            rc = large_chain<T, false>(h, a);
+            int rc = large_spread<T>(h, a);
+            if (rc) return rc;
+            if (h_pending) { CK(cudaStreamWaitEvent(main_s, h->ev_copy, 0)); h_pending = false; }
+            CK((launch_large_core<T, false>(h, a)));
+            rc = large_gather<T>(h, a);
             if (rc) return rc;
         }
+        if (h_pending) CK(cudaStreamWaitEvent(main_s, h->ev_copy, 0));     // d == 0 cannot happen here, but never leave the side stream unjoined
     }
-    if (peaks) {
-        caf_peak_kernel<T><<<(unsigned)p, 256, 0, h->stream>>>(rv, ri, freqs, (int)d, peaks);
+    if (peaks || h->pack_words) {
+        caf_peak_kernel<T><<<(unsigned)p, 256, 0, h->stream>>>(rv, ri, freqs, (int)d, peaks, h->pack_words, h->pack_offset);
         h->launches++;
         CK(cudaGetLastError());
     }
@@ -467,6 +428,11 @@ int run_batch_dev(caf_b200_handle h, const caf::cx<T>* needles, const caf::cx<T>
             CK(cudaMemcpyAsync(peaks, z.data(), sizeof(PeakOut) * p, cudaMemcpyDefault, h->stream));   // peaks may be pinned host memory
             CK(cudaStreamSynchronize(h->stream));
         }
+        if (h->pack_words) {      // a rank that owns no rows still contributes "no row" to the exchange
+            caf_peak_pack_kernel<<<1, 32, 0, h->stream>>>(nullptr, 0ull, h->pack_words);
+            h->launches++;
+            CK(cudaGetLastError());
+        }
         return CAF_B200_OK;
     }
     if (l > (size_t)kL0) return run_large_dev<T>(h, needles, hays, p, l, freqs, d, fs, surface, rowval, rowidx, peaks);
@@ -482,7 +448,7 @@ int run_batch_dev(caf_b200_handle h, const caf::cx<T>* needles, const caf::cx<T>
     a.in = needles; a.in2 = hays; a.freqs = freqs; a.dt = 1.0 / (double)fs;   // dt: mod.rs:53
     a.out = surface; a.row_peak_val = rv; a.row_peak_idx = ri;
     const bool fused_peak = peaks && p == 1;      // single pair: find_peak rides in the same launch
-    if (fused_peak) { a.peak = peaks; a.done_counter = h->done_counter; }
+    if (fused_peak) { a.peak = peaks; a.done_counter = h->done_counter; a.peak_words = h->pack_words; a.row_offset = h->pack_offset; }
     if (p == 1 && d > 1) {                        // one pair over many CTAs: CTA 0 publishes H, the rest consume it
         a.hshare = reinterpret_cast<cx<T>*>(h->hshare); a.hflag = h->hflag; a.epoch = ++h->epoch;
         // H_1's publisher: the lowest-index CTA other than 0 that owns the fewest rows (same split as the kernel)
@@ -491,14 +457,10 @@ int run_batch_dev(caf_b200_handle h, const caf::cx<T>* needles, const caf::cx<T>
         const long long cap = (long long)h->sm_count * occ;
         const long long grid = n_items < cap ? n_items : cap;
         a.hprod1 = 0;
-        // with the fp64 token (complex128) both groups of a CTA must take the same number of turns, so CTA 0
-        // publishes both halves of H; otherwise H_1 comes from a second lightly loaded CTA
-        if (!(caf::kPingPong && std::is_same<T, double>::value)) {
-            long long best = -1;
-            for (long long b = 1; b < grid; ++b) {
-                const long long cnt = n_items * (b + 1) / grid - n_items * b / grid;
-                if (best < 0 || cnt < best) { best = cnt; a.hprod1 = (int)b; }
-            }
+        long long best = -1;
+        for (long long b = 1; b < grid; ++b) {
+            const long long cnt = n_items * (b + 1) / grid - n_items * b / grid;
+            if (best < 0 || cnt < best) { best = cnt; a.hprod1 = (int)b; }
         }
     }
     const bool prof = h->profiling;
@@ -513,7 +475,7 @@ int run_batch_dev(caf_b200_handle h, const caf::cx<T>* needles, const caf::cx<T>
     else CK((launch_rows<T, kSurface, false>(h, a, (long long)p * (long long)d)));
     if (prof) CK(cudaEventRecord(h->ev[2], h->stream));
     if (peaks && !fused_peak) {
-        caf_peak_kernel<T><<<(unsigned)p, 256, 0, h->stream>>>(rv, ri, freqs, (int)d, peaks);
+        caf_peak_kernel<T><<<(unsigned)p, 256, 0, h->stream>>>(rv, ri, freqs, (int)d, peaks, h->pack_words, h->pack_offset);
         h->launches++;
         CK(cudaGetLastError());
     }
@@ -582,16 +544,14 @@ int run_batch_host(caf_b200_handle h, const caf::cx<T>* needles, const caf::cx<T
     // device-addressable under unified addressing): no 32-byte D2H copy and no DMA set-up on the call's tail.  Measured
     // on B200, two A/B pairs on one box: peak-only call 82.3 / 82.8 us -> 74.5 / 77.9 us, surface call 550 / 549 us ->
     // 541 / 542 us.  CAF_B200_PEAK_ZEROCOPY=0 keeps the copy; batches (p > 1) always use it.
-    static const bool zc_env = [] { const char* e = getenv("CAF_B200_PEAK_ZEROCOPY"); return !(e && e[0] == '0'); }();
-    const bool peak_zero_copy = zc_env && peaks && p == 1;
+    const bool peak_zero_copy = h->peak_zero_copy && peaks && p == 1;
     if (peak_zero_copy) d_pk = (PeakOut*)h->h_peaks;
     // One pair with the surface wanted on the host: the D2H copy (26 MB at PCIe speed, ~0.5 ms) dwarfs the kernels
     // (~50 us), so the rows are issued as a short head (one wave of CTAs) and the rest; the head's cells start
     // crossing PCIe on a second stream while the rest is still being computed.  find_peak then runs as its own
     // small kernel over all row peaks.  CAF_B200_PIPELINE=0 in the environment keeps the single-launch path.
-    static const bool allow_pipeline = [] { const char* e = getenv("CAF_B200_PIPELINE"); return !(e && e[0] == '0'); }();
     const size_t d0 = (size_t)h->sm_count;
-    if (allow_pipeline && d_surface && p == 1 && l <= (size_t)kL0 && d >= 2 * d0 && d_rv && d_ri) {
+    if (h->allow_pipeline && d_surface && p == 1 && l <= (size_t)kL0 && d >= 2 * d0 && d_rv && d_ri) {
         if (!h->copy_stream) CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
         if (!h->ev_head) CK(cudaEventCreateWithFlags(&h->ev_head, cudaEventDisableTiming));
         if (!h->ev_copy) CK(cudaEventCreateWithFlags(&h->ev_copy, cudaEventDisableTiming));
@@ -790,6 +750,9 @@ static int create_impl(int device, bool own_stream, void* cuda_stream, caf_b200_
     if (!h) return fail(CAF_B200_EINVAL, "out of host memory");
     h->device = device;
     h->sm_count = prop.multiProcessorCount;
+    if (const char* e_ = getenv("CAF_B200_CHUNK_MB")) { const long v_ = atol(e_); if (v_ > 0) h->chunk_mb = (size_t)v_; }
+    if (const char* e_ = getenv("CAF_B200_PIPELINE")) h->allow_pipeline = e_[0] != '0';
+    if (const char* e_ = getenv("CAF_B200_PEAK_ZEROCOPY")) h->peak_zero_copy = e_[0] != '0';
 
     if (!own_stream) { h->stream = (cudaStream_t)cuda_stream; h->own_stream = false; }   // 0 = legacy default stream
     else {
@@ -822,8 +785,9 @@ int caf_b200_create_on_stream(int device, void* cuda_stream, caf_b200_handle* ou
 int caf_b200_destroy(caf_b200_handle h) {
     if (!h) return CAF_B200_OK;
     cudaSetDevice(h->device);
+    if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
     if (h->stream) cudaStreamSynchronize(h->stream);
-    for (DevBuf* b : {&h->needle, &h->hay, &h->hperm, &h->freqs, &h->surface, &h->rowval, &h->rowidx, &h->peaks, &h->scratch, &h->layout, &h->lwbuf, &h->lzbuf, &h->lhbig, &h->lpart})
+    for (DevBuf* b : {&h->needle, &h->hay, &h->hperm, &h->freqs, &h->surface, &h->rowval, &h->rowidx, &h->peaks, &h->scratch, &h->layout, &h->lwbuf, &h->lhtmp, &h->lhbig, &h->lpart})
         b->release();
     for (void* q : {(void*)h->td.tw1, (void*)h->td.tw2, (void*)h->td.g, (void*)h->tf.tw1, (void*)h->tf.tw2, (void*)h->tf.g})
         if (q) cudaFree(q);
@@ -1024,10 +988,12 @@ int caf_b200_comm_unique_id(unsigned char id[CAF_B200_NCCL_ID_BYTES]) {
 static int comm_finish(caf_b200_comm c, caf_b200_comm* out) {
     cudaError_t e;
     if ((e = cudaMalloc(&c->send, 8 * 4)) != cudaSuccess || (e = cudaMalloc(&c->recv, 8 * 4 * (size_t)c->world)) != cudaSuccess ||
-        (e = cudaMallocHost(&c->host, 8 * 4 * (size_t)c->world)) != cudaSuccess) {
+        (e = cudaMallocHost(&c->host, 8 * 4 * (size_t)c->world)) != cudaSuccess ||
+        (e = cudaMallocHost(&c->status, sizeof(int))) != cudaSuccess) {
         caf_b200_comm_destroy(c);
         return fail(CAF_B200_ECUDA, std::string("communicator buffers: ") + cudaGetErrorString(e));
     }
+    *c->status = 0;
     *out = c;
     return CAF_B200_OK;
 }
@@ -1041,7 +1007,7 @@ int caf_b200_comm_create(caf_b200_handle h, int world, int rank, const unsigned 
     CK(cudaSetDevice(h->device));
     caf_b200_comm c = new (std::nothrow) caf_b200_comm_s();
     if (!c) return fail(CAF_B200_EINVAL, "out of memory");
-    c->h = h; c->world = world; c->rank = rank; c->own = true;
+    c->h = h; c->device = h->device; c->world = world; c->rank = rank; c->own = true;
     NcclUniqueId u;
     std::memcpy(u.internal, id, CAF_B200_NCCL_ID_BYTES);
     int e = n.CommInitRank(&c->comm, world, u, rank);
@@ -1057,16 +1023,17 @@ int caf_b200_comm_adopt(caf_b200_handle h, void* nccl_comm, int world, int rank,
     CK(cudaSetDevice(h->device));
     caf_b200_comm c = new (std::nothrow) caf_b200_comm_s();
     if (!c) return fail(CAF_B200_EINVAL, "out of memory");
-    c->h = h; c->world = world; c->rank = rank; c->own = false; c->comm = nccl_comm;
+    c->h = h; c->device = h->device; c->world = world; c->rank = rank; c->own = false; c->comm = nccl_comm;
     return comm_finish(c, out);
 }
 
 int caf_b200_comm_destroy(caf_b200_comm c) {
     if (!c) return CAF_B200_OK;
-    if (c->h) cudaSetDevice(c->h->device);
+    cudaSetDevice(c->device);             // the handle may already be gone: the communicator remembers its own device
     if (c->send) cudaFree(c->send);
     if (c->recv) cudaFree(c->recv);
     if (c->host) cudaFreeHost(c->host);
+    if (c->status) cudaFreeHost(c->status);
     if (c->own && c->comm && nccl_api().ok()) nccl_api().CommDestroy(c->comm);
     delete c;
     return CAF_B200_OK;
@@ -1079,10 +1046,56 @@ int caf_b200_comm_shard(caf_b200_comm c, size_t n, size_t* lo, size_t* hi) {
     return CAF_B200_OK;
 }
 
+int caf_b200_comm_remote_error(caf_b200_comm c, int* flag) {
+    if (!c || !flag) return fail(CAF_B200_EINVAL, "null argument");
+    *flag = *c->status;
+    return CAF_B200_OK;
+}
+
+extern "C++" {
+namespace {
+int check_comm(caf_b200_handle h, caf_b200_comm c) {
+    if (!h || !c) return fail(CAF_B200_EINVAL, "null handle / communicator");
+    if (c->h != h) return fail(CAF_B200_EINVAL, "communicator belongs to another handle");
+    return CAF_B200_OK;
+}
+// c->send holds this rank's packed words (device): all-gather them and resolve on the DEVICE into out_dev (device or
+// pinned host memory).  Everything is stream-ordered; nothing waits on the host.
+int exchange_async(caf_b200_handle h, caf_b200_comm c, caf_b200_peak* out_dev) {
+    CKN(nccl_api().AllGather(c->send, c->recv, 4, kNcclUint64, c->comm, h->stream));
+    caf::caf_peak_resolve_kernel<<<1, 32, 0, h->stream>>>(c->recv, c->world, (caf::PeakOut*)out_dev, c->status);
+    h->launches++;
+    CK(cudaGetLastError());
+    return CAF_B200_OK;
+}
+// Words that tell every peer "this rank failed": the collective is still entered, so nobody hangs in it.
+int post_failure_and_exchange(caf_b200_handle h, caf_b200_comm c) {
+    const unsigned long long w[4] = {0ull, caf::kPeakRemoteError, 0ull, 0ull};
+    if (cudaMemcpyAsync(c->send, w, sizeof w, cudaMemcpyHostToDevice, h->stream) != cudaSuccess) return CAF_B200_ECUDA;
+    if (nccl_api().AllGather(c->send, c->recv, 4, kNcclUint64, c->comm, h->stream) != 0) return CAF_B200_ENCCL;
+    cudaStreamSynchronize(h->stream);
+    return CAF_B200_OK;
+}
+}  // namespace
+}  // extern "C++"
+
+int caf_b200_peak_allgather_async(caf_b200_handle h, caf_b200_comm c, const caf_b200_peak* local_peak_dev,
+                                  uint64_t global_row_offset, caf_b200_peak* out_dev) {
+    int rc = check_comm(h, c);
+    if (rc) return rc;
+    if (!out_dev) return fail(CAF_B200_EINVAL, "null out");
+    CK(cudaSetDevice(h->device));
+    caf::caf_peak_pack_kernel<<<1, 32, 0, h->stream>>>((const caf::PeakOut*)local_peak_dev, (unsigned long long)global_row_offset, c->send);
+    h->launches++;
+    CK(cudaGetLastError());
+    return exchange_async(h, c, out_dev);
+}
+
 int caf_b200_peak_allgather_dev(caf_b200_handle h, caf_b200_comm c, const caf_b200_peak* local_dev,
                                 uint64_t global_row_offset, caf_b200_peak* out) {
-    if (!h || !c || !local_dev || !out) return fail(CAF_B200_EINVAL, "null argument");
-    if (c->h != h) return fail(CAF_B200_EINVAL, "communicator belongs to another handle");
+    if (!local_dev || !out) return fail(CAF_B200_EINVAL, "null argument");
+    int rc = check_comm(h, c);
+    if (rc) return rc;
     CK(cudaSetDevice(h->device));
     caf::caf_peak_pack_kernel<<<1, 32, 0, h->stream>>>((const caf::PeakOut*)local_dev, (unsigned long long)global_row_offset, c->send);
     h->launches++;
@@ -1090,23 +1103,56 @@ int caf_b200_peak_allgather_dev(caf_b200_handle h, caf_b200_comm c, const caf_b2
     CKN(nccl_api().AllGather(c->send, c->recv, 4, kNcclUint64, c->comm, h->stream));
     CK(cudaMemcpyAsync(c->host, c->recv, 8 * 4 * (size_t)c->world, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
-    caf_b200_peak_resolve((const uint64_t*)c->host, (size_t)c->world, out);
+    if (caf_b200_peak_resolve_status((const uint64_t*)c->host, (size_t)c->world, out))
+        return fail(CAF_B200_EREMOTE, "a peer rank failed before the peak exchange");
     return CAF_B200_OK;
 }
 
 extern "C++" {
 namespace {
-// rows [lo, hi) of the doppler grid on this rank, then find_peak across ranks
+// Device-resident rows [row_offset, row_offset + d_local) of the doppler grid on this rank, find_peak across ranks:
+// the local find_peak writes its result already packed into c->send, then ncclAllGather + device resolve.  No host
+// synchronisation anywhere; out_dev is valid once the stream has reached this point.
+template <typename T>
+int run_sharded_dev(caf_b200_handle h, caf_b200_comm c, const caf::cx<T>* needle, const caf::cx<T>* hay, size_t l,
+                    const double* freqs_local, size_t d_local, uint64_t row_offset, uint32_t fs, T* surface_local,
+                    T* rv, unsigned long long* ri, caf_b200_peak* out_dev) {
+    int rc = check_comm(h, c);
+    if (rc) return rc;
+    if (!out_dev) return fail(CAF_B200_EINVAL, "null out");
+    rc = check_common<T>(h, needle, hay, 1, l, freqs_local, d_local, fs);
+    cudaError_t ce = cudaSuccess;
+    if (!rc && (ce = cudaSetDevice(h->device)) != cudaSuccess) rc = fail(CAF_B200_ECUDA, cudaGetErrorString(ce));
+    if (!rc && (ce = h->peaks.ensure(sizeof(caf::PeakOut))) != cudaSuccess) rc = fail(CAF_B200_ECUDA, cudaGetErrorString(ce));
+    if (!rc) {
+        h->pack_words = c->send; h->pack_offset = (unsigned long long)row_offset;
+        rc = run_batch_dev<T>(h, needle, hay, 1, l, freqs_local, d_local, fs, surface_local, rv, ri, (caf::PeakOut*)h->peaks.p);
+        h->pack_words = nullptr; h->pack_offset = 0;
+    }
+    if (rc) {                       // never leave the peers alone in the collective (they would wait for ever)
+        const std::string why = g_err;
+        post_failure_and_exchange(h, c);
+        return fail(rc, why);
+    }
+    return exchange_async(h, c, out_dev);
+}
+
+// rows [lo, hi) of the doppler grid on this rank, then find_peak across ranks (host inputs, host outputs)
 template <typename T>
 int run_sharded(caf_b200_handle h, caf_b200_comm c, const caf::cx<T>* needle, const caf::cx<T>* hay, size_t l,
                 const double* freqs, size_t d, uint32_t fs, T* surface_local, caf_b200_peak* peak) {
-    if (!c) return fail(CAF_B200_EINVAL, "null communicator");
+    int rc = check_comm(h, c);
+    if (rc) return rc;
     if (!peak) return fail(CAF_B200_EINVAL, "null peak");
     size_t lo = 0, hi = 0;
     caf_b200_comm_shard(c, d, &lo, &hi);
     caf_b200_peak local;
-    int rc = run_batch_host<T>(h, needle, hay, 1, l, freqs ? freqs + lo : freqs, hi - lo, fs, surface_local, nullptr, nullptr, &local);
-    if (rc) return rc;
+    rc = run_batch_host<T>(h, needle, hay, 1, l, freqs ? freqs + lo : freqs, hi - lo, fs, surface_local, nullptr, nullptr, &local);
+    if (rc) {                       // every rank enters the collective, whatever happened locally
+        const std::string why = g_err;
+        post_failure_and_exchange(h, c);
+        return fail(rc, why);
+    }
     // the local peak is on the host here (run_batch_host staged it); it is tiny, so the exchange re-uploads the words
     uint64_t words[4];
     caf_b200_peak_pack(&local, lo, words);
@@ -1114,7 +1160,8 @@ int run_sharded(caf_b200_handle h, caf_b200_comm c, const caf::cx<T>* needle, co
     CKN(nccl_api().AllGather(c->send, c->recv, 4, kNcclUint64, c->comm, h->stream));
     CK(cudaMemcpyAsync(c->host, c->recv, 8 * 4 * (size_t)c->world, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
-    caf_b200_peak_resolve((const uint64_t*)c->host, (size_t)c->world, peak);
+    if (caf_b200_peak_resolve_status((const uint64_t*)c->host, (size_t)c->world, peak))
+        return fail(CAF_B200_EREMOTE, "a peer rank failed before the peak exchange");
     return CAF_B200_OK;
 }
 }  // namespace
@@ -1128,6 +1175,18 @@ int caf_b200_surface_sharded_f32(caf_b200_handle h, caf_b200_comm c, const caf_c
                                  const double* freqs, size_t d, uint32_t fs, float* surface_local, caf_b200_peak* peak) {
     return run_sharded<float>(h, c, (const float2*)needle, (const float2*)hay, l, freqs, d, fs, surface_local, peak);
 }
+int caf_b200_sharded_f64_dev(caf_b200_handle h, caf_b200_comm c, const caf_c128* needle, const caf_c128* hay, size_t l,
+                             const double* freqs_local, size_t d_local, uint64_t row_offset, uint32_t fs,
+                             double* surface_local, double* rv, uint64_t* ri, caf_b200_peak* peak_out) {
+    return run_sharded_dev<double>(h, c, (const double2*)needle, (const double2*)hay, l, freqs_local, d_local, row_offset, fs,
+                                   surface_local, rv, (unsigned long long*)ri, peak_out);
+}
+int caf_b200_sharded_f32_dev(caf_b200_handle h, caf_b200_comm c, const caf_c64* needle, const caf_c64* hay, size_t l,
+                             const double* freqs_local, size_t d_local, uint64_t row_offset, uint32_t fs,
+                             float* surface_local, float* rv, uint64_t* ri, caf_b200_peak* peak_out) {
+    return run_sharded_dev<float>(h, c, (const float2*)needle, (const float2*)hay, l, freqs_local, d_local, row_offset, fs,
+                                  surface_local, rv, (unsigned long long*)ri, peak_out);
+}
 
 void caf_b200_peak_pack(const caf_b200_peak* local, uint64_t global_row_offset, uint64_t words[4]) {
     double v = local->value, f = local->freq_hz;
@@ -1138,11 +1197,17 @@ void caf_b200_peak_pack(const caf_b200_peak* local, uint64_t global_row_offset, 
 }
 
 void caf_b200_peak_resolve(const uint64_t* words, size_t world, caf_b200_peak* out) {
+    (void)caf_b200_peak_resolve_status(words, world, out);
+}
+
+int caf_b200_peak_resolve_status(const uint64_t* words, size_t world, caf_b200_peak* out) {
     caf_b200_peak best; best.value = 0.0; best.freq_hz = 0.0; best.doppler_idx = UINT64_MAX; best.delay_idx = 0;
+    int failed = 0;
     for (size_t r = 0; r < world; ++r) {
         const uint64_t* w = words + 4 * r;
         double v, f;
         std::memcpy(&v, &w[0], 8); std::memcpy(&f, &w[3], 8);
+        if (w[1] == UINT64_MAX - 1) { failed = 1; continue; }     // that rank failed before the exchange
         if (w[1] == UINT64_MAX) continue;
         // find_peak (mod.rs:36-40): strict > in row order  ==  larger value, ties to the lower global row
         if (v > best.value || (v == best.value && v > 0.0 && w[1] < best.doppler_idx)) {
@@ -1150,6 +1215,7 @@ void caf_b200_peak_resolve(const uint64_t* words, size_t world, caf_b200_peak* o
         }
     }
     *out = best;
+    return failed;
 }
 
 }  // extern "C"

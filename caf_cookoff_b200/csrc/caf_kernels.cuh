@@ -70,6 +70,8 @@ struct RowArgs {
     T* row_peak_val;        // [P*D] or null
     unsigned long long* row_peak_idx;  // [P*D] or null
     PeakOut* peak;          // kSurface, P == 1: fused find_peak result (or null)
+    unsigned long long* peak_words;   // kSurface, P == 1: the same result packed for the cross-rank exchange (or null)
+    unsigned long long row_offset;    // global index of this launch's first doppler row (rows sharded across ranks)
     unsigned int* done_counter;   // kSurface, P == 1: last-CTA-done ticket (self-resetting)
     const cx<T>* tw1;       // [16][256]  W_4096^{k1 t}
     const cx<T>* tw2;       // [16][16]   W_256^{a b}
@@ -103,27 +105,14 @@ struct SmemLayout {
 // of a warp sit 256 elements apart (same banks), so bit 3 of the in-region index is flipped by
 // (region parity ^ bit 4 of the index): every access pattern of X1..X4 is then conflict free for both element sizes
 // (complex64 rows: 13.0 k -> 11.0 k cycles per row on B200).
-// -DCAF_FAB_SOA keeps complex128 as two planes per pipeline (re[4096] | im[4096]) moved with 64-bit accesses.  On
-// B200 a conflict-free LDS.128 costs 8 cycles per warp (64 B/clk) against 2 x 2 cycles for two LDS.64
-// (scripts/micro/mio_cost.cu), so the planes halve the load time of every exchange -- and the row time does not move
-// (20.27 k vs 20.21 k cycles): the rows are not bound by shared-memory bandwidth.  Kept as an option, off by default.
 // ------------------------------------------------------------------------------------------------
 template <typename T> struct Fab;
-#ifdef CAF_FAB_SOA
-template <> struct Fab<double> {
-    using E = double;
-    static constexpr int kPipe = 2 * kL0;          // elements per pipeline
-    static __device__ __forceinline__ void st(E* p, int i, double2 v) { p[i] = v.x; p[kL0 + i] = v.y; }
-    static __device__ __forceinline__ double2 ld(const E* p, int i) { return make_double2(p[i], p[kL0 + i]); }
-};
-#else
-template <> struct Fab<double> {       // default: interleaved complex128, 128-bit accesses
+template <> struct Fab<double> {       // interleaved complex128, 128-bit accesses
     using E = double2;
     static constexpr int kPipe = kL0;
     static __device__ __forceinline__ void st(E* p, int i, double2 v) { p[i] = v; }
     static __device__ __forceinline__ double2 ld(const E* p, int i) { return p[i]; }
 };
-#endif
 template <> struct Fab<float> {
     using E = float2;
     static constexpr int kPipe = kL0;
@@ -140,7 +129,6 @@ struct Ctx {
     int wb;          // 256 w: this thread's region (sub-transform k1 = w) inside the pipeline
     int hs[2];       // h with bit 3 flipped by (sub ^ p): in-region column for an index whose bit 4 is p
     int hr;          // h with bit 3 flipped by (sub ^ h[0]): column base of the transposed X2/X3 reads (bit 4 = h[0])
-    uint32_t gate_scratch;   // shared-memory address of a scratch word (target of the never-taken release store)
     long long* tr;   // CAF_TRACE: this warp's slot array for the current item (lane 0 writes)
 
     __device__ __forceinline__ void init(unsigned char* smem_raw, int tid) {
@@ -156,7 +144,6 @@ struct Ctx {
         hr = h ^ (((sub ^ h) & 1) << 3);
         Sr = reinterpret_cast<typename Fab<T>::E*>(smem_raw) + r * Fab<T>::kPipe;
         ptab = nullptr; tm_tw = 0; tr = nullptr;
-        gate_scratch = (uint32_t)__cvta_generic_to_shared(smem_raw + SmemLayout<T>::offMisc + 8);
     }
     // block exchange X1 / X4 / mailbox: element (region k, column t)
     __device__ __forceinline__ int ix_block(int k) const { return k * 256 + 16 * w + hs[k & 1]; }
@@ -272,19 +259,6 @@ __device__ __forceinline__ float2 tmem_ld1(uint32_t taddr, float) {
     tmem_wait_ld();
     return make_float2(__uint_as_float(r[0]), __uint_as_float(r[1]));
 }
-// the real part of one slot (the ping-pong gate, 1.0)
-__device__ __forceinline__ double tmem_ld_gate(uint32_t taddr, double) {
-    uint32_t r[2];
-    tmem_ld_x2(taddr, r);
-    tmem_wait_ld();
-    return __hiloint2double((int)r[1], (int)r[0]);
-}
-__device__ __forceinline__ float tmem_ld_gate(uint32_t taddr, float) {
-    uint32_t r;
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];\n" : "=r"(r) : "r"(taddr) : "memory");
-    tmem_wait_ld();
-    return __uint_as_float(r);
-}
 __device__ __forceinline__ void tmem_st1(uint32_t taddr, double2 v) {
     uint32_t r[4] = {(uint32_t)__double2loint(v.x), (uint32_t)__double2hiint(v.x), (uint32_t)__double2loint(v.y), (uint32_t)__double2hiint(v.y)};
     tmem_st_x4(taddr, r);
@@ -318,77 +292,6 @@ __device__ __forceinline__ double2 unit_phasor(double n, double phi, double exac
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void bar_group(int r) { asm volatile("bar.sync %0, 256;\n" :: "r"(r + 1) : "memory"); }
 
-// Ping-pong of the fp64 pipe between the two groups (the FlashAttention-3 warpgroup schedule), -DCAF_PINGPONG=1:
-// a group runs its butterfly blocks only while it holds the token and does its shared-memory exchange while the
-// other group computes.
-//   acquire = bar.sync on the own barrier (256 waiters + 256 arrivals from the other group)
-//   release = bar.arrive on the other group's barrier
-// A barrier orders memory operations, not register arithmetic: ptxas floated two thirds of every butterfly block
-// out of its token window (SASS of the first attempt: 31 fp64 instructions left between BAR.SYNC and BAR.ARV).
-// The window is therefore closed with DATA dependencies:
-//   * acquire returns g == 1.0 read from TMEM after the barrier (tcgen05.ld is not queued behind the other
-//     group's shared-memory traffic) and the first butterfly level is computed as a +- g b (fft16_impl<GATED>), so
-//     no arithmetic of the block can start before the token is held;
-//   * release folds the bit patterns of every value of the row into one word and issues a shared-memory store
-//     predicated on that word (never true in practice, harmless if it were); bar.arrive cannot be moved above a
-//     store, so all arithmetic of the block is complete when the token is handed over.
-// Measured on B200 (scripts/trace_rows.py, scripts/quick_bench.py): the windows are then truly exclusive, and the
-// row gets SLOWER (21.1 k cycles against 20.2 k free-running; 21.9 k with CAF_PP_EARLY): with one group computing,
-// two warps per scheduler reach only ~75 % of the fp64 issue rate inside a window (exposed tcgen05.ld / barrier /
-// chain latencies that the other group's warps hide when both run free) and every hand-over leaves the pipe idle
-// for 30-400 cycles.  The free-running groups are the better schedule; the token stays in the source, off.
-#ifndef CAF_PINGPONG
-#define CAF_PINGPONG 0
-#endif
-constexpr bool kPingPong = (CAF_PINGPONG != 0);
-// Early release: the token is handed over after the butterfly of a block, so the twiddle multiplies (40 % of a
-// block) overlap the other group's start-up latency (barrier, gate load, first dependent levels).
-#ifndef CAF_PP_EARLY
-#define CAF_PP_EARLY 1
-#endif
-constexpr bool kEarlyRelease = (CAF_PP_EARLY != 0);
-
-__device__ __forceinline__ uint32_t fold_bits(const double2 (&v)[16]) {
-    uint32_t x = 0;
-#pragma unroll
-    for (int i = 0; i < 16; ++i) x ^= (uint32_t)__double2hiint(v[i].x) ^ (uint32_t)__double2hiint(v[i].y);
-    return x;
-}
-__device__ __forceinline__ uint32_t fold_bits(const float2 (&v)[16]) {
-    uint32_t x = 0;
-#pragma unroll
-    for (int i = 0; i < 16; ++i) x ^= __float_as_uint(v[i].x) ^ __float_as_uint(v[i].y);
-    return x;
-}
-__device__ __forceinline__ uint32_t fold_bits(double a, double b) { return (uint32_t)__double2hiint(a) ^ (uint32_t)__double2hiint(b); }
-__device__ __forceinline__ uint32_t fold_bits(float a, float b) { return __float_as_uint(a) ^ __float_as_uint(b); }
-
-template <bool PP, typename T>
-__device__ __forceinline__ T pp_acquire(const Ctx<T>& c) {
-    if constexpr (PP) {
-        asm volatile("bar.sync %0, 512;\n" :: "r"(3 + c.r) : "memory");
-        return tmem_ld_gate(c.tm_tw + 5 * TmemGeom<T>::kColsPerC, T());
-    } else {
-        return (T)1;
-    }
-}
-// hand the token over once `bits` (a fold of every result of the block) exists
-template <bool PP, typename T>
-__device__ __forceinline__ void pp_release_bits(const Ctx<T>& c, uint32_t bits) {
-    if constexpr (PP) {
-        asm volatile("{\n.reg .pred p;\nsetp.eq.u32 p, %0, 0x7ff5a5a5;\n@p st.shared.u32 [%1], %0;\nbar.arrive %2, 512;\n}\n"
-                     :: "r"(bits), "r"(c.gate_scratch), "r"(4 - c.r) : "memory");
-    }
-}
-template <bool PP, typename T>
-__device__ __forceinline__ void pp_release(const Ctx<T>& c, const cx<T> (&v)[16]) {
-    if constexpr (PP) pp_release_bits<PP, T>(c, fold_bits(v));
-}
-template <bool PP>
-__device__ __forceinline__ void pp_release_plain(int r) {
-    if constexpr (PP) asm volatile("bar.arrive %0, 512;\n" :: "r"(4 - r) : "memory");
-}
-
 __device__ __forceinline__ void mbar_init(uint64_t* mb, int count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" :: "r"((uint32_t)__cvta_generic_to_shared(mb)), "r"(count) : "memory");
 }
@@ -404,111 +307,78 @@ __device__ __forceinline__ void mbar_wait(uint64_t* mb, int parity) {
 
 // ------------------------------------------------------------------------------------------------
 // forward: v[i] = u_r[t + 256 i]  ->  v[k3] = U_r[k1 + 16 h + 256 k3]          (xcor_rustfft.rs:59,61)
-// Token discipline: entered HOLDING the fp64 token, returns HOLDING it.  Every shared-memory load a butterfly
-// block needs (twiddle bases) is issued in the exchange phase BEFORE the token is re-acquired, so a block never
-// waits behind the other group's exchange traffic in the LSU queue.
 // The five per-thread twiddle bases live in TMEM (tcgen05.ld is not queued behind shared-memory traffic).
 // `empty_mb` (group 1 only): the mailbox barrier to wait on before the fabric half is overwritten.
 // `hook()` runs in the exchange phase after the block barriers (deferred row-peak reduction), `hook3()` before the
 // last butterfly (a consumer CTA polls the H publication flag there, one pass ahead of its first use).
 // ------------------------------------------------------------------------------------------------
-// development experiments (never defined in the product build): drop the exchanges or the butterflies to see
-// how much of a row each side costs on its own (results are then wrong by construction)
-#ifdef CAF_EXP_NOXCHG
-#define CAF_XCHG(...) do { } while (0)
-#else
-#define CAF_XCHG(...) do { __VA_ARGS__; } while (0)
-#endif
-#ifdef CAF_EXP_NOFP
-#define CAF_FP(...) do { } while (0)
-#else
-#define CAF_FP(...) do { __VA_ARGS__; } while (0)
-#endif
-
-template <typename T, bool PP, typename Hook, typename Hook3>
+template <typename T, typename Hook, typename Hook3>
 __device__ __forceinline__ void forward_4096(cx<T> (&v)[16], const Ctx<T>& c,
                                              uint64_t* empty_mb, int empty_parity, Hook&& hook, Hook3&& hook3) {
     constexpr int kC = TmemGeom<T>::kColsPerC;
-    CAF_FP(fft16<T, false>(v));
-    if (kEarlyRelease) pp_release<PP, T>(c, v);
-    CAF_FP(twiddle_powers<false>(v, tmem_ld1(c.tm_tw, T())));           // W_4096^{t k}
-    if (!kEarlyRelease) pp_release<PP, T>(c, v);
+    fft16<T, false>(v);
+    twiddle_powers<false>(v, tmem_ld1(c.tm_tw, T()));           // W_4096^{t k}
     CAF_TR(c, 3);
     if (empty_mb) mbar_wait(empty_mb, empty_parity);   // group 0 has drained the previous row's mailbox
     bar_group(c.r);    // every earlier reader of this half of the fabric (previous X4 / X2) is done
 #pragma unroll
-    CAF_XCHG(for (int k = 0; k < 16; ++k) Fab<T>::st(c.Sr, c.ix_block(k), v[k]));
+    for (int k = 0; k < 16; ++k) Fab<T>::st(c.Sr, c.ix_block(k), v[k]);
     CAF_TR(c, 4);
     bar_group(c.r);
 #pragma unroll
-    CAF_XCHG(for (int i = 0; i < 16; ++i) v[i] = Fab<T>::ld(c.Sr, c.ix_own(i)));
+    for (int i = 0; i < 16; ++i) v[i] = Fab<T>::ld(c.Sr, c.ix_own(i));
     hook();
     CAF_TR(c, 5);
 
-    T g = pp_acquire<PP, T>(c);
-    CAF_TR(c, 25);
-    CAF_FP(fft16_impl<T, false, PP>(v, g));
-    if (kEarlyRelease) pp_release<PP, T>(c, v);
-    CAF_FP(twiddle_powers<false>(v, tmem_ld1(c.tm_tw + kC, T())));      // W_256^{h k}
-    if (!kEarlyRelease) pp_release<PP, T>(c, v);
+    fft16<T, false>(v);
+    twiddle_powers<false>(v, tmem_ld1(c.tm_tw + kC, T()));      // W_256^{h k}
     CAF_TR(c, 6);
     __syncwarp();
 #pragma unroll
-    CAF_XCHG(for (int k = 0; k < 16; ++k) Fab<T>::st(c.Sr, c.ix_tw(k), v[k]));
+    for (int k = 0; k < 16; ++k) Fab<T>::st(c.Sr, c.ix_tw(k), v[k]);
     __syncwarp();
 #pragma unroll
-    CAF_XCHG(for (int m = 0; m < 16; ++m) v[m] = Fab<T>::ld(c.Sr, c.ix_tr(m)));
+    for (int m = 0; m < 16; ++m) v[m] = Fab<T>::ld(c.Sr, c.ix_tr(m));
     hook3();
     CAF_TR(c, 7);
 
-    g = pp_acquire<PP, T>(c);
-    CAF_TR(c, 26);
-    CAF_FP(fft16_impl<T, false, PP>(v, g));    // returns holding the token
+    fft16<T, false>(v);
     CAF_TR(c, 8);
 }
 
 // ------------------------------------------------------------------------------------------------
 // inverse: v[k3] = Y_r[k1 + 16 h + 256 k3]  ->  v[n1] = A_r[t + 256 n1]  (unnormalised, xcor_rustfft.rs:76)
-// Entered and left HOLDING the token.
 // ------------------------------------------------------------------------------------------------
-template <typename T, bool PP>
+template <typename T>
 __device__ __forceinline__ void inverse_4096(cx<T> (&v)[16], const Ctx<T>& c) {
     constexpr int kC = TmemGeom<T>::kColsPerC;
-    CAF_FP(fft16<T, true>(v));
-    if (kEarlyRelease) pp_release<PP, T>(c, v);
-    CAF_FP(twiddle_powers<true>(v, tmem_ld1(c.tm_tw + kC, T())));       // conj W_256^{h k}
-    if (!kEarlyRelease) pp_release<PP, T>(c, v);
+    fft16<T, true>(v);
+    twiddle_powers<true>(v, tmem_ld1(c.tm_tw + kC, T()));       // conj W_256^{h k}
     CAF_TR(c, 10);
     __syncwarp();
 #pragma unroll
-    CAF_XCHG(for (int k = 0; k < 16; ++k) Fab<T>::st(c.Sr, c.ix_tw(k), v[k]));
+    for (int k = 0; k < 16; ++k) Fab<T>::st(c.Sr, c.ix_tw(k), v[k]);
     __syncwarp();
 #pragma unroll
-    CAF_XCHG(for (int m = 0; m < 16; ++m) v[m] = Fab<T>::ld(c.Sr, c.ix_tr(m)));
+    for (int m = 0; m < 16; ++m) v[m] = Fab<T>::ld(c.Sr, c.ix_tr(m));
     CAF_TR(c, 11);
 
-    T g = pp_acquire<PP, T>(c);
-    CAF_TR(c, 27);
-    CAF_FP(fft16_impl<T, true, PP>(v, g));
-    if (kEarlyRelease) pp_release<PP, T>(c, v);
+    fft16<T, true>(v);
     {
         const cx<T> b = tmem_ld1(c.tm_tw + 2 * kC, T()), rho = tmem_ld1(c.tm_tw + 3 * kC, T());
-        CAF_FP(twiddle_geometric<true>(v, b, rho));                     // conj W_4096^{k1 (16 k + h)}
+        twiddle_geometric<true>(v, b, rho);                     // conj W_4096^{k1 (16 k + h)}
     }
-    if (!kEarlyRelease) pp_release<PP, T>(c, v);
     CAF_TR(c, 12);
     __syncwarp();
 #pragma unroll
-    CAF_XCHG(for (int k = 0; k < 16; ++k) Fab<T>::st(c.Sr, c.ix_own(k), v[k]));
+    for (int k = 0; k < 16; ++k) Fab<T>::st(c.Sr, c.ix_own(k), v[k]);
     CAF_TR(c, 13);
     bar_group(c.r);
 #pragma unroll
-    CAF_XCHG(for (int k = 0; k < 16; ++k) v[k] = Fab<T>::ld(c.Sr, c.ix_block(k)));
+    for (int k = 0; k < 16; ++k) v[k] = Fab<T>::ld(c.Sr, c.ix_block(k));
     CAF_TR(c, 14);
 
-    g = pp_acquire<PP, T>(c);
-    CAF_TR(c, 28);
-    CAF_FP(fft16_impl<T, true, PP>(v, g));     // returns holding the token
+    fft16<T, true>(v);
     CAF_TR(c, 15);
 }
 
@@ -525,6 +395,16 @@ __device__ __forceinline__ cx<T> mul_w32_inv(cx<T> a) {
     else if constexpr (J == 8) return mk<T>(-a.y, a.x);                                   // +j
     else if constexpr (J < 8) return mk<T>(a.x * Cc[J] - a.y * Ss[J], a.x * Ss[J] + a.y * Cc[J]);
     else return mk<T>(-a.x * Ss[J - 8] - a.y * Cc[J - 8], a.x * Cc[J - 8] - a.y * Ss[J - 8]);   // (+j) * W_32^{-(J-8)}
+}
+
+// caf_b200_peak_pack on the device: [value bits, global doppler row (or ~0), delay, freq bits] -- the 32 bytes a rank
+// contributes to the cross-rank find_peak (mod.rs:31-42 over rows that live on several GPUs)
+__device__ __forceinline__ void pack_peak_words(const PeakOut& p, unsigned long long global_row_offset,
+                                                unsigned long long* __restrict__ words) {
+    words[0] = (unsigned long long)__double_as_longlong(p.value);
+    words[1] = (p.doppler_idx == ~0ull) ? ~0ull : p.doppler_idx + global_row_offset;
+    words[2] = p.delay_idx;
+    words[3] = (unsigned long long)__double_as_longlong(p.freq_hz);
 }
 
 // argmax helper: larger value wins, ties go to the lower index (== first strict-> maximum, mod.rs:148)
@@ -566,8 +446,6 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
     constexpr bool kHalfZero = (MODE == kSurface || MODE == kSpectrumHalf || MODE == kXcorHalf);
     constexpr bool kWritesH = (MODE == kSpectrumHalf || MODE == kSpectrumFull);
     constexpr bool kUseTmem = (MODE == kSurface);   // H and the needle live in TMEM (the twiddle bases always do)
-    // the fp64 token: surface rows in complex128 (the complex64 rows are not fp32-pipe bound)
-    constexpr bool PP = kPingPong && MODE == kSurface && std::is_same<T, double>::value;
 
     // ---- work split: contiguous ranges of (pair, row) items so a CTA changes pair as rarely as possible ----
     const int rows_per_pair = (MODE == kSurface) ? a.D : 1;
@@ -633,7 +511,6 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
         tmem_st1(c.tm_tw + 2 * TG::kColsPerC, tb2);
         tmem_st1(c.tm_tw + 3 * TG::kColsPerC, tb3);
         tmem_st1(c.tm_tw + 4 * TG::kColsPerC, tb4);
-        tmem_st1(c.tm_tw + 5 * TG::kColsPerC, mk<T>((T)1, (T)0));           // the ping-pong gate
         tmem_wait_st();
     }
 
@@ -655,9 +532,8 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
         Ph p; p.d1 = pt[1]; p.d8 = pt[8]; p.pw = pt[16 + w]; p.ph = pt[32 + h];
         return p;
     };
-    // g: the token gate (1.0); scaling the leading factor by it makes the whole phasor block depend on the acquire
-    auto phasor_mul = [&](C (&v)[16], const Ph& p, T g) {
-        C qa = cmul(mk<T>(p.pw.x * g, p.pw.y * g), p.ph), qb = cmul(qa, p.d8);
+    auto phasor_mul = [&](C (&v)[16], const Ph& p) {
+        C qa = cmul(p.pw, p.ph), qb = cmul(qa, p.d8);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             v[i] = cmul(v[i], qa);
@@ -701,8 +577,6 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
         else { mb = nullptr; par = 0; }
     };
 
-    if (r == 0) pp_release_plain<PP>(0);     // group 1 computes first: hand it the token
-
     c.tr = nullptr;
     for (int item = lo; item < hi; ++item, buf ^= 1) {
 #ifdef CAF_TRACE
@@ -736,11 +610,10 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
 #endif
                     CAF_TR(c, 0);
                     const Ph ph0 = phasor_load(buf);
-                    const T g0 = pp_acquire<PP, T>(c);
-                    phasor_mul(v, ph0, g0);
+                    phasor_mul(v, ph0);
                     uint64_t* mb; int par;
                     empty_gate(mb, par);
-                    forward_4096<T, PP>(v, c, mb, par, []{}, []{});
+                    forward_4096<T>(v, c, mb, par, []{}, []{});
                     const T sc = (T)(1.0 / 8192.0);   // the /n of xcor_rustfft.rs:72 (n = transform length)
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
@@ -752,7 +625,6 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
                         }
                         tmem_st4(tm_h + 4 * q * TG::kColsPerC, tmp);
                     }
-                    pp_release<PP, T>(c, v);
                     if (shared_h) {
                         __threadfence();
                         bar_group(r);
@@ -799,9 +671,7 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
                 // phasors of the next row: produced here, while this group waits for the token anyway; the group
                 // barriers of this row order them before their first use
                 if ((item + 1 < hi) && (row + 1 < a.D)) fill_ptab(buf ^ 1, a.freqs[row + 1] * a.dt);
-                const T g0 = pp_acquire<PP, T>(c);
-                CAF_TR(c, 24);
-                phasor_mul(v, ph0, g0);
+                phasor_mul(v, ph0);
             }
             CAF_TR(c, 2);
         } else if constexpr (kHalfZero) {
@@ -811,7 +681,7 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
             bar_group(r);
             {
                 const Ph ph0 = phasor_load(buf);
-                phasor_mul(v, ph0, (T)1);
+                phasor_mul(v, ph0);
             }
         } else {
             // general 8192-sample input: explicit first radix-2 stage
@@ -830,7 +700,7 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
             uint64_t* mb; int par;
             empty_gate(mb, par);
             // the previous row's per-warp maxima are folded in the first exchange phase (two group barriers have passed)
-            forward_4096<T, PP>(v, c, mb, par, [&] { if constexpr (MODE == kSurface) flush_peak((buf ^ 1) & 1); },
+            forward_4096<T>(v, c, mb, par, [&] { if constexpr (MODE == kSurface) flush_peak((buf ^ 1) & 1); },
                                 [&] {
                                     // first row of a consumer CTA: wait for H's publication here, while the last
                                     // butterfly is still ahead, so the L2 round trip of the flag is off the critical path
@@ -897,11 +767,10 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
 
             CAF_TR(c, 9);
             // ---------------- inverse transform ----------------
-            inverse_4096<T, PP>(v, c);   // v[n1] = A_r[t + 256 n1]
+            inverse_4096<T>(v, c);   // v[n1] = A_r[t + 256 n1]
 
             // ---------------- final radix-2 across the pipelines:  y[n] = A + B', y[n + 4096] = A - B',
             //                  B' = B W_8192^{-n},  n = t + 256 n1,  W_8192^{-n} = g[t] W_32^{-n1} ----------------
-            if (kEarlyRelease) pp_release<PP, T>(c, v);     // the last butterfly is done: the radix-2 / epilogue tail overlaps
             if (r == 1) {
                 const C gt = tmem_ld1(c.tm_tw + 4 * TG::kColsPerC, T());
                 auto post = [&](auto jt) {
@@ -910,7 +779,6 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
                 };
                 post(ic<0>{}); post(ic<1>{}); post(ic<2>{}); post(ic<3>{}); post(ic<4>{}); post(ic<5>{}); post(ic<6>{}); post(ic<7>{});
                 post(ic<8>{}); post(ic<9>{}); post(ic<10>{}); post(ic<11>{}); post(ic<12>{}); post(ic<13>{}); post(ic<14>{}); post(ic<15>{});
-                if (!kEarlyRelease) pp_release<PP, T>(c, v);
                 CAF_TR(c, 16);
                 bar_group(1);                 // all X4 reads of this half are done: it becomes the mailbox
 #pragma unroll
@@ -920,8 +788,6 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
                 ++posts;
                 drain_pending = true;
             } else {
-                // group 0 keeps the token through the epilogue: group 1 posted B' right after ITS last block,
-                // which precedes this one in token order, so the mailbox is normally full already
                 const int L = FULL ? kL0 : a.L;
                 const int nout = 2 * L, skip = kM - nout;
                 T* orow = (MODE == kSurface && a.out) ? reinterpret_cast<T*>(a.out) + item * (long long)nout : nullptr;
@@ -961,7 +827,6 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
                     emit(csub(v[k], Bp), n + kL0, best1, bidx1);       // lag index n + 4096
                 }
                 mbar_arrive(mb_empty);
-                if (!kEarlyRelease) pp_release_bits<PP, T>(c, fold_bits(best0, best1));
                 CAF_TR(c, 18);
                 ++posts;
 
@@ -1040,6 +905,7 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
                         p.value = 0.0; p.freq_hz = 0.0; p.doppler_idx = ~0ull; p.delay_idx = 0;
                     }
                     *a.peak = p;
+                    if (a.peak_words) pack_peak_words(p, a.row_offset, a.peak_words);
                     *a.done_counter = 0u;   // ready for the next launch on this stream
                 }
             }
@@ -1059,7 +925,9 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
 template <typename T>
 __global__ void __launch_bounds__(256) caf_peak_kernel(const T* __restrict__ row_val,
                                                        const unsigned long long* __restrict__ row_idx,
-                                                       const double* __restrict__ freqs, int D, PeakOut* out) {
+                                                       const double* __restrict__ freqs, int D, PeakOut* out,
+                                                       unsigned long long* words = nullptr,
+                                                       unsigned long long row_offset = 0ull) {
     __shared__ double sv[8];
     __shared__ int si[8];
     const long long base = (long long)blockIdx.x * D;
@@ -1086,20 +954,43 @@ __global__ void __launch_bounds__(256) caf_peak_kernel(const T* __restrict__ row
         } else {   // dummy row of find_peak: (0.0, 0)
             p.value = 0.0; p.freq_hz = 0.0; p.doppler_idx = ~0ull; p.delay_idx = 0;
         }
-        out[blockIdx.x] = p;
+        if (out) out[blockIdx.x] = p;
+        if (words && blockIdx.x == 0) pack_peak_words(p, row_offset, words);   // sharded rows: one pair per launch
     }
 }
 
-// caf_b200_peak_pack on the device: [value bits, global doppler row (or ~0), delay, freq bits] for the NCCL all-gather
+// caf_b200_peak_pack on the device for a peak that already exists (caf_b200_peak_allgather_dev); the sharded entry
+// points do not need it: their find_peak writes the packed words itself.  local == nullptr packs "no row".
 __global__ void caf_peak_pack_kernel(const PeakOut* __restrict__ local, unsigned long long global_row_offset,
                                      unsigned long long* __restrict__ words) {
     if (threadIdx.x == 0) {
-        const PeakOut p = *local;
-        words[0] = (unsigned long long)__double_as_longlong(p.value);
-        words[1] = (p.doppler_idx == ~0ull) ? ~0ull : p.doppler_idx + global_row_offset;
-        words[2] = p.delay_idx;
-        words[3] = (unsigned long long)__double_as_longlong(p.freq_hz);
+        PeakOut p;
+        if (local) p = *local;
+        else { p.value = 0.0; p.freq_hz = 0.0; p.doppler_idx = ~0ull; p.delay_idx = 0; }
+        pack_peak_words(p, global_row_offset, words);
     }
+}
+
+// caf_b200_peak_resolve on the device: find_peak (mod.rs:36-40) over the packed words of all ranks -- strict > in global
+// row order == larger value, ties to the lower global row.  A rank whose words[1] is the error sentinel (~0 - 1) makes
+// every rank report the failure (status word).
+constexpr unsigned long long kPeakNone = ~0ull, kPeakRemoteError = ~0ull - 1ull;
+__global__ void caf_peak_resolve_kernel(const unsigned long long* __restrict__ words, int world, PeakOut* out,
+                                        int* __restrict__ status) {
+    if (threadIdx.x != 0) return;
+    PeakOut best; best.value = 0.0; best.freq_hz = 0.0; best.doppler_idx = ~0ull; best.delay_idx = 0;
+    int st = 0;
+    for (int r = 0; r < world; ++r) {
+        const unsigned long long* w = words + 4 * r;
+        if (w[1] == kPeakRemoteError) { st = 1; continue; }
+        if (w[1] == kPeakNone) continue;
+        const double v = __longlong_as_double((long long)w[0]);
+        if (v > best.value || (v == best.value && v > 0.0 && w[1] < best.doppler_idx)) {
+            best.value = v; best.freq_hz = __longlong_as_double((long long)w[3]); best.doppler_idx = w[1]; best.delay_idx = w[2];
+        }
+    }
+    *out = best;
+    if (status) *status = st;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -23,7 +23,6 @@ template <typename T>
 struct LargeArgs {
     const cx<T>* in;                   // top spread: [L] needle (or haystack) of the current pair
     const double* freqs;               // [rows] doppler shifts of this chunk, or null for the haystack (no shift)
-    cx<T>* zbuf;                       // two levels: [rows][2][Ra][65536] scratch between the levels
     cx<T>* wbuf;                       // [units][4096] scratch around the core (units = rows * 2 * N/8192)
     cx<T>* hbig;                       // [N/8192 * 2][16][256]  H in the core's per-thread order
     T* surface;                        // [rows][2L] or null
@@ -69,7 +68,7 @@ __global__ void __launch_bounds__(256) caf_large_spread_top(const LargeArgs<T> a
     // the phasor step over one block of `inner` samples is the same for every column of the row: two threads compute it
     if (threadIdx.x < 2)
         s_step[threadIdx.x] = unit_phasor((double)inner, phi, (double)threadIdx.x * (double)inner / (double)a.N);
-    C* out = (inner == 4096) ? a.wbuf : a.zbuf;
+    C* out = a.wbuf;
     C x[R];
 #pragma unroll
     for (int rho = 0; rho < R; ++rho) {
@@ -99,27 +98,6 @@ __global__ void __launch_bounds__(256) caf_large_spread_top(const LargeArgs<T> a
             dst[(size_t)s * inner] = mul_by_d<T>(v[s], tw);
             tw = cmul_d(tw, om);
         }
-    }
-}
-
-// spread_mid: zbuf [unit][65536] -> wbuf [unit][16][4096], unit = (row, r, s_top); one thread per (unit, m)
-template <typename T>
-__global__ void __launch_bounds__(256, 3) caf_large_spread_mid(const LargeArgs<T> a) {
-    using C = cx<T>;
-    const int m = blockIdx.x * 256 + threadIdx.x;
-    const size_t unit = blockIdx.y;
-    const C* src = a.zbuf + unit * 65536 + m;
-    C v[16];
-#pragma unroll
-    for (int rho = 0; rho < 16; ++rho) v[rho] = src[4096 * rho];
-    fft16<T, false>(v);
-    const double2 om = root_of_unity(m, 65536, -1.0);                    // W_{65536}^{m}
-    double2 tw = make_double2(1.0, 0.0);
-    C* dst = a.wbuf + unit * 65536 + m;
-#pragma unroll
-    for (int s = 0; s < 16; ++s) {
-        dst[4096 * s] = mul_by_d<T>(v[s], tw);
-        tw = cmul_d(tw, om);
     }
 }
 
@@ -191,7 +169,7 @@ __global__ void __launch_bounds__(kThreads, 1) caf_large_core(const LargeArgs<T>
         C* buf = a.wbuf + ((size_t)row * units_per_row + hu) * kL0;
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] = buf[t + 256 * i];
-        forward_4096<T, false>(v, c, nullptr, 0, [] {}, [] {});
+        forward_4096<T>(v, c, nullptr, 0, [] {}, [] {});
         if (HMODE) {
 #pragma unroll
             for (int k = 0; k < 16; ++k) hp[k * 256] = mk<T>(v[k].x * scale, v[k].y * scale);
@@ -210,7 +188,7 @@ __global__ void __launch_bounds__(kThreads, 1) caf_large_core(const LargeArgs<T>
 #pragma unroll
                 for (int i = 0; i < 4; ++i) v[8 * q + 4 + i] = cmulc(hv[i], v[8 * q + 4 + i]);
             }
-            inverse_4096<T, false>(v, c);                                                       // v[n1] at m = t + 256 n1
+            inverse_4096<T>(v, c);                                                       // v[n1] at m = t + 256 n1
             {
                 const C b = tmem_ld1(c.tm_tw + 5 * TG::kColsPerC, T()), rho = tmem_ld1(c.tm_tw + 6 * TG::kColsPerC, T());
                 twiddle_geometric<false>(v, b, rho);
@@ -222,29 +200,6 @@ __global__ void __launch_bounds__(kThreads, 1) caf_large_core(const LargeArgs<T>
     asm volatile("tcgen05.fence::before_thread_sync;\n");
     __syncthreads();
     if (hw_warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" :: "r"(misc[0]), "n"(TG::kAlloc));
-}
-
-// gather_mid: wbuf [unit][16][4096] -> zbuf [unit][65536]: inverse 16-point DFT across s, then the conjugate twiddle
-// of the TOP level, conj(W_{N/2}^{j s_top}), j = m + 4096 rho, so that gather_top is a plain inverse DFT.
-template <typename T>
-__global__ void __launch_bounds__(256, 3) caf_large_gather_mid(const LargeArgs<T> a) {
-    using C = cx<T>;
-    const int m = blockIdx.x * 256 + threadIdx.x;
-    const size_t unit = blockIdx.y;
-    const int s_top = (int)(unit % a.Rtop), Lp = a.N / 2;
-    const C* src = a.wbuf + unit * 65536 + m;
-    C v[16];
-#pragma unroll
-    for (int s = 0; s < 16; ++s) v[s] = src[4096 * s];
-    fft16<T, true>(v);
-    double2 tw = root_of_unity((long long)m * s_top, Lp, 1.0);
-    const double2 step = root_of_unity(4096LL * s_top, Lp, 1.0);
-    C* dst = a.zbuf + unit * 65536 + m;
-#pragma unroll
-    for (int rho = 0; rho < 16; ++rho) {
-        dst[4096 * rho] = mul_by_d<T>(v[rho], tw);
-        tw = cmul_d(tw, step);
-    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -261,7 +216,7 @@ __global__ void __launch_bounds__(256, R <= 8 ? 3 : 1) caf_large_gather_top(cons
     const int j = blockIdx.x * 256 + threadIdx.x, row = blockIdx.y;
     const int inner = a.inner_top, Lp = a.N / 2, L = a.L;
     const long long nout = 2LL * L, skip = (long long)a.N - nout;
-    const C* in = (inner == 4096) ? a.wbuf : a.zbuf;
+    const C* in = a.wbuf;
     C a0[16], a1[16];
     const C* src = in + ((size_t)(row * 2) * R) * inner + j;
 #pragma unroll
@@ -566,368 +521,6 @@ __global__ void __launch_bounds__(16 * J, J == 16 ? 3 : J == 8 ? 6 : 1) caf_larg
             a.row_ticket[row] = 0u;          // self-resetting for the next chunk
         }
     }
-}
-
-// ================================================================================================
-// Cluster-fused long rows (16 384 <= N <= 65 536, i.e. R = N/8192 = 2, 4 or 8 units per pipeline; BASELINE config 3).
-//
-// One thread-block CLUSTER of R CTAs owns a row: CTA c hosts unit s = c of both pipelines (warp group r = pipeline r), so
-// the 2R units of a row sit on R SMs at once and the two transposes that the spread / core / gather chain above sends
-// through L2 (4 x 64 KB per unit) go through DISTRIBUTED SHARED MEMORY instead.  Per row:
-//   S  every thread takes 16/R sample columns j of its CTA's slice (4096/R columns) with all R blocks rho: needle from
-//      TMEM x phasor (mod.rs:46-65), R-point DFT over rho, twiddle W_{N/2}^{j s}; value (j, s) is stored straight into
-//      the fabric of CTA s (st.shared::cluster), where it is element j of that CTA's 4096-point unit
-//   C  cluster barrier; forward_4096, x H (this CTA's 2 x 4096 bins of H never change: TMEM), inverse_4096, conjugate
-//      inner twiddle -- the same in-register core as everywhere else
-//   G  cluster barrier; element m of unit s goes to the CTA that owns column m (remote stores again); cluster barrier;
-//      inverse R-point DFT over s, W_N^{-n} on pipeline 1, the two groups swap half of their columns through their own
-//      fabric halves, then radix-2 across the pipelines, |.|^2 (mod.rs:147), store, row argmax (mod.rs:141-153)
-// Nothing but the needle (once), H (once), the surface cells and 16 bytes of row peak per CTA touches L2.
-// Four cluster barrier generations per row; two of them are split (arrive early, wait late).
-// ================================================================================================
-__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r)); return r; }
-__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory"); }
-__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory"); }
-__device__ __forceinline__ uint32_t dsmem_map(uint32_t local_addr, uint32_t rank) {
-    uint32_t r;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(r) : "r"(local_addr), "r"(rank));
-    return r;
-}
-__device__ __forceinline__ void dsmem_st(uint32_t addr, double2 v) {
-    asm volatile("st.shared::cluster.v2.f64 [%0], {%1, %2};\n" :: "r"(addr), "d"(v.x), "d"(v.y) : "memory");
-}
-__device__ __forceinline__ void dsmem_st(uint32_t addr, float2 v) {
-    asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};\n" :: "r"(addr), "f"(v.x), "f"(v.y) : "memory");
-}
-
-// v[RHO] *= e^{+2 pi j RHO / (2R)} for RHO = 0..R-1 (compile-time roots through mul_w32_inv)
-template <typename T, int R, int RHO = 0>
-__device__ __forceinline__ void mul_w2r_inv(cx<T> (&v)[16]) {
-    if constexpr (RHO < R) {
-        v[RHO] = mul_w32_inv<T, (16 / R) * RHO>(v[RHO]);
-        mul_w2r_inv<T, R, RHO + 1>(v);
-    }
-}
-
-template <typename T, int R>
-__global__ void __launch_bounds__(kThreads, 1) caf_cluster_rows_kernel(const LargeArgs<T> a) {
-    using C = cx<T>;
-    using SL = SmemLayout<T>;
-    using TG = TmemGeom<T>;
-    constexpr int Q = 16 / R;              // sample columns per thread
-    constexpr int Wj = kL0 / R;            // columns per CTA slice (= 256 Q)
-    static_assert(R == 2 || R == 4 || R == 8, "cluster size");
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    C* ptab = reinterpret_cast<C*>(smem_raw + SL::offPtab);
-    unsigned long long* red_idx = reinterpret_cast<unsigned long long*>(smem_raw + SL::offRed);
-    double* red_val = reinterpret_cast<double*>(smem_raw + SL::offRed + 128);
-    uint32_t* misc = reinterpret_cast<uint32_t*>(smem_raw + SL::offMisc);
-
-    const int tid = threadIdx.x, hw_warp = tid >> 5, tg = tid & 255;
-    Ctx<T> c;
-    c.init(smem_raw, tid);
-    c.ptab = ptab;
-    const int r = c.r, t = c.t, lane = c.lane;
-    const int crank = (int)cluster_ctarank();                 // = unit s of this CTA
-    const int n_clusters = gridDim.x / R, cluster_id = blockIdx.x / R;
-    const int J0 = crank * Wj;
-    const int N = a.N, Lp = N / 2, L = a.L;
-    // plain interleaved views of the two fabric halves for the spread / gather / swap exchanges (the core re-indexes
-    // the same bytes through Fab<T>; the phases are separated by barriers)
-    C* half_own = reinterpret_cast<C*>(smem_raw) + r * kL0;
-    C* half_other = reinterpret_cast<C*>(smem_raw) + (r ^ 1) * kL0;
-    const uint32_t half_own_addr = (uint32_t)__cvta_generic_to_shared(half_own);
-
-    // ---- global loads first: twiddle bases of the core, the needle columns, H of this CTA's unit ----
-    const C tb0 = ldg<T>(a.tw1 + 256 + t), tb1 = ldg<T>(a.tw2 + 16 + c.h), tb2 = ldg<T>(a.tw1 + c.w * 256 + c.h),
-            tb3 = ldg<T>(a.tw2 + 16 + c.w);
-    C v[16];
-#pragma unroll
-    for (int q = 0; q < Q; ++q)
-#pragma unroll
-        for (int rho = 0; rho < R; ++rho) {
-            const long long n = (long long)J0 + tg + 256 * q + (long long)kL0 * rho;
-            v[q * R + rho] = (n < L) ? __ldg(a.in + n) : mk<T>((T)0, (T)0);
-        }
-    if (hw_warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n"
-                     :: "l"((uint64_t)__cvta_generic_to_shared(&misc[0])), "n"(TG::kAlloc));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;\n");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;\n");
-    const uint32_t tbase = misc[0] + ((uint32_t)(32 * (hw_warp & 3)) << 16);
-    const int jw = hw_warp >> 2;
-    const uint32_t tm_h = tbase + (uint32_t)((16 * jw) * TG::kColsPerC);
-    const uint32_t tm_n = tbase + (uint32_t)((64 + 16 * (jw & 1)) * TG::kColsPerC);     // shared by the two groups
-    c.tm_tw = tbase + (uint32_t)((96 + 8 * jw) * TG::kColsPerC);
-    {
-        // per-thread constants: the core's bases (slots 0-3), rho / b of the conjugate inner twiddle (4, 7),
-        // W_N^{-j0} and its step over 256 columns (5, 6)
-        const int tot = Lp;
-        const double2 rho_ = root_of_unity(256LL * crank, tot, 1.0), b_ = root_of_unity((long long)t * crank, tot, 1.0);
-        const double2 g0 = root_of_unity(J0 + tg, N, 1.0), g256 = root_of_unity(256, N, 1.0);
-        tmem_st1(c.tm_tw + 0 * TG::kColsPerC, tb0);
-        tmem_st1(c.tm_tw + 1 * TG::kColsPerC, tb1);
-        tmem_st1(c.tm_tw + 2 * TG::kColsPerC, tb2);
-        tmem_st1(c.tm_tw + 3 * TG::kColsPerC, tb3);
-        tmem_st1(c.tm_tw + 4 * TG::kColsPerC, mk<T>((T)rho_.x, (T)rho_.y));
-        tmem_st1(c.tm_tw + 5 * TG::kColsPerC, mk<T>((T)g0.x, (T)g0.y));
-        tmem_st1(c.tm_tw + 6 * TG::kColsPerC, mk<T>((T)g256.x, (T)g256.y));
-        tmem_st1(c.tm_tw + 7 * TG::kColsPerC, mk<T>((T)b_.x, (T)b_.y));
-#pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4) {
-            C tmp[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) tmp[i] = v[4 * q4 + i];
-            tmem_st4(tm_n + 4 * q4 * TG::kColsPerC, tmp);                    // both groups store the same samples
-        }
-        const C* hp = a.hbig + ((size_t)(r * R + crank) * 16) * 256 + tg;    // [unit][k][thread], as caf_large_core wrote it
-#pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4) {
-            C tmp[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) tmp[i] = ldg<T>(hp + (4 * q4 + i) * 256);
-            tmem_st4(tm_h + 4 * q4 * TG::kColsPerC, tmp);
-        }
-        tmem_wait_st();
-    }
-
-    // phasor tables of one row: ptab[buf][r][0..15] = e(16 a), [16..31] = e(b), [32] = e(J0), [33] = e(256), [34] = e(4096)
-    // with e(n) = exp(j 2 pi n (f/fs - r/N))
-    auto fill_ptab = [&](int buf, double phi) {
-        if (tg < 35) {
-            const int e = tg;
-            const int n = (e < 16) ? 16 * e : (e < 32) ? (e - 16) : (e == 32) ? J0 : (e == 33) ? 256 : kL0;
-            const double2 pz = unit_phasor((double)n, phi, (double)((long long)r * n) / (double)N);
-            ptab[(buf * 2 + r) * 48 + e] = mk<T>((T)pz.x, (T)pz.y);
-        }
-    };
-    auto load4 = [&](uint32_t base, C (&dst)[16]) {
-        typename raw4_of<T>::type q0, q1, q2, q3;
-        tmem_ld4_issue(base + 0 * TG::kColsPerC, q0); tmem_ld4_issue(base + 4 * TG::kColsPerC, q1);
-        tmem_ld4_issue(base + 8 * TG::kColsPerC, q2); tmem_ld4_issue(base + 12 * TG::kColsPerC, q3);
-        tmem_wait_ld();
-        C tmp[4];
-        tmem_unpack4(q0, tmp); dst[0] = tmp[0]; dst[1] = tmp[1]; dst[2] = tmp[2]; dst[3] = tmp[3];
-        tmem_unpack4(q1, tmp); dst[4] = tmp[0]; dst[5] = tmp[1]; dst[6] = tmp[2]; dst[7] = tmp[3];
-        tmem_unpack4(q2, tmp); dst[8] = tmp[0]; dst[9] = tmp[1]; dst[10] = tmp[2]; dst[11] = tmp[3];
-        tmem_unpack4(q3, tmp); dst[12] = tmp[0]; dst[13] = tmp[1]; dst[14] = tmp[2]; dst[15] = tmp[3];
-    };
-
-    int buf = 0;
-    if (cluster_id < a.rows) fill_ptab(0, a.freqs[cluster_id] * a.dt);
-    __syncthreads();
-    cluster_arrive();                                  // generation "a" of the first row: every fabric is free
-    const long long nout = 2LL * L, skip = (long long)N - nout;
-
-#ifdef CAF_TRACE
-    int tr_i = 0;
-#define CL_TR(slot_) do { if (a.trace && tg == 0 && tr_i < 8) a.trace[(((long long)blockIdx.x * 2 + r) * 8 + tr_i) * 16 + (slot_)] = clock64(); } while (0)
-#else
-#define CL_TR(slot_) do { } while (0)
-#endif
-    for (int row = cluster_id; row < a.rows; row += n_clusters, buf ^= 1) {
-        CL_TR(0);
-        // ---------------- S: needle x phasor, R-point DFT over the blocks, outer twiddle ----------------
-        load4(tm_n, v);
-        {
-            const C* pt = ptab + (buf * 2 + r) * 48;
-            const C d256 = pt[33], d4096 = pt[34];
-            C pq = cmul(cmul(pt[32], pt[tg >> 4]), pt[16 + (tg & 15)]);          // e(J0 + tg)
-#pragma unroll
-            for (int q = 0; q < Q; ++q) {
-                C pr = pq;
-#pragma unroll
-                for (int rho = 0; rho < R; ++rho) {
-                    v[q * R + rho] = cmul(v[q * R + rho], pr);
-                    if (rho + 1 < R) pr = cmul(pr, d4096);
-                }
-                if (q + 1 < Q) pq = cmul(pq, d256);
-            }
-        }
-        {
-            const C g256 = tmem_ld1(c.tm_tw + 6 * TG::kColsPerC, T());
-            C gj = tmem_ld1(c.tm_tw + 5 * TG::kColsPerC, T());                   // W_N^{-j}, j = J0 + tg + 256 q
-#pragma unroll
-            for (int q = 0; q < Q; ++q) {
-                C blk[16];
-#pragma unroll
-                for (int i = 0; i < R; ++i) blk[i] = v[q * R + i];
-                dft_small<T, R, false>(blk);
-                const C om = csq(gj);                                            // conj(om) = W_{N/2}^{j}
-                C tw = mk<T>(om.x, -om.y);
-                v[q * R] = blk[0];
-#pragma unroll
-                for (int s_ = 1; s_ < R; ++s_) {
-                    v[q * R + s_] = cmul(blk[s_], tw);
-                    if (s_ + 1 < R) tw = cmulc(tw, om);
-                }
-                if (q + 1 < Q) gj = cmul(gj, g256);
-            }
-        }
-        CL_TR(1);
-        cluster_wait();                                // "a": nobody still reads last row's data in any fabric
-        CL_TR(2);
-#pragma unroll
-        for (int s_ = 0; s_ < R; ++s_) {
-            const uint32_t dst = dsmem_map(half_own_addr, (uint32_t)s_);
-#pragma unroll
-            for (int q = 0; q < Q; ++q)
-                dsmem_st(dst + (uint32_t)sizeof(C) * (uint32_t)(J0 + tg + 256 * q), v[q * R + s_]);
-        }
-        CL_TR(3);
-        cluster_arrive();
-        // next row's phasor tables: computed while the remote stores drain (ptab[buf ^ 1] was last read in the previous
-        // row; the barriers of this row order it before its first use)
-        if (row + n_clusters < a.rows) fill_ptab(buf ^ 1, a.freqs[row + n_clusters] * a.dt);
-        cluster_wait();                                // "b": this CTA's units are complete
-        CL_TR(4);
-
-        // ---------------- C: the 4096-point core on unit (r, crank) ----------------
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = half_own[t + 256 * i];
-        forward_4096<T, false>(v, c, nullptr, 0, [] {}, [] {});
-        {
-            C hv[16];
-            load4(tm_h, hv);
-#pragma unroll
-            for (int k = 0; k < 16; ++k) v[k] = cmulc(hv[k], v[k]);              // H conj(X), xcor_rustfft.rs:64-73
-        }
-        inverse_4096<T, false>(v, c);                                            // v[n1] at m = t + 256 n1
-        CL_TR(5);
-        cluster_arrive();                              // "c": this thread no longer touches its fabric half
-        {
-            const C b = tmem_ld1(c.tm_tw + 7 * TG::kColsPerC, T()), rho = tmem_ld1(c.tm_tw + 4 * TG::kColsPerC, T());
-            twiddle_geometric<false>(v, b, rho);                                 // conj(W_{N/2}^{m s})
-        }
-
-        CL_TR(6);
-        cluster_wait();                                // every core of the cluster is done: the fabrics are free
-        CL_TR(7);
-
-        // ---------------- G: element m of unit s -> the CTA that owns column m, slot [s][m - J0'] ----------------
-#pragma unroll
-        for (int k = 0; k < 16; ++k) {
-            const int m = t + 256 * k;
-            const uint32_t dst = dsmem_map(half_own_addr, (uint32_t)(m / Wj));
-            dsmem_st(dst + (uint32_t)sizeof(C) * (uint32_t)(crank * Wj + (m % Wj)), v[k]);
-        }
-        CL_TR(8);
-        cluster_arrive();
-        cluster_wait();                                // "d"
-        CL_TR(9);
-#pragma unroll
-        for (int q = 0; q < Q; ++q)
-#pragma unroll
-            for (int s_ = 0; s_ < R; ++s_) v[q * R + s_] = half_own[s_ * Wj + tg + 256 * q];
-        {
-            const C g256 = tmem_ld1(c.tm_tw + 6 * TG::kColsPerC, T());
-            C gj = tmem_ld1(c.tm_tw + 5 * TG::kColsPerC, T());
-#pragma unroll
-            for (int q = 0; q < Q; ++q) {
-                C blk[16];
-#pragma unroll
-                for (int i = 0; i < R; ++i) blk[i] = v[q * R + i];
-                dft_small<T, R, true>(blk);                                      // A_r[j + 4096 rho]
-                if (r == 1) {
-                    // B' = B W_N^{-n}, n = j + 4096 rho:  W_N^{-j} e^{+2 pi j rho / (2R)}
-#pragma unroll
-                    for (int i = 0; i < R; ++i) blk[i] = cmul(blk[i], gj);
-                    mul_w2r_inv<T, R>(blk);
-                }
-#pragma unroll
-                for (int i = 0; i < R; ++i) v[q * R + i] = blk[i];
-                if (q + 1 < Q) gj = cmul(gj, g256);
-            }
-        }
-        // the groups swap half of their columns: group 0 finishes q < Q/2, group 1 finishes q >= Q/2
-        bar_group(r);                                  // the gather data of this half has been read by the whole group
-        constexpr int Qh = Q / 2;
-#pragma unroll
-        for (int q = 0; q < Qh; ++q)
-#pragma unroll
-            for (int i = 0; i < R; ++i)                                          // the columns the OTHER group finishes
-                half_own[tg + 256 * (q * R + i)] = (r == 0) ? v[(q + Qh) * R + i] : v[q * R + i];
-        __syncthreads();
-        T best = (T)0;
-        long long bidx = 0x7fffffffffffffffLL;
-        T* orow = a.surface ? a.surface + (size_t)row * nout : nullptr;
-#pragma unroll
-        for (int q = 0; q < Qh; ++q) {
-            const int qm = (r == 0) ? q : q + Qh;                                // the columns this group finishes
-#pragma unroll
-            for (int i = 0; i < R; ++i) {
-                const C other = half_other[tg + 256 * (q * R + i)];
-                const C mine = (r == 0) ? v[q * R + i] : v[(q + Qh) * R + i];    // compile-time register indices
-                const C A = (r == 0) ? mine : other;
-                const C B = (r == 0) ? other : mine;
-                const long long n = (long long)J0 + tg + 256 * qm + (long long)kL0 * i;
-#pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    const C y = half ? csub(A, B) : cadd(A, B);
-                    const long long kp = n + (long long)half * Lp;
-                    const T mag = y.x * y.x + y.y * y.y;                         // norm_sqr, mod.rs:147
-                    long long k = -1;
-                    if (kp <= L) k = kp; else if (kp > (long long)N - L) k = kp - skip;   // the reference's 2L-cell layout
-                    if (k >= 0 && k < nout) {
-                        if (orow) orow[k] = mag;
-                        if (mag > best || (mag == best && k < bidx)) { best = mag; bidx = k; }
-                    }
-                }
-            }
-        }
-        CL_TR(10);
-        cluster_arrive();                              // "a" of the next row: this thread is done with both halves
-        // ---------------- row argmax (mod.rs:141-153): CTA partial, last CTA of the cluster folds ----------------
-        {
-            double bv = (double)best;
-            long long bi = bidx;
-#pragma unroll
-            for (int off = 16; off > 0; off >>= 1) {
-                const double ov = __shfl_xor_sync(0xffffffffu, bv, off);
-                const long long oi = __shfl_xor_sync(0xffffffffu, bi, off);
-                if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
-            }
-            if (lane == 0) { red_val[hw_warp] = bv; red_idx[hw_warp] = (unsigned long long)bi; }
-            __syncthreads();
-            if (tid == 0) {
-                for (int w_ = 1; w_ < 16; ++w_) {
-                    const double ov = red_val[w_];
-                    const long long oi = (long long)red_idx[w_];
-                    if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
-                }
-                a.part_val[(size_t)row * R + crank] = bv;
-                a.part_idx[(size_t)row * R + crank] = (int)(bi > 0x7fffffffLL ? 0x7fffffff : bi);
-                __threadfence();
-                const unsigned int ticket = atomicAdd(a.row_ticket + row, 1u);
-                if (ticket == (unsigned int)R - 1) {
-                    __threadfence();
-                    double b2 = 0.0;
-                    int i2 = 0x7fffffff;
-                    for (int q = 0; q < R; ++q) {
-                        const double pv = __ldcg(a.part_val + (size_t)row * R + q);
-                        const int pi_ = __ldcg(a.part_idx + (size_t)row * R + q);
-                        if (pv > b2 || (pv == b2 && pi_ < i2)) { b2 = pv; i2 = pi_; }
-                    }
-                    if (!(b2 > 0.0)) i2 = 0;
-                    if (a.row_peak_val) a.row_peak_val[row] = (T)b2;
-                    if (a.row_peak_idx) a.row_peak_idx[row] = (unsigned long long)i2;
-                    a.row_ticket[row] = 0u;
-                }
-            }
-            __syncthreads();                           // red_* are reused by the next row
-        }
-        CL_TR(11);
-#ifdef CAF_TRACE
-        ++tr_i;
-#endif
-    }
-    cluster_wait();                                    // balance the last arrive; no CTA leaves while a peer may write to it
-    asm volatile("tcgen05.fence::before_thread_sync;\n");
-    __syncthreads();
-    if (hw_warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" :: "r"(misc[0]), "n"(TG::kAlloc));
 }
 
 }  // namespace caf

@@ -85,16 +85,6 @@ template <typename T, bool INV>
 __device__ __forceinline__ void radix4(cx<T>& a0, cx<T>& a1, cx<T>& a2, cx<T>& a3) {
     radix4_tail<T, INV>(cadd(a0, a2), csub(a0, a2), cadd(a1, a3), csub(a1, a3), a0, a1, a2, a3);
 }
-// Gated butterfly: the first level is written a + g b / a - g b with g == 1.0 fetched at run time (after a
-// barrier).  fma(g, b, a) rounds b + a once, so the result is bit-identical to the plain butterfly, but every
-// operation of the transform now depends on g: ptxas cannot start the arithmetic before g exists.
-template <typename T, bool INV>
-__device__ __forceinline__ void radix4_gated(cx<T>& a0, cx<T>& a1, cx<T>& a2, cx<T>& a3, T g) {
-    const cx<T> t0 = mk<T>(fma(g, a2.x, a0.x), fma(g, a2.y, a0.y)), t1 = mk<T>(fma(-g, a2.x, a0.x), fma(-g, a2.y, a0.y));
-    const cx<T> t2 = mk<T>(fma(g, a3.x, a1.x), fma(g, a3.y, a1.y)), t3 = mk<T>(fma(-g, a3.x, a1.x), fma(-g, a3.y, a1.y));
-    radix4_tail<T, INV>(t0, t1, t2, t3, a0, a1, a2, a3);
-}
-
 // a *= W16^E (forward sign e^{-2 pi j E/16}; conjugated when INV)
 template <typename T, int E, bool INV>
 __device__ __forceinline__ cx<T> mul_w16(cx<T> a) {
@@ -152,15 +142,11 @@ __device__ __forceinline__ void radix4_twiddled(cx<T>& a0, cx<T>& a1, cx<T>& a2,
 }
 
 // In-place 16-point DFT, natural order in and out: v[k] <- sum_i v[i] e^{-+2 pi j i k/16}
-// GATED: first level through radix4_gated (g == 1.0 at run time, see above).
-template <typename T, bool INV, bool GATED>
-__device__ __forceinline__ void fft16_impl(cx<T> (&v)[16], T g) {
+template <typename T, bool INV>
+__device__ __forceinline__ void fft16(cx<T> (&v)[16]) {
     // stage A: i = c + 4a  ->  A[c][ka] left at v[c + 4 ka]
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-        if constexpr (GATED) radix4_gated<T, INV>(v[c], v[c + 4], v[c + 8], v[c + 12], g);
-        else radix4<T, INV>(v[c], v[c + 4], v[c + 8], v[c + 12]);
-    }
+    for (int c = 0; c < 4; ++c) radix4<T, INV>(v[c], v[c + 4], v[c + 8], v[c + 12]);
     // stage B: over c for each ka -> X[ka + 4 kb] left at v[4 ka + kb]; the twiddles W16^{c ka} ride in the butterflies
     radix4<T, INV>(v[0], v[1], v[2], v[3]);
     radix4_twiddled<T, INV, 1, 2, 3>(v[4], v[5], v[6], v[7]);
@@ -175,10 +161,6 @@ __device__ __forceinline__ void fft16_impl(cx<T> (&v)[16], T g) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = o[i];
 }
-template <typename T, bool INV>
-__device__ __forceinline__ void fft16(cx<T> (&v)[16]) { fft16_impl<T, INV, false>(v, (T)1); }
-template <typename T, bool INV>
-__device__ __forceinline__ void fft16_gated(cx<T> (&v)[16], T g) { fft16_impl<T, INV, true>(v, g); }
 
 // In-place R-point DFT (R = 2, 4, 8 or 16) on v[0..R), natural order in and out.  Used by the long-row spread /
 // gather steps, whose radix is N / 8192.

@@ -21,10 +21,8 @@
  *    not thread-safe; distinct handles are independent.
  *  - there is NO CPU fallback: if no sm_100 device is usable, create() fails.
  *
- * Environment (development / measurement switches, read by the library; none is needed for normal use):
- *    CAF_B200_CHUNK_MB=<n>   scratch budget per buffer for rows longer than 8192 cells (default 6144)
- *    CAF_B200_FUSED2=0       two-level rows: the five-pass spread/gather chain instead of the fused kernels
- *    CAF_B200_CLUSTER=1      one-level long rows: the cluster / distributed-shared-memory kernel (measured slower)
+ * Environment (development / measurement switches, read ONCE when a handle is created; none is needed for normal use):
+ *    CAF_B200_CHUNK_MB=<n>   scratch budget for rows longer than 8192 cells (default 6144)
  *    CAF_B200_PIPELINE=0     host surface calls: one launch + one D2H copy instead of head/rest overlap
  *    CAF_B200_PEAK_ZEROCOPY=0  single-pair host calls: copy the peak back instead of storing it into pinned host memory
  *    CAF_B200_NCCL_LIB=<so>  which libnccl to dlopen for caf_b200_comm_* (default: the loaded one, then libnccl.so.2)
@@ -57,7 +55,8 @@ typedef enum {
     CAF_B200_EUNSUPPORTED = -3,  /* size outside what this build implements */
     CAF_B200_ECUDA = -4,         /* CUDA runtime error (message in last_error) */
     CAF_B200_ENODEVICE = -5,     /* no usable sm_100 GPU — there is no CPU fallback */
-    CAF_B200_ENCCL = -6          /* NCCL missing or an NCCL call failed (message in last_error) */
+    CAF_B200_ENCCL = -6,         /* NCCL missing or an NCCL call failed (message in last_error) */
+    CAF_B200_EREMOTE = -7        /* sharded call: a PEER rank failed before the peak exchange (every rank still left the collective) */
 } caf_b200_status;
 
 /* Result of CafSurface::find_peak (mod.rs:31-42).  When no row beats the dummy 0.0 row (empty or
@@ -178,6 +177,9 @@ int caf_b200_surface_layout_f32(caf_b200_handle h, const caf_c64* needle, const 
  * doppler row).  Pure host helpers; no GPU work. */
 void caf_b200_peak_pack(const caf_b200_peak* local, uint64_t global_row_offset, uint64_t words[4]);
 void caf_b200_peak_resolve(const uint64_t* words, size_t world, caf_b200_peak* out);
+/* same, and returns 1 when some rank's words carry the failure mark (words[1] == UINT64_MAX - 1: that rank could not
+ * compute its shard but still took part in the collective), else 0 */
+int caf_b200_peak_resolve_status(const uint64_t* words, size_t world, caf_b200_peak* out);
 
 /* ---- the same exchange inside the library: NCCL over NVLink, one process per GPU ---------------------
  * For callers without their own collective layer (the Rust shim).  libnccl.so.2 is dlopen()ed on first use —
@@ -199,6 +201,25 @@ int caf_b200_comm_shard(caf_b200_comm c, size_t n, size_t* lo, size_t* hi);
  * the handle's stream) and resolved with find_peak's tie-break.  Every rank gets the same `out` (host). */
 int caf_b200_peak_allgather_dev(caf_b200_handle h, caf_b200_comm c, const caf_b200_peak* local_peak_dev,
                                 uint64_t global_row_offset, caf_b200_peak* out);
+/* The same exchange with NO host synchronisation: pack (local_peak_dev == NULL packs "this rank owns no row"),
+ * ncclAllGather and the resolution all run on the handle's stream; out_dev (device memory, or pinned host memory) holds
+ * the global peak once the stream reaches that point.  caf_b200_comm_remote_error() afterwards (after a sync) tells
+ * whether a peer had failed. */
+int caf_b200_peak_allgather_async(caf_b200_handle h, caf_b200_comm c, const caf_b200_peak* local_peak_dev,
+                                  uint64_t global_row_offset, caf_b200_peak* out_dev);
+int caf_b200_comm_remote_error(caf_b200_comm c, int* flag);
+/* Device-resident sharded surface (mod.rs:185 par_iter over rows + mod.rs:31-42 across GPUs), fully asynchronous:
+ * this rank's rows freqs_local[0..d_local) are global rows row_offset.., every pointer is device memory; the local
+ * find_peak writes its result already packed for the exchange, then ONE ncclAllGather of 32 bytes per rank and a
+ * device-side resolve leave the global peak in peak_out (device or pinned host memory).  No host synchronisation.
+ * If the local computation cannot be issued, the rank still enters the collective with a failure mark, every peer's
+ * next resolve reports CAF_B200_EREMOTE / remote_error, and this call returns the local error. */
+int caf_b200_sharded_f64_dev(caf_b200_handle h, caf_b200_comm c, const caf_c128* needle, const caf_c128* haystack, size_t l,
+                             const double* freqs_local, size_t d_local, uint64_t row_offset, uint32_t fs,
+                             double* surface_local, double* row_peak_val, uint64_t* row_peak_idx, caf_b200_peak* peak_out);
+int caf_b200_sharded_f32_dev(caf_b200_handle h, caf_b200_comm c, const caf_c64* needle, const caf_c64* haystack, size_t l,
+                             const double* freqs_local, size_t d_local, uint64_t row_offset, uint32_t fs,
+                             float* surface_local, float* row_peak_val, uint64_t* row_peak_idx, caf_b200_peak* peak_out);
 /* CafSurface::caf_surface + find_peak with the doppler ROWS sharded across the communicator (mod.rs:185 par_iter
  * over rows, one GPU per block of rows): every rank passes the SAME host inputs and the full grid; rank r computes
  * rows [lo, hi) = caf_b200_comm_shard(d), writes them to surface_local ((hi-lo) x 2l, or NULL) and receives the

@@ -42,11 +42,7 @@ def main():
     if args.exchange == "abi" and args.config in (3, 5):
         import tempfile
         id_path = os.path.join(tempfile.gettempdir(), "caf_nccl_id_%s_%s" % (os.environ.get("MASTER_PORT", "0"), os.environ.get("TORCHELASTIC_RUN_ID", "x")))
-        if rank == 0 and os.path.exists(id_path):
-            os.remove(id_path)
-        if world > 1:
-            dist.barrier()
-        comm = cdist.Comm(h, world, rank, id_path)
+        comm = cdist.Comm(h, world, rank, id_path)        # per-run nonce inside the file: a stale id is never picked up
     if args.config in (3, 5):
         L = 32768 if args.config == 3 else 1 << 19
         D = args.rows or (4096 if args.config == 3 else 16384)

@@ -9,9 +9,9 @@ from caf_cookoff_b200 import Handle, bench_shifts, read_file_c64, surface_arrays
 from caf_cookoff_b200.dist import Comm
 
 rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", "0"), ("WORLD_SIZE", "1"), ("LOCAL_RANK", "0")))
-id_path = os.environ.get("CAF_NCCL_ID_FILE") or os.path.join(tempfile.gettempdir(), "caf_nccl_id_%s" % os.environ.get("MASTER_PORT", "0"))
-if rank == 0 and os.path.exists(id_path):
-    os.remove(id_path)
+# the path is unique per launch (torchrun's run id); Comm additionally checks a per-run nonce inside the file
+id_path = os.environ.get("CAF_NCCL_ID_FILE") or os.path.join(tempfile.gettempdir(), "caf_nccl_id_%s_%s" % (
+    os.environ.get("MASTER_PORT", "0"), os.environ.get("TORCHELASTIC_RUN_ID", "x")))
 import torch
 torch.cuda.set_device(local)
 h = Handle(local)
@@ -40,5 +40,26 @@ tie[0] = torch.tensor(np.float64(5.0).view(np.int64)); tie[1] = torch.tensor(np.
 torch.cuda.synchronize()
 t = comm.peak_allgather_dev(tie.data_ptr(), lo)
 assert (t.value, t.doppler_idx, t.delay_idx) == (5.0, 0, 7), (t.value, t.doppler_idx, t.delay_idx)
+# the fully asynchronous device path: local rows, find_peak packed in the kernel, ncclAllGather, device-side resolve
+outp = torch.zeros(4, dtype=torch.int64, device="cuda")
+comm.sharded_dev(nd.data_ptr(), hd.data_ptr(), 4096, fd.data_ptr(), hi - lo, lo, 48000, outp.data_ptr(),
+                 row_val_dev=rv.data_ptr(), row_idx_dev=ri.data_ptr())
+h.sync()
+o = outp.cpu().numpy()
+assert (float(o.view(np.float64)[1]), int(o[3]), int(o[2])) == (69.0, 202, 338), o
+assert not comm.remote_error()
+# a rank that cannot compute its shard (fs = 0 is rejected before any launch) must still enter the collective: the
+# healthy ranks get CAF_B200_EREMOTE semantics (remote_error) instead of hanging in ncclAllGather
+from caf_cookoff_b200.api import CafError
+bad = (rank == world - 1) and world > 1
+try:
+    comm.sharded_dev(nd.data_ptr(), hd.data_ptr(), 4096, fd.data_ptr(), hi - lo, lo, 0 if bad else 48000, outp.data_ptr())
+    failed_here = False
+except CafError:
+    failed_here = True
+h.sync()
+assert failed_here == bad
+if world > 1 and not bad:
+    assert comm.remote_error(), "the peer's failure mark did not arrive"
 comm.close()
 print(f"rank {rank}/{world}: rows [{lo},{hi}) ok, global peak (69.0 Hz, delay 202, row 338) via the library's NCCL communicator", flush=True)

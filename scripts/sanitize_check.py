@@ -19,7 +19,6 @@ surface_layout(needle, hay, f, 48000, 1); surface_layout(needle, hay, f, 48000, 
 for l in (5000, 20001):                                                                   # one level, R = 2 and 8
     n2, h2 = G.as_inputs(G.pair(0, seed=0, chirp_length=l))
     surface_arrays(n2, h2, f[:3], 48000)
-    os.environ["CAF_B200_CLUSTER"] = "1"; surface_arrays(n2, h2, f[:3], 48000); del os.environ["CAF_B200_CLUSTER"]
 n3, h3 = G.as_inputs(G.pair(0, seed=0, chirp_length=100000))                              # two levels, fused kernels
 _, pi3, _, pk3 = surface_arrays(n3, h3, f[:2], 48000, want_surface=False); print("two-level", pk3.freq_hz, pk3.delay_idx)
 print("sanitize pass done")

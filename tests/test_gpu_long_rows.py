@@ -35,26 +35,6 @@ def test_long_rows_match_oracle(l):
     assert (pk.freq_hz, int(pk.delay_idx)) == NO.find_peak(shifts, opidx, opval)
 
 
-@pytest.mark.parametrize("l", [4097, 8192, 10000, 16384, 20001, 32768])
-def test_cluster_fused_rows_match_the_chain(l, monkeypatch):
-    """The opt-in cluster kernel (one cluster of R = 2, 4, 8 CTAs per row, transposes through distributed shared
-    memory) against the oracle and against the default chain through L2."""
-    needle, hay = _pair(l)
-    shifts = np.linspace(-60.0, 75.0, 37)
-    ref, ridx, rval, rpk = caf.surface_arrays(needle, hay, shifts, FS)
-    monkeypatch.setenv("CAF_B200_CLUSTER", "1")
-    surf, pidx, pval, pk = caf.surface_arrays(needle, hay, shifts, FS)
-    _, pidx2, pval2, pk2 = caf.surface_arrays(needle, hay, shifts, FS, want_surface=False)
-    monkeypatch.delenv("CAF_B200_CLUSTER")
-    assert rel_max(surf, ref) <= 1e-12
-    assert np.array_equal(pidx, ridx) and np.array_equal(pidx2, ridx)
-    assert rel_max(pval, rval) <= 1e-12 and np.array_equal(pval2, pval)
-    assert (pk.freq_hz, pk.delay_idx, pk.doppler_idx) == (rpk.freq_hz, rpk.delay_idx, rpk.doppler_idx)
-    if l & (l - 1) == 0:
-        osurf, opidx, _ = O.caf_surface(needle, hay, shifts, FS)
-        assert rel_max(surf, osurf) <= 1e-9 and np.array_equal(pidx, opidx)
-
-
 def test_config3_miniature_and_peak_only():
     """4096 doppler x 65536 delay is config 3; here 96 rows (two L2 chunks) of the same row length."""
     needle, hay = _pair(32768)
