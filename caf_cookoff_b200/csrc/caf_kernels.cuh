@@ -88,47 +88,55 @@ struct RowArgs {
 };
 
 // ------------------------------------------------------------------------------------------------
+// Exchange fabric: per pipeline 16 regions (one per sub-transform k1) of 16 x 16 elements.
+//   complex128 (16-byte elements, 128-bit accesses: a wavefront is a quarter-warp, 8 lanes with consecutive h): the
+//     block exchanges X1 / X4 are conflict free as they are; the 16 x 16 transposes X2 / X3 use a PADDED region, row
+//     stride 17 elements (write (k, h) at 17 k + h, read (h, m) at 17 h + m: banks (h + m) mod 8 are distinct over a
+//     quarter-warp).  Every fabric address of a thread is then  base + compile-time immediate  with four bases in all --
+//     no per-access index arithmetic and no table of sixteen pre-computed addresses (round 1's XOR swizzle needed one
+//     LOP3 per transposed access and kept 16 + 9 address words per thread, 22 of them spilled to local memory).
+//   complex64 (8-byte elements: a wavefront is a half-warp, i.e. the lanes (h[2:0], sub) of one h[3]; the two
+//     sub-transforms of a warp sit one region apart and would collide): bit 3 of the in-region index is flipped by
+//     (region parity ^ bit 4 of the index) and the transposes use an XOR swizzle (13.0 k -> 11.0 k cycles per row).
+// ------------------------------------------------------------------------------------------------
+template <typename T> struct Fab;
+template <> struct Fab<double> {       // interleaved complex128, 128-bit accesses, padded regions
+    using E = double2;
+    static constexpr int kRegion = 16 * 17;            // elements per region (272: row stride 17)
+    static constexpr int kPipe = 16 * kRegion;         // elements per pipeline
+    static __device__ __forceinline__ void st(E* p, int i, double2 v) { p[i] = v; }
+    static __device__ __forceinline__ double2 ld(const E* p, int i) { return p[i]; }
+};
+template <> struct Fab<float> {
+    using E = float2;
+    static constexpr int kRegion = 256;
+    static constexpr int kPipe = 16 * kRegion;
+    static __device__ __forceinline__ void st(E* p, int i, float2 v) { p[i] = v; }
+    static __device__ __forceinline__ float2 ld(const E* p, int i) { return p[i]; }
+};
+
+// ------------------------------------------------------------------------------------------------
 // shared-memory carve-up
 // ------------------------------------------------------------------------------------------------
 template <typename T>
 struct SmemLayout {
-    static constexpr size_t kS = sizeof(cx<T>) * 2 * kL0;        // exchange fabric [2][4096]
+    static constexpr size_t kS = sizeof(cx<T>) * 2 * Fab<T>::kPipe;   // exchange fabric [2 pipelines][16 regions]
     static constexpr size_t kPtab = sizeof(cx<T>) * 2 * 2 * 48;  // [2 buf][2 r][3][16]
     static constexpr size_t kRed = 16 * 8 + 16 * 8;              // argmax scratch
     static constexpr size_t kMisc = 64;                          // tmem base, flags, mbarriers
     static constexpr size_t offPtab = kS, offRed = offPtab + kPtab, offMisc = offRed + kRed, kTotal = offMisc + kMisc;
 };
 
-// ------------------------------------------------------------------------------------------------
-// Exchange fabric.  An element is 16 bytes (complex128, 128-bit accesses: a wavefront is a quarter-warp) or 8 bytes
-// (complex64 as float2: a wavefront is a half-warp, i.e. the lanes (h[2:0], sub) of one h[3]).  The two sub-transforms
-// of a warp sit 256 elements apart (same banks), so bit 3 of the in-region index is flipped by
-// (region parity ^ bit 4 of the index): every access pattern of X1..X4 is then conflict free for both element sizes
-// (complex64 rows: 13.0 k -> 11.0 k cycles per row on B200).
-// ------------------------------------------------------------------------------------------------
-template <typename T> struct Fab;
-template <> struct Fab<double> {       // interleaved complex128, 128-bit accesses
-    using E = double2;
-    static constexpr int kPipe = kL0;
-    static __device__ __forceinline__ void st(E* p, int i, double2 v) { p[i] = v; }
-    static __device__ __forceinline__ double2 ld(const E* p, int i) { return p[i]; }
-};
-template <> struct Fab<float> {
-    using E = float2;
-    static constexpr int kPipe = kL0;
-    static __device__ __forceinline__ void st(E* p, int i, float2 v) { p[i] = v; }
-    static __device__ __forceinline__ float2 ld(const E* p, int i) { return p[i]; }
-};
-
 template <typename T>
 struct Ctx {
+    static constexpr bool kPadded = std::is_same<T, double>::value;
     typename Fab<T>::E* Sr;   // this thread's pipeline half of the fabric
     cx<T>* ptab;
     uint32_t tm_tw;  // TMEM address of this thread's five twiddle bases: W_4096^t, W_256^h, W_4096^{k1 h}, W_256^{k1}, W_8192^{-t}
     int w, lane, r, h, t;
-    int wb;          // 256 w: this thread's region (sub-transform k1 = w) inside the pipeline
-    int hs[2];       // h with bit 3 flipped by (sub ^ p): in-region column for an index whose bit 4 is p
-    int hr;          // h with bit 3 flipped by (sub ^ h[0]): column base of the transposed X2/X3 reads (bit 4 = h[0])
+    int wb;          // first element of this thread's region (sub-transform k1 = w) inside the pipeline
+    int hs[2];       // complex64: h with bit 3 flipped by (sub ^ p): in-region column for an index whose bit 4 is p
+    int hr;          // complex64: h with bit 3 flipped by (sub ^ h[0]): column base of the transposed X2/X3 reads
     long long* tr;   // CAF_TRACE: this warp's slot array for the current item (lane 0 writes)
 
     __device__ __forceinline__ void init(unsigned char* smem_raw, int tid) {
@@ -139,19 +147,31 @@ struct Ctx {
         const int sub = (lane >> 3) & 1;
         w = 2 * (hw_warp & 7) + sub;
         t = 16 * w + h;
-        wb = 256 * w;
+        wb = Fab<T>::kRegion * w;
         hs[0] = h ^ (sub << 3); hs[1] = hs[0] ^ 8;
         hr = h ^ (((sub ^ h) & 1) << 3);
         Sr = reinterpret_cast<typename Fab<T>::E*>(smem_raw) + r * Fab<T>::kPipe;
         ptab = nullptr; tm_tw = 0; tr = nullptr;
     }
     // block exchange X1 / X4 / mailbox: element (region k, column t)
-    __device__ __forceinline__ int ix_block(int k) const { return k * 256 + 16 * w + hs[k & 1]; }
+    __device__ __forceinline__ int ix_block(int k) const {
+        if constexpr (kPadded) return k * Fab<T>::kRegion + t;
+        else return k * 256 + 16 * w + hs[k & 1];
+    }
     // own region, element 16 i + h
-    __device__ __forceinline__ int ix_own(int i) const { return wb + 16 * i + hs[i & 1]; }
-    // own region, 16 x 16 transpose: write (k, h ^ k), read (h, m ^ h)
-    __device__ __forceinline__ int ix_tw(int k) const { return wb + 16 * k + (hs[k & 1] ^ k); }
-    __device__ __forceinline__ int ix_tr(int m) const { return wb + 16 * h + (m ^ hr); }
+    __device__ __forceinline__ int ix_own(int i) const {
+        if constexpr (kPadded) return wb + 16 * i + h;
+        else return wb + 16 * i + hs[i & 1];
+    }
+    // own region, 16 x 16 transpose: write (k, h), read (h, m)
+    __device__ __forceinline__ int ix_tw(int k) const {
+        if constexpr (kPadded) return wb + 17 * k + h;
+        else return wb + 16 * k + (hs[k & 1] ^ k);
+    }
+    __device__ __forceinline__ int ix_tr(int m) const {
+        if constexpr (kPadded) return wb + 17 * h + m;
+        else return wb + 16 * h + (m ^ hr);
+    }
 };
 
 #ifdef CAF_TRACE
