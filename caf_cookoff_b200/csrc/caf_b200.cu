@@ -221,8 +221,8 @@ cudaError_t configure_all(int* occ) {
     if ((e = configure_kernel<T, caf::kSpectrumFull>(nullptr)) != cudaSuccess) return e;
     if ((e = configure_kernel<T, caf::kXcorFull>(nullptr)) != cudaSuccess) return e;
     if ((e = configure_kernel<T, caf::kXcorHalf>(nullptr)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(caf::caf_large_core<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<T>())) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(caf::caf_large_core<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<T>())) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(caf::caf_large_core<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)caf::SmemLayout<T>::kTotalNoNeedle)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(caf::caf_large_core<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)caf::SmemLayout<T>::kTotalNoNeedle)) != cudaSuccess) return e;
     return cudaSuccess;
 }
 
@@ -298,7 +298,7 @@ cudaError_t launch_large_core(caf_b200_handle h, const caf::LargeArgs<T>& a) {
     long long groups = units < 2LL * h->sm_count ? units : 2LL * h->sm_count;
     if (groups > upr) groups = groups / upr * upr;
     long long ctas = (groups + 1) / 2;
-    caf::caf_large_core<T, HMODE><<<(unsigned)ctas, caf::kThreads, smem_bytes<T>(), h->stream>>>(a);
+    caf::caf_large_core<T, HMODE><<<(unsigned)ctas, caf::kThreads, caf::SmemLayout<T>::kTotalNoNeedle, h->stream>>>(a);
     h->launches++;
     return cudaGetLastError();
 }

@@ -1,18 +1,19 @@
 // caf_kernels.cuh — the fused filterbank-CAF kernel for sm_100a (rows of N = 8192 delay cells).
 //
 // One persistent CTA (512 threads = 16 warps) per SM owns one doppler row at a time and keeps the
-// whole row in REGISTERS (16 complex values per thread).  Row-invariant operands — the needle samples
-// and H = FFT(haystack)/n that every row of a pair re-uses — live in TENSOR MEMORY (TMEM, 256 KB/SM),
-// used here as a software-managed per-thread scratchpad through tcgen05.st / tcgen05.ld: each thread
-// owns exactly the 16 needle samples and the 16 H bins it needs, 512 B, which is the whole TMEM.
-// Shared memory holds the exchange fabric between passes (128 KB) and the twiddle tables (72 KB).
-// After the per-pair prologue a row touches HBM/L2 only to write its |xcor|^2 cells.
+// whole row in REGISTERS (16 complex values per thread).  Row-invariant per-thread operands live in TENSOR MEMORY
+// (TMEM, 256 KB/SM), used here as a software-managed per-thread scratchpad through tcgen05.st / tcgen05.ld:
+// the 16 bins of H = FFT(haystack)/n every row of a pair multiplies with, and the thread's TWIDDLE TABLES
+// (W_4096^{t k} and W_256^{h k}, k = 0..15) -- round 1 regenerated those powers in registers in every pass
+// (59 of a pass's 119 twiddle instructions); read back from TMEM they cost no fp64 issue slot at all.
+// Shared memory holds the exchange fabric between passes (136 KB), the needle of the current pair (64 KB, planar)
+// and the phasor tables.  After the per-pair prologue a row touches HBM/L2 only to write its |xcor|^2 cells.
 //
 // What it replaces in the reference, per row (paths relative to /root/reference):
-//   caf_rust/src/caf/mod.rs:46-65            apply_freq_shift  -> phasor folded into the load
+//   caf_rust/src/caf/mod.rs:46-65            apply_freq_shift  -> phasor folded into the first butterfly level
 //   caf_rust/src/caf/xcor_rustfft.rs:58-59   FFT(haystack), recomputed per row there -> once per pair per CTA
 //   caf_rust/src/caf/xcor_rustfft.rs:60-61   FFT(shifted)      -> two 4096-point DIF FFTs (see below)
-//   caf_rust/src/caf/xcor_rustfft.rs:64-73   conj, product, /n -> one multiply with H
+//   caf_rust/src/caf/xcor_rustfft.rs:64-73   conj, product, /n -> H folded into the inverse's first butterfly level
 //   caf_rust/src/caf/xcor_rustfft.rs:76      IFFT              -> two 4096-point DIT IFFTs + radix-2
 //   caf_rust/src/caf/mod.rs:141-153          norm_sqr + strict-> argmax -> fused epilogue
 //   caf_rust/src/caf/mod.rs:31-42            find_peak         -> last-CTA-done reduction (single pair)
@@ -26,14 +27,16 @@
 // frequency (natural in, digit-reversed out), inverse runs decimation in time (digit-reversed in,
 // natural out), so the spectrum is never reordered; H is kept in that digit-reversed order.
 //
-// Thread map.  warp w (0..15), lane = h[2:0] | r<<3 | h[3]<<4: each warp works on both pipelines
-// r = 0/1 with identical indices h, so twiddle loads broadcast between adjacent quarter-warps.  4096 = 16 x 16 x 16:
-//   pass 1  radix-16 over i,  elements n = t + 256 i,      t = 16 w + h      (twiddle W_4096^{t k1})
+// Thread map.  warp w (0..15), lane = h[2:0] | sub<<3 | h[3]<<4: each warp works on two sub-transforms k1 = 2 warp + sub
+// with identical indices h.  4096 = 16 x 16 x 16:
+//   pass 1  [x phasor, folded in] radix-16 over i, elements n = t + 256 i, t = 16 w + h;  x W_4096^{t k1} (table A)
 //   X1      block exchange    S_r[k1][t]  ->  warp k1 owns sub-transform k1
-//   pass 2  radix-16 over i', elements t = h + 16 i'                          (twiddle W_256^{h k2})
-//   X2      16x16 transpose inside the half-warp (XOR swizzle, conflict free)
-//   pass 3  radix-16 over m   -> bin q = w + 16 h + 256 k3 in register k3
-//   ... multiply by H, then passes 1', 2', 3' mirror 3, 2, 1 with conjugated twiddles.
+//   pass 2  radix-16 over i', elements t = h + 16 i'
+//   X2      16x16 transpose inside the half-warp (padded rows, conflict free)
+//   pass 3  [x W_256^{h m}, table B, folded in] radix-16 over m   -> bin q = w + 16 h + 256 k3 in register k3
+//   inverse: pass 1' [x H conj(.), folded in], X3, pass 2' [x conj B, folded in], X4, pass 3' [x conj A, folded in].
+// "Folded in": a per-element factor on the INPUT of a 16-point DFT merges with the first add/subtract level
+// (fft16.cuh, radix4_in) -- five of the six factor multiplies of a row ride that way.
 #pragma once
 #include <cstdint>
 #include <type_traits>
@@ -89,23 +92,29 @@ struct RowArgs {
 
 // ------------------------------------------------------------------------------------------------
 // Exchange fabric: per pipeline 16 regions (one per sub-transform k1) of 16 x 16 elements.
-//   complex128 (16-byte elements, 128-bit accesses: a wavefront is a quarter-warp, 8 lanes with consecutive h): the
-//     block exchanges X1 / X4 are conflict free as they are; the 16 x 16 transposes X2 / X3 use a PADDED region, row
-//     stride 17 elements (write (k, h) at 17 k + h, read (h, m) at 17 h + m: banks (h + m) mod 8 are distinct over a
-//     quarter-warp).  Every fabric address of a thread is then  base + compile-time immediate  with four bases in all --
-//     no per-access index arithmetic and no table of sixteen pre-computed addresses (round 1's XOR swizzle needed one
-//     LOP3 per transposed access and kept 16 + 9 address words per thread, 22 of them spilled to local memory).
+//   complex128: PLANAR (a real plane and an imaginary plane per pipeline) and moved with 64-bit accesses.  On B200 a
+//     conflict-free LDS.128 costs the SM's one load/store port 8 cycles per warp (64 B/clk) against 2 x 2 cycles for two
+//     LDS.64, STS.128 4.6 against 2 x 2 (scripts/micro/mio_cost.cu) -- and the exchanges of a row, issued by the eight
+//     warps of a group right after their barrier, are bound by exactly that port (14.5 k of a 19.4 k-cycle row with
+//     128-bit accesses).  A wavefront is a half-warp: the lanes (h[2:0], sub) of one h[3].  The 16 x 16 transposes
+//     X2 / X3 use a PADDED region, row stride 17 elements (write (k, h) at 17 k + h, read (h, m) at 17 h + m: 34 h mod 32
+//     = 2 h, eight lanes on distinct bank pairs), and a region is 280 elements (= 64 B mod 128 B) so the two
+//     sub-transforms of a warp fall on the two halves of the banks.  Every fabric address of a thread is
+//     base + compile-time immediate with four bases in all -- no per-access index arithmetic and no table of
+//     pre-computed addresses (round 1's XOR swizzle needed one LOP3 per transposed access and kept 25 address words
+//     per thread, 22 of them spilled to local memory).
 //   complex64 (8-byte elements: a wavefront is a half-warp, i.e. the lanes (h[2:0], sub) of one h[3]; the two
 //     sub-transforms of a warp sit one region apart and would collide): bit 3 of the in-region index is flipped by
 //     (region parity ^ bit 4 of the index) and the transposes use an XOR swizzle (13.0 k -> 11.0 k cycles per row).
 // ------------------------------------------------------------------------------------------------
 template <typename T> struct Fab;
-template <> struct Fab<double> {       // interleaved complex128, 128-bit accesses, padded regions
-    using E = double2;
-    static constexpr int kRegion = 16 * 17;            // elements per region (272: row stride 17)
-    static constexpr int kPipe = 16 * kRegion;         // elements per pipeline
-    static __device__ __forceinline__ void st(E* p, int i, double2 v) { p[i] = v; }
-    static __device__ __forceinline__ double2 ld(const E* p, int i) { return p[i]; }
+template <> struct Fab<double> {       // planar complex128 (re plane | im plane per pipeline), 64-bit accesses
+    using E = double;
+    static constexpr int kRegion = 280;                // elements per region: 16 rows of stride 17, padded to 64 B mod 128 B
+    static constexpr int kPlane = 16 * kRegion;        // elements per plane
+    static constexpr int kPipe = 2 * kPlane;           // E's per pipeline
+    static __device__ __forceinline__ void st(E* p, int i, double2 v) { p[i] = v.x; p[kPlane + i] = v.y; }
+    static __device__ __forceinline__ double2 ld(const E* p, int i) { return make_double2(p[i], p[kPlane + i]); }
 };
 template <> struct Fab<float> {
     using E = float2;
@@ -120,11 +129,16 @@ template <> struct Fab<float> {
 // ------------------------------------------------------------------------------------------------
 template <typename T>
 struct SmemLayout {
-    static constexpr size_t kS = sizeof(cx<T>) * 2 * Fab<T>::kPipe;   // exchange fabric [2 pipelines][16 regions]
+    static constexpr size_t kS = sizeof(typename Fab<T>::E) * 2 * Fab<T>::kPipe;   // exchange fabric [2 pipelines][16 regions]
     static constexpr size_t kPtab = sizeof(cx<T>) * 2 * 2 * 48;  // [2 buf][2 r][3][16]
-    static constexpr size_t kRed = 16 * 8 + 16 * 8;              // argmax scratch
+    static constexpr size_t kRed = 16 * 8 + 16 * 8;              // argmax scratch of the fused find_peak tail
+    static constexpr size_t kCand = 2 * 256 * (8 + 4);           // per-lane row-maximum candidates of group 0, two rows deep
     static constexpr size_t kMisc = 64;                          // tmem base, flags, mbarriers
-    static constexpr size_t offPtab = kS, offRed = offPtab + kPtab, offMisc = offRed + kRed, kTotal = offMisc + kMisc;
+    static constexpr size_t kNeedle = sizeof(T) * 2 * kL0;       // the current pair's needle, planar: re[4096] | im[4096]
+    static constexpr size_t offPtab = kS, offRed = offPtab + kPtab, offCand = offRed + kRed, offMisc = offCand + kCand,
+                            offNeedle = offMisc + kMisc;
+    static constexpr size_t kTotalNoNeedle = offNeedle;          // kernels that never hold a needle (long-row core)
+    static constexpr size_t kTotal = offNeedle + kNeedle;
 };
 
 template <typename T>
@@ -132,7 +146,9 @@ struct Ctx {
     static constexpr bool kPadded = std::is_same<T, double>::value;
     typename Fab<T>::E* Sr;   // this thread's pipeline half of the fabric
     cx<T>* ptab;
-    uint32_t tm_tw;  // TMEM address of this thread's five twiddle bases: W_4096^t, W_256^h, W_4096^{k1 h}, W_256^{k1}, W_8192^{-t}
+    uint32_t tm_A;   // TMEM: this thread's table A[4 c + a] = W_4096^{t (c + 4 a)}
+    uint32_t tm_B;   // TMEM: this thread's table B[4 c + a] = W_256^{h (c + 4 a)}
+    uint32_t tm_g;   // TMEM: W_8192^{-t} (the final radix-2 twiddle), followed by two slots for the long rows' inner twiddle
     int w, lane, r, h, t;
     int wb;          // first element of this thread's region (sub-transform k1 = w) inside the pipeline
     int hs[2];       // complex64: h with bit 3 flipped by (sub ^ p): in-region column for an index whose bit 4 is p
@@ -151,16 +167,16 @@ struct Ctx {
         hs[0] = h ^ (sub << 3); hs[1] = hs[0] ^ 8;
         hr = h ^ (((sub ^ h) & 1) << 3);
         Sr = reinterpret_cast<typename Fab<T>::E*>(smem_raw) + r * Fab<T>::kPipe;
-        ptab = nullptr; tm_tw = 0; tr = nullptr;
+        ptab = nullptr; tm_A = tm_B = tm_g = 0; tr = nullptr;
     }
     // block exchange X1 / X4 / mailbox: element (region k, column t)
     __device__ __forceinline__ int ix_block(int k) const {
-        if constexpr (kPadded) return k * Fab<T>::kRegion + t;
+        if constexpr (kPadded) return k * Fab<T>::kRegion + (t ^ ((t & 16) >> 1));   // bit 3 flipped by bit 4: the warp's two sub-transforms (16 columns apart) use different bank halves
         else return k * 256 + 16 * w + hs[k & 1];
     }
     // own region, element 16 i + h
     __device__ __forceinline__ int ix_own(int i) const {
-        if constexpr (kPadded) return wb + 16 * i + h;
+        if constexpr (kPadded) return wb + 16 * i + (h ^ ((i & 1) << 3));
         else return wb + 16 * i + hs[i & 1];
     }
     // own region, 16 x 16 transpose: write (k, h), read (h, m)
@@ -223,10 +239,12 @@ __device__ __forceinline__ void tmem_st_x2(uint32_t taddr, const uint32_t (&r)[2
 }
 
 template <typename T> struct TmemGeom;
-// TMEM map of one lane quarter (the 4 warps q, q+4, q+8, q+12 share lanes 32q..32q+31), in units of one complex
-// value (kColsPerC 32-bit columns):   [0, 64)  H bins, 16 per warp        (j = warp / 4 selects the 16)
-//                                     [64, 96) needle samples, 16 per t   (warps j and j + 2 hold the same t: shared)
-//                                     [96, 128) twiddle bases, 8 slots per warp (5 used)
+// TMEM map of one lane quarter (the 4 warps q, q+4, q+8, q+12 share lanes 32q..32q+31; j = warp / 4), in units of one
+// complex value (kColsPerC 32-bit columns):
+//     [0, 64)    H bins, 16 per warp, chunk c = bins k3 = c, c+4, c+8, c+12 (the order the folded butterfly reads)
+//     [64, 96)   table A, 16 per t: warps j and j + 2 (the two pipelines) hold the same t and share one copy
+//     [96, 112)  table B, 16 per h: the same for all four warps
+//     [112, 128) 4 slots per warp: W_8192^{-t}, and the long rows' conjugate inner twiddle (base, ratio)
 template <> struct TmemGeom<double> { static constexpr int kColsPerC = 4, kAlloc = 512; };
 template <> struct TmemGeom<float>  { static constexpr int kColsPerC = 2, kAlloc = 256; };
 
@@ -326,20 +344,92 @@ __device__ __forceinline__ void mbar_wait(uint64_t* mb, int parity) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// forward: v[i] = u_r[t + 256 i]  ->  v[k3] = U_r[k1 + 16 h + 256 k3]          (xcor_rustfft.rs:59,61)
-// The five per-thread twiddle bases live in TMEM (tcgen05.ld is not queued behind shared-memory traffic).
+// Per-thread factor tables in TMEM.  A table is 16 complex values in "chunk" order: chunk c (one tcgen05.ld of four
+// values) = entries k = c, c + 4, c + 8, c + 12 -- the four inputs of one first-level radix-4 butterfly of fft16.
+// ------------------------------------------------------------------------------------------------
+// table[4 c + a] = w^{c + 4 a}.  Built once per CTA (product depth <= 5: w^2, w^4 by squaring, then steps of w^4).
+template <typename T>
+__device__ __forceinline__ void tmem_store_power_table(uint32_t taddr, cx<T> w) {
+    constexpr int kC = TmemGeom<T>::kColsPerC;
+    const cx<T> w2 = csq(w), w4 = csq(w2);
+    cx<T> q[4];
+    q[0] = mk<T>((T)1, (T)0); q[1] = w4; q[2] = csq(w4); q[3] = cmul(q[2], w4);
+    tmem_st4(taddr, q);
+    q[0] = w; q[1] = cmul(q[0], w4); q[2] = cmul(q[1], w4); q[3] = cmul(q[2], w4);
+    tmem_st4(taddr + 4 * kC, q);
+    q[0] = w2; q[1] = cmul(q[0], w4); q[2] = cmul(q[1], w4); q[3] = cmul(q[2], w4);
+    tmem_st4(taddr + 8 * kC, q);
+    q[0] = cmul(w2, w); q[1] = cmul(q[0], w4); q[2] = cmul(q[1], w4); q[3] = cmul(q[2], w4);
+    tmem_st4(taddr + 12 * kC, q);
+}
+
+// 16-point DFT of v[k] (*) table[k]: the factors are folded into the first butterfly level (radix4_in).  The next
+// chunk is in flight while the current butterfly runs.  Q0_ONE: table[0] == 1 (power tables).
+template <typename T, bool INV, int MODE, bool Q0_ONE>
+__device__ __forceinline__ void fft16_in_tmem(cx<T> (&v)[16], uint32_t taddr) {
+    constexpr int kC = TmemGeom<T>::kColsPerC;
+    typename raw4_of<T>::type r0, r1, r2, r3;
+    cx<T> q[4];
+    tmem_ld4_issue(taddr, r0);
+    tmem_wait_ld();
+    tmem_ld4_issue(taddr + 4 * kC, r1);
+    tmem_unpack4(r0, q);
+    radix4_in<T, INV, MODE, Q0_ONE>(v[0], v[4], v[8], v[12], q[0], q[1], q[2], q[3]);
+    tmem_wait_ld();
+    tmem_ld4_issue(taddr + 8 * kC, r2);
+    tmem_unpack4(r1, q);
+    radix4_in<T, INV, MODE, false>(v[1], v[5], v[9], v[13], q[0], q[1], q[2], q[3]);
+    tmem_wait_ld();
+    tmem_ld4_issue(taddr + 12 * kC, r3);
+    tmem_unpack4(r2, q);
+    radix4_in<T, INV, MODE, false>(v[2], v[6], v[10], v[14], q[0], q[1], q[2], q[3]);
+    tmem_wait_ld();
+    tmem_unpack4(r3, q);
+    radix4_in<T, INV, MODE, false>(v[3], v[7], v[11], v[15], q[0], q[1], q[2], q[3]);
+    fft16_stage_b<T, INV>(v);
+}
+
+// v[k] <- v[k] (*) table[k], k = 1..15 (table[0] == 1): the one factor multiply of a row that sits on the OUTPUT side
+// of a butterfly (forward pass 1 -> X1) and cannot be folded.
+template <typename T, int MODE>
+__device__ __forceinline__ void mul_table_tmem(cx<T> (&v)[16], uint32_t taddr) {
+    constexpr int kC = TmemGeom<T>::kColsPerC;
+    typename raw4_of<T>::type r0, r1, r2, r3;
+    cx<T> q[4];
+    tmem_ld4_issue(taddr, r0);
+    tmem_ld4_issue(taddr + 4 * kC, r1);
+    tmem_wait_ld();
+    tmem_ld4_issue(taddr + 8 * kC, r2);
+    tmem_ld4_issue(taddr + 12 * kC, r3);
+    tmem_unpack4(r0, q);
+#pragma unroll
+    for (int a = 1; a < 4; ++a) v[4 * a] = tw_apply<MODE>(v[4 * a], q[a]);
+    tmem_unpack4(r1, q);
+#pragma unroll
+    for (int a = 0; a < 4; ++a) v[1 + 4 * a] = tw_apply<MODE>(v[1 + 4 * a], q[a]);
+    tmem_wait_ld();
+    tmem_unpack4(r2, q);
+#pragma unroll
+    for (int a = 0; a < 4; ++a) v[2 + 4 * a] = tw_apply<MODE>(v[2 + 4 * a], q[a]);
+    tmem_unpack4(r3, q);
+#pragma unroll
+    for (int a = 0; a < 4; ++a) v[3 + 4 * a] = tw_apply<MODE>(v[3 + 4 * a], q[a]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward, AFTER the caller's first 16-point DFT (plain, or with the doppler phasor folded in):
+// v[k1] = first-pass output of thread t  ->  v[k3] = U_r[k1 + 16 h + 256 k3]          (xcor_rustfft.rs:59,61)
 // `empty_mb` (group 1 only): the mailbox barrier to wait on before the fabric half is overwritten.
-// `hook()` runs in the exchange phase after the block barriers (deferred row-peak reduction), `hook3()` before the
-// last butterfly (a consumer CTA polls the H publication flag there, one pass ahead of its first use).
+// `hook()` runs right after that gate (group 1's per-row chores: next row's phasor tables, previous row's peak fold),
+// `hook3()` before the last butterfly (a consumer CTA polls the H publication flag there, one pass ahead of its first use).
 // ------------------------------------------------------------------------------------------------
 template <typename T, typename Hook, typename Hook3>
-__device__ __forceinline__ void forward_4096(cx<T> (&v)[16], const Ctx<T>& c,
+__device__ __forceinline__ void forward_tail(cx<T> (&v)[16], const Ctx<T>& c,
                                              uint64_t* empty_mb, int empty_parity, Hook&& hook, Hook3&& hook3) {
-    constexpr int kC = TmemGeom<T>::kColsPerC;
-    fft16<T, false>(v);
-    twiddle_powers<false>(v, tmem_ld1(c.tm_tw, T()));           // W_4096^{t k}
+    mul_table_tmem<T, kTwMul>(v, c.tm_A);                       // W_4096^{t k}
     CAF_TR(c, 3);
     if (empty_mb) mbar_wait(empty_mb, empty_parity);   // group 0 has drained the previous row's mailbox
+    hook();
     bar_group(c.r);    // every earlier reader of this half of the fabric (previous X4 / X2) is done
 #pragma unroll
     for (int k = 0; k < 16; ++k) Fab<T>::st(c.Sr, c.ix_block(k), v[k]);
@@ -347,11 +437,9 @@ __device__ __forceinline__ void forward_4096(cx<T> (&v)[16], const Ctx<T>& c,
     bar_group(c.r);
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = Fab<T>::ld(c.Sr, c.ix_own(i));
-    hook();
     CAF_TR(c, 5);
 
     fft16<T, false>(v);
-    twiddle_powers<false>(v, tmem_ld1(c.tm_tw + kC, T()));      // W_256^{h k}
     CAF_TR(c, 6);
     __syncwarp();
 #pragma unroll
@@ -362,18 +450,25 @@ __device__ __forceinline__ void forward_4096(cx<T> (&v)[16], const Ctx<T>& c,
     hook3();
     CAF_TR(c, 7);
 
-    fft16<T, false>(v);
+    fft16_in_tmem<T, false, kTwMul, true>(v, c.tm_B);           // x W_256^{h m}, then the DFT over m
     CAF_TR(c, 8);
+}
+template <typename T, typename Hook, typename Hook3>
+__device__ __forceinline__ void forward_4096(cx<T> (&v)[16], const Ctx<T>& c,
+                                             uint64_t* empty_mb, int empty_parity, Hook&& hook, Hook3&& hook3) {
+    fft16<T, false>(v);
+    forward_tail<T>(v, c, empty_mb, empty_parity, hook, hook3);
 }
 
 // ------------------------------------------------------------------------------------------------
-// inverse: v[k3] = Y_r[k1 + 16 h + 256 k3]  ->  v[n1] = A_r[t + 256 n1]  (unnormalised, xcor_rustfft.rs:76)
+// inverse: v[k3] = X_r[k1 + 16 h + 256 k3]  ->  v[n1] = A_r[t + 256 n1]  (unnormalised, xcor_rustfft.rs:76)
+// tm_h != 0: the spectral product H conj(X) (xcor_rustfft.rs:64-73) is folded into the first butterfly level, H read
+// from TMEM; tm_h == 0 (HFUSED false): the caller has already formed the product.
 // ------------------------------------------------------------------------------------------------
-template <typename T>
-__device__ __forceinline__ void inverse_4096(cx<T> (&v)[16], const Ctx<T>& c) {
-    constexpr int kC = TmemGeom<T>::kColsPerC;
-    fft16<T, true>(v);
-    twiddle_powers<true>(v, tmem_ld1(c.tm_tw + kC, T()));       // conj W_256^{h k}
+template <typename T, bool HFUSED>
+__device__ __forceinline__ void inverse_4096(cx<T> (&v)[16], const Ctx<T>& c, uint32_t tm_h) {
+    if constexpr (HFUSED) fft16_in_tmem<T, true, kTwConjX, false>(v, tm_h);
+    else fft16<T, true>(v);
     CAF_TR(c, 10);
     __syncwarp();
 #pragma unroll
@@ -383,11 +478,7 @@ __device__ __forceinline__ void inverse_4096(cx<T> (&v)[16], const Ctx<T>& c) {
     for (int m = 0; m < 16; ++m) v[m] = Fab<T>::ld(c.Sr, c.ix_tr(m));
     CAF_TR(c, 11);
 
-    fft16<T, true>(v);
-    {
-        const cx<T> b = tmem_ld1(c.tm_tw + 2 * kC, T()), rho = tmem_ld1(c.tm_tw + 3 * kC, T());
-        twiddle_geometric<true>(v, b, rho);                     // conj W_4096^{k1 (16 k + h)}
-    }
+    fft16_in_tmem<T, true, kTwMulConj, true>(v, c.tm_B);        // x conj W_256^{h m}
     CAF_TR(c, 12);
     __syncwarp();
 #pragma unroll
@@ -398,7 +489,7 @@ __device__ __forceinline__ void inverse_4096(cx<T> (&v)[16], const Ctx<T>& c) {
     for (int k = 0; k < 16; ++k) v[k] = Fab<T>::ld(c.Sr, c.ix_block(k));
     CAF_TR(c, 14);
 
-    fft16<T, true>(v);
+    fft16_in_tmem<T, true, kTwMulConj, true>(v, c.tm_A);        // x conj W_4096^{t k}
     CAF_TR(c, 15);
 }
 
@@ -447,6 +538,8 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
     C* ptab = reinterpret_cast<C*>(smem_raw + SL::offPtab);
     unsigned long long* red_idx = reinterpret_cast<unsigned long long*>(smem_raw + SL::offRed);
     double* red_val = reinterpret_cast<double*>(smem_raw + SL::offRed + 128);
+    double* cand_val = reinterpret_cast<double*>(smem_raw + SL::offCand);            // [2][256]
+    int* cand_idx = reinterpret_cast<int*>(smem_raw + SL::offCand + 2 * 256 * 8);     // [2][256]
     uint32_t* misc = reinterpret_cast<uint32_t*>(smem_raw + SL::offMisc);
     uint64_t* mb_full = reinterpret_cast<uint64_t*>(smem_raw + SL::offMisc + 16);
     uint64_t* mb_empty = reinterpret_cast<uint64_t*>(smem_raw + SL::offMisc + 24);
@@ -465,7 +558,9 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
 
     constexpr bool kHalfZero = (MODE == kSurface || MODE == kSpectrumHalf || MODE == kXcorHalf);
     constexpr bool kWritesH = (MODE == kSpectrumHalf || MODE == kSpectrumFull);
-    constexpr bool kUseTmem = (MODE == kSurface);   // H and the needle live in TMEM (the twiddle bases always do)
+    constexpr bool kUseTmem = (MODE == kSurface);   // H lives in TMEM and the needle in shared memory (the twiddle tables always do)
+    T* const ndl_re = reinterpret_cast<T*>(smem_raw + SL::offNeedle);   // the current pair's needle, planar
+    T* const ndl_im = ndl_re + kL0;
 
     // ---- work split: contiguous ranges of (pair, row) items so a CTA changes pair as rarely as possible ----
     const int rows_per_pair = (MODE == kSurface) ? a.D : 1;
@@ -478,14 +573,12 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
     int posts = 0;            // mailbox posts so far (group 1) / mailbox reads so far (group 0)
     bool drain_pending = false;   // group 1: a posted mailbox that group 0 may still be reading
     bool h_from_share = false;    // consumer CTA: H still has to be fetched from CTA 0's publication
-    int peak_pending = -1;        // group 0: item whose per-warp maxima wait in red_* for the deferred reduction
     C v[16];
 
     // ---- everything the prologue needs from global memory is requested NOW, so the DRAM / L2 round trips run
     //      behind the TMEM allocation instead of after it: the five twiddle bases, the first operand block
     //      (haystack for a group that publishes H, else the needle) and the first doppler shift ----
-    const C tb0 = ldg<T>(a.tw1 + 256 + t), tb1 = ldg<T>(a.tw2 + 16 + h), tb2 = ldg<T>(a.tw1 + w * 256 + h),
-            tb3 = ldg<T>(a.tw2 + 16 + w), tb4 = ldg<T>(a.g + t);
+    const C tb0 = ldg<T>(a.tw1 + 256 + t), tb1 = ldg<T>(a.tw2 + 16 + h), tb4 = ldg<T>(a.g + t);
     bool preloaded = false;        // v already holds the first operand block of the first pair
     double phi_first = 0.0;
     if constexpr (MODE == kSurface) {
@@ -510,7 +603,7 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
     }
 
     // ---- TMEM: the tensor memory of this SM becomes the per-thread operand store ----
-    uint32_t tm_h = 0, tm_n = 0;
+    uint32_t tm_h = 0;
     {
         if (hw_warp == 0) {
             asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n"
@@ -523,15 +616,19 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
         const uint32_t base = misc[0] + ((uint32_t)(32 * (hw_warp & 3)) << 16);
         const int j = hw_warp >> 2;
         tm_h = base + (uint32_t)((16 * j) * TG::kColsPerC);                 // 16 H bins
-        tm_n = base + (uint32_t)((64 + 16 * (j & 1)) * TG::kColsPerC);      // 16 needle samples (shared by both groups)
-        c.tm_tw = base + (uint32_t)((96 + 8 * j) * TG::kColsPerC);          // 5 twiddle bases
-        // per-thread twiddle bases, once per CTA: W_4096^t, W_256^h, W_4096^{k1 h}, W_256^{k1}, W_8192^{-t}
-        tmem_st1(c.tm_tw + 0 * TG::kColsPerC, tb0);
-        tmem_st1(c.tm_tw + 1 * TG::kColsPerC, tb1);
-        tmem_st1(c.tm_tw + 2 * TG::kColsPerC, tb2);
-        tmem_st1(c.tm_tw + 3 * TG::kColsPerC, tb3);
-        tmem_st1(c.tm_tw + 4 * TG::kColsPerC, tb4);
+        c.tm_A = base + (uint32_t)((64 + 16 * (j & 1)) * TG::kColsPerC);    // table A (the two pipelines share it)
+        c.tm_B = base + (uint32_t)(96 * TG::kColsPerC);                     // table B (all four warps share it)
+        c.tm_g = base + (uint32_t)((112 + 4 * j) * TG::kColsPerC);
+        // per-thread twiddle tables, once per CTA: powers of W_4096^t and of W_256^h; and W_8192^{-t}.  Warps that share
+        // a table write identical values.
+        tmem_store_power_table<T>(c.tm_A, tb0);
+        tmem_store_power_table<T>(c.tm_B, tb1);
+        tmem_st1(c.tm_g, tb4);
         tmem_wait_st();
+        // tables shared across warps must be complete before any sharer reads them
+        asm volatile("tcgen05.fence::before_thread_sync;\n");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;\n");
     }
 
     // phasor factor tables of this group's pipeline: ptab[buf][r][0][i] = e^{j2pi 256 i phi_r}, [1][a] = 16 a, [2][b] = b
@@ -544,22 +641,32 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
             ptab[(buf * 2 + r) * 48 + e] = mk<T>((T)p.x, (T)p.y);
         }
     };
-    // v[i] *= phasor_r(t + 256 i) = [e^{j 2 pi 16 w phi} e^{j 2 pi h phi}] * (e^{j 2 pi 256 phi})^i: two product chains
-    // of 8.  The four table entries are fetched by phasor_load() in the exchange phase, before the token is taken.
-    struct Ph { C d1, d8, pw, ph; };
-    auto phasor_load = [&](int buf) {
-        const C* pt = ptab + (buf * 2 + r) * 48;
-        Ph p; p.d1 = pt[1]; p.d8 = pt[8]; p.pw = pt[16 + w]; p.ph = pt[32 + h];
-        return p;
-    };
-    auto phasor_mul = [&](C (&v)[16], const Ph& p) {
-        C qa = cmul(p.pw, p.ph), qb = cmul(qa, p.d8);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            v[i] = cmul(v[i], qa);
-            v[i + 8] = cmul(v[i + 8], qb);
-            if (i < 7) { qa = cmul(qa, p.d1); qb = cmul(qb, p.d1); }
+    // The same tables for BOTH pipelines, produced by group 1 (threads 0..95 of the group) -- see g1_chores below
+    auto fill_ptab_both = [&](int buf, double phi) {
+        if (tg < 96) {
+            const int rr = tg >= 48, e = tg - 48 * rr, which = e >> 4, idx = e & 15;
+            const int n = idx << (which == 0 ? 8 : which == 1 ? 4 : 0);
+            double2 p = unit_phasor((double)n, phi, (double)(rr * n) * (1.0 / 8192.0));
+            ptab[(buf * 2 + rr) * 48 + e] = mk<T>((T)p.x, (T)p.y);
         }
+    };
+    // First pass of the forward transform with the doppler phasor (mod.rs:46-65) folded into its first butterfly level:
+    // input i carries phasor_r(t + 256 i) = [e^{j 2 pi 16 w phi} e^{j 2 pi h phi}] * s^i, s = e^{j 2 pi 256 phi}.  Column c
+    // of the first level needs s^{c + 4 a}, a = 0..3: start from base s^c (table entries s, s^2, s^3) and step by s^4.
+    auto phasor_fft16 = [&](C (&v)[16], int buf) {
+        const C* pt = ptab + (buf * 2 + r) * 48;
+        const C s4 = pt[4];
+        const C base = cmul(pt[16 + w], pt[32 + h]);
+        {
+            const C q1 = cmul(base, s4), q2 = cmul(q1, s4), q3 = cmul(q2, s4);
+            radix4_in<T, false, kTwMul, false>(v[0], v[4], v[8], v[12], base, q1, q2, q3);
+        }
+#pragma unroll
+        for (int cc = 1; cc < 4; ++cc) {
+            const C q0 = cmul(base, pt[cc]), q1 = cmul(q0, s4), q2 = cmul(q1, s4), q3 = cmul(q2, s4);
+            radix4_in<T, false, kTwMul, false>(v[cc], v[cc + 4], v[cc + 8], v[cc + 12], q0, q1, q2, q3);
+        }
+        fft16_stage_b<T, false>(v);
     };
     // v[i] = src[t + 256 i]  (zero beyond L)
     auto load_half = [&](C (&v)[16], const C* src, int L) {
@@ -571,24 +678,35 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
     };
 
 
-    // fold the 8 per-warp maxima of a finished row (parked in red_*[slot]) into its row peak: warp 0 of group 0
-    auto flush_peak = [&](int slot) {
-        if (r == 0 && wg == 0 && peak_pending >= 0) {
-            double bv = (lane < 8) ? red_val[slot * 8 + lane] : 0.0;
-            int bi = (lane < 8) ? (int)red_idx[slot * 8 + lane] : 0x7fffffff;
+    // Load balance between the groups.  Group 0 carries the epilogue of every row (radix-2, |.|^2, stores, argmax) and is
+    // the critical path; group 1 idles ~2.5 k cycles per row at the mailbox gate (it may not overwrite its fabric half
+    // before group 0 has drained the mail).  So group 1 does the row's chores right after that gate:
+    //   * the phasor tables of the NEXT row for both pipelines (96 sincospi; round 1 had warps 0-1 of each group compute
+    //     48, and every barrier of the group then waited for those two warps);
+    //   * the fold of the PREVIOUS row's 256 per-lane maxima that group 0 left in cand_* (round 1: a five-round shuffle
+    //     reduction in every group-0 warp plus a fold by warp 0 inside its next forward transform).
+    // Ordering: group 0 stores its candidates before it arrives on mb_empty, group 1 reads them after waiting on it;
+    // group 1 writes the tables before it arrives on mb_full for this row, group 0 reads them after its wait for that mail.
+    auto fold_candidates = [&](int slot, int it) {       // one warp of group 1
+        double bv = 0.0;
+        int bi = 0x7fffffff;
 #pragma unroll
-            for (int off = 4; off > 0; off >>= 1) {
-                double ov = __shfl_xor_sync(0xffffffffu, bv, off);
-                int oi = __shfl_xor_sync(0xffffffffu, bi, off);
-                amax_take<double>(bv, bi, ov, oi);
-            }
-            if (lane == 0) {
-                if (!(bv > 0.0)) bi = 0;   // nothing beat the initial max = 0.0 (mod.rs:143-144)
-                if (a.row_peak_val) a.row_peak_val[peak_pending] = (T)bv;
-                if (a.row_peak_idx) a.row_peak_idx[peak_pending] = (unsigned long long)bi;
-            }
+        for (int q = 0; q < 8; ++q) {
+            const double cv = cand_val[slot * 256 + lane + 32 * q];
+            const int ci = cand_idx[slot * 256 + lane + 32 * q];
+            amax_take<double>(bv, bi, cv, ci);
         }
-        peak_pending = -1;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            double ov = __shfl_xor_sync(0xffffffffu, bv, off);
+            int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+            amax_take<double>(bv, bi, ov, oi);
+        }
+        if (lane == 0) {
+            if (!(bv > 0.0)) bi = 0;   // nothing beat the initial max = 0.0 (mod.rs:143-144)
+            if (a.row_peak_val) a.row_peak_val[it] = (T)bv;
+            if (a.row_peak_idx) a.row_peak_idx[it] = (unsigned long long)bi;
+        }
     };
 
     auto empty_gate = [&](uint64_t*& mb, int& par) {
@@ -629,19 +747,20 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
                     if (a.trace && item == lo) c.tr = a.trace + ((((long long)blockIdx.x * 16 + hw_warp) * 8 + 7) * 32);
 #endif
                     CAF_TR(c, 0);
-                    const Ph ph0 = phasor_load(buf);
-                    phasor_mul(v, ph0);
+                    phasor_fft16(v, buf);
                     uint64_t* mb; int par;
                     empty_gate(mb, par);
-                    forward_4096<T>(v, c, mb, par, []{}, []{});
+                    forward_tail<T>(v, c, mb, par, [&] {     // (the last row of the previous pair, drained at this gate)
+                                        if (r == 1 && mb != nullptr && wg == 3) fold_candidates((buf ^ 1) & 1, item - 1);
+                                    }, []{});
                     const T sc = (T)(1.0 / 8192.0);   // the /n of xcor_rustfft.rs:72 (n = transform length)
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
+                    for (int q = 0; q < 4; ++q) {      // TMEM chunk q = bins k3 = q, q + 4, q + 8, q + 12
                         C tmp[4];
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
-                            tmp[i] = mk<T>(v[4 * q + i].x * sc, v[4 * q + i].y * sc);
-                            if (shared_h) __stcg(a.hshare + (4 * q + i) * kThreads + tid, tmp[i]);
+                            tmp[i] = mk<T>(v[q + 4 * i].x * sc, v[q + 4 * i].y * sc);
+                            if (shared_h) __stcg(a.hshare + (q + 4 * i) * kThreads + tid, tmp[i]);
                         }
                         tmem_st4(tm_h + 4 * q * TG::kColsPerC, tmp);
                     }
@@ -661,48 +780,30 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
                 if (!preloaded) load_half(v, a.in + (long long)pair * a.L, a.L);
                 const bool first_row_phi = preloaded || (item == lo);
                 preloaded = false;
+                // the needle of this pair goes to shared memory, planar; both groups hold the same samples, group r
+                // stores component r.  CTA-wide barriers on both sides: the groups drift up to a row apart, and the
+                // other group may still be reading the previous pair's needle.
+                __syncthreads();
+                {
+                    T* const dst = (r == 0) ? ndl_re : ndl_im;
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    C tmp[4];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) tmp[i] = v[4 * q + i];
-                    tmem_st4(tm_n + 4 * q * TG::kColsPerC, tmp);
+                    for (int i = 0; i < 16; ++i) dst[t + 256 * i] = (r == 0) ? v[i].x : v[i].y;
                 }
-                tmem_wait_st();
-                bar_group(r);                     // ptab[buf] (phi = 0) is dead from here
-                fill_ptab(buf, first_row_phi ? phi_first : a.freqs[row] * a.dt);
-                bar_group(r);
+                fill_ptab(buf, first_row_phi ? phi_first : a.freqs[row] * a.dt);   // ptab[buf] (phi = 0) died at the barrier
+                __syncthreads();
             }
             CAF_TR(c, 1);
-            // ---- needle samples back from TMEM: four loads in flight behind one wait ----
-            {
-                typename raw4_of<T>::type q0, q1, q2, q3;
-                tmem_ld4_issue(tm_n + 0 * TG::kColsPerC, q0); tmem_ld4_issue(tm_n + 4 * TG::kColsPerC, q1);
-                tmem_ld4_issue(tm_n + 8 * TG::kColsPerC, q2); tmem_ld4_issue(tm_n + 12 * TG::kColsPerC, q3);
-                tmem_wait_ld();
-                C tmp[4];
-                tmem_unpack4(q0, tmp); v[0] = tmp[0]; v[1] = tmp[1]; v[2] = tmp[2]; v[3] = tmp[3];
-                tmem_unpack4(q1, tmp); v[4] = tmp[0]; v[5] = tmp[1]; v[6] = tmp[2]; v[7] = tmp[3];
-                tmem_unpack4(q2, tmp); v[8] = tmp[0]; v[9] = tmp[1]; v[10] = tmp[2]; v[11] = tmp[3];
-                tmem_unpack4(q3, tmp); v[12] = tmp[0]; v[13] = tmp[1]; v[14] = tmp[2]; v[15] = tmp[3];
-            }
-            {
-                const Ph ph0 = phasor_load(buf);
-                // phasors of the next row: produced here, while this group waits for the token anyway; the group
-                // barriers of this row order them before their first use
-                if ((item + 1 < hi) && (row + 1 < a.D)) fill_ptab(buf ^ 1, a.freqs[row + 1] * a.dt);
-                phasor_mul(v, ph0);
-            }
+            // ---- needle samples from shared memory (planar, 64-bit accesses: 2 wavefronts per warp and load) ----
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = mk<T>(ndl_re[t + 256 * i], ndl_im[t + 256 * i]);
+            phasor_fft16(v, buf);
             CAF_TR(c, 2);
         } else if constexpr (kHalfZero) {
             bar_group(r);
             fill_ptab(buf, 0.0);
             load_half(v, a.in + (long long)pair * a.L, a.L);
             bar_group(r);
-            {
-                const Ph ph0 = phasor_load(buf);
-                phasor_mul(v, ph0);
-            }
+            phasor_fft16(v, buf);
         } else {
             // general 8192-sample input: explicit first radix-2 stage
             const C* src = a.in + (long long)pair * kM;
@@ -713,14 +814,22 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
                 if (r == 0) v[i] = cadd(x0, x1);
                 else v[i] = cmulc(csub(x0, x1), ldg<T>(a.g + n));   // * W_8192^{+n} = conj(g[n])
             }
+            fft16<T, false>(v);
         }
 
         // ---------------- forward transform ----------------
         {
             uint64_t* mb; int par;
             empty_gate(mb, par);
-            // the previous row's per-warp maxima are folded in the first exchange phase (two group barriers have passed)
-            forward_4096<T>(v, c, mb, par, [&] { if constexpr (MODE == kSurface) flush_peak((buf ^ 1) & 1); },
+            const bool had_mail = (mb != nullptr);     // group 1: a row of this CTA whose mail group 0 has drained at this gate
+            forward_tail<T>(v, c, mb, par, [&] {
+                                    if constexpr (MODE == kSurface) {      // group 1's chores, right after the mailbox gate
+                                        if (r == 1) {
+                                            if ((item + 1 < hi) && (row + 1 < a.D)) fill_ptab_both(buf ^ 1, a.freqs[row + 1] * a.dt);
+                                            if (had_mail && wg == 3) fold_candidates((buf ^ 1) & 1, item - 1);
+                                        }
+                                    }
+                                },
                                 [&] {
                                     // first row of a consumer CTA: wait for H's publication here, while the last
                                     // butterfly is still ahead, so the L2 round trip of the flag is off the critical path
@@ -755,44 +864,29 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
 #pragma unroll
                     for (int k = 0; k < 16; ++k) v[k] = __ldcg(a.hshare + k * kThreads + tid);
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
+                    for (int q = 0; q < 4; ++q) {      // TMEM chunk q = bins k3 = q, q + 4, q + 8, q + 12
                         C hv[4];
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) hv[i] = v[4 * q + i];
+                        for (int i = 0; i < 4; ++i) hv[i] = v[q + 4 * i];
                         tmem_st4(tm_h + 4 * q * TG::kColsPerC, hv);
                     }
 #pragma unroll
-                    for (int k = 0; k < 16; ++k) v[k] = cmulc(v[k], Fab<T>::ld(c.Sr, c.ix_own(k)));
+                    for (int k = 0; k < 16; ++k) v[k] = Fab<T>::ld(c.Sr, c.ix_own(k));
                     tmem_wait_st();
-                } else {
-#pragma unroll
-                    for (int q = 0; q < 2; ++q) {
-                        typename raw4_of<T>::type qa, qb;
-                        tmem_ld4_issue(tm_h + (8 * q) * TG::kColsPerC, qa);
-                        tmem_ld4_issue(tm_h + (8 * q + 4) * TG::kColsPerC, qb);
-                        tmem_wait_ld();
-                        C hv[4];
-                        tmem_unpack4(qa, hv);
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) v[8 * q + i] = cmulc(hv[i], v[8 * q + i]);
-                        tmem_unpack4(qb, hv);
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) v[8 * q + 4 + i] = cmulc(hv[i], v[8 * q + 4 + i]);
-                    }
                 }
+                CAF_TR(c, 9);
+                inverse_4096<T, true>(v, c, tm_h);    // H conj(X) folded in; v[n1] = A_r[t + 256 n1]
             } else {
 #pragma unroll
                 for (int k = 0; k < 16; ++k) v[k] = cmulc(ldg<T>(hp + ((k * 16 + w) * 2 + r) * 16 + h), v[k]);
+                CAF_TR(c, 9);
+                inverse_4096<T, false>(v, c, 0u);
             }
-
-            CAF_TR(c, 9);
-            // ---------------- inverse transform ----------------
-            inverse_4096<T>(v, c);   // v[n1] = A_r[t + 256 n1]
 
             // ---------------- final radix-2 across the pipelines:  y[n] = A + B', y[n + 4096] = A - B',
             //                  B' = B W_8192^{-n},  n = t + 256 n1,  W_8192^{-n} = g[t] W_32^{-n1} ----------------
             if (r == 1) {
-                const C gt = tmem_ld1(c.tm_tw + 4 * TG::kColsPerC, T());
+                const C gt = tmem_ld1(c.tm_g, T());
                 auto post = [&](auto jt) {
                     constexpr int j = decltype(jt)::value;
                     v[j] = cmul(v[j], mul_w32_inv<T, j>(gt));
@@ -807,6 +901,7 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
                 CAF_TR(c, 17);
                 ++posts;
                 drain_pending = true;
+
             } else {
                 const int L = FULL ? kL0 : a.L;
                 const int nout = 2 * L, skip = kM - nout;
@@ -846,26 +941,17 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
                     emit(cadd(v[k], Bp), n, best0, bidx0);             // lag index n
                     emit(csub(v[k], Bp), n + kL0, best1, bidx1);       // lag index n + 4096
                 }
-                mbar_arrive(mb_empty);
-                CAF_TR(c, 18);
-                ++posts;
-
                 if constexpr (MODE == kSurface) {
-                    // ---------------- row argmax (mod.rs:141-153) ----------------
+                    // ---------------- row argmax (mod.rs:141-153): this lane's candidate; group 1 folds the 256 of them ----
                     T best = best0;
                     int bidx = bidx0;
                     if (best1 > best) { best = best1; bidx = bidx1; }   // every index of half 1 is above half 0
-#pragma unroll
-                    for (int off = 16; off > 0; off >>= 1) {
-                        T ov = __shfl_xor_sync(0xffffffffu, best, off);
-                        int oi = __shfl_xor_sync(0xffffffffu, bidx, off);
-                        amax_take<T>(best, bidx, ov, oi);
-                    }
-                    // per-warp maxima are parked in shared memory; one warp folds them after the NEXT group barrier
-                    // (inside the next forward transform), so no barrier is spent on the reduction
-                    if (lane == 0) { red_val[(buf & 1) * 8 + wg] = (double)best; red_idx[(buf & 1) * 8 + wg] = (unsigned long long)bidx; }
-                    peak_pending = item;
+                    cand_val[(buf & 1) * 256 + tg] = (double)best;
+                    cand_idx[(buf & 1) * 256 + tg] = bidx;
                 }
+                mbar_arrive(mb_empty);        // releases the mailbox AND publishes the candidates
+                CAF_TR(c, 18);
+                ++posts;
             }
         }
         CAF_TR(c, 19);
@@ -873,7 +959,11 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
         if (++row == rows_per_pair) { row = 0; ++pair; }
     }
     if constexpr (MODE == kSurface) {
-        if (r == 0) { bar_group(0); flush_peak((buf ^ 1) & 1); }   // the last row of this CTA
+        // the last row of this CTA: group 1 waits for group 0's drain of the last mail and folds its candidates
+        if (r == 1 && drain_pending) {           // (buf has toggled once more since the last row)
+            mbar_wait(mb_empty, (posts - 1) & 1);
+            if (wg == 3) fold_candidates((buf ^ 1) & 1, hi - 1);
+        }
     }
 
     {

@@ -118,8 +118,7 @@ __global__ void __launch_bounds__(kThreads, 1) caf_large_core(const LargeArgs<T>
     c.init(smem_raw, tid);                                // c.r = warp group (selects the fabric half and the barrier)
     const int t = c.t, tg = tid & 255;
 
-    const C tb0 = ldg<T>(a.tw1 + 256 + t), tb1 = ldg<T>(a.tw2 + 16 + c.h), tb2 = ldg<T>(a.tw1 + c.w * 256 + c.h),
-            tb3 = ldg<T>(a.tw2 + 16 + c.w), tb4 = ldg<T>(a.g + t);
+    const C tb0 = ldg<T>(a.tw1 + 256 + t), tb1 = ldg<T>(a.tw2 + 16 + c.h);
     if (hw_warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n"
                      :: "l"((uint64_t)__cvta_generic_to_shared(&misc[0])), "n"(TG::kAlloc));
@@ -128,13 +127,20 @@ __global__ void __launch_bounds__(kThreads, 1) caf_large_core(const LargeArgs<T>
     asm volatile("tcgen05.fence::before_thread_sync;\n");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;\n");
-    c.tm_tw = misc[0] + ((uint32_t)(32 * (hw_warp & 3)) << 16) + (uint32_t)((96 + 8 * (hw_warp >> 2)) * TG::kColsPerC);
-    tmem_st1(c.tm_tw + 0 * TG::kColsPerC, tb0);
-    tmem_st1(c.tm_tw + 1 * TG::kColsPerC, tb1);
-    tmem_st1(c.tm_tw + 2 * TG::kColsPerC, tb2);
-    tmem_st1(c.tm_tw + 3 * TG::kColsPerC, tb3);
-    tmem_st1(c.tm_tw + 4 * TG::kColsPerC, tb4);
-    tmem_wait_st();
+    {
+        // TMEM map as in caf_rows_kernel: H | table A (shared by the two groups) | table B (shared by all) | 4 slots per warp
+        const uint32_t base = misc[0] + ((uint32_t)(32 * (hw_warp & 3)) << 16);
+        const int j = hw_warp >> 2;
+        c.tm_A = base + (uint32_t)((64 + 16 * (j & 1)) * TG::kColsPerC);
+        c.tm_B = base + (uint32_t)(96 * TG::kColsPerC);
+        c.tm_g = base + (uint32_t)((112 + 4 * j) * TG::kColsPerC);
+        tmem_store_power_table<T>(c.tm_A, tb0);
+        tmem_store_power_table<T>(c.tm_B, tb1);
+        tmem_wait_st();
+        asm volatile("tcgen05.fence::before_thread_sync;\n");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;\n");
+    }
 
     const int units_per_row = a.N / kL0 / 2 * 2;          // 2 pipelines x N/2/4096
     const int tot = (a.inner_top == kL0) ? a.N / 2 : 65536;   // length of the innermost factored array
@@ -153,13 +159,13 @@ __global__ void __launch_bounds__(kThreads, 1) caf_large_core(const LargeArgs<T>
     if (active && !HMODE) {
         // conj(W_tot^{m s}) = e^{+2 pi j (t + 256 n1) s / tot}: base and ratio
         const double2 b = root_of_unity((long long)t * s, tot, 1.0), rho = root_of_unity(256LL * s, tot, 1.0);
-        tmem_st1(c.tm_tw + 5 * TG::kColsPerC, mk<T>((T)b.x, (T)b.y));
-        tmem_st1(c.tm_tw + 6 * TG::kColsPerC, mk<T>((T)rho.x, (T)rho.y));
+        tmem_st1(c.tm_g + 1 * TG::kColsPerC, mk<T>((T)b.x, (T)b.y));
+        tmem_st1(c.tm_g + 2 * TG::kColsPerC, mk<T>((T)rho.x, (T)rho.y));
 #pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4) {
+        for (int q4 = 0; q4 < 4; ++q4) {           // TMEM chunk q4 = bins k3 = q4, q4 + 4, q4 + 8, q4 + 12
             C tmp[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) tmp[i] = ldg<T>(hp + (4 * q4 + i) * 256);
+            for (int i = 0; i < 4; ++i) tmp[i] = ldg<T>(hp + (q4 + 4 * i) * 256);
             tmem_st4(tm_h + 4 * q4 * TG::kColsPerC, tmp);
         }
         tmem_wait_st();
@@ -174,23 +180,9 @@ __global__ void __launch_bounds__(kThreads, 1) caf_large_core(const LargeArgs<T>
 #pragma unroll
             for (int k = 0; k < 16; ++k) hp[k * 256] = mk<T>(v[k].x * scale, v[k].y * scale);
         } else {
-#pragma unroll
-            for (int q = 0; q < 2; ++q) {                                                       // H conj(X), xcor_rustfft.rs:64-73
-                typename raw4_of<T>::type qa, qb;
-                tmem_ld4_issue(tm_h + (8 * q) * TG::kColsPerC, qa);
-                tmem_ld4_issue(tm_h + (8 * q + 4) * TG::kColsPerC, qb);
-                tmem_wait_ld();
-                C hv[4];
-                tmem_unpack4(qa, hv);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) v[8 * q + i] = cmulc(hv[i], v[8 * q + i]);
-                tmem_unpack4(qb, hv);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) v[8 * q + 4 + i] = cmulc(hv[i], v[8 * q + 4 + i]);
-            }
-            inverse_4096<T>(v, c);                                                       // v[n1] at m = t + 256 n1
+            inverse_4096<T, true>(v, c, tm_h);            // H conj(X) (xcor_rustfft.rs:64-73) folded in; v[n1] at m = t + 256 n1
             {
-                const C b = tmem_ld1(c.tm_tw + 5 * TG::kColsPerC, T()), rho = tmem_ld1(c.tm_tw + 6 * TG::kColsPerC, T());
+                const C b = tmem_ld1(c.tm_g + 1 * TG::kColsPerC, T()), rho = tmem_ld1(c.tm_g + 2 * TG::kColsPerC, T());
                 twiddle_geometric<false>(v, b, rho);
             }
 #pragma unroll

@@ -40,22 +40,6 @@ template <typename C> __device__ __forceinline__ C csq(C a) {
     C r; r.x = a.x * a.x - a.y * a.y; r.y = (a.x + a.x) * a.y; return r;
 }
 
-// v[k] *= w^k (conjugated when INV), k = 1..15.  The powers are generated in registers (two interleaved product
-// chains, odd and even exponents, stepping by w^2: 3 values live) instead of 15 shared-memory loads: a 128-bit
-// load costs the SM's single LSU port 4 wavefront cycles, a complex product costs the four fp64 pipes 2 cycles
-// in total, and the LSU port is what the pass-to-pass exchanges need.  Rounding: <= 8 products deep, ~1e-15.
-template <bool INV, typename C>
-__device__ __forceinline__ void twiddle_powers(C (&v)[16], C w) {
-    const C w2 = csq(w);
-    C po = w, pe = w2;
-#pragma unroll
-    for (int k = 1; k < 16; k += 2) {
-        v[k] = ctw<INV>(v[k], po);
-        if (k + 1 < 16) v[k + 1] = ctw<INV>(v[k + 1], pe);
-        if (k + 2 < 16) { po = cmul(po, w2); pe = cmul(pe, w2); }
-    }
-}
-
 // v[k] *= b * rho^k (conjugated when INV), k = 0..15: two interleaved product chains of length 8
 template <bool INV, typename C>
 __device__ __forceinline__ void twiddle_geometric(C (&v)[16], C b, C rho) {
@@ -141,18 +125,14 @@ __device__ __forceinline__ void radix4_twiddled(cx<T>& a0, cx<T>& a1, cx<T>& a2,
     radix4_tail<T, INV>(t0, t1, t2, t3, a0, a1, a2, a3);
 }
 
-// In-place 16-point DFT, natural order in and out: v[k] <- sum_i v[i] e^{-+2 pi j i k/16}
+// stage B of the 16-point DFT: over c for each ka -> X[ka + 4 kb] left at v[4 ka + kb] (the twiddles W16^{c ka} ride in
+// the butterflies), then the 4x4 register transpose back to natural order (pure renaming once unrolled)
 template <typename T, bool INV>
-__device__ __forceinline__ void fft16(cx<T> (&v)[16]) {
-    // stage A: i = c + 4a  ->  A[c][ka] left at v[c + 4 ka]
-#pragma unroll
-    for (int c = 0; c < 4; ++c) radix4<T, INV>(v[c], v[c + 4], v[c + 8], v[c + 12]);
-    // stage B: over c for each ka -> X[ka + 4 kb] left at v[4 ka + kb]; the twiddles W16^{c ka} ride in the butterflies
+__device__ __forceinline__ void fft16_stage_b(cx<T> (&v)[16]) {
     radix4<T, INV>(v[0], v[1], v[2], v[3]);
     radix4_twiddled<T, INV, 1, 2, 3>(v[4], v[5], v[6], v[7]);
     radix4_twiddled<T, INV, 2, 4, 6>(v[8], v[9], v[10], v[11]);
     radix4_twiddled<T, INV, 3, 6, 9>(v[12], v[13], v[14], v[15]);
-    // 4x4 register transpose back to natural order (pure renaming once unrolled)
     cx<T> o[16];
 #pragma unroll
     for (int ka = 0; ka < 4; ++ka)
@@ -160,6 +140,56 @@ __device__ __forceinline__ void fft16(cx<T> (&v)[16]) {
         for (int kb = 0; kb < 4; ++kb) o[ka + 4 * kb] = v[4 * ka + kb];
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = o[i];
+}
+
+// In-place 16-point DFT, natural order in and out: v[k] <- sum_i v[i] e^{-+2 pi j i k/16}
+template <typename T, bool INV>
+__device__ __forceinline__ void fft16(cx<T> (&v)[16]) {
+    // stage A: i = c + 4a  ->  A[c][ka] left at v[c + 4 ka]
+#pragma unroll
+    for (int c = 0; c < 4; ++c) radix4<T, INV>(v[c], v[c + 4], v[c + 8], v[c + 12]);
+    fft16_stage_b<T, INV>(v);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Run-time factors folded into the FIRST level of a butterfly.  Every pass of the 4096-point transforms is
+// "multiply the 16 inputs by per-element factors, then a 16-point DFT": the exchange twiddles, the doppler phasor and
+// the spectral product with H are all of that form.  Applied on the INPUT side the multiply merges with the first
+// add / subtract level:   plus = base + q x  (4 FMA),   minus = 2 base - plus  (2 FMA)
+// -- 6 instructions instead of 8 (complex multiply, add, subtract), i.e. 16 fewer fp64 instructions per 16-point DFT.
+// minus carries the absolute rounding error of plus, which is what an FFT stage needs (same device as fused_pm).
+// How a factor q meets its element x:
+enum TwMode : int {
+    kTwMul = 0,      // x * q
+    kTwMulConj = 1,  // x * conj(q)        (inverse transforms: conjugated twiddles)
+    kTwConjX = 2     // conj(x) * q        (spectral product H conj(X), xcor_rustfft.rs:64-73)
+};
+template <int MODE, typename C> __device__ __forceinline__ C tw_apply(C x, C q) {
+    if constexpr (MODE == kTwMul) return cmul(x, q);
+    else if constexpr (MODE == kTwMulConj) return cmulc(x, q);
+    else return cmulc(q, x);
+}
+// plus = base + (x (*) q), minus = base - (x (*) q)
+template <int MODE, typename T>
+__device__ __forceinline__ void tw_pm(cx<T> base, cx<T> x, cx<T> q, cx<T>& plus, cx<T>& minus) {
+    if constexpr (MODE == kTwMul)            // (x.x q.x - x.y q.y) + j (x.x q.y + x.y q.x)
+        plus = mk<T>(fma(-q.y, x.y, fma(q.x, x.x, base.x)), fma(q.x, x.y, fma(q.y, x.x, base.y)));
+    else if constexpr (MODE == kTwMulConj)   // (x.x q.x + x.y q.y) + j (x.y q.x - x.x q.y)
+        plus = mk<T>(fma(q.y, x.y, fma(q.x, x.x, base.x)), fma(q.x, x.y, fma(-q.y, x.x, base.y)));
+    else                                     // conj(x) q = (x.x q.x + x.y q.y) + j (x.x q.y - x.y q.x)
+        plus = mk<T>(fma(q.y, x.y, fma(q.x, x.x, base.x)), fma(-q.x, x.y, fma(q.y, x.x, base.y)));
+    minus = mk<T>(fma((T)2, base.x, -plus.x), fma((T)2, base.y, -plus.y));
+}
+// radix-4 butterfly over inputs a_i (*) q_i.  Q0_ONE: q0 == 1 and is not applied (MODE != kTwConjX only).
+template <typename T, bool INV, int MODE, bool Q0_ONE>
+__device__ __forceinline__ void radix4_in(cx<T>& a0, cx<T>& a1, cx<T>& a2, cx<T>& a3, cx<T> q0, cx<T> q1, cx<T> q2, cx<T> q3) {
+    static_assert(!(Q0_ONE && MODE == kTwConjX), "conj(x) * 1 still conjugates");
+    cx<T> t0, t1, t2, t3;
+    const cx<T> p0 = Q0_ONE ? a0 : tw_apply<MODE>(a0, q0);
+    tw_pm<MODE, T>(p0, a2, q2, t0, t1);
+    const cx<T> p1 = tw_apply<MODE>(a1, q1);
+    tw_pm<MODE, T>(p1, a3, q3, t2, t3);
+    radix4_tail<T, INV>(t0, t1, t2, t3, a0, a1, a2, a3);
 }
 
 // In-place R-point DFT (R = 2, 4, 8 or 16) on v[0..R), natural order in and out.  Used by the long-row spread /
