@@ -619,10 +619,10 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
         c.tm_A = base + (uint32_t)((64 + 16 * (j & 1)) * TG::kColsPerC);    // table A (the two pipelines share it)
         c.tm_B = base + (uint32_t)(96 * TG::kColsPerC);                     // table B (all four warps share it)
         c.tm_g = base + (uint32_t)((112 + 4 * j) * TG::kColsPerC);
-        // per-thread twiddle tables, once per CTA: powers of W_4096^t and of W_256^h; and W_8192^{-t}.  Warps that share
-        // a table write identical values.
-        tmem_store_power_table<T>(c.tm_A, tb0);
-        tmem_store_power_table<T>(c.tm_B, tb1);
+        // per-thread twiddle tables, once per CTA: powers of W_4096^t and of W_256^h; and W_8192^{-t}.  A table shared by
+        // several warps is written by one of them.
+        if (r == 0) tmem_store_power_table<T>(c.tm_A, tb0);     // group 1 reads group 0's copy (same t)
+        else if (j == 2) tmem_store_power_table<T>(c.tm_B, tb1);   // one of the four warps of the lane quarter
         tmem_st1(c.tm_g, tb4);
         tmem_wait_st();
         // tables shared across warps must be complete before any sharer reads them
@@ -643,6 +643,8 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
     };
     // The same tables for BOTH pipelines, produced by group 1 (threads 0..95 of the group) -- see g1_chores below
     auto fill_ptab_both = [&](int buf, double phi) {
+        // three full warps (spreading the 96 entries over 12 lanes of all eight warps was measured slower: 18.25 k against
+        // 17.84 k cycles per row -- every warp then pays the latency of the divergent sincospi stream)
         if (tg < 96) {
             const int rr = tg >= 48, e = tg - 48 * rr, which = e >> 4, idx = e & 15;
             const int n = idx << (which == 0 ? 8 : which == 1 ? 4 : 0);

@@ -134,8 +134,8 @@ __global__ void __launch_bounds__(kThreads, 1) caf_large_core(const LargeArgs<T>
         c.tm_A = base + (uint32_t)((64 + 16 * (j & 1)) * TG::kColsPerC);
         c.tm_B = base + (uint32_t)(96 * TG::kColsPerC);
         c.tm_g = base + (uint32_t)((112 + 4 * j) * TG::kColsPerC);
-        tmem_store_power_table<T>(c.tm_A, tb0);
-        tmem_store_power_table<T>(c.tm_B, tb1);
+        if (c.r == 0) tmem_store_power_table<T>(c.tm_A, tb0);      // shared tables are written by one of their warps
+        else if (j == 2) tmem_store_power_table<T>(c.tm_B, tb1);
         tmem_wait_st();
         asm volatile("tcgen05.fence::before_thread_sync;\n");
         __syncthreads();

@@ -48,7 +48,7 @@ def child():
         if i >= 1: tb.append(e0.elapsed_time(e1) * 1e3)
     pb = pkb.cpu().numpy().reshape(P, 4); okb = all(float(q.view(np.float64)[1]) == peak[0] and int(q.view(np.uint64)[3]) == peak[1] for q in pb)
     cyc_row = np.median(tb) / D * 1.965e3
-    print(f"{os.environ.get('CAF_B200_SO', 'default'):50s} surface {np.median(ts):6.2f} us (min {np.min(ts):6.2f})  steady {np.median(tb)/D:6.3f} us/row = {cyc_row:6.0f} cyc  peak {peak} batch_ok {okb}", flush=True)
+    print(f"{os.environ.get('CAF_B200_SO', 'default'):50s} surface mean {np.mean(ts):6.2f} us (median {np.median(ts):6.2f}, min {np.min(ts):6.2f}; events tick at ~1 us)  steady {np.median(tb)/D:6.3f} us/row = {cyc_row:6.0f} cyc  peak {peak} batch_ok {okb}", flush=True)
 
 if __name__ == "__main__":
     if os.environ.get("QB_CHILD"):
