@@ -6,14 +6,15 @@ fp64 CAF surface + find_peak on the chirp_0 pair) on B200, one process per GPU.
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 A step = one pass of the hot path over one surface: FFT(s1) once, the fused row kernel over all doppler
-rows, find_peak.  At N > 1 every rank owns its own s0/s1 pair (pairs sharded, no data-path collective:
-"scaling": "weak").  `value` is device-resident throughput (inputs already in HBM), `e2e` goes through the
-host-pointer C ABI (pinned host buffers, H2D + kernels + D2H of the whole surface every step).
-Between timed steps L2 is flushed by overwriting a 256 MiB buffer; each step is timed with its own pair
-of CUDA events on the launching stream and the K durations are summed (max over ranks).
-At N = 1 the line also carries `working_set_gt_l2`: the same kernel over a working set larger than L2 (320 seeded
-pairs, 8 surface buffers) with one event pair around the back-to-back launches (scripts/bench_stream.py) —
-informational, `value` and `roofline` stay on the flushed per-step figure.
+rows, find_peak -- ONE kernel launch.  At N > 1 every rank owns its own s0/s1 pairs (pairs sharded, no data-path
+collective: "scaling": "weak").  `value` is device-resident throughput (inputs already in HBM): W warm-up steps, then
+exactly K steps between two barriers with one CUDA event pair on the launching stream, max over ranks.  L2 is kept cold
+by the working set (the steps rotate over 320 seeded pairs and 8 surface buffers = 252 MB > the 126 MB L2); round 1's
+method (L2 flushed before every step, one event pair per step) is reported beside it as `flushed_per_step`.
+`e2e` goes through the host-pointer C ABI (pinned host buffers, H2D + kernels + D2H of the whole surface every step).
+The same run also measures the SHARDED path at every N (`sharded`: config 3 with its doppler rows sharded over the ranks
++ the library's NCCL peak exchange, strong scaling; a config-4 slice with pairs sharded + gather) and, at N = 1, compact
+config-2 and config-5-row blocks.
 
 --impl reference times the reference's CPU algorithm (oracle port of CafRustFFTThreadpool, all host
 cores) on the same workload; the Rust crate itself cannot be compiled in this image.
@@ -567,34 +568,93 @@ def run_b200(args):
             s1.record(stream)
         return evs
 
-    # ---- warm-up, then the timed region ------------------------------------------------------------------
-    for _ in range(max(args.warmup, 3)):
-        flush.zero_()
-        step_dev()
+    # ---- the timed region (the contract's base form: W warm-up steps, then EXACTLY K steps between two barriers +
+    #      synchronise, one CUDA event pair on the launching stream, max over ranks).  L2 is kept cold by the WORKING SET,
+    #      not by a flush: the steps rotate over `n_pairs` distinct seeded s0/s1 pairs (utils/generate.py port; pair 0 of
+    #      rank 0 is the README's chirp_0 pair) and `n_surf` surface buffers of 26.2 MB -- 320 pairs + 8 surfaces = 252 MB
+    #      against the 126 MB L2 -- so nothing a step reads or writes (twiddle tables and code aside) was left in L2 by an
+    #      earlier step.  Every pair that ran is checked against the lag / offset the generator planted.
+    #      (Round 1 flushed L2 before every step and gave each step its own event pair; that charges every ~41 us kernel the
+    #      ~6 us ANY kernel pays between two events after a 256 MiB memset.  That figure is still measured: `flushed_per_step`.)
+    from caf_cookoff_b200 import generate as G
+    n_pairs, n_surf = 320, 8
+    needles_np = np.empty((n_pairs, L), dtype=cdt); hays_np = np.empty((n_pairs, L), dtype=cdt)
+    planted = []
+    i_ = 0
+    seed_ = 32 * rank                                   # ten pairs per seed; every rank draws its own seeds
+    while i_ < n_pairs:
+        for p_ in G.pairs(seed=seed_, count=min(10, n_pairs - i_)):
+            n__, h__ = G.as_inputs(p_)
+            needles_np[i_], hays_np[i_] = n__.astype(cdt), h__[:L].astype(cdt)
+            planted.append((p_.lag, p_.foffset_hz))
+            i_ += 1
+        seed_ += 1
+    nd_all = torch.from_numpy(needles_np).to(dev); hd_all = torch.from_numpy(hays_np).to(dev)
+    surfs = [surf_d] + [torch.empty((D, N), dtype=trdt, device=dev) for _ in range(n_surf - 1)]
+    rv_all = torch.empty((n_pairs, D), dtype=trdt, device=dev)
+    ri_all = torch.empty((n_pairs, D), dtype=torch.int64, device=dev)
+    pk_all = torch.zeros((n_pairs, 4), dtype=torch.int64, device=dev)
+
+    def step_rot(k):
+        i = k % n_pairs
+        rc = dev_fn(h.raw, nd_all[i].data_ptr(), hd_all[i].data_ptr(), 1, L, freqs_d.data_ptr(), D, FS,
+                    surfs[k % n_surf].data_ptr(), rv_all[i].data_ptr(), ri_all[i].data_ptr(), pk_all[i].data_ptr())
+        if rc != 0:
+            raise RuntimeError(lib.caf_b200_last_error().decode())
+
+    warm = max(args.warmup, 3)
+    for k in range(warm):
+        step_rot(k)
     barrier()
     sampler = ClockSampler(local)
     launches0 = h.launch_count
     sampler.start()
     barrier()
-    evs = timed_pass(step_dev, args.steps)
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for k in range(warm, warm + args.steps):
+        step_rot(k)
+    e1.record(stream)
     sampler.sample()
     barrier()
     sampler.stop()
     launches = h.launch_count - launches0
-    per_step = np.array([a.elapsed_time(b) for a, b in evs])   # ms
-    total_ms = float(per_step.sum())
+    total_ms = float(e0.elapsed_time(e1))
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms_max = float(t.item())
     cells_step = D * N
     value = world * cells_step * args.steps / (total_ms_max * 1e-3)
+    step_ms = total_ms_max / args.steps
 
-    # correctness of what was just timed: the peak must be the known answer of this pair (asserted below: a wrong
-    # peak marks the line check_ok = false and the process exits non-zero)
+    # correctness of what was just timed (asserted below: a wrong peak marks the line check_ok = false and the process
+    # exits non-zero): every pair that ran sits on its planted lag, on a doppler bin next to the planted offset; the
+    # README pair (rank 0, pair 0) gives its known answer on the 0.5 Hz grid, (69.0 Hz, 202)
+    w_ = pk_all.cpu().numpy()
+    ran = sorted({k % n_pairs for k in range(warm + args.steps)})
+    off = []
+    for i in ran:
+        f_ = float(w_[i].view(np.float64)[1]); lag_ = int(w_[i].view(np.uint64)[3])
+        if lag_ != planted[i][0] % N or abs(f_ - planted[i][1]) > 0.5:
+            off.append((i, f_, lag_))
+    peak_freq = float(w_[0].view(np.float64)[1]); peak_delay = int(w_[0].view(np.uint64)[3])
+    checks = {"device": not off and (rank != 0 or (peak_freq, peak_delay) == (69.0, 202))}
+
+    # ---- the round-1 figure beside it: L2 flushed (256 MiB overwrite) before every step, one event pair per step ----
+    fl_steps = min(args.steps, 200)
+    for _ in range(3):
+        flush.zero_(); step_dev()
+    barrier()
+    evs = timed_pass(step_dev, fl_steps)
+    barrier()
+    per_step = np.array([a.elapsed_time(b) for a, b in evs])   # ms
+    t = torch.tensor([float(per_step.sum())], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    flushed_ms = float(t.item()) / fl_steps
     pk = pk_d.cpu().numpy()
-    peak_freq = float(pk.view(np.float64)[1]); peak_delay = int(pk.view(np.uint64)[3])
-    checks = {"device": peak_is_planted(rank, peak_freq, peak_delay)}
+    checks["device_flushed"] = peak_is_planted(rank, float(pk.view(np.float64)[1]), int(pk.view(np.uint64)[3]))
 
     # ---- roofline pass: the row kernel alone, same flush regimen, CUDA events inside the library ----------
     lib.caf_b200_set_profiling(h.raw, 1)
@@ -606,7 +666,10 @@ def run_b200(args):
         lib.caf_b200_last_kernel_ms(h.raw, C.byref(a_), C.byref(b_), C.byref(c_))
         spec_ms.append(a_.value); rows_ms.append(b_.value); peak_ms.append(c_.value)
     lib.caf_b200_set_profiling(h.raw, 0)
-    rows_avg_ms = float(np.mean(rows_ms))
+    rows_flushed_ms = float(np.mean(rows_ms))
+    # the dominant kernel's average launch duration over the TIMED REGION: the region holds nothing but K launches of it
+    # (one fused launch per step), so it is the region's time / K on this rank
+    rows_avg_ms = total_ms / args.steps
     tf = C.c_double()
     lib.caf_b200_probe_fma_tflops(h.raw, 0 if f32 else 1, C.byref(tf))
     row_flops = D * (10.0 * N * np.log2(N) + 15.0 * N)
@@ -624,7 +687,10 @@ def run_b200(args):
         "hbm": {"achieved": surf_bytes / (rows_avg_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                 "frac": surf_bytes / (rows_avg_ms * 1e-3) / 1e9 / hbm_peak,
                 "peak_source": "MEASURED_PEAKS.json (measured)" if mp else "fallback 6650 GB/s"},
-        "step_share": {"spectrum_ms": float(np.mean(spec_ms)), "rows_ms": rows_avg_ms, "peak_ms": float(np.mean(peak_ms))},
+        "step_share": {"spectrum_ms": 0.0, "rows_ms": rows_avg_ms, "peak_ms": 0.0,
+                       "note": "one fused launch per step: FFT(s1), the rows and find_peak are the same kernel"},
+        "flushed_per_step": {"kernel_ms": rows_flushed_ms, "frac": row_flops / (rows_flushed_ms * 1e-3) / 1e12 / tf.value if tf.value else None,
+                             "note": "the same kernel timed alone by CUDA events inside the library, L2 flushed before every launch (round 1's figure)"},
     }
     # the other roofline the north star names: shared memory.  A row moves every value of its two pipelines through the
     # exchange fabric 4 times each way plus the radix-2 mailbox: 72 stores and 72 loads of one complex value per thread
@@ -641,82 +707,88 @@ def run_b200(args):
     except Exception as e:      # never let the extra figure break the bench line
         roofline["smem"] = {"error": repr(e)}
 
-    # ---- e2e: the host-pointer C ABI with pinned host buffers, H2D + D2H inside the timed region ----------
-    needle_h = torch.from_numpy(needle.astype(cdt)).pin_memory()
-    hay_h = torch.from_numpy(hay.astype(cdt)).pin_memory()
-    freqs_h = torch.from_numpy(freqs).pin_memory()
+    # ---- e2e: the host-pointer C ABI, H2D + D2H inside the timed region.  The caller's three inputs sit back to back in
+    #      ONE pinned block from caf_b200_host_alloc (needle | haystack | freqs): the library then moves them with a single
+    #      DMA (three small H2D copies cost ~6 us each on B200).  `*_pageable` repeats both calls with plain pageable numpy
+    #      buffers -- what a caller that knows nothing about pinned memory (the Rust shim's Vecs, std::vector) pays. -----
+    csz = np.dtype(cdt).itemsize
+    blk = C.c_void_p()
+    if lib.caf_b200_host_alloc(C.byref(blk), 2 * L * csz + D * 8) != 0:
+        raise RuntimeError(lib.caf_b200_last_error().decode())
+    raw_blk = (C.c_ubyte * (2 * L * csz + D * 8)).from_address(blk.value)
+    needle_h = np.frombuffer(raw_blk, dtype=cdt, count=L, offset=0); needle_h[:] = needle.astype(cdt)
+    hay_h = np.frombuffer(raw_blk, dtype=cdt, count=L, offset=L * csz); hay_h[:] = hay.astype(cdt)
+    freqs_h = np.frombuffer(raw_blk, dtype=np.float64, count=D, offset=2 * L * csz); freqs_h[:] = freqs
     surf_h = torch.empty((D, N), dtype=trdt).pin_memory()
     rv_h = torch.empty(D, dtype=trdt).pin_memory()
     ri_h = torch.empty(D, dtype=torch.int64).pin_memory()
-    pk_h = _lib.Peak()
     host_fn = getattr(lib, f"caf_b200_surface_{sfx}")
-
-    def step_host():
-        rc = host_fn(h.raw, needle_h.data_ptr(), hay_h.data_ptr(), L, freqs_h.data_ptr(), D, FS,
-                     surf_h.data_ptr(), rv_h.data_ptr(), ri_h.data_ptr(), C.cast(C.byref(pk_h), C.c_void_p))
-        if rc != 0:
-            raise RuntimeError(lib.caf_b200_last_error().decode())
-
+    peak_fn = getattr(lib, f"caf_b200_peak_{sfx}")
     e2e_steps = min(args.steps, 200)
-    for _ in range(3):
-        step_host()
-    barrier()
-    t0 = time.perf_counter()
-    evs = timed_pass(step_host, e2e_steps)
-    barrier()
-    wall = time.perf_counter() - t0
-    e2e_ms = float(sum(a.elapsed_time(b) for a, b in evs))
-    t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_ms_max = float(t.item())
-    h2d = needle_h.numel() * needle_h.element_size() + hay_h.numel() * hay_h.element_size() + freqs_h.numel() * 8
+    h2d = 2 * L * csz + D * 8
     d2h = surf_h.numel() * surf_h.element_size() + rv_h.numel() * rv_h.element_size() + ri_h.numel() * 8 + 32
-    e2e = {"value": world * cells_step * e2e_steps / (e2e_ms_max * 1e-3), "unit": "cells/s",
-           "ms_per_step": e2e_ms_max / e2e_steps, "steps": e2e_steps, "wall_ms_per_step_incl_flush": 1e3 * wall / e2e_steps,
-           "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+
+    def time_host(step):
+        for _ in range(3):
+            step()
+        barrier()
+        t0 = time.perf_counter()
+        evs = timed_pass(step, e2e_steps)
+        barrier()
+        wall = time.perf_counter() - t0
+        tt = torch.tensor([float(sum(a.elapsed_time(b) for a, b in evs))], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item()) / e2e_steps, 1e3 * wall / e2e_steps
+
+    def surface_call(n_, h_, f_, s_, rv_, ri_, pk_):
+        def step():
+            rc = host_fn(h.raw, n_.ctypes.data, h_.ctypes.data, L, f_.ctypes.data, D, FS, s_, rv_, ri_, C.cast(C.byref(pk_), C.c_void_p))
+            if rc != 0:
+                raise RuntimeError(lib.caf_b200_last_error().decode())
+        return step
+
+    def peak_call(n_, h_, f_, pk_):
+        def step():
+            rc = peak_fn(h.raw, n_.ctypes.data, h_.ctypes.data, L, f_.ctypes.data, D, FS, C.cast(C.byref(pk_), C.c_void_p))
+            if rc != 0:
+                raise RuntimeError(lib.caf_b200_last_error().decode())
+        return step
+
+    pk_h = _lib.Peak()
+    ms, wall_ms = time_host(surface_call(needle_h, hay_h, freqs_h, surf_h.data_ptr(), rv_h.data_ptr(), ri_h.data_ptr(), pk_h))
+    e2e = {"value": world * cells_step / (ms * 1e-3), "unit": "cells/s", "ms_per_step": ms, "steps": e2e_steps,
+           "wall_ms_per_step_incl_flush": wall_ms, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+           "host_buffers": "pinned: inputs in one caf_b200_host_alloc block (one H2D), outputs in pinned memory",
            "peak": [pk_h.freq_hz, int(pk_h.delay_idx)]}
     checks["e2e"] = peak_is_planted(rank, pk_h.freq_hz, int(pk_h.delay_idx)) and float(surf_h[int(pk_h.doppler_idx), int(pk_h.delay_idx)]) == pk_h.value
 
-    # ---- the same call without the surface crossing PCIe: caf_b200_peak_* (what caf_bench.rs's closure observes:
-    #      find_peak(caf_surface(..)) returns (freq, delay); CafSurfaceRow's fields are private, mod.rs:17-22) --------
-    peak_fn = getattr(lib, f"caf_b200_peak_{sfx}")
+    # the same call without the surface crossing PCIe: caf_b200_peak_* (what caf_bench.rs's closure observes:
+    # find_peak(caf_surface(..)) returns (freq, delay); CafSurfaceRow's fields are private, mod.rs:17-22)
     pk2 = _lib.Peak()
-
-    def step_peak():
-        rc = peak_fn(h.raw, needle_h.data_ptr(), hay_h.data_ptr(), L, freqs_h.data_ptr(), D, FS,
-                     C.cast(C.byref(pk2), C.c_void_p))
-        if rc != 0:
-            raise RuntimeError(lib.caf_b200_last_error().decode())
-
-    for _ in range(3):
-        step_peak()
-    barrier()
-    evs = timed_pass(step_peak, e2e_steps)
-    barrier()
-    pk_ms = float(sum(a.elapsed_time(b) for a, b in evs))
-    t = torch.tensor([pk_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_peak = {"value": world * cells_step * e2e_steps / (float(t.item()) * 1e-3), "unit": "cells/s",
-                "ms_per_step": float(t.item()) / e2e_steps, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 32,
-                "peak": [pk2.freq_hz, int(pk2.delay_idx)],
-                "note": "host inputs in, (freq, delay) out: the surface stays on the GPU (caf_b200_peak_*)"}
+    ms, _ = time_host(peak_call(needle_h, hay_h, freqs_h, pk2))
+    e2e_peak = {"value": world * cells_step / (ms * 1e-3), "unit": "cells/s", "ms_per_step": ms,
+                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 32 + 4, "peak": [pk2.freq_hz, int(pk2.delay_idx)],
+                "note": "host inputs in (one pinned block, one H2D), (freq, delay) out: the surface stays on the GPU (caf_b200_peak_*); "
+                        "the kernel stores the peak into pinned host memory and the host spins on a sequence word next to it"}
     checks["e2e_peak_only"] = peak_is_planted(rank, pk2.freq_hz, int(pk2.delay_idx))
 
-    # ---- second timing method (N = 1 only; last thing that touches the GPU): working set larger than L2, K back-to-back
-    #      launches in ONE event pair, so the ~6 us every kernel pays between two events is not charged to each step
-    #      (scripts/bench_stream.py; measured there at 43.1 us per surface against 47.7 us with per-step event pairs).
-    #      Informational: `value` and `roofline` above stay on the flushed per-step figure. ---------------------------
-    stream_fig = None
-    if rank == 0 and world == 1:
-        try:
-            sys.path.insert(0, os.path.join(ROOT, "scripts"))
-            import bench_stream
-            stream_fig = bench_stream.measure(lib, h, stream, dev, pairs=320, surfaces=8, steps=min(max(args.steps, 50), 300),
-                                              warmup=40, f32=f32)
-        except BaseException as e:      # never let the extra figure break the bench line
-            stream_fig = {"error": repr(e)}
+    # pageable host memory on both sides (numpy arrays): the drop-in caller's cost
+    n_pg, h_pg, f_pg = needle.astype(cdt).copy(), hay.astype(cdt).copy(), freqs.copy()
+    surf_pg = np.empty((D, N), dtype=rdt); rv_pg = np.empty(D, dtype=rdt); ri_pg = np.empty(D, dtype=np.uint64)
+    pk3, pk4 = _lib.Peak(), _lib.Peak()
+    ms, _ = time_host(surface_call(n_pg, h_pg, f_pg, surf_pg.ctypes.data, rv_pg.ctypes.data, ri_pg.ctypes.data, pk3))
+    e2e_pageable = {"value": world * cells_step / (ms * 1e-3), "unit": "cells/s", "ms_per_step": ms,
+                    "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "peak": [pk3.freq_hz, int(pk3.delay_idx)],
+                    "host_buffers": "pageable numpy arrays for inputs AND outputs (std::vector / Vec<Complex64> callers)"}
+    checks["e2e_pageable"] = peak_is_planted(rank, pk3.freq_hz, int(pk3.delay_idx)) and float(surf_pg[int(pk3.doppler_idx), int(pk3.delay_idx)]) == pk3.value
+    ms, _ = time_host(peak_call(n_pg, h_pg, f_pg, pk4))
+    e2e_peak_pageable = {"value": world * cells_step / (ms * 1e-3), "unit": "cells/s", "ms_per_step": ms,
+                         "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 32 + 4, "peak": [pk4.freq_hz, int(pk4.delay_idx)],
+                         "host_buffers": "pageable numpy inputs (staged through the library's pinned block: one memcpy, one H2D)"}
+    checks["e2e_peak_only_pageable"] = peak_is_planted(rank, pk4.freq_hz, int(pk4.delay_idx))
+    del needle_h, hay_h, freqs_h, raw_blk
+    lib.caf_b200_host_free(blk)
 
     # ---- the other BASELINE configs in the same run: the SHARDED path at every N (cfg3 rows sharded + NCCL peak
     #      exchange, strong scaling; a cfg4 slice, pairs sharded + gather), and at N = 1 compact cfg2 / cfg5-row blocks ----
@@ -730,7 +802,7 @@ def run_b200(args):
     else:
         ctx.tf64 = tf.value
         t32 = C.c_double(); lib.caf_b200_probe_fma_tflops(h.raw, 0, C.byref(t32)); ctx.tf32 = t32.value
-    del surf_d, surf_h
+    del surf_h, surfs
     sharded, extra = {}, {}
 
     def run_block(store, key, fn):
@@ -762,23 +834,27 @@ def run_b200(args):
         line = {
             "metric": "CAF cells/s (400x8192 %s surface + peak)" % ("fp32" if f32 else "fp64"),
             "value": value, "unit": "cells/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": total_ms_max / args.steps, "ms_per_surface": total_ms_max / args.steps,
+            "ms_per_step": step_ms, "ms_per_surface": step_ms,
             "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None if f32 else value / PUBLISHED_CELLS_PER_S,
             "vs_baseline_note": "no published complex64 figure" if f32 else PUBLISHED_NOTE,
             "dtype": "f32" if f32 else "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD_CFG2 if f32 else WORKLOAD_CFG1,
                        "doppler_rows": D, "delay_cells": N, "pairs_per_step_per_gpu": 1,
-                       "l2": "flushed between timed steps (256 MiB overwrite); each step timed with its own CUDA event pair",
+                       "l2": "working set larger than L2: the steps rotate over 320 seeded pairs and 8 surface buffers (252 MB); one CUDA "
+                             "event pair around the K back-to-back steps (flushed_per_step = round 1's method, beside it)",
+                       "pairs_in_rotation": n_pairs, "surface_buffers": n_surf,
                        "parallelism": f"pairs sharded x{world}, no data-path collective",
                        "host_cpus_bound_to_gpu": numa},
-            "e2e": e2e, "e2e_peak_only": e2e_peak, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
-            "working_set_gt_l2": stream_fig,
+            "e2e": e2e, "e2e_peak_only": e2e_peak, "e2e_pageable": e2e_pageable, "e2e_peak_only_pageable": e2e_peak_pageable, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+            "flushed_per_step": {"ms_per_step": flushed_ms, "cells_per_s": world * cells_step / (flushed_ms * 1e-3), "steps": fl_steps,
+                                 "method": "L2 flushed (256 MiB overwrite) before every step, one CUDA event pair per step, summed"},
             "sharded": sharded, **extra,
             "clocks": sampler.summary(),
             "check": {"peak_freq_hz": peak_freq, "peak_delay": peak_delay, "checks": checks},
             "check_ok": all(checks.values()),
-            "step_ms_min_med_max": [float(per_step.min()), float(np.median(per_step)), float(per_step.max())],
+            "flushed_step_ms_min_med_max": [float(per_step.min()), float(np.median(per_step)), float(per_step.max())],
+            "pairs_checked": len(ran), "peaks_off": off[:5],
         }
         emit(line)
     ok_t = torch.tensor([1 if all(checks.values()) else 0], dtype=torch.int32, device=dev)

@@ -121,12 +121,17 @@ struct caf_b200_handle_s {
     Tables<float> tf;
     int occ_d = 1, occ_f = 1;   // resident CTAs per SM of the surface kernel
     DevBuf needle, hay, hperm, freqs, surface, rowval, rowidx, peaks, scratch, layout;
+    DevBuf in_block;            // small host calls: needle | haystack | freqs in ONE device block (one H2D instead of three)
+    void* h_stage = nullptr;    // pinned host mirror of in_block for callers whose three inputs are not one contiguous block
+    size_t h_stage_cap = 0;
     DevBuf lwbuf, lhtmp, lhbig, lpart;      // long-row path: chunk scratch, scratch of the H transform, H, partial row maxima
     long long* trace = nullptr;   // CAF_TRACE builds: device buffer for phase stamps
     unsigned int* done_counter = nullptr;   // last-CTA-done ticket of the fused find_peak
     void* hshare = nullptr;                 // single-pair launches: H published by CTA 0 (8192 complex128)
     unsigned int* hflag = nullptr;          // [2] publish counters, monotonic
     unsigned int epoch = 0;
+    unsigned int* seq_ptr = nullptr;            // single-pair host calls: pinned word the fused find_peak signals (see run_batch_host)
+    unsigned int seq_val = 0, seq_counter = 0;
     unsigned long long* pack_words = nullptr;   // sharded rows: find_peak also writes its result packed for the exchange
     unsigned long long pack_offset = 0;         // global index of the first local doppler row
     void* h_peaks = nullptr;    // pinned staging for peaks
@@ -448,7 +453,10 @@ int run_batch_dev(caf_b200_handle h, const caf::cx<T>* needles, const caf::cx<T>
     a.in = needles; a.in2 = hays; a.freqs = freqs; a.dt = 1.0 / (double)fs;   // dt: mod.rs:53
     a.out = surface; a.row_peak_val = rv; a.row_peak_idx = ri;
     const bool fused_peak = peaks && p == 1;      // single pair: find_peak rides in the same launch
-    if (fused_peak) { a.peak = peaks; a.done_counter = h->done_counter; a.peak_words = h->pack_words; a.row_offset = h->pack_offset; }
+    if (fused_peak) {
+        a.peak = peaks; a.done_counter = h->done_counter; a.peak_words = h->pack_words; a.row_offset = h->pack_offset;
+        a.peak_seq = h->seq_ptr; a.seq_val = h->seq_val;
+    }
     if (p == 1 && d > 1) {                        // one pair over many CTAs: CTA 0 publishes H, the rest consume it
         a.hshare = reinterpret_cast<cx<T>*>(h->hshare); a.hflag = h->hflag; a.epoch = ++h->epoch;
         // H_1's publisher: the lowest-index CTA other than 0 that owns the fewest rows (same split as the kernel)
@@ -513,15 +521,50 @@ int run_batch_host(caf_b200_handle h, const caf::cx<T>* needles, const caf::cx<T
     if (p == 0) return CAF_B200_OK;
     const size_t n = 2 * l, rows = p * d;
     cudaStream_t s = h->stream;
-    if (l) {
-        CK(h->needle.ensure(sizeof(cx<T>) * p * l));
-        CK(h->hay.ensure(sizeof(cx<T>) * p * l));
-        CK(cudaMemcpyAsync(h->needle.p, needles, sizeof(cx<T>) * p * l, cudaMemcpyHostToDevice, s));
-        CK(cudaMemcpyAsync(h->hay.p, hays, sizeof(cx<T>) * p * l, cudaMemcpyHostToDevice, s));
-    }
-    if (d) {
-        CK(h->freqs.ensure(sizeof(double) * d));
-        CK(cudaMemcpyAsync(h->freqs.p, freqs, sizeof(double) * d, cudaMemcpyHostToDevice, s));
+    // ---- inputs.  Three small H2D copies cost ~6 us EACH on B200 (DMA set-up, not bytes: 19 us of a 69 us peak-only
+    //      call), so a small call moves needle | haystack | freqs as ONE block: straight from the caller's memory when the
+    //      three already sit back to back (a caller that stages them in one caf_b200_host_alloc block), else through a
+    //      pinned staging block (one 131 KB memcpy on the CPU is cheaper than two more DMAs). ----
+    const cx<T>* d_needle = nullptr; const cx<T>* d_hay = nullptr; const double* d_freqs = nullptr;
+    const size_t sig_bytes = sizeof(cx<T>) * p * l, fr_bytes = sizeof(double) * d;
+    const size_t sig_pad = (sig_bytes + 15) & ~(size_t)15;
+    if (l && d && 2 * sig_pad + fr_bytes <= ((size_t)1 << 20)) {
+        const size_t tot = 2 * sig_pad + fr_bytes;
+        CK(h->in_block.ensure(tot));
+        bool moved = false;
+        if (sig_pad == sig_bytes && (const char*)hays == (const char*)needles + sig_bytes &&
+            (const char*)freqs == (const char*)hays + sig_bytes) {
+            // already one block in the caller's memory.  Adjacent addresses need not be ONE pinned allocation (a copy may
+            // not span two): such a copy is refused at once and the staging block below takes over.
+            if (cudaMemcpyAsync(h->in_block.p, needles, tot, cudaMemcpyHostToDevice, s) == cudaSuccess) moved = true;
+            else (void)cudaGetLastError();
+        }
+        if (!moved) {
+            if (h->h_stage_cap < tot) {
+                if (h->h_stage) cudaFreeHost(h->h_stage);
+                h->h_stage = nullptr; h->h_stage_cap = 0;
+                CK(cudaMallocHost(&h->h_stage, tot + tot / 4));
+                h->h_stage_cap = tot + tot / 4;
+            }
+            // the previous call on this handle ended with a stream synchronise (or saw its result), so the block is free
+            char* st = (char*)h->h_stage;
+            std::memcpy(st, needles, sig_bytes); std::memcpy(st + sig_pad, hays, sig_bytes); std::memcpy(st + 2 * sig_pad, freqs, fr_bytes);
+            CK(cudaMemcpyAsync(h->in_block.p, st, tot, cudaMemcpyHostToDevice, s));
+        }
+        d_needle = (const cx<T>*)h->in_block.p; d_hay = (const cx<T>*)((char*)h->in_block.p + sig_pad);
+        d_freqs = (const double*)((char*)h->in_block.p + 2 * sig_pad);
+    } else {
+        if (l) {
+            CK(h->needle.ensure(sig_bytes));
+            CK(h->hay.ensure(sig_bytes));
+            CK(cudaMemcpyAsync(h->needle.p, needles, sig_bytes, cudaMemcpyHostToDevice, s));
+            CK(cudaMemcpyAsync(h->hay.p, hays, sig_bytes, cudaMemcpyHostToDevice, s));
+        }
+        if (d) {
+            CK(h->freqs.ensure(fr_bytes));
+            CK(cudaMemcpyAsync(h->freqs.p, freqs, fr_bytes, cudaMemcpyHostToDevice, s));
+        }
+        d_needle = (const cx<T>*)h->needle.p; d_hay = (const cx<T>*)h->hay.p; d_freqs = (const double*)h->freqs.p;
     }
     T* d_surface = nullptr;
     if (surface && rows && n) { CK(h->surface.ensure(sizeof(T) * rows * n)); d_surface = (T*)h->surface.p; }
@@ -536,8 +579,9 @@ int run_batch_host(caf_b200_handle h, const caf::cx<T>* needles, const caf::cx<T
         if (h->h_peaks_cap < sizeof(PeakOut) * p) {
             if (h->h_peaks) cudaFreeHost(h->h_peaks);
             h->h_peaks = nullptr; h->h_peaks_cap = 0;
-            CK(cudaMallocHost(&h->h_peaks, sizeof(PeakOut) * p));
+            CK(cudaMallocHost(&h->h_peaks, sizeof(PeakOut) * p + 64));      // + the completion word of the spin wait
             h->h_peaks_cap = sizeof(PeakOut) * p;
+            *reinterpret_cast<volatile unsigned int*>((char*)h->h_peaks + h->h_peaks_cap) = 0u;
         }
     }
     // A single pair's peak is stored by the kernel straight into the pinned staging buffer (cudaMallocHost memory is
@@ -551,23 +595,24 @@ int run_batch_host(caf_b200_handle h, const caf::cx<T>* needles, const caf::cx<T
     // crossing PCIe on a second stream while the rest is still being computed.  find_peak then runs as its own
     // small kernel over all row peaks.  CAF_B200_PIPELINE=0 in the environment keeps the single-launch path.
     const size_t d0 = (size_t)h->sm_count;
+    bool spin = false;
     if (h->allow_pipeline && d_surface && p == 1 && l <= (size_t)kL0 && d >= 2 * d0 && d_rv && d_ri) {
         if (!h->copy_stream) CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
         if (!h->ev_head) CK(cudaEventCreateWithFlags(&h->ev_head, cudaEventDisableTiming));
         if (!h->ev_copy) CK(cudaEventCreateWithFlags(&h->ev_copy, cudaEventDisableTiming));
-        const double* fq = (const double*)h->freqs.p;
+        const double* fq = d_freqs;
         // an error return below must not leave the head's DMA into the caller's buffer in flight
         struct Drain {
             cudaStream_t a, b; bool armed = true;
             ~Drain() { if (armed) { cudaStreamSynchronize(a); cudaStreamSynchronize(b); } }
         } drain{h->copy_stream, s};
-        rc = run_batch_dev<T>(h, (const cx<T>*)h->needle.p, (const cx<T>*)h->hay.p, 1, l, fq, d0, fs, d_surface, d_rv, d_ri, nullptr);
+        rc = run_batch_dev<T>(h, d_needle, d_hay, 1, l, fq, d0, fs, d_surface, d_rv, d_ri, nullptr);
         if (rc) return rc;
         CK(cudaEventRecord(h->ev_head, s));
         CK(cudaStreamWaitEvent(h->copy_stream, h->ev_head, 0));
         CK(cudaMemcpyAsync(surface, d_surface, sizeof(T) * d0 * n, cudaMemcpyDeviceToHost, h->copy_stream));
         CK(cudaEventRecord(h->ev_copy, h->copy_stream));
-        rc = run_batch_dev<T>(h, (const cx<T>*)h->needle.p, (const cx<T>*)h->hay.p, 1, l, fq + d0, d - d0, fs,
+        rc = run_batch_dev<T>(h, d_needle, d_hay, 1, l, fq + d0, d - d0, fs,
                               d_surface + d0 * n, d_rv + d0, d_ri + d0, nullptr);
         if (rc) return rc;
         if (d_pk) {
@@ -579,15 +624,30 @@ int run_batch_host(caf_b200_handle h, const caf::cx<T>* needles, const caf::cx<T
         CK(cudaStreamWaitEvent(s, h->ev_copy, 0));
         drain.armed = false;      // from here on the final synchronise of s covers both streams
     } else {
-        rc = run_batch_dev<T>(h, (const cx<T>*)h->needle.p, (const cx<T>*)h->hay.p, p, l, (const double*)h->freqs.p, d,
-                              fs, d_surface, d_rv, d_ri, d_pk);
+        // Peak-only call on the fused path: the kernel stores the peak into pinned host memory and then a sequence word
+        // next to it; the host spins on that word (with a stream query now and then, so a failed launch cannot hang it)
+        // instead of cudaStreamSynchronize, whose wake-up alone costs several microseconds of a ~55 us call.
+        spin = peak_zero_copy && !d_surface && !rowval && !rowidx && l && d && l <= (size_t)kL0;
+        if (spin) { h->seq_ptr = reinterpret_cast<unsigned int*>((char*)h->h_peaks + h->h_peaks_cap); h->seq_val = ++h->seq_counter; }
+        rc = run_batch_dev<T>(h, d_needle, d_hay, p, l, d_freqs, d, fs, d_surface, d_rv, d_ri, d_pk);
+        h->seq_ptr = nullptr;
         if (rc) return rc;
         if (d_surface) CK(cudaMemcpyAsync(surface, d_surface, sizeof(T) * rows * n, cudaMemcpyDeviceToHost, s));
     }
     if (rowval && rows) CK(cudaMemcpyAsync(rowval, d_rv, sizeof(T) * rows, cudaMemcpyDeviceToHost, s));
     if (rowidx && rows) CK(cudaMemcpyAsync(rowidx, d_ri, sizeof(uint64_t) * rows, cudaMemcpyDeviceToHost, s));
     if (peaks && !peak_zero_copy) CK(cudaMemcpyAsync(h->h_peaks, d_pk, sizeof(PeakOut) * p, cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
+    if (spin) {
+        volatile unsigned int* seq = reinterpret_cast<volatile unsigned int*>((char*)h->h_peaks + h->h_peaks_cap);
+        const unsigned int want = h->seq_counter;
+        unsigned int polls = 0;
+        while (*seq != want) {
+            if ((++polls & 0xfffu) == 0u && cudaStreamQuery(s) != cudaErrorNotReady) break;   // finished (or failed) without the word
+        }
+        if (*seq != want) CK(cudaStreamSynchronize(s));      // surfaces a launch / execution error
+    } else {
+        CK(cudaStreamSynchronize(s));
+    }
     if (peaks)
         for (size_t i = 0; i < p; ++i) to_public(reinterpret_cast<PeakOut*>(h->h_peaks)[i], &peaks[i]);
     return CAF_B200_OK;
@@ -787,11 +847,12 @@ int caf_b200_destroy(caf_b200_handle h) {
     cudaSetDevice(h->device);
     if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
     if (h->stream) cudaStreamSynchronize(h->stream);
-    for (DevBuf* b : {&h->needle, &h->hay, &h->hperm, &h->freqs, &h->surface, &h->rowval, &h->rowidx, &h->peaks, &h->scratch, &h->layout, &h->lwbuf, &h->lhtmp, &h->lhbig, &h->lpart})
+    for (DevBuf* b : {&h->in_block, &h->needle, &h->hay, &h->hperm, &h->freqs, &h->surface, &h->rowval, &h->rowidx, &h->peaks, &h->scratch, &h->layout, &h->lwbuf, &h->lhtmp, &h->lhbig, &h->lpart})
         b->release();
     for (void* q : {(void*)h->td.tw1, (void*)h->td.tw2, (void*)h->td.g, (void*)h->tf.tw1, (void*)h->tf.tw2, (void*)h->tf.g})
         if (q) cudaFree(q);
     if (h->h_peaks) cudaFreeHost(h->h_peaks);
+    if (h->h_stage) cudaFreeHost(h->h_stage);
     if (h->done_counter) cudaFree(h->done_counter);
     if (h->hshare) cudaFree(h->hshare);
     if (h->hflag) cudaFree(h->hflag);

@@ -75,6 +75,8 @@ struct RowArgs {
     PeakOut* peak;          // kSurface, P == 1: fused find_peak result (or null)
     unsigned long long* peak_words;   // kSurface, P == 1: the same result packed for the cross-rank exchange (or null)
     unsigned long long row_offset;    // global index of this launch's first doppler row (rows sharded across ranks)
+    unsigned int* peak_seq;           // kSurface, P == 1: host-visible word that receives seq_val once `peak` is written (or null)
+    unsigned int seq_val;
     unsigned int* done_counter;   // kSurface, P == 1: last-CTA-done ticket (self-resetting)
     const cx<T>* tw1;       // [16][256]  W_4096^{k1 t}
     const cx<T>* tw2;       // [16][16]   W_256^{a b}
@@ -1019,6 +1021,10 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
                     *a.peak = p;
                     if (a.peak_words) pack_peak_words(p, a.row_offset, a.peak_words);
                     *a.done_counter = 0u;   // ready for the next launch on this stream
+                    if (a.peak_seq) {       // the host spins on this word instead of paying a stream synchronise's wake-up
+                        __threadfence_system();
+                        *reinterpret_cast<volatile unsigned int*>(a.peak_seq) = a.seq_val;
+                    }
                 }
             }
         }

@@ -91,6 +91,47 @@ def test_peak_only_entry_matches_surface_entry(chirp0):
     assert caf.CafB200F32.caf_peak(needle, hay, shifts, FS) == (69.25, 202)
 
 
+def test_host_inputs_in_one_block_scattered_or_adjacent_allocations(chirp0):
+    """Small host calls move needle | haystack | freqs with ONE H2D copy: straight from the caller when the three sit
+    back to back in one allocation, through the library's pinned staging block otherwise.  Two pinned allocations that
+    merely happen to be adjacent must not be copied as one (a DMA may not span allocations): every placement gives the
+    same bits."""
+    import torch
+    from caf_cookoff_b200 import bench_shifts
+    needle, hay = chirp0
+    freqs = bench_shifts()[:64].copy()
+    lib = _lib.load()
+    h = api.default_handle()
+    L, D = needle.size, freqs.size
+
+    def call(n_ptr, h_ptr, f_ptr):
+        surf = np.empty((D, 2 * L)); pk = _lib.Peak()
+        rc = lib.caf_b200_surface_f64(h.raw, n_ptr, h_ptr, L, f_ptr, D, FS, surf.ctypes.data, None, None, C.cast(C.byref(pk), C.c_void_p))
+        assert rc == 0, lib.caf_b200_last_error()
+        pk2 = _lib.Peak()
+        assert lib.caf_b200_peak_f64(h.raw, n_ptr, h_ptr, L, f_ptr, D, FS, C.cast(C.byref(pk2), C.c_void_p)) == 0
+        assert (pk.value, pk.freq_hz, pk.doppler_idx, pk.delay_idx) == (pk2.value, pk2.freq_hz, pk2.doppler_idx, pk2.delay_idx)
+        return surf, (pk.value, pk.freq_hz, int(pk.doppler_idx), int(pk.delay_idx))
+
+    ref = call(needle.ctypes.data, hay.ctypes.data, freqs.ctypes.data)                       # three pageable arrays
+    # one pageable block
+    blk = np.empty(2 * L * 16 + D * 8, dtype=np.uint8)
+    blk[: L * 16] = needle.view(np.uint8); blk[L * 16: 2 * L * 16] = hay.view(np.uint8); blk[2 * L * 16:] = freqs.view(np.uint8)
+    got = call(blk.ctypes.data, blk.ctypes.data + L * 16, blk.ctypes.data + 2 * L * 16)
+    assert np.array_equal(got[0], ref[0]) and got[1] == ref[1]
+    # one pinned block from the library
+    pb = C.c_void_p()
+    assert lib.caf_b200_host_alloc(C.byref(pb), blk.size) == 0
+    C.memmove(pb.value, blk.ctypes.data, blk.size)
+    got = call(pb.value, pb.value + L * 16, pb.value + 2 * L * 16)
+    assert np.array_equal(got[0], ref[0]) and got[1] == ref[1]
+    lib.caf_b200_host_free(pb)
+    # separate pinned allocations (torch's caching allocator often hands out adjacent ones)
+    tn, th, tf = (torch.from_numpy(x).pin_memory() for x in (needle, hay, freqs))
+    got = call(tn.data_ptr(), th.data_ptr(), tf.data_ptr())
+    assert np.array_equal(got[0], ref[0]) and got[1] == ref[1]
+
+
 def test_repeated_calls_are_deterministic(chirp0):
     needle, hay = chirp0
     shifts = caf.bench_shifts()
