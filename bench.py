@@ -787,6 +787,24 @@ def run_b200(args):
                          "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 32 + 4, "peak": [pk4.freq_hz, int(pk4.delay_idx)],
                          "host_buffers": "pageable numpy inputs (staged through the library's pinned block: one memcpy, one H2D)"}
     checks["e2e_peak_only_pageable"] = peak_is_planted(rank, pk4.freq_hz, int(pk4.delay_idx))
+    # what the reference-facing call sequence costs now: CafSurface::caf_surface + find_peak as the Rust shim / the C++
+    # mirror issue it (caf_b200_surface_create + _find_peak + _destroy, pageable Vec inputs): the rows stay on the GPU
+    # behind CafSurfaceRow (its fields are private upstream), nothing but find_peak's answer crosses PCIe
+    so = C.c_void_p(); pk5 = _lib.Peak()
+    create_fn = getattr(lib, f"caf_b200_surface_create_{sfx}")
+
+    def step_dropin():
+        rc = create_fn(h.raw, n_pg.ctypes.data, h_pg.ctypes.data, L, f_pg.ctypes.data, D, FS, C.byref(so))
+        if rc != 0:
+            raise RuntimeError(lib.caf_b200_last_error().decode())
+        lib.caf_b200_surface_find_peak(so, C.byref(pk5))
+        lib.caf_b200_surface_destroy(so)
+    ms, _ = time_host(step_dropin)
+    e2e_dropin = {"value": world * cells_step / (ms * 1e-3), "unit": "cells/s", "ms_per_step": ms,
+                  "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 32 + 4, "peak": [pk5.freq_hz, int(pk5.delay_idx)],
+                  "note": "caf_surface + find_peak as rust/src/caf/mod.rs and include/caf_b200.hpp issue them: device-resident "
+                          "surface object with lazy rows (caf_bench.rs:163-167's closure)"}
+    checks["e2e_dropin"] = peak_is_planted(rank, pk5.freq_hz, int(pk5.delay_idx))
     del needle_h, hay_h, freqs_h, raw_blk
     lib.caf_b200_host_free(blk)
 
@@ -846,7 +864,7 @@ def run_b200(args):
                        "pairs_in_rotation": n_pairs, "surface_buffers": n_surf,
                        "parallelism": f"pairs sharded x{world}, no data-path collective",
                        "host_cpus_bound_to_gpu": numa},
-            "e2e": e2e, "e2e_peak_only": e2e_peak, "e2e_pageable": e2e_pageable, "e2e_peak_only_pageable": e2e_peak_pageable, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+            "e2e": e2e, "e2e_peak_only": e2e_peak, "e2e_pageable": e2e_pageable, "e2e_peak_only_pageable": e2e_peak_pageable, "e2e_dropin": e2e_dropin, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
             "flushed_per_step": {"ms_per_step": flushed_ms, "cells_per_s": world * cells_step / (flushed_ms * 1e-3), "steps": fl_steps,
                                  "method": "L2 flushed (256 MiB overwrite) before every step, one CUDA event pair per step, summed"},
             "sharded": sharded, **extra,

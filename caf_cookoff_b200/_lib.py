@@ -110,6 +110,13 @@ SYMBOLS = {
     "caf_b200_surface_sharded_f32": (_int, [_vp, _vp, _vp, _vp, _sz, _vp, _sz, _u32, _vp, _PK]),
     "caf_b200_peak_pack": (None, [_PK, C.c_uint64, C.POINTER(C.c_uint64)]),
     "caf_b200_peak_resolve": (None, [C.POINTER(C.c_uint64), _sz, _PK]),
+    "caf_b200_surface_create_f64": (_int, [_vp, _vp, _vp, _sz, _vp, _sz, _u32, C.POINTER(_vp)]),
+    "caf_b200_surface_create_f32": (_int, [_vp, _vp, _vp, _sz, _vp, _sz, _u32, C.POINTER(_vp)]),
+    "caf_b200_surface_shape": (_int, [_vp, C.POINTER(_sz), C.POINTER(_sz)]),
+    "caf_b200_surface_row_peaks": (_int, [_vp, _vp, _vp, _vp]),
+    "caf_b200_surface_find_peak": (_int, [_vp, _PK]),
+    "caf_b200_surface_fetch_rows": (_int, [_vp, _sz, _sz, _vp]),
+    "caf_b200_surface_destroy": (_int, [_vp]),
     "caf_b200_peak_resolve_status": (_int, [C.POINTER(C.c_uint64), _sz, _PK]),
     "caf_b200_peak_allgather_async": (_int, [_vp, _vp, _vp, C.c_uint64, _vp]),
     "caf_b200_comm_remote_error": (_int, [_vp, C.POINTER(_int)]),

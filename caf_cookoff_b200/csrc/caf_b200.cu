@@ -8,7 +8,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <new>
+#include <set>
 #include <string>
 #include <vector>
 
@@ -121,6 +123,7 @@ struct caf_b200_handle_s {
     Tables<float> tf;
     int occ_d = 1, occ_f = 1;   // resident CTAs per SM of the surface kernel
     DevBuf needle, hay, hperm, freqs, surface, rowval, rowidx, peaks, scratch, layout;
+    std::vector<std::pair<void*, size_t>> surf_pool;   // device buffers of released surface objects, reused by the next one
     DevBuf in_block;            // small host calls: needle | haystack | freqs in ONE device block (one H2D instead of three)
     void* h_stage = nullptr;    // pinned host mirror of in_block for callers whose three inputs are not one contiguous block
     size_t h_stage_cap = 0;
@@ -147,7 +150,28 @@ struct caf_b200_handle_s {
     bool ev_valid = false;
 };
 
+// ---- device-resident surface objects (caf_b200_surface_*): CafSurfaceRow's fields are private in the reference
+//      (mod.rs:17-22), so the drop-in caller can only observe find_peak's result; the 26 MB of a surface stay on the GPU
+//      and a row crosses PCIe when somebody asks for it. ----
+struct caf_b200_surface_s {
+    caf_b200_handle h = nullptr;
+    int device = 0;
+    bool f32 = false;
+    size_t d = 0, n = 0, bytes = 0;
+    void* dev = nullptr;
+    void* dev_rv = nullptr;             // row peaks on the device (tail of the same buffer), fetched on first request
+    unsigned long long* dev_ri = nullptr;
+    bool peaks_on_host = false;
+    std::vector<double> pval;
+    std::vector<uint64_t> pidx;
+    std::vector<double> freqs;
+    caf_b200_peak peak{};
+};
+
 namespace {
+
+std::mutex g_live_mu;
+std::set<caf_b200_handle> g_live_handles;     // a surface object outliving its handle frees its buffer itself
 
 template <typename T> Tables<T>& tables(caf_b200_handle h);
 template <> Tables<double>& tables<double>(caf_b200_handle h) { return h->td; }
@@ -510,10 +534,12 @@ int check_common(caf_b200_handle h, const void* needle, const void* hay, size_t 
 }
 
 // Host-pointer batch: stage in, run, stage out.
+// keep: compute the surface and the row peaks into these DEVICE buffers and leave them there (surface objects).
+template <typename T> struct DevKeep { T* surface; T* rv; unsigned long long* ri; };
 template <typename T>
 int run_batch_host(caf_b200_handle h, const caf::cx<T>* needles, const caf::cx<T>* hays, size_t p, size_t l,
                    const double* freqs, size_t d, uint32_t fs, T* surface, T* rowval, uint64_t* rowidx,
-                   caf_b200_peak* peaks) {
+                   caf_b200_peak* peaks, const DevKeep<T>* keep = nullptr) {
     using namespace caf;
     int rc = check_common<T>(h, needles, hays, p, l, freqs, d, fs);
     if (rc) return rc;
@@ -567,9 +593,11 @@ int run_batch_host(caf_b200_handle h, const caf::cx<T>* needles, const caf::cx<T
         d_needle = (const cx<T>*)h->needle.p; d_hay = (const cx<T>*)h->hay.p; d_freqs = (const double*)h->freqs.p;
     }
     T* d_surface = nullptr;
-    if (surface && rows && n) { CK(h->surface.ensure(sizeof(T) * rows * n)); d_surface = (T*)h->surface.p; }
+    if (keep) d_surface = keep->surface;
+    else if (surface && rows && n) { CK(h->surface.ensure(sizeof(T) * rows * n)); d_surface = (T*)h->surface.p; }
     T* d_rv = nullptr; unsigned long long* d_ri = nullptr;
-    if (rows && (rowval || rowidx || peaks)) {
+    if (keep) { d_rv = keep->rv; d_ri = keep->ri; }
+    else if (rows && (rowval || rowidx || peaks)) {
         CK(h->rowval.ensure(sizeof(T) * rows)); CK(h->rowidx.ensure(sizeof(unsigned long long) * rows));
         d_rv = (T*)h->rowval.p; d_ri = (unsigned long long*)h->rowidx.p;
     }
@@ -596,7 +624,7 @@ int run_batch_host(caf_b200_handle h, const caf::cx<T>* needles, const caf::cx<T
     // small kernel over all row peaks.  CAF_B200_PIPELINE=0 in the environment keeps the single-launch path.
     const size_t d0 = (size_t)h->sm_count;
     bool spin = false;
-    if (h->allow_pipeline && d_surface && p == 1 && l <= (size_t)kL0 && d >= 2 * d0 && d_rv && d_ri) {
+    if (h->allow_pipeline && surface && d_surface && p == 1 && l <= (size_t)kL0 && d >= 2 * d0 && d_rv && d_ri) {
         if (!h->copy_stream) CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
         if (!h->ev_head) CK(cudaEventCreateWithFlags(&h->ev_head, cudaEventDisableTiming));
         if (!h->ev_copy) CK(cudaEventCreateWithFlags(&h->ev_copy, cudaEventDisableTiming));
@@ -627,12 +655,12 @@ int run_batch_host(caf_b200_handle h, const caf::cx<T>* needles, const caf::cx<T
         // Peak-only call on the fused path: the kernel stores the peak into pinned host memory and then a sequence word
         // next to it; the host spins on that word (with a stream query now and then, so a failed launch cannot hang it)
         // instead of cudaStreamSynchronize, whose wake-up alone costs several microseconds of a ~55 us call.
-        spin = peak_zero_copy && !d_surface && !rowval && !rowidx && l && d && l <= (size_t)kL0;
+        spin = peak_zero_copy && !surface && !rowval && !rowidx && l && d && l <= (size_t)kL0;
         if (spin) { h->seq_ptr = reinterpret_cast<unsigned int*>((char*)h->h_peaks + h->h_peaks_cap); h->seq_val = ++h->seq_counter; }
         rc = run_batch_dev<T>(h, d_needle, d_hay, p, l, d_freqs, d, fs, d_surface, d_rv, d_ri, d_pk);
         h->seq_ptr = nullptr;
         if (rc) return rc;
-        if (d_surface) CK(cudaMemcpyAsync(surface, d_surface, sizeof(T) * rows * n, cudaMemcpyDeviceToHost, s));
+        if (surface && d_surface) CK(cudaMemcpyAsync(surface, d_surface, sizeof(T) * rows * n, cudaMemcpyDeviceToHost, s));
     }
     if (rowval && rows) CK(cudaMemcpyAsync(rowval, d_rv, sizeof(T) * rows, cudaMemcpyDeviceToHost, s));
     if (rowidx && rows) CK(cudaMemcpyAsync(rowidx, d_ri, sizeof(uint64_t) * rows, cudaMemcpyDeviceToHost, s));
@@ -833,6 +861,7 @@ static int create_impl(int device, bool own_stream, void* cuda_stream, caf_b200_
         caf_b200_destroy(h);
         return fail(CAF_B200_ECUDA, m);
     }
+    { std::lock_guard<std::mutex> lk(g_live_mu); g_live_handles.insert(h); }
     *out = h;
     return CAF_B200_OK;
 }
@@ -844,7 +873,10 @@ int caf_b200_create_on_stream(int device, void* cuda_stream, caf_b200_handle* ou
 
 int caf_b200_destroy(caf_b200_handle h) {
     if (!h) return CAF_B200_OK;
+    { std::lock_guard<std::mutex> lk(g_live_mu); g_live_handles.erase(h); }
     cudaSetDevice(h->device);
+    for (auto& b : h->surf_pool) if (b.first) cudaFree(b.first);
+    h->surf_pool.clear();
     if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
     if (h->stream) cudaStreamSynchronize(h->stream);
     for (DevBuf* b : {&h->in_block, &h->needle, &h->hay, &h->hperm, &h->freqs, &h->surface, &h->rowval, &h->rowidx, &h->peaks, &h->scratch, &h->layout, &h->lwbuf, &h->lhtmp, &h->lhbig, &h->lpart})
@@ -1026,6 +1058,116 @@ int caf_b200_batch_f32_dev(caf_b200_handle h, const caf_c64* needles, const caf_
     CK(cudaSetDevice(h->device));
     return run_batch_dev<float>(h, (const float2*)needles, (const float2*)hays, p, l, freqs, d, fs, surface, rv,
                                 (unsigned long long*)ri, (caf::PeakOut*)peaks);
+}
+
+
+// ---- device-resident surface objects ------------------------------------------------------------------------
+extern "C++" {
+namespace {
+template <typename T>
+int surface_create_impl(caf_b200_handle h, const caf::cx<T>* needle, const caf::cx<T>* hay, size_t l, const double* freqs,
+                        size_t d, uint32_t fs, caf_b200_surface* out) {
+    if (!out) return fail(CAF_B200_EINVAL, "null out");
+    *out = nullptr;
+    int rc = check_common<T>(h, needle, hay, 1, l, freqs, d, fs);
+    if (rc) return rc;
+    CK(cudaSetDevice(h->device));
+    caf_b200_surface s = new (std::nothrow) caf_b200_surface_s();
+    if (!s) return fail(CAF_B200_EINVAL, "out of host memory");
+    s->h = h; s->device = h->device; s->f32 = std::is_same<T, float>::value; s->d = d; s->n = 2 * l;
+    const size_t surf_bytes = (sizeof(T) * d * 2 * l + 255) & ~(size_t)255;
+    s->bytes = surf_bytes + 16 * d;                       // surface | row_peak_idx (u64) | row_peak_val
+    s->freqs.assign(freqs, freqs + d);
+    s->peak.value = 0.0; s->peak.freq_hz = 0.0; s->peak.doppler_idx = UINT64_MAX; s->peak.delay_idx = 0;
+    if (d && l) {
+        // a buffer a released surface left behind, else a fresh one (cudaMalloc costs more than the whole computation)
+        size_t best = (size_t)-1;
+        for (size_t i = 0; i < h->surf_pool.size(); ++i)
+            if (h->surf_pool[i].second >= s->bytes && (best == (size_t)-1 || h->surf_pool[i].second < h->surf_pool[best].second)) best = i;
+        if (best != (size_t)-1) {
+            s->dev = h->surf_pool[best].first; s->bytes = h->surf_pool[best].second;
+            h->surf_pool.erase(h->surf_pool.begin() + (long)best);
+        } else {
+            cudaError_t e = cudaMalloc(&s->dev, s->bytes);
+            if (e != cudaSuccess) { delete s; return fail(CAF_B200_ECUDA, std::string("surface buffer: ") + cudaGetErrorString(e)); }
+        }
+        s->dev_ri = (unsigned long long*)((char*)s->dev + surf_bytes);
+        s->dev_rv = (void*)(s->dev_ri + d);
+        // nothing but the fused find_peak result comes back now: the call is a peak-only call that leaves the surface
+        // and its row peaks on the device
+        const DevKeep<T> keep{(T*)s->dev, (T*)s->dev_rv, s->dev_ri};
+        rc = run_batch_host<T>(h, needle, hay, 1, l, freqs, d, fs, nullptr, nullptr, nullptr, &s->peak, &keep);
+        if (rc) { const std::string why = g_err; caf_b200_surface_destroy(s); return fail(rc, why); }
+    } else {
+        s->peaks_on_host = true; s->pval.assign(d, 0.0); s->pidx.assign(d, 0);      // empty rows: peak 0.0 at index 0 (mod.rs:143-144)
+    }
+    *out = s;
+    return CAF_B200_OK;
+}
+}  // namespace
+}  // extern "C++"
+
+int caf_b200_surface_create_f64(caf_b200_handle h, const caf_c128* needle, const caf_c128* hay, size_t l, const double* freqs,
+                                size_t d, uint32_t fs, caf_b200_surface* out) {
+    return surface_create_impl<double>(h, (const double2*)needle, (const double2*)hay, l, freqs, d, fs, out);
+}
+int caf_b200_surface_create_f32(caf_b200_handle h, const caf_c64* needle, const caf_c64* hay, size_t l, const double* freqs,
+                                size_t d, uint32_t fs, caf_b200_surface* out) {
+    return surface_create_impl<float>(h, (const float2*)needle, (const float2*)hay, l, freqs, d, fs, out);
+}
+int caf_b200_surface_shape(caf_b200_surface s, size_t* rows, size_t* cells_per_row) {
+    if (!s) return fail(CAF_B200_EINVAL, "null surface");
+    if (rows) *rows = s->d;
+    if (cells_per_row) *cells_per_row = s->n;
+    return CAF_B200_OK;
+}
+int caf_b200_surface_row_peaks(caf_b200_surface s, double* freq_hz, double* peak_val, uint64_t* peak_idx) {
+    if (!s) return fail(CAF_B200_EINVAL, "null surface");
+    if (!s->peaks_on_host && (peak_val || peak_idx)) {       // first request: one copy of 16 bytes per row
+        CK(cudaSetDevice(s->device));
+        std::vector<unsigned char> raw(16 * s->d);
+        CK(cudaMemcpy(raw.data(), s->dev_ri, 16 * s->d, cudaMemcpyDeviceToHost));
+        s->pidx.resize(s->d); s->pval.resize(s->d);
+        std::memcpy(s->pidx.data(), raw.data(), 8 * s->d);
+        if (s->f32) { const float* v = (const float*)(raw.data() + 8 * s->d); for (size_t i = 0; i < s->d; ++i) s->pval[i] = (double)v[i]; }
+        else std::memcpy(s->pval.data(), raw.data() + 8 * s->d, 8 * s->d);
+        s->peaks_on_host = true;
+    }
+    for (size_t i = 0; i < s->d; ++i) {
+        if (freq_hz) freq_hz[i] = s->freqs[i];
+        if (peak_val) peak_val[i] = s->pval[i];
+        if (peak_idx) peak_idx[i] = s->pidx[i];
+    }
+    return CAF_B200_OK;
+}
+int caf_b200_surface_find_peak(caf_b200_surface s, caf_b200_peak* out) {
+    if (!s || !out) return fail(CAF_B200_EINVAL, "null argument");
+    *out = s->peak;
+    return CAF_B200_OK;
+}
+// rows [row0, row0 + count) of the surface, count * cells_per_row values of the surface's precision.  Thread-safe: the
+// surface was complete when create returned, and the copy does not touch the handle or its stream.
+int caf_b200_surface_fetch_rows(caf_b200_surface s, size_t row0, size_t count, void* out) {
+    if (!s || (count && !out)) return fail(CAF_B200_EINVAL, "null argument");
+    if (row0 > s->d || count > s->d - row0) return fail(CAF_B200_EINVAL, "row range outside the surface");
+    if (!count || !s->n) return CAF_B200_OK;
+    CK(cudaSetDevice(s->device));
+    const size_t esz = s->f32 ? sizeof(float) : sizeof(double);
+    CK(cudaMemcpy(out, (const char*)s->dev + row0 * s->n * esz, count * s->n * esz, cudaMemcpyDeviceToHost));
+    return CAF_B200_OK;
+}
+int caf_b200_surface_destroy(caf_b200_surface s) {
+    if (!s) return CAF_B200_OK;
+    if (s->dev) {
+        bool pooled = false;
+        {
+            std::lock_guard<std::mutex> lk(g_live_mu);
+            if (g_live_handles.count(s->h) && s->h->surf_pool.size() < 4) { s->h->surf_pool.emplace_back(s->dev, s->bytes); pooled = true; }
+        }
+        if (!pooled) { cudaSetDevice(s->device); cudaFree(s->dev); }
+    }
+    delete s;
+    return CAF_B200_OK;
 }
 
 // ---- multi-GPU peak words: [0] = bits(value), [1] = global doppler row (UINT64_MAX if none),

@@ -151,6 +151,28 @@ int caf_b200_batch_f32_dev(caf_b200_handle h, const caf_c64* needles, const caf_
                            size_t l, const double* freqs_hz, size_t d, uint32_t fs,
                            float* surface, float* row_peak_val, uint64_t* row_peak_idx, caf_b200_peak* peaks);
 
+/* ---- device-resident surface objects ---------------------------------------------------------------------
+ * CafSurfaceRow's fields are PRIVATE in the reference (mod.rs:17-22): a caller of caf_surface can hand the rows to
+ * find_peak and nothing else, so copying 26 MB of |xcor|^2 to the host on every call (0.5 ms against a ~45 us kernel)
+ * buys nothing.  caf_b200_surface_create_* runs caf_surface and keeps the surface on the GPU; what comes back at once is
+ * per row (freq, xcor_peak_val, xcor_peak_idx) -- 24 bytes -- and find_peak's answer.  The Rust shim's CafSurfaceRow holds
+ * a reference-counted surface object + its row number and fetches xcor_mag only if asked (rust/src/caf/mod.rs).
+ * A surface object belongs to the handle that made it (its buffer returns to that handle's pool on destroy; destroying
+ * the handle first is allowed).  fetch_rows is thread-safe; create / destroy follow the handle's threading rule. */
+typedef struct caf_b200_surface_s* caf_b200_surface;
+int caf_b200_surface_create_f64(caf_b200_handle h, const caf_c128* needle, const caf_c128* haystack, size_t l,
+                                const double* freqs_hz, size_t d, uint32_t fs, caf_b200_surface* out);
+int caf_b200_surface_create_f32(caf_b200_handle h, const caf_c64* needle, const caf_c64* haystack, size_t l,
+                                const double* freqs_hz, size_t d, uint32_t fs, caf_b200_surface* out);
+int caf_b200_surface_shape(caf_b200_surface s, size_t* rows, size_t* cells_per_row);
+/* CafSurfaceRow::{freq, xcor_peak_val, xcor_peak_idx} of every row (any pointer may be NULL) */
+int caf_b200_surface_row_peaks(caf_b200_surface s, double* freq_hz, double* peak_val, uint64_t* peak_idx);
+/* CafSurface::find_peak (mod.rs:31-42) over the rows in freqs_hz order, computed by the kernel that made them */
+int caf_b200_surface_find_peak(caf_b200_surface s, caf_b200_peak* out);
+/* CafSurfaceRow::xcor_mag of rows [row0, row0 + count): count * cells_per_row doubles (floats for an f32 surface) */
+int caf_b200_surface_fetch_rows(caf_b200_surface s, size_t row0, size_t count, void* out);
+int caf_b200_surface_destroy(caf_b200_surface s);
+
 /* ---- the sibling programs' layouts of the same surface -------------------
  * The reference's Go and Python programs compute this correlation with the operands swapped and keep the
  * magnitude |xcor| (cmplx.Abs, np.abs) where the Rust crate keeps |xcor|^2 (norm_sqr):

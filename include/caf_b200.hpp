@@ -13,6 +13,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <fstream>
+#include <memory>
 #include <stdexcept>
 #include <string>
 #include <utility>
@@ -42,41 +43,87 @@ inline caf_b200_handle thread_handle() {
     return holder.h;
 }
 
+// One surface on the GPU, shared by its rows (caf_b200_surface_*).  The reference's CafSurfaceRow owns a Vec<f64> per row
+// (mod.rs:17-22) but keeps every field PRIVATE, so no caller of the crate can read it: here a row is (surface, row number)
+// and the 2L doubles of xcor_mag cross PCIe only when xcor_mag() is called.
+class DeviceSurface {
+    caf_b200_surface s_ = nullptr;
+    std::size_t rows_ = 0, cells_ = 0;
+    mutable bool have_peaks_ = false;
+    mutable std::vector<double> freq_, pval_;
+    mutable std::vector<uint64_t> pidx_;
+public:
+    explicit DeviceSurface(caf_b200_surface s) : s_(s) { check(caf_b200_surface_shape(s_, &rows_, &cells_)); }
+    DeviceSurface(const DeviceSurface&) = delete;
+    DeviceSurface& operator=(const DeviceSurface&) = delete;
+    ~DeviceSurface() { if (s_) caf_b200_surface_destroy(s_); }
+    std::size_t rows() const { return rows_; }
+    std::size_t cells_per_row() const { return cells_; }
+    caf_b200_peak fused_peak() const { caf_b200_peak p; check(caf_b200_surface_find_peak(s_, &p)); return p; }
+    void need_peaks() const {                      // one 16-byte-per-row copy, the first time a row's peak is looked at
+        if (have_peaks_) return;
+        freq_.resize(rows_); pval_.resize(rows_); pidx_.resize(rows_);
+        check(caf_b200_surface_row_peaks(s_, freq_.data(), pval_.data(), pidx_.data()));
+        have_peaks_ = true;
+    }
+    double freq(std::size_t r) const { need_peaks(); return freq_[r]; }
+    double peak_val(std::size_t r) const { need_peaks(); return pval_[r]; }
+    std::size_t peak_idx(std::size_t r) const { need_peaks(); return (std::size_t)pidx_[r]; }
+    std::vector<double> fetch_rows(std::size_t row0, std::size_t count) const {
+        std::vector<double> out(count * cells_);
+        check(caf_b200_surface_fetch_rows(s_, row0, count, out.data()));
+        return out;
+    }
+};
+
 // mod.rs:17-22 (fields are private in the reference; accessors added so results can be inspected)
 class CafSurfaceRow {
+    std::shared_ptr<const DeviceSurface> surf_;
+    std::size_t row_ = 0;
 public:
-    double freq = 0.0;
-    std::vector<double> xcor_mag;
-    std::size_t xcor_peak_idx = 0;
-    double xcor_peak_val = 0.0;
+    CafSurfaceRow() = default;
+    CafSurfaceRow(std::shared_ptr<const DeviceSurface> s, std::size_t row) : surf_(std::move(s)), row_(row) {}
+    double freq() const { return surf_ ? surf_->freq(row_) : 0.0; }
+    std::size_t xcor_peak_idx() const { return surf_ ? surf_->peak_idx(row_) : 0; }
+    double xcor_peak_val() const { return surf_ ? surf_->peak_val(row_) : 0.0; }
+    std::vector<double> xcor_mag() const { return surf_ ? surf_->fetch_rows(row_, 1) : std::vector<double>(); }   // lazy: one row over PCIe
+    const std::shared_ptr<const DeviceSurface>& surface() const { return surf_; }
+    std::size_t row() const { return row_; }
 };
 
 struct CafB200 {
-    // mod.rs:121-166 (every strategy struct computes this)
+    // mod.rs:121-166 (every strategy struct computes this).  Costs a peak-only call: inputs up, one fused launch, the
+    // 32-byte find_peak result down; the surface and its row peaks stay on the GPU behind the rows.
     static std::vector<CafSurfaceRow> caf_surface(const std::vector<Complex64>& needle, const std::vector<Complex64>& haystack,
                                                   const std::vector<double>& freqs_hz, uint32_t fs) {
         if (needle.size() != haystack.size()) throw Panic("assertion failed: a.len() == self.n (xcor_rustfft.rs:54-55)");
-        const std::size_t l = needle.size(), d = freqs_hz.size(), n = 2 * l;
-        std::vector<double> surface(d * n), pval(d);
-        std::vector<uint64_t> pidx(d);
-        check(caf_b200_surface_f64(thread_handle(), reinterpret_cast<const caf_c128*>(needle.data()),
-                                   reinterpret_cast<const caf_c128*>(haystack.data()), l, freqs_hz.data(), d, fs,
-                                   surface.data(), pval.data(), pidx.data(), nullptr));
-        std::vector<CafSurfaceRow> rows(d);
-        for (std::size_t r = 0; r < d; ++r) {
-            rows[r].freq = freqs_hz[r];
-            rows[r].xcor_mag.assign(surface.begin() + r * n, surface.begin() + (r + 1) * n);
-            rows[r].xcor_peak_idx = (std::size_t)pidx[r];
-            rows[r].xcor_peak_val = pval[r];
-        }
+        caf_b200_surface raw = nullptr;
+        check(caf_b200_surface_create_f64(thread_handle(), reinterpret_cast<const caf_c128*>(needle.data()),
+                                          reinterpret_cast<const caf_c128*>(haystack.data()), needle.size(), freqs_hz.data(),
+                                          freqs_hz.size(), fs, &raw));
+        auto surf = std::make_shared<const DeviceSurface>(raw);
+        std::vector<CafSurfaceRow> rows;
+        rows.reserve(freqs_hz.size());
+        for (std::size_t r = 0; r < freqs_hz.size(); ++r) rows.emplace_back(surf, r);
         return rows;
     }
-    // mod.rs:31-42: strict > from a dummy row (0.0, peak 0.0); consumes the surface like the reference
+    // mod.rs:31-42: strict > from a dummy row (0.0, peak 0.0) in VECTOR order; consumes the surface like the reference.
+    // When `arr` is what caf_surface returned, untouched (all rows of one surface, in order), that scan is exactly what
+    // the kernel's fused find_peak already did; any other vector (reordered, truncated, rows of several surfaces) is
+    // scanned here from the rows' peaks.
     static std::pair<double, std::size_t> find_peak(std::vector<CafSurfaceRow> arr) {
+        if (!arr.empty() && arr[0].surface() && arr.size() == arr[0].surface()->rows()) {
+            bool whole = true;
+            for (std::size_t i = 0; i < arr.size() && whole; ++i) whole = arr[i].surface() == arr[0].surface() && arr[i].row() == i;
+            if (whole) {
+                const caf_b200_peak pk = arr[0].surface()->fused_peak();
+                return {pk.freq_hz, (std::size_t)pk.delay_idx};
+            }
+        }
         double best = 0.0, f = 0.0;
         std::size_t idx = 0;
         for (const auto& row : arr)
-            if (row.xcor_peak_val > best) { best = row.xcor_peak_val; f = row.freq; idx = row.xcor_peak_idx; }
+            if (row.xcor_peak_val() > best) { best = row.xcor_peak_val(); f = row.freq(); idx = row.xcor_peak_idx(); }
         return {f, idx};
     }
     // caf_surface + find_peak fused on the GPU, the surface never leaves the chip

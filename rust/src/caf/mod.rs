@@ -1,42 +1,74 @@
 //! The reference's `caf` module surface (caf_rust/src/caf/mod.rs:13-462) on the B200 library:
 //! `CafSurfaceRow`, `trait CafSurface { caf_surface, find_peak, apply_freq_shift }` and the seven strategy
 //! structs the tests and benches name (caf_bench.rs:12-19).  Every strategy is the same GPU path.
+use std::os::raw::c_void;
+use std::sync::Arc;
+
 use num_complex::Complex64;
+use once_cell::sync::OnceCell;
 
 use crate::ffi;
 
+/// One surface on the GPU (caf_b200_surface_*), shared by its rows.  The reference's `CafSurfaceRow` owns a `Vec<f64>` per
+/// row but keeps every field private (mod.rs:17-22), so no caller of the crate can read it: `tests/test.rs` and
+/// `benches/caf_bench.rs` hand the rows to `find_peak` and look at nothing else.  Here a row is (surface, row number) and
+/// the 2L doubles of `xcor_mag` cross PCIe only if `xcor_mag()` is called.
+pub struct DeviceSurface {
+    raw: ffi::caf_b200_surface,
+    rows: usize,
+    cells: usize,
+    peaks: OnceCell<(Vec<f64>, Vec<f64>, Vec<u64>)>,      // (freq, xcor_peak_val, xcor_peak_idx), 24 bytes per row, on demand
+}
+// the object is immutable after creation and caf_b200_surface_fetch_rows / _row_peaks do not touch the handle's stream
+unsafe impl Send for DeviceSurface {}
+unsafe impl Sync for DeviceSurface {}
+impl DeviceSurface {
+    fn peaks(&self) -> &(Vec<f64>, Vec<f64>, Vec<u64>) {
+        self.peaks.get_or_init(|| {
+            let (mut f, mut v, mut i) = (vec![0f64; self.rows], vec![0f64; self.rows], vec![0u64; self.rows]);
+            ffi::check(unsafe { ffi::caf_b200_surface_row_peaks(self.raw, f.as_mut_ptr(), v.as_mut_ptr(), i.as_mut_ptr()) });
+            (f, v, i)
+        })
+    }
+    fn fused_peak(&self) -> ffi::caf_b200_peak {
+        let mut pk = ffi::caf_b200_peak::default();
+        ffi::check(unsafe { ffi::caf_b200_surface_find_peak(self.raw, &mut pk) });
+        pk
+    }
+}
+impl Drop for DeviceSurface {
+    fn drop(&mut self) { unsafe { ffi::caf_b200_surface_destroy(self.raw); } }
+}
+
 #[allow(dead_code)]
 pub struct CafSurfaceRow {
-    freq: f64,
-    xcor_mag: Vec<f64>,
-    xcor_peak_idx: usize,
-    xcor_peak_val: f64,
+    surface: Arc<DeviceSurface>,
+    row: usize,
 }
 
 impl CafSurfaceRow {
     // accessors are an addition: the reference keeps the fields private (mod.rs:18-21)
-    pub fn freq(&self) -> f64 { self.freq }
-    pub fn xcor_mag(&self) -> &[f64] { &self.xcor_mag }
-    pub fn xcor_peak_idx(&self) -> usize { self.xcor_peak_idx }
-    pub fn xcor_peak_val(&self) -> f64 { self.xcor_peak_val }
+    pub fn freq(&self) -> f64 { self.surface.peaks().0[self.row] }
+    pub fn xcor_peak_val(&self) -> f64 { self.surface.peaks().1[self.row] }
+    pub fn xcor_peak_idx(&self) -> usize { self.surface.peaks().2[self.row] as usize }
+    /// lazy: this row's 2L cells come over PCIe now (one cudaMemcpy), not when the surface was computed
+    pub fn xcor_mag(&self) -> Vec<f64> {
+        let mut out = vec![0f64; self.surface.cells];
+        ffi::check(unsafe { ffi::caf_b200_surface_fetch_rows(self.surface.raw, self.row, 1, out.as_mut_ptr() as *mut c_void) });
+        out
+    }
 }
 
+/// inputs up (one pinned block, one H2D), ONE fused launch, the 32-byte find_peak result down: the cost of a peak-only call
 fn surface_on_gpu(needle: &[Complex64], haystack: &[Complex64], freqs_hz: &[f64], fs: u32) -> Vec<CafSurfaceRow> {
     assert!(needle.len() == haystack.len());            // xcor_rustfft.rs:54-55
-    let (l, d, n) = (needle.len(), freqs_hz.len(), 2 * needle.len());
-    let mut surface = vec![0f64; d * n];
-    let mut pval = vec![0f64; d];
-    let mut pidx = vec![0u64; d];
+    let mut raw: ffi::caf_b200_surface = std::ptr::null_mut();
     ffi::HANDLE.with(|h| ffi::check(unsafe {
-        ffi::caf_b200_surface_f64(h.0, needle.as_ptr(), haystack.as_ptr(), l, freqs_hz.as_ptr(), d, fs,
-                                  surface.as_mut_ptr(), pval.as_mut_ptr(), pidx.as_mut_ptr(), std::ptr::null_mut())
+        ffi::caf_b200_surface_create_f64(h.0, needle.as_ptr(), haystack.as_ptr(), needle.len(), freqs_hz.as_ptr(),
+                                         freqs_hz.len(), fs, &mut raw)
     }));
-    (0..d).map(|r| CafSurfaceRow {
-        freq: freqs_hz[r],
-        xcor_mag: surface[r * n..(r + 1) * n].to_vec(),
-        xcor_peak_idx: pidx[r] as usize,
-        xcor_peak_val: pval[r],
-    }).collect()
+    let surface = Arc::new(DeviceSurface { raw, rows: freqs_hz.len(), cells: 2 * needle.len(), peaks: OnceCell::new() });
+    (0..freqs_hz.len()).map(|row| CafSurfaceRow { surface: surface.clone(), row }).collect()
 }
 
 pub trait CafSurface {
@@ -44,11 +76,21 @@ pub trait CafSurface {
         surface_on_gpu(needle, haystack, freqs_hz, fs)
     }
 
-    // mod.rs:31-42, unchanged semantics: strict > from a dummy row
+    // mod.rs:31-42, unchanged semantics: strict > from a dummy row, in VECTOR order.  When `arr` is what caf_surface
+    // returned, untouched (every row of one surface, in order), that scan is what the kernel's fused find_peak already
+    // did; any other vector (reordered, truncated, rows of several surfaces) is scanned here from the rows' peaks.
     fn find_peak(arr: Vec<CafSurfaceRow>) -> (f64, usize) {
+        if let Some(first) = arr.first() {
+            let whole = arr.len() == first.surface.rows
+                && arr.iter().enumerate().all(|(i, r)| r.row == i && Arc::ptr_eq(&r.surface, &first.surface));
+            if whole {
+                let pk = first.surface.fused_peak();
+                return (pk.freq_hz, pk.delay_idx as usize);
+            }
+        }
         let (mut best, mut out) = (0.0f64, (0.0f64, 0usize));
         for row in arr.iter() {
-            if row.xcor_peak_val > best { best = row.xcor_peak_val; out = (row.freq, row.xcor_peak_idx); }
+            if row.xcor_peak_val() > best { best = row.xcor_peak_val(); out = (row.freq(), row.xcor_peak_idx()); }
         }
         out
     }

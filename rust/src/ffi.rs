@@ -29,6 +29,14 @@ extern "C" {
                                 row_peak_val: *mut f64, row_peak_idx: *mut u64, peak: *mut caf_b200_peak) -> c_int;
     pub fn caf_b200_peak_f64(h: caf_b200_handle, needle: *const Complex64, haystack: *const Complex64, l: usize,
                              freqs_hz: *const f64, d: usize, fs: u32, peak: *mut caf_b200_peak) -> c_int;
+    // device-resident surface objects: what CafSurfaceRow holds (fields are private upstream, mod.rs:17-22)
+    pub fn caf_b200_surface_create_f64(h: caf_b200_handle, needle: *const Complex64, haystack: *const Complex64, l: usize,
+                                       freqs_hz: *const f64, d: usize, fs: u32, out: *mut caf_b200_surface) -> c_int;
+    pub fn caf_b200_surface_shape(s: caf_b200_surface, rows: *mut usize, cells_per_row: *mut usize) -> c_int;
+    pub fn caf_b200_surface_row_peaks(s: caf_b200_surface, freq_hz: *mut f64, peak_val: *mut f64, peak_idx: *mut u64) -> c_int;
+    pub fn caf_b200_surface_find_peak(s: caf_b200_surface, out: *mut caf_b200_peak) -> c_int;
+    pub fn caf_b200_surface_fetch_rows(s: caf_b200_surface, row0: usize, count: usize, out: *mut c_void) -> c_int;
+    pub fn caf_b200_surface_destroy(s: caf_b200_surface) -> c_int;
     pub fn caf_b200_host_alloc(out: *mut *mut c_void, bytes: usize) -> c_int;
     pub fn caf_b200_host_free(p: *mut c_void) -> c_int;
     // sibling layouts (caf_go / caf_python conventions): layout 1 = Python [d][l], 2 = Go [d][2l], |xcor|
@@ -44,6 +52,10 @@ extern "C" {
                                         haystack: *const Complex64, l: usize, freqs_hz: *const f64, d: usize, fs: u32,
                                         surface_local: *mut f64, peak: *mut caf_b200_peak) -> c_int;
 }
+
+#[repr(C)]
+pub struct caf_b200_surface_s { _private: [u8; 0] }
+pub type caf_b200_surface = *mut caf_b200_surface_s;
 
 #[repr(C)]
 pub struct caf_b200_comm_s { _private: [u8; 0] }

@@ -1,5 +1,6 @@
 // C++ restatement of caf_rust/tests/test.rs (all 13 tests) on the C++ mirror of the reference API.
 // Built and run by tests/test_gpu_cpp.py on the GPU box:  ./test_rs <data dir>
+#include <algorithm>
 #include <cstdio>
 #include <string>
 #include "caf_b200.hpp"
@@ -54,6 +55,37 @@ int main(int argc, char** argv) {
         auto [f, idx] = CafB200::caf_peak(needle, hay, shifts, 48000);
         std::printf("Frequency offset: %.1fHz\nTime offset: %zu samples (%.3fms)\n", f, idx, (double)idx / 48.0);
         ASSERT_EQ(f, 69.0); ASSERT_EQ(idx, (std::size_t)202);
+        // lazy rows: caf_surface leaves the surface on the GPU; a row's xcor_mag crosses PCIe only when asked for, and is
+        // the same bits the host-surface entry point delivers; find_peak on a reordered / truncated vector scans the rows
+        {
+            auto rows = CafRustFFT::caf_surface(needle, hay, shifts, 48000);
+            ASSERT_EQ(rows.size(), shifts.size());
+            ASSERT_EQ(rows[0].surface()->cells_per_row(), (std::size_t)8192);
+            std::vector<double> dense(shifts.size() * 8192), pv(shifts.size());
+            std::vector<uint64_t> pi(shifts.size());
+            check(caf_b200_surface_f64(thread_handle(), reinterpret_cast<const caf_c128*>(needle.data()),
+                                       reinterpret_cast<const caf_c128*>(hay.data()), needle.size(), shifts.data(), shifts.size(), 48000,
+                                       dense.data(), pv.data(), pi.data(), nullptr));
+            for (std::size_t r : {std::size_t(0), std::size_t(338), shifts.size() - 1}) {
+                auto mag = rows[r].xcor_mag();
+                ASSERT_EQ(mag.size(), (std::size_t)8192);
+                ASSERT_EQ(std::equal(mag.begin(), mag.end(), dense.begin() + (std::ptrdiff_t)(r * 8192)), true);
+                ASSERT_EQ(rows[r].xcor_peak_val(), pv[r]); ASSERT_EQ(rows[r].xcor_peak_idx(), (std::size_t)pi[r]); ASSERT_EQ(rows[r].freq(), shifts[r]);
+                ASSERT_EQ(mag[rows[r].xcor_peak_idx()], rows[r].xcor_peak_val());
+            }
+            auto whole = CafRustFFT::find_peak(rows);                              // untouched: the kernel's fused answer
+            ASSERT_EQ(whole.first, 69.0); ASSERT_EQ(whole.second, (std::size_t)202);
+            std::vector<CafSurfaceRow> rev(rows.rbegin(), rows.rend());           // reordered: scanned in vector order
+            auto r2 = CafRustFFT::find_peak(rev);
+            ASSERT_EQ(r2.first, 69.0); ASSERT_EQ(r2.second, (std::size_t)202);
+            std::vector<CafSurfaceRow> head(rows.begin(), rows.begin() + 100);   // truncated: the best of rows 0..99
+            auto r3 = CafRustFFT::find_peak(head);
+            double bv = 0.0, bf = 0.0; std::size_t bi = 0;
+            for (std::size_t r = 0; r < 100; ++r) if (pv[r] > bv) { bv = pv[r]; bf = shifts[r]; bi = (std::size_t)pi[r]; }
+            ASSERT_EQ(r3.first, bf); ASSERT_EQ(r3.second, bi);
+            rows.clear(); rev.clear();                                            // `head` keeps the surface alive
+            ASSERT_EQ(head[5].xcor_mag().size(), (std::size_t)8192);
+        }
         // main.go:13-35 equivalent on the chirp_4 pair: "caf result: 70 samples 83 hz"
         {
             auto apple = read_file_c64(dir + "/chirp_4_raw.c64");
