@@ -21,4 +21,26 @@ for l in (5000, 20001):                                                         
     surface_arrays(n2, h2, f[:3], 48000)
 n3, h3 = G.as_inputs(G.pair(0, seed=0, chirp_length=100000))                              # two levels, fused kernels
 _, pi3, _, pk3 = surface_arrays(n3, h3, f[:2], 48000, want_surface=False); print("two-level", pk3.freq_hz, pk3.delay_idx)
+# round 2 paths: device-resident surface object with lazy rows, peak-only call (pinned completion word, spin wait),
+# inputs in one block / scattered, the sharded entry over a world-1 communicator (pack in the kernel, device resolve)
+import ctypes as C, tempfile
+from caf_cookoff_b200 import _lib, default_handle
+from caf_cookoff_b200.dist import Comm
+lib = _lib.load(); h = default_handle()
+so = C.c_void_p(); pk = _lib.Peak()
+assert lib.caf_b200_surface_create_f64(h.raw, needle.ctypes.data, hay.ctypes.data, 4096, f.ctypes.data, f.size, 48000, C.byref(so)) == 0
+row = np.empty(8192); assert lib.caf_b200_surface_fetch_rows(so, 1, 1, row.ctypes.data) == 0
+pv = np.empty(f.size); pi_ = np.empty(f.size, dtype=np.uint64); fz = np.empty(f.size)
+assert lib.caf_b200_surface_row_peaks(so, fz.ctypes.data, pv.ctypes.data, pi_.ctypes.data) == 0
+assert lib.caf_b200_surface_find_peak(so, C.byref(pk)) == 0 and row[int(pi_[1])] == pv[1]
+lib.caf_b200_surface_destroy(so)
+assert lib.caf_b200_peak_f64(h.raw, needle.ctypes.data, hay.ctypes.data, 4096, f.ctypes.data, f.size, 48000, C.byref(pk)) == 0
+print("surface object / peak-only", pk.freq_hz, pk.delay_idx)
+import torch
+comm = Comm(h, 1, 0, os.path.join(tempfile.gettempdir(), "caf_sanitize_id_%d" % os.getpid()))
+nd = torch.from_numpy(needle).cuda(); hd = torch.from_numpy(hay).cuda(); fd = torch.from_numpy(f).cuda(); outp = torch.zeros(4, dtype=torch.int64, device="cuda")
+comm.sharded_dev(nd.data_ptr(), hd.data_ptr(), 4096, fd.data_ptr(), f.size, 0, 48000, outp.data_ptr()); h.sync()
+n3d = torch.from_numpy(n3).cuda(); h3d = torch.from_numpy(h3).cuda()
+comm.sharded_dev(n3d.data_ptr(), h3d.data_ptr(), n3.size, fd.data_ptr(), 2, 0, 48000, outp.data_ptr()); h.sync()
+comm.close()
 print("sanitize pass done")

@@ -132,6 +132,30 @@ def test_host_inputs_in_one_block_scattered_or_adjacent_allocations(chirp0):
     assert np.array_equal(got[0], ref[0]) and got[1] == ref[1]
 
 
+def test_stress_bitwise_determinism_over_many_launches(chirp0):
+    """compute-sanitizer is closed on this GPU pool (profiles/r02_sanitizer.txt), so the hand-rolled synchronisation of
+    the row kernel -- named barriers per warp group, the mailbox mbarrier pair, the cross-CTA H publication flag, the
+    last-CTA-done ticket, group 1 folding group 0's candidates -- is held to the strongest black-box property a race
+    would break: every one of many launches, over shapes that change the rows per CTA (1, 2-3, dozens) and the pair
+    boundaries inside a CTA, returns bit-identical surfaces, row peaks and peaks, equal to the oracle-checked first."""
+    from caf_cookoff_b200 import bench_shifts
+    needle, hay = chirp0
+    for shifts in (bench_shifts(), bench_shifts()[:148], bench_shifts()[:7], np.linspace(-100, 100, 1777, endpoint=False)):
+        ref = caf.surface_arrays(needle, hay, shifts, FS)
+        for _ in range(25):
+            got = caf.surface_arrays(needle, hay, shifts, FS)
+            assert np.array_equal(got[0], ref[0]) and np.array_equal(got[1], ref[1]) and np.array_equal(got[2], ref[2])
+            assert (got[3].value, got[3].doppler_idx, got[3].delay_idx) == (ref[3].value, ref[3].doppler_idx, ref[3].delay_idx)
+    # batches: pair boundaries fall inside CTAs; peaks only (the fused path) and with surfaces
+    ns = np.stack([needle, needle[::-1].copy(), needle * 0.5]); hs = np.stack([hay, hay, hay[::-1].copy()])
+    ref = caf.batch_arrays(ns, hs, bench_shifts()[:200], FS, want_surface=True)
+    for k in range(15):
+        got = caf.batch_arrays(ns, hs, bench_shifts()[:200], FS, want_surface=(k % 2 == 0))
+        assert np.array_equal(got[1], ref[1]) and np.array_equal(got[2], ref[2])
+        assert got[0] is None or np.array_equal(got[0], ref[0])
+        assert [(q.value, q.doppler_idx, q.delay_idx) for q in got[3]] == [(q.value, q.doppler_idx, q.delay_idx) for q in ref[3]]
+
+
 def test_repeated_calls_are_deterministic(chirp0):
     needle, hay = chirp0
     shifts = caf.bench_shifts()
