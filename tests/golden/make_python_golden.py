@@ -69,6 +69,23 @@ def main():
     surf = caf.amb_surf(n64, h64, grid[360:372], FS)            # rows 80.0 .. 85.5 Hz contain the maximum
     fmax, tmax = np.unravel_index(surf.argmax(), surf.shape)
     out["main_report"] = np.array([len(n64) // 2 - tmax, grid[360 + fmax]])
+    # case E (round 2): ONE FULL 400-row surface of the README pair (chirp_0, caf_bench.rs' grid -100 .. 99.5 Hz), complex128
+    # inputs: 400 x 4096 doubles = 13 MB, so what is committed is its SHA-256, every row's maximum and arg-maximum, and
+    # 1 % of its cells (16 384 cells at positions drawn by a seeded generator), not the array
+    import hashlib
+    n0, h0 = load("chirp_0_raw.c64").astype(np.complex128), load("chirp_0_T+202samp_F+69.25Hz.c64", 4096).astype(np.complex128)
+    grid = np.arange(-100000, 100000, 500) / 1e3                # caf_bench.rs:32-35
+    full = caf.amb_surf(n0, h0, grid, FS)
+    assert full.shape == (400, 4096) and full.dtype == np.float64
+    rs = np.random.RandomState(20261018)
+    flat = np.sort(rs.choice(full.size, size=16384, replace=False))
+    out["e_freqs"] = grid
+    out["e_sha256"] = np.frombuffer(hashlib.sha256(np.ascontiguousarray(full).tobytes()).digest(), dtype=np.uint8)
+    out["e_cells_flat_index"] = flat.astype(np.int64)
+    out["e_cells_value"] = full.ravel()[flat]
+    out["e_row_max"] = full.max(axis=1)
+    out["e_row_argmax"] = full.argmax(axis=1).astype(np.int64)
+    out["e_surface_max"] = np.array([full.max()])
     path = os.path.join(HERE, "python_sibling.npz")
     np.savez(path, **out)
     print("wrote", path, {k: v.shape for k, v in out.items()}, "main_report", out["main_report"])

@@ -82,6 +82,37 @@ def test_oracle_xcor_magnitudes():
     assert rel_max(np.abs(r[(L // 2 - j) % (2 * L)]), G["xcor_abs_same"]) <= 1e-12
 
 
+def pair0():
+    n = O.read_file_c64(os.path.join(DATA, "chirp_0_raw.c64"))
+    h = O.read_file_c64(os.path.join(DATA, "chirp_0_T+202samp_F+69.25Hz.c64"))[:4096]
+    return n, h
+
+
+def check_full_surface_against_reference_values(surf_rust, tol):
+    """ONE FULL 400-row surface of the README pair from the unmodified caf.py (13 MB: its SHA-256, every row's maximum and
+    arg-maximum and 1 % of its cells are committed): the given Rust-layout surface, mapped to caf.py's layout, agrees at
+    all 16 384 sampled cells, and every row's maximum sits where caf.py has it."""
+    py = rust_to_python(surf_rust, 4096)
+    assert py.shape == (400, 4096)
+    big = float(G["e_surface_max"][0])
+    got = py.ravel()[G["e_cells_flat_index"]]
+    assert np.abs(got - G["e_cells_value"]).max() / big <= tol
+    assert np.abs(py.max(axis=1) - G["e_row_max"]).max() / big <= tol
+    # arg-maxima: identical wherever the row's two best cells differ by more than the tolerance (they all do here)
+    assert np.array_equal(py.argmax(axis=1), G["e_row_argmax"])
+    fm = int(np.argmax(G["e_row_max"]))
+    assert (float(G["e_freqs"][fm]), 4096 // 2 - int(G["e_row_argmax"][fm])) == (69.0, 202)      # caf_bench.rs' pair on its grid
+    return float(np.abs(got - G["e_cells_value"]).max() / big)
+
+
+def test_oracle_full_400_row_surface_fp64():
+    n, h = pair0()
+    surf, _, _ = O.caf_surface(n, h, G["e_freqs"], FS)
+    err = check_full_surface_against_reference_values(surf, 1e-12)
+    assert err <= 1e-12
+    assert G["e_sha256"].size == 32            # the digest of caf.py's own array (regeneration check, make_python_golden.py)
+
+
 def test_python_program_report_matches_rust_answer():
     """caf.py's __main__ prints tau_max = 70, freq_max = 83.0 for the chirp_4 pair on its 0.5 Hz grid; the Rust
     convention's peak of the same rows is (83.0, 70) (known answer test.rs:157-170 is 82.9 on the 0.1 Hz grid)."""
@@ -102,6 +133,15 @@ def test_cuda_surface_magnitudes_fp64():
     n, h = pair7()
     surf, _, _, _ = surface_arrays(n, h, G["c_freqs"], FS)
     assert rel_max(rust_to_python(surf, 1000), G["c_surf_c128"]) <= 1e-9
+
+
+@pytest.mark.gpu
+def test_cuda_full_400_row_surface_fp64():
+    from caf_cookoff_b200 import surface_arrays
+    n, h = pair0()
+    surf, _, _, pk = surface_arrays(n, h, G["e_freqs"], FS)
+    check_full_surface_against_reference_values(surf, 1e-9)        # north-star tolerance; measured ~1e-13
+    assert (pk.freq_hz, int(pk.delay_idx)) == (69.0, 202)
 
 
 @pytest.mark.gpu
