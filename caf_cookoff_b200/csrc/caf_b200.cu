@@ -261,8 +261,20 @@ cudaError_t launch_rows(caf_b200_handle h, const caf::RowArgs<T>& a, long long n
     const int occ = std::is_same<T, double>::value ? h->occ_d : h->occ_f;
     long long cap = (long long)h->sm_count * occ;
     int grid = (int)(n_items < cap ? n_items : cap);
-    caf::caf_rows_kernel<T, MODE, FULL><<<grid, caf::kThreads, smem_bytes<T>(), h->stream>>>(a);
     h->launches++;
+    if (MODE == caf::kSurface) {
+        // programmatic stream serialisation: this launch may begin (TMEM, tables -- nothing that touches caller memory)
+        // while the kernel before it on the stream drains; see griddepcontrol.wait in caf_rows_kernel
+        cudaLaunchConfig_t cfg{};
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(caf::kThreads);
+        cfg.dynamicSmemBytes = smem_bytes<T>(); cfg.stream = h->stream;
+        return cudaLaunchKernelEx(&cfg, caf::caf_rows_kernel<T, MODE, FULL>, a);
+    }
+    caf::caf_rows_kernel<T, MODE, FULL><<<grid, caf::kThreads, smem_bytes<T>(), h->stream>>>(a);
     return cudaGetLastError();
 }
 
