@@ -1008,22 +1008,32 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
     }
 #endif
     // ---------------- fused find_peak (mod.rs:31-42), single pair: the last CTA to finish reduces the rows ----------------
+    // Every row peak of this CTA was stored by ONE thread (lane 0 of group 1's fold warp), so that warp alone runs the
+    // tail: a fence for that thread's own stores (not for the CTA's 64 KB of surface cells still in flight), one ticket,
+    // and in the last CTA a one-warp scan of the D row peaks.  (Neutral for the launch time, as round 1's leaner tail was
+    // -- the tail is not on the critical path -- but it frees registers and code in the other fifteen warps.)
     if constexpr (MODE == kSurface) {
-        if (a.peak != nullptr && a.done_counter != nullptr) {
-            __threadfence();
-            __syncthreads();
-            if (tid == 0) {
-                unsigned int ticket = atomicAdd(a.done_counter, 1u);
-                misc[1] = (ticket == gridDim.x - 1) ? 1u : 0u;
+        if (a.peak != nullptr && a.done_counter != nullptr && r == 1 && wg == 3) {
+            unsigned int last = 0;
+            if (lane == 0) {
+                __threadfence();
+                last = (atomicAdd(a.done_counter, 1u) == gridDim.x - 1) ? 1u : 0u;
             }
-            __syncthreads();
-            if (misc[1]) {
+            last = __shfl_sync(0xffffffffu, last, 0);
+            if (last) {
                 __threadfence();
                 double best = 0.0;
                 int brow = 0x7fffffff;
-                for (int d = tid; d < a.D; d += kThreads) {
-                    double val = (double)__ldcg(a.row_peak_val + d);
-                    if (val > best) { best = val; brow = d; }      // d ascending per thread: first max kept
+                for (int d0 = 0; d0 < a.D; d0 += 128) {              // four loads in flight per lane
+                    double vv[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int d = d0 + 32 * q + lane;
+                        vv[q] = (d < a.D) ? (double)__ldcg(a.row_peak_val + d) : 0.0;
+                    }
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        if (vv[q] > best) { best = vv[q]; brow = d0 + 32 * q + lane; }   // ascending per lane: first max kept
                 }
 #pragma unroll
                 for (int off = 16; off > 0; off >>= 1) {
@@ -1031,10 +1041,7 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
                     int oi = __shfl_xor_sync(0xffffffffu, brow, off);
                     amax_take<double>(best, brow, ov, oi);
                 }
-                if (lane == 0) { red_val[hw_warp] = best; red_idx[hw_warp] = (unsigned long long)(unsigned int)brow; }
-                __syncthreads();
-                if (tid == 0) {
-                    for (int q = 1; q < 16; ++q) amax_take<double>(best, brow, red_val[q], (int)red_idx[q]);
+                if (lane == 0) {
                     PeakOut p;
                     if (best > 0.0 && brow != 0x7fffffff) {
                         p.value = best; p.freq_hz = a.freqs[brow];
