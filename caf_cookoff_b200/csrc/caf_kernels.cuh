@@ -886,7 +886,7 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
                     // is kept in TMEM for the later rows.  The spectrum is parked in this warp's own fabric region for
                     // a moment so that all 16 loads of H are in flight at once: one L2 round trip instead of four.
                     h_from_share = false;
-                    bar_group(r);
+                    __syncwarp();      // the own region is only ever touched by its own half-warp (X1 read, X2, X3): no group barrier
 #pragma unroll
                     for (int k = 0; k < 16; ++k) Fab<T>::st(c.Sr, c.ix_own(k), v[k]);
 #pragma unroll
