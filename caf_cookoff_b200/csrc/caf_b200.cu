@@ -208,9 +208,9 @@ cudaError_t upload_tables(Tables<T>& t, cudaStream_t s) {
     return cudaStreamSynchronize(s);   // the host vectors die at scope exit
 }
 
-template <typename T, int MODE, bool FULL = false>
+template <typename T, int MODE, bool FULL = false, bool SHARED = false>
 cudaError_t configure_kernel(int* occ_out) {
-    auto k = caf::caf_rows_kernel<T, MODE, FULL>;
+    auto k = caf::caf_rows_kernel<T, MODE, FULL, SHARED>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<T>());
     if (e != cudaSuccess) return e;
     if (occ_out) {
@@ -244,8 +244,10 @@ cudaError_t configure_all(int* occ) {
     if ((e = configure_fused<T, 2>()) != cudaSuccess) return e;
     if ((e = configure_fused<T, 4>()) != cudaSuccess) return e;
     if ((e = configure_fused<T, 8>()) != cudaSuccess) return e;
-    if ((e = configure_kernel<T, caf::kSurface, true>(occ)) != cudaSuccess) return e;
-    if ((e = configure_kernel<T, caf::kSurface, false>(nullptr)) != cudaSuccess) return e;
+    if ((e = configure_kernel<T, caf::kSurface, true, true>(occ)) != cudaSuccess) return e;
+    if ((e = configure_kernel<T, caf::kSurface, false, true>(nullptr)) != cudaSuccess) return e;
+    if ((e = configure_kernel<T, caf::kSurface, true, false>(nullptr)) != cudaSuccess) return e;
+    if ((e = configure_kernel<T, caf::kSurface, false, false>(nullptr)) != cudaSuccess) return e;
     if ((e = configure_kernel<T, caf::kSpectrumHalf>(nullptr)) != cudaSuccess) return e;
     if ((e = configure_kernel<T, caf::kSpectrumFull>(nullptr)) != cudaSuccess) return e;
     if ((e = configure_kernel<T, caf::kXcorFull>(nullptr)) != cudaSuccess) return e;
@@ -272,7 +274,8 @@ cudaError_t launch_rows(caf_b200_handle h, const caf::RowArgs<T>& a, long long n
         cfg.attrs = attr; cfg.numAttrs = 1;
         cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(caf::kThreads);
         cfg.dynamicSmemBytes = smem_bytes<T>(); cfg.stream = h->stream;
-        return cudaLaunchKernelEx(&cfg, caf::caf_rows_kernel<T, MODE, FULL>, a);
+        if (a.hshare != nullptr) return cudaLaunchKernelEx(&cfg, caf::caf_rows_kernel<T, MODE, FULL, true>, a);
+        return cudaLaunchKernelEx(&cfg, caf::caf_rows_kernel<T, MODE, FULL, false>, a);
     }
     caf::caf_rows_kernel<T, MODE, FULL><<<grid, caf::kThreads, smem_bytes<T>(), h->stream>>>(a);
     return cudaGetLastError();
@@ -488,7 +491,7 @@ int run_batch_dev(caf_b200_handle h, const caf::cx<T>* needles, const caf::cx<T>
     a.L = (int)l; a.P = (int)p; a.D = (int)d;
     a.in = needles; a.in2 = hays; a.freqs = freqs; a.dt = 1.0 / (double)fs;   // dt: mod.rs:53
     a.out = surface; a.row_peak_val = rv; a.row_peak_idx = ri;
-    const bool fused_peak = peaks && p == 1;      // single pair: find_peak rides in the same launch
+    const bool fused_peak = peaks && p == 1 && d > 1;      // single pair over many CTAs: find_peak rides in the same launch
     if (fused_peak) {
         a.peak = peaks; a.done_counter = h->done_counter; a.peak_words = h->pack_words; a.row_offset = h->pack_offset;
         a.peak_seq = h->seq_ptr; a.seq_val = h->seq_val;
@@ -667,7 +670,7 @@ int run_batch_host(caf_b200_handle h, const caf::cx<T>* needles, const caf::cx<T
         // Peak-only call on the fused path: the kernel stores the peak into pinned host memory and then a sequence word
         // next to it; the host spins on that word (with a stream query now and then, so a failed launch cannot hang it)
         // instead of cudaStreamSynchronize, whose wake-up alone costs several microseconds of a ~55 us call.
-        spin = peak_zero_copy && !surface && !rowval && !rowidx && l && d && l <= (size_t)kL0;
+        spin = peak_zero_copy && !surface && !rowval && !rowidx && l && d > 1 && l <= (size_t)kL0;
         if (spin) { h->seq_ptr = reinterpret_cast<unsigned int*>((char*)h->h_peaks + h->h_peaks_cap); h->seq_val = ++h->seq_counter; }
         rc = run_batch_dev<T>(h, d_needle, d_hay, p, l, d_freqs, d, fs, d_surface, d_rv, d_ri, d_pk);
         h->seq_ptr = nullptr;

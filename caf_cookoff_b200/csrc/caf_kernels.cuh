@@ -531,7 +531,9 @@ template <int I> using ic = std::integral_constant<int, I>;
 // FULL = the reference's shape, L == 4096: every one of the 8192 cells is an output cell (no index remap).
 // One CTA per SM for both precisions: two complex64 CTAs per SM fit (64 regs, 64 KB fabric) but measured slower
 // (36.9 vs 33.0 us per surface) because every CTA pays the per-launch prologue for half as many rows.
-template <typename T, int MODE, bool FULL>
+// SHARED = one pair spread over many CTAs (a.hshare != nullptr): H comes from the publishing CTAs, find_peak is fused.  The
+// batch instantiation (whole pairs per CTA) carries none of that code.
+template <typename T, int MODE, bool FULL, bool SHARED = false>
 __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> a) {
     using C = cx<T>;
     using SL = SmemLayout<T>;
@@ -590,8 +592,7 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
     double phi_first = 0.0;
     if constexpr (MODE == kSurface) {
         if (lo < hi) {
-            const bool shared_h0 = (a.hshare != nullptr);
-            const bool producer0 = !shared_h0 || (int)blockIdx.x == ((r == 0) ? 0 : a.hprod1);
+            const bool producer0 = !SHARED || (int)blockIdx.x == ((r == 0) ? 0 : a.hprod1);
             const C* src = (producer0 ? a.in2 : a.in) + (long long)pair * a.L;
 #pragma unroll
             for (int q = 0; q < (int)sizeof(C) / 8; ++q) {      // 128-byte lines tg, tg + 256: the group's whole operand block
@@ -644,8 +645,7 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
     if constexpr (MODE == kSurface) {
         asm volatile("griddepcontrol.wait;\n" ::: "memory");
         if (lo < hi) {
-            const bool shared_h0 = (a.hshare != nullptr);
-            const bool producer0 = !shared_h0 || (int)blockIdx.x == ((r == 0) ? 0 : a.hprod1);
+            const bool producer0 = !SHARED || (int)blockIdx.x == ((r == 0) ? 0 : a.hprod1);
             const C* src = (producer0 ? a.in2 : a.in) + (long long)pair * a.L;
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
@@ -755,7 +755,7 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
                 // Single pair split over many CTAs: only CTA 0 transforms the haystack and publishes H through L2;
                 // the others start their first row at once and pick H up just before they need it.
                 cur_pair = pair;
-                const bool shared_h = (a.hshare != nullptr);
+                constexpr bool shared_h = SHARED;
                 // H_0 is published by CTA 0 and H_1 by CTA hprod1 (both own one row fewer than the critical path).
                 // In a publishing CTA the other group parks at barrier 0 so the publisher has the SM's fp64 pipes
                 // to itself and H is ready before any consumer needs it.
@@ -862,7 +862,7 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
                                     // first row of a consumer CTA: wait for H's publication here, while the last
                                     // butterfly is still ahead, so the L2 round trip of the flag is off the critical path
                                     if constexpr (kUseTmem) {
-                                        if (h_from_share && tg == 0) {
+                                        if (SHARED && h_from_share && tg == 0) {
                                             unsigned int seen;
                                             do {
                                                 asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(seen) : "l"(a.hflag + r) : "memory");
@@ -881,7 +881,7 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
         } else {
             // ---------------- H * conj(X)  (xcor_rustfft.rs:64-73) ----------------
             if constexpr (kUseTmem) {
-                if (h_from_share) {
+                if (SHARED && h_from_share) {
                     // first row of a consumer CTA: H arrives from the publishing CTA through L2 (flag seen in hook3) and
                     // is kept in TMEM for the later rows.  The spectrum is parked in this warp's own fabric region for
                     // a moment so that all 16 loads of H are in flight at once: one L2 round trip instead of four.
@@ -1013,7 +1013,7 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
     // and in the last CTA a one-warp scan of the D row peaks.  (Neutral for the launch time, as round 1's leaner tail was
     // -- the tail is not on the critical path -- but it frees registers and code in the other fifteen warps.)
     if constexpr (MODE == kSurface) {
-        if (a.peak != nullptr && a.done_counter != nullptr && r == 1 && wg == 3) {
+        if (SHARED && a.peak != nullptr && a.done_counter != nullptr && r == 1 && wg == 3) {
             unsigned int last = 0;
             if (lane == 0) {
                 __threadfence();
