@@ -711,9 +711,11 @@ def run_b200(args):
         roofline["smem"] = {"error": repr(e)}
 
     # ---- e2e: the host-pointer C ABI, H2D + D2H inside the timed region.  The caller's three inputs sit back to back in
-    #      ONE pinned block from caf_b200_host_alloc (needle | haystack | freqs): the library then moves them with a single
-    #      DMA (three small H2D copies cost ~6 us each on B200).  `*_pageable` repeats both calls with plain pageable numpy
-    #      buffers -- what a caller that knows nothing about pinned memory (the Rust shim's Vecs, std::vector) pays. -----
+    #      ONE pinned block from caf_b200_host_alloc (needle | haystack | freqs).  The surface call (pipelined D2H) moves it
+    #      with a single DMA (three small H2D copies cost ~6 us each on B200); the peak-only and drop-in calls issue NO copy:
+    #      the row kernel's own CTAs read the block across PCIe while they set up (RowArgs::pull_*, CAF_B200_PULL=0 restores
+    #      the DMA).  `*_pageable` repeats the calls with plain pageable numpy buffers -- what a caller that knows nothing
+    #      about pinned memory (the Rust shim's Vecs, std::vector) pays: one memcpy into the library's pinned block first. -----
     csz = np.dtype(cdt).itemsize
     blk = C.c_void_p()
     if lib.caf_b200_host_alloc(C.byref(blk), 2 * L * csz + D * 8) != 0:
@@ -772,8 +774,9 @@ def run_b200(args):
     ms, _ = time_host(peak_call(needle_h, hay_h, freqs_h, pk2))
     e2e_peak = {"value": world * cells_step / (ms * 1e-3), "unit": "cells/s", "ms_per_step": ms,
                 "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 32 + 4, "peak": [pk2.freq_hz, int(pk2.delay_idx)],
-                "note": "host inputs in (one pinned block, one H2D), (freq, delay) out: the surface stays on the GPU (caf_b200_peak_*); "
-                        "the kernel stores the peak into pinned host memory and the host spins on a sequence word next to it"}
+                "note": "host inputs in (one pinned block, read across PCIe by the kernel's own CTAs: no H2D DMA in front of the launch), "
+                        "(freq, delay) out: the surface stays on the GPU (caf_b200_peak_*); the kernel stores the peak into pinned "
+                        "host memory and the host spins on a sequence word next to it"}
     checks["e2e_peak_only"] = peak_is_planted(rank, pk2.freq_hz, int(pk2.delay_idx))
 
     # pageable host memory on both sides (numpy arrays): the drop-in caller's cost
@@ -788,7 +791,7 @@ def run_b200(args):
     ms, _ = time_host(peak_call(n_pg, h_pg, f_pg, pk4))
     e2e_peak_pageable = {"value": world * cells_step / (ms * 1e-3), "unit": "cells/s", "ms_per_step": ms,
                          "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 32 + 4, "peak": [pk4.freq_hz, int(pk4.delay_idx)],
-                         "host_buffers": "pageable numpy inputs (staged through the library's pinned block: one memcpy, one H2D)"}
+                         "host_buffers": "pageable numpy inputs (one memcpy into the library's pinned block, which the kernel reads across PCIe itself)"}
     checks["e2e_peak_only_pageable"] = peak_is_planted(rank, pk4.freq_hz, int(pk4.delay_idx))
     # what the reference-facing call sequence costs now: CafSurface::caf_surface + find_peak as the Rust shim / the C++
     # mirror issue it (caf_b200_surface_create + _find_peak + _destroy, pageable Vec inputs): the rows stay on the GPU
@@ -806,7 +809,8 @@ def run_b200(args):
     e2e_dropin = {"value": world * cells_step / (ms * 1e-3), "unit": "cells/s", "ms_per_step": ms,
                   "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 32 + 4, "peak": [pk5.freq_hz, int(pk5.delay_idx)],
                   "note": "caf_surface + find_peak as rust/src/caf/mod.rs and include/caf_b200.hpp issue them: device-resident "
-                          "surface object with lazy rows (caf_bench.rs:163-167's closure)"}
+                          "surface object with lazy rows (caf_bench.rs:163-167's closure); pageable inputs, one memcpy into the library's pinned "
+                          "block, which the kernel reads across PCIe itself; the peak comes back through pinned memory"}
     checks["e2e"] = peak_is_planted(rank, pk5.freq_hz, int(pk5.delay_idx))
     del needle_h, hay_h, freqs_h, raw_blk
     lib.caf_b200_host_free(blk)

@@ -5,6 +5,7 @@
 // kernel launches on the handle's stream.  No CPU compute path exists here: without an
 // sm_100 device create() fails (CAF_B200_ENODEVICE).
 #include <cmath>
+#include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -133,6 +134,12 @@ struct caf_b200_handle_s {
     void* hshare = nullptr;                 // single-pair launches: H published by CTA 0 (8192 complex128)
     unsigned int* hflag = nullptr;          // [2] publish counters, monotonic
     unsigned int epoch = 0;
+    // small single-pair host calls: the kernel pulls its inputs out of pinned host memory itself (RowArgs::pull_*)
+    unsigned int* pull_counter = nullptr;       // device word the grid meets on, monotonic
+    unsigned int pull_total = 0;                // its value after every launch issued so far
+    const void* pull_src = nullptr;             // set by run_batch_host around ONE run_batch_dev call
+    size_t pull_bytes = 0;
+    bool allow_pull = true;                     // CAF_B200_PULL
     unsigned int* seq_ptr = nullptr;            // single-pair host calls: pinned word the fused find_peak signals (see run_batch_host)
     unsigned int seq_val = 0, seq_counter = 0;
     unsigned long long* pack_words = nullptr;   // sharded rows: find_peak also writes its result packed for the exchange
@@ -169,6 +176,16 @@ struct caf_b200_surface_s {
 };
 
 namespace {
+
+// blocks handed out by caf_b200_host_alloc: pinned and device-addressable, so a kernel may read inputs straight from them
+std::mutex g_pinned_mu;
+std::vector<std::pair<const char*, size_t>> g_pinned_blocks;
+bool pinned_block_holds(const void* p, size_t bytes) {
+    std::lock_guard<std::mutex> lk(g_pinned_mu);
+    for (const auto& b : g_pinned_blocks)
+        if ((const char*)p >= b.first && (const char*)p + bytes <= b.first + b.second) return true;
+    return false;
+}
 
 std::mutex g_live_mu;
 std::set<caf_b200_handle> g_live_handles;     // a surface object outliving its handle frees its buffer itself
@@ -509,6 +526,13 @@ int run_batch_dev(caf_b200_handle h, const caf::cx<T>* needles, const caf::cx<T>
             const long long cnt = n_items * (b + 1) / grid - n_items * b / grid;
             if (best < 0 || cnt < best) { best = cnt; a.hprod1 = (int)b; }
         }
+        if (h->pull_src) {      // the grid fetches needle | haystack | freqs from pinned host memory itself
+            a.pull_src = reinterpret_cast<const uint4*>(h->pull_src);
+            a.pull_dst = reinterpret_cast<uint4*>(const_cast<cx<T>*>(needles));
+            a.pull_n16 = (unsigned int)(h->pull_bytes / 16);
+            a.pull_counter = h->pull_counter;
+            a.pull_target = h->pull_total + 2u * (unsigned int)grid;      // two pulling warps per CTA
+        }
     }
     const bool prof = h->profiling;
     if (prof) {
@@ -520,6 +544,7 @@ int run_batch_dev(caf_b200_handle h, const caf::cx<T>* needles, const caf::cx<T>
     // one fused launch: per pair FFT(s1) -> TMEM, then per row shift -> FFT -> xH -> IFFT -> |.|^2 -> argmax
     if (l == (size_t)kL0) CK((launch_rows<T, kSurface, true>(h, a, (long long)p * (long long)d)));
     else CK((launch_rows<T, kSurface, false>(h, a, (long long)p * (long long)d)));
+    if (a.pull_src) h->pull_total = a.pull_target;      // only a launch that was accepted moves the meeting point
     if (prof) CK(cudaEventRecord(h->ev[2], h->stream));
     if (peaks && !fused_peak) {
         caf_peak_kernel<T><<<(unsigned)p, 256, 0, h->stream>>>(rv, ri, freqs, (int)d, peaks, h->pack_words, h->pack_offset);
@@ -562,6 +587,7 @@ int run_batch_host(caf_b200_handle h, const caf::cx<T>* needles, const caf::cx<T
     if (p == 0) return CAF_B200_OK;
     const size_t n = 2 * l, rows = p * d;
     cudaStream_t s = h->stream;
+    struct PullReset { caf_b200_handle h; ~PullReset() { h->pull_src = nullptr; } } pull_reset{h};   // never outlives this call
     // ---- inputs.  Three small H2D copies cost ~6 us EACH on B200 (DMA set-up, not bytes: 19 us of a 69 us peak-only
     //      call), so a small call moves needle | haystack | freqs as ONE block: straight from the caller's memory when the
     //      three already sit back to back (a caller that stages them in one caf_b200_host_alloc block), else through a
@@ -571,9 +597,33 @@ int run_batch_host(caf_b200_handle h, const caf::cx<T>* needles, const caf::cx<T
     const size_t sig_pad = (sig_bytes + 15) & ~(size_t)15;
     if (l && d && 2 * sig_pad + fr_bytes <= ((size_t)1 << 20)) {
         const size_t tot = 2 * sig_pad + fr_bytes;
-        CK(h->in_block.ensure(tot));
+        const size_t tot16 = (tot + 15) & ~(size_t)15;
+        CK(h->in_block.ensure(tot16));
         bool moved = false;
-        if (sig_pad == sig_bytes && (const char*)hays == (const char*)needles + sig_bytes &&
+        // One pair over many CTAs, nothing pipelined behind it: no copy at all -- the kernel's own CTAs read the block out
+        // of pinned host memory while they set up (caf_kernels.cuh, RowArgs::pull_*).  The caller's memory is used as it
+        // is when the three inputs are one run inside a caf_b200_host_alloc block, else the staging block.
+        const bool pipelined = h->allow_pipeline && surface && p == 1 && l <= (size_t)kL0 && d >= 2 * (size_t)h->sm_count;
+        if (h->allow_pull && h->pull_counter && p == 1 && d > 1 && l <= (size_t)kL0 && !pipelined) {
+            const bool one_run = sig_pad == sig_bytes && (const char*)hays == (const char*)needles + sig_bytes &&
+                                 (const char*)freqs == (const char*)hays + sig_bytes;
+            if (one_run && ((uintptr_t)needles & 15) == 0 && pinned_block_holds(needles, tot16)) {
+                h->pull_src = needles;
+            } else {
+                if (h->h_stage_cap < tot16) {
+                    if (h->h_stage) cudaFreeHost(h->h_stage);
+                    h->h_stage = nullptr; h->h_stage_cap = 0;
+                    CK(cudaMallocHost(&h->h_stage, tot16 + tot16 / 4));
+                    h->h_stage_cap = tot16 + tot16 / 4;
+                }
+                char* st = (char*)h->h_stage;
+                std::memcpy(st, needles, sig_bytes); std::memcpy(st + sig_pad, hays, sig_bytes); std::memcpy(st + 2 * sig_pad, freqs, fr_bytes);
+                h->pull_src = st;
+            }
+            h->pull_bytes = tot16;
+            moved = true;
+        }
+        if (!moved && sig_pad == sig_bytes && (const char*)hays == (const char*)needles + sig_bytes &&
             (const char*)freqs == (const char*)hays + sig_bytes) {
             // already one block in the caller's memory.  Adjacent addresses need not be ONE pinned allocation (a copy may
             // not span two): such a copy is refused at once and the staging block below takes over.
@@ -673,7 +723,7 @@ int run_batch_host(caf_b200_handle h, const caf::cx<T>* needles, const caf::cx<T
         spin = peak_zero_copy && !surface && !rowval && !rowidx && l && d > 1 && l <= (size_t)kL0;
         if (spin) { h->seq_ptr = reinterpret_cast<unsigned int*>((char*)h->h_peaks + h->h_peaks_cap); h->seq_val = ++h->seq_counter; }
         rc = run_batch_dev<T>(h, d_needle, d_hay, p, l, d_freqs, d, fs, d_surface, d_rv, d_ri, d_pk);
-        h->seq_ptr = nullptr;
+        h->seq_ptr = nullptr; h->pull_src = nullptr;
         if (rc) return rc;
         if (surface && d_surface) CK(cudaMemcpyAsync(surface, d_surface, sizeof(T) * rows * n, cudaMemcpyDeviceToHost, s));
     }
@@ -856,6 +906,7 @@ static int create_impl(int device, bool own_stream, void* cuda_stream, caf_b200_
     if (const char* e_ = getenv("CAF_B200_CHUNK_MB")) { const long v_ = atol(e_); if (v_ > 0) h->chunk_mb = (size_t)v_; }
     if (const char* e_ = getenv("CAF_B200_PIPELINE")) h->allow_pipeline = e_[0] != '0';
     if (const char* e_ = getenv("CAF_B200_PEAK_ZEROCOPY")) h->peak_zero_copy = e_[0] != '0';
+    if (const char* e_ = getenv("CAF_B200_PULL")) h->allow_pull = e_[0] != '0';
 
     if (!own_stream) { h->stream = (cudaStream_t)cuda_stream; h->own_stream = false; }   // 0 = legacy default stream
     else {
@@ -866,6 +917,8 @@ static int create_impl(int device, bool own_stream, void* cuda_stream, caf_b200_
     if ((e = cudaMalloc(&h->hshare, sizeof(double2) * caf::kM)) != cudaSuccess ||
         (e = cudaMalloc(&h->hflag, 2 * sizeof(unsigned int))) != cudaSuccess ||
         (e = cudaMemsetAsync(h->hflag, 0, 2 * sizeof(unsigned int), h->stream)) != cudaSuccess ||
+        (e = cudaMalloc(&h->pull_counter, sizeof(unsigned int))) != cudaSuccess ||
+        (e = cudaMemsetAsync(h->pull_counter, 0, sizeof(unsigned int), h->stream)) != cudaSuccess ||
         (e = cudaMalloc(&h->done_counter, sizeof(unsigned int))) != cudaSuccess ||
         (e = cudaMemsetAsync(h->done_counter, 0, sizeof(unsigned int), h->stream)) != cudaSuccess ||
         (e = upload_tables<double>(h->td, h->stream)) != cudaSuccess ||
@@ -901,6 +954,7 @@ int caf_b200_destroy(caf_b200_handle h) {
     if (h->h_peaks) cudaFreeHost(h->h_peaks);
     if (h->h_stage) cudaFreeHost(h->h_stage);
     if (h->done_counter) cudaFree(h->done_counter);
+    if (h->pull_counter) cudaFree(h->pull_counter);
     if (h->hshare) cudaFree(h->hshare);
     if (h->hflag) cudaFree(h->hflag);
     for (auto& e : h->ev) if (e) cudaEventDestroy(e);
@@ -987,11 +1041,21 @@ int caf_b200_host_alloc(void** out, size_t bytes) {
     if (!out) return fail(CAF_B200_EINVAL, "null out");
     *out = nullptr;
     if (bytes == 0) return CAF_B200_OK;
-    CK(cudaMallocHost(out, bytes));
+    // (a few bytes of slack: the kernel-side input pull reads whole 16-byte chunks)
+    CK(cudaMallocHost(out, bytes + 16));
+    std::lock_guard<std::mutex> lk(g_pinned_mu);
+    g_pinned_blocks.emplace_back((const char*)*out, bytes + 16);
     return CAF_B200_OK;
 }
 int caf_b200_host_free(void* p) {
-    if (p) CK(cudaFreeHost(p));
+    if (p) {
+        {
+            std::lock_guard<std::mutex> lk(g_pinned_mu);
+            for (size_t i = 0; i < g_pinned_blocks.size(); ++i)
+                if (g_pinned_blocks[i].first == (const char*)p) { g_pinned_blocks.erase(g_pinned_blocks.begin() + (long)i); break; }
+        }
+        CK(cudaFreeHost(p));
+    }
     return CAF_B200_OK;
 }
 

@@ -89,6 +89,14 @@ struct RowArgs {
     unsigned int* hflag;    // [2] per-group publish counters (monotonic across launches)
     unsigned int epoch;     // this launch's counter value
     int hprod1;             // CTA that publishes H_1 (H_0 comes from CTA 0); 0 = CTA 0 publishes both
+    // kSurface, P == 1, small host calls: the grid fetches its own inputs.  pull_src is the caller's (or the library's) PINNED
+    // host block needle | haystack | freqs, pull_dst the device block `in`, `in2` and `freqs` point into; two warps of every
+    // CTA move one slice of it across PCIe while the CTA sets up, then the grid meets on pull_counter (monotonic).
+    const uint4* pull_src;
+    uint4* pull_dst;
+    unsigned int pull_n16;          // 16-byte chunks
+    unsigned int* pull_counter;
+    unsigned int pull_target;       // counter value once every pulling warp of THIS launch has arrived
     long long* trace;       // CAF_TRACE builds only: [cta][warp][8 items][32 slots] clock64 stamps
 };
 
@@ -604,6 +612,19 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
         }
     }
 
+    // ---- small host calls: the inputs are still in the caller's pinned memory.  Warps 14 and 15 of every CTA read one
+    //      512-byte slice each across PCIe NOW (the host wrote the block before the launch, so nothing on the stream is
+    //      awaited), the round trip hides behind the TMEM / table set-up below, and the slice is stored to the device
+    //      block after griddepcontrol.wait.  This replaces a cudaMemcpyAsync in front of the kernel (~10 us of a ~64 us
+    //      peak-only call: DMA set-up and a second launch latency, not bytes). ----
+    uint4 pulled = make_uint4(0u, 0u, 0u, 0u);
+    const unsigned int pull_i = blockIdx.x * 64u + (unsigned int)(tid - 448);
+    if constexpr (MODE == kSurface && SHARED) {
+        if (a.pull_src != nullptr && tid >= 448 && pull_i < a.pull_n16)
+            asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];\n"
+                         : "=r"(pulled.x), "=r"(pulled.y), "=r"(pulled.z), "=r"(pulled.w) : "l"(a.pull_src + pull_i) : "memory");
+    }
+
     if (tid == 0) {
         mbar_init(mb_full, 256);
         mbar_init(mb_empty, 256);
@@ -644,16 +665,41 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
     //      was measured: 39.8 against 39.25 us per surface back to back.) ----
     if constexpr (MODE == kSurface) {
         asm volatile("griddepcontrol.wait;\n" ::: "memory");
+        if constexpr (SHARED) {
+            if (a.pull_src != nullptr) {
+                if (tid >= 448) {
+                    unsigned int i = pull_i;
+                    if (i < a.pull_n16) __stcg(a.pull_dst + i, pulled);
+                    for (i += gridDim.x * 64u; i < a.pull_n16; i += gridDim.x * 64u) {     // blocks beyond 148 x 1 KB
+                        uint4 q;
+                        asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];\n"
+                                     : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "l"(a.pull_src + i) : "memory");
+                        __stcg(a.pull_dst + i, q);
+                    }
+                    __threadfence();
+                    __syncwarp();
+                    if (lane == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;\n" :: "l"(a.pull_counter) : "memory");
+                }
+                if (tid == 0) {
+                    unsigned int seen;
+                    do {
+                        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(seen) : "l"(a.pull_counter) : "memory");
+                    } while ((int)(seen - a.pull_target) < 0);
+                }
+                __syncthreads();
+            }
+        }
         if (lo < hi) {
             const bool producer0 = !SHARED || (int)blockIdx.x == ((r == 0) ? 0 : a.hprod1);
             const C* src = (producer0 ? a.in2 : a.in) + (long long)pair * a.L;
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
                 const int n = t + 256 * i;
-                v[i] = (n < a.L) ? ldg<T>(src + n) : mk<T>((T)0, (T)0);
+                // (SHARED: the block may have been written by other CTAs of this very grid -- L2, not the read-only path)
+                v[i] = (n < a.L) ? (SHARED ? __ldcg(src + n) : ldg<T>(src + n)) : mk<T>((T)0, (T)0);
             }
             preloaded = true;
-            phi_first = __ldg(a.freqs + row) * a.dt;
+            phi_first = (SHARED ? __ldcg(a.freqs + row) : __ldg(a.freqs + row)) * a.dt;
         }
     }
 
@@ -861,8 +907,11 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
                                 [&] {
                                     // first row of a consumer CTA: wait for H's publication here, while the last
                                     // butterfly is still ahead, so the L2 round trip of the flag is off the critical path
+                                    // EVERY warp polls for itself (lane 0, then the __syncwarp in front of the H loads
+                                    // carries the acquire to the other lanes): no group barrier stands between this
+                                    // point and those loads, so a poll by one thread of the group would order nobody else.
                                     if constexpr (kUseTmem) {
-                                        if (SHARED && h_from_share && tg == 0) {
+                                        if (SHARED && h_from_share && lane == 0) {
                                             unsigned int seen;
                                             do {
                                                 asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(seen) : "l"(a.hflag + r) : "memory");
@@ -886,7 +935,7 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
                     // is kept in TMEM for the later rows.  The spectrum is parked in this warp's own fabric region for
                     // a moment so that all 16 loads of H are in flight at once: one L2 round trip instead of four.
                     h_from_share = false;
-                    __syncwarp();      // the own region is only ever touched by its own half-warp (X1 read, X2, X3): no group barrier
+                    __syncwarp();      // (a) lane 0's acquire of the H flag (hook3) now covers the whole warp; (b) the own region is only ever touched by its own half-warp (X1 read, X2, X3): no group barrier
 #pragma unroll
                     for (int k = 0; k < 16; ++k) Fab<T>::st(c.Sr, c.ix_own(k), v[k]);
 #pragma unroll

@@ -25,6 +25,8 @@
  *    CAF_B200_CHUNK_MB=<n>   scratch budget for rows longer than 8192 cells (default 6144)
  *    CAF_B200_PIPELINE=0     host surface calls: one launch + one D2H copy instead of head/rest overlap
  *    CAF_B200_PEAK_ZEROCOPY=0  single-pair host calls: copy the peak back instead of storing it into pinned host memory
+ *    CAF_B200_PULL=0         single-pair host calls: one H2D copy in front of the kernel instead of the kernel's own CTAs
+ *                            reading the pinned input block across PCIe
  *    CAF_B200_NCCL_LIB=<so>  which libnccl to dlopen for caf_b200_comm_* (default: the loaded one, then libnccl.so.2)
  *
  * Sizes.  l = samples per input signal (needle and haystack must be equal length, as the reference's

@@ -7,6 +7,7 @@ Tolerances (BASELINE.json north_star, with the metric fixed in SURVEY.md section
   - complex64 variant: <= 1e-4 (measured ~5e-7)
 """
 import ctypes as C
+import json
 import os
 
 import numpy as np
@@ -130,6 +131,70 @@ def test_host_inputs_in_one_block_scattered_or_adjacent_allocations(chirp0):
     tn, th, tf = (torch.from_numpy(x).pin_memory() for x in (needle, hay, freqs))
     got = call(tn.data_ptr(), th.data_ptr(), tf.data_ptr())
     assert np.array_equal(got[0], ref[0]) and got[1] == ref[1]
+
+
+def test_kernel_side_input_pull_matches_the_copy_path(chirp0, monkeypatch):
+    """Small single-pair host calls carry no H2D copy: the grid reads needle | haystack | freqs out of pinned host memory
+    itself and meets on a device counter (caf_kernels.cuh, RowArgs::pull_*).  Against a handle created with
+    CAF_B200_PULL=0 (cudaMemcpyAsync in front of the kernel) every shape gives the same bits -- grids of 2 ... 148 CTAs,
+    blocks that need several rounds per CTA, byte counts that are no multiple of 16, complex64 -- call after call (the
+    meeting point is a monotonic counter that has to stay in step with the launches)."""
+    from caf_cookoff_b200 import bench_shifts
+    needle, hay = chirp0
+    monkeypatch.setenv("CAF_B200_PULL", "0")
+    h_copy = api.Handle(0)
+    monkeypatch.setenv("CAF_B200_PULL", "1")
+    h_pull = api.Handle(0)
+    shapes = [(4096, bench_shifts()), (4096, bench_shifts()[:2]), (1000, bench_shifts()[:3]), (17, np.linspace(-90, 90, 1777)),
+              (4095, bench_shifts()[:149]), (4096, bench_shifts()[:147])]
+    for rep in range(3):
+        for l, shifts in shapes:
+            for variant in (api._Variant, api._Variant32):
+                want_surface = (rep == 0)
+                a = caf.surface_arrays(needle[:l], hay[:l], shifts, FS, variant=variant, want_surface=want_surface, handle=h_copy)
+                b = caf.surface_arrays(needle[:l], hay[:l], shifts, FS, variant=variant, want_surface=want_surface, handle=h_pull)
+                if a[0] is not None and not np.array_equal(a[0], b[0]):
+                    bad = np.nonzero((a[0] != b[0]).any(axis=1))[0]
+                    raise AssertionError(f"l={l} d={shifts.size} {variant.sfx} rep={rep}: rows {bad[:8]} ({bad.size}) differ, "
+                                         f"cells {int((a[0] != b[0]).sum())}, first cols {np.nonzero(a[0][bad[0]] != b[0][bad[0]])[0][:8]}")
+                assert np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+                assert (a[3].value, a[3].freq_hz, a[3].doppler_idx, a[3].delay_idx) == (b[3].value, b[3].freq_hz, b[3].doppler_idx, b[3].delay_idx)
+    # peak-only calls (the spin-wait path) keep the known answer of the pair
+    lib = _lib.load()
+    f = bench_shifts()
+    for _ in range(20):
+        pk = _lib.Peak()
+        assert lib.caf_b200_peak_f64(h_pull.raw, needle.ctypes.data, hay.ctypes.data, needle.size, f.ctypes.data, f.size, FS,
+                                     C.cast(C.byref(pk), C.c_void_p)) == 0
+        assert (pk.freq_hz, int(pk.delay_idx)) == (69.0, 202)
+    h_copy.close(); h_pull.close()
+
+
+def test_alternating_pairs_never_see_a_stale_haystack_spectrum():
+    """One pair over many CTAs: CTA 0 / CTA hprod1 publish H = FFT(haystack)/n through L2 and every other CTA picks it up
+    behind a release/acquire flag.  A consumer that read the buffer too early would see the PREVIOUS call's H -- invisible
+    to any test that repeats one pair.  Alternate different pairs on one handle (and start on fresh handles, whose buffer
+    holds no H at all) and hold every surface to the batch kernel's bits (whole pairs per CTA, no hand-over)."""
+    from caf_cookoff_b200 import bench_shifts
+    from oracle import oracle as O
+    cases = [c for c in json.load(open(os.path.join(os.path.dirname(__file__), "golden", "known_answers.json")))["cases"]][:4]
+    pairs = []
+    for c in cases:
+        n = O.read_file_c64(os.path.join(DATA, "chirp_%d_raw.c64" % c["chirp"]))
+        pairs.append((n, O.read_file_c64(os.path.join(DATA, c["haystack"]))[: n.size]))
+    shifts = bench_shifts()
+    ref = caf.batch_arrays(np.stack([p[0] for p in pairs]), np.stack([p[1] for p in pairs]), shifts, FS, want_surface=True)
+    for fresh in range(6):
+        h = api.Handle(0)
+        for k in range(12):
+            i = (k + fresh) % len(pairs)
+            want_surface = (k % 3 != 2)
+            got = caf.surface_arrays(pairs[i][0], pairs[i][1], shifts if k % 2 == 0 else shifts[:147], FS,
+                                     want_surface=want_surface, handle=h)
+            d = shifts.size if k % 2 == 0 else 147
+            if want_surface: assert np.array_equal(got[0], ref[0][i][:d]), (fresh, k, i)
+            assert np.array_equal(got[1], ref[1][i][:d]) and np.array_equal(got[2], ref[2][i][:d]), (fresh, k, i)
+        h.close()
 
 
 def test_stress_bitwise_determinism_over_many_launches(chirp0):
