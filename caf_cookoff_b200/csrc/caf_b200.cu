@@ -352,13 +352,11 @@ cudaError_t launch_large_fused(caf_b200_handle h, const caf::LargeArgs<T>& a, bo
 }
 template <typename T, bool HMODE>
 cudaError_t launch_large_core(caf_b200_handle h, const caf::LargeArgs<T>& a) {
-    // one warp group per (row, position) unit, at most two groups per SM; whole sets of positions only (the kernel keeps a
-    // group on one position of the row so that its H stays in TMEM)
+    // two warp groups per SM; the kernel cuts the (position, row) units into one contiguous share per group
     const long long upr = a.N / caf::kL0;
     const long long units = (long long)a.rows * upr;
-    long long groups = units < 2LL * h->sm_count ? units : 2LL * h->sm_count;
-    if (groups > upr) groups = groups / upr * upr;
-    long long ctas = (groups + 1) / 2;
+    const long long groups = units < 2LL * h->sm_count ? units : 2LL * h->sm_count;
+    const long long ctas = (groups + 1) / 2;
     caf::caf_large_core<T, HMODE><<<(unsigned)ctas, caf::kThreads, caf::SmemLayout<T>::kTotalNoNeedle, h->stream>>>(a);
     h->launches++;
     return cudaGetLastError();

@@ -146,33 +146,43 @@ __global__ void __launch_bounds__(kThreads, 1) caf_large_core(const LargeArgs<T>
     const int tot = (a.inner_top == kL0) ? a.N / 2 : 65536;   // length of the innermost factored array
     const int Rin = tot / kL0;
     const T scale = (T)(1.0 / (double)a.N);              // the /n of xcor_rustfft.rs:72
-    // Every warp group keeps ONE position hu inside the row for the whole launch and walks down the rows, so its 4096
-    // bins of H (TMEM) and the roots of its conjugate inner twiddle (TMEM) are fetched once instead of once per unit:
-    // that is a third of the kernel's L2 reads and two sincospi per thread and unit.  Groups beyond the last full set
-    // of positions stay idle (296 groups, 16 positions for config 3: 288 work).
+    // The launch's units, ordered position-major (all rows of position 0, then of position 1, ...), are cut into one
+    // contiguous, equal share per warp group: a group stays on ONE position of the row while it walks down the rows -- its
+    // 4096 bins of H and the roots of its conjugate inner twiddle live in TMEM and are fetched once per position instead
+    // of once per unit (a third of the kernel's L2 reads and two sincospi per thread and unit) -- and changes position at
+    // most a few times per launch.  (Round 1 gave every group exactly one position, which leaves 296 - 256 = 40 of the
+    // groups idle on a 2^20-cell row and 8 on a 65 536-cell row.)
     const int n_groups = 2 * gridDim.x, g = 2 * blockIdx.x + c.r;
-    const int sets = n_groups / units_per_row;           // >= 1: the host launches at least one group per position
-    const bool active = g < sets * units_per_row;
-    const int hu = g % units_per_row, s = hu % Rin;
+    const long long total = (long long)a.rows * units_per_row;
+    const long long share = (total + n_groups - 1) / n_groups;
+    const long long u0 = (long long)g * share, u1 = (u0 + share < total) ? u0 + share : total;
     const uint32_t tm_h = misc[0] + ((uint32_t)(32 * (hw_warp & 3)) << 16) + (uint32_t)((16 * (hw_warp >> 2)) * TG::kColsPerC);
-    C* hp = a.hbig + ((size_t)hu * 16) * 256 + tg;
-    if (active && !HMODE) {
-        // conj(W_tot^{m s}) = e^{+2 pi j (t + 256 n1) s / tot}: base and ratio
-        const double2 b = root_of_unity((long long)t * s, tot, 1.0), rho = root_of_unity(256LL * s, tot, 1.0);
-        tmem_st1(c.tm_g + 1 * TG::kColsPerC, mk<T>((T)b.x, (T)b.y));
-        tmem_st1(c.tm_g + 2 * TG::kColsPerC, mk<T>((T)rho.x, (T)rho.y));
-#pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4) {           // TMEM chunk q4 = bins k3 = q4, q4 + 4, q4 + 8, q4 + 12
-            C tmp[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) tmp[i] = ldg<T>(hp + (q4 + 4 * i) * 256);
-            tmem_st4(tm_h + 4 * q4 * TG::kColsPerC, tmp);
-        }
-        tmem_wait_st();
-    }
+    int hu = -1, row = 0;
+    C* hp = nullptr;
     C v[16];
-    for (long long row = active ? g / units_per_row : a.rows; row < a.rows; row += sets) {
+    for (long long u = u0; u < u1; ++u, ++row) {
+        if (hu < 0 || row == a.rows) {
+            hu = (int)(u / a.rows); row = (int)(u - (long long)hu * a.rows);
+            hp = a.hbig + ((size_t)hu * 16) * 256 + tg;
+            if (!HMODE) {
+                // conj(W_tot^{m s}) = e^{+2 pi j (t + 256 n1) s / tot}: base and ratio
+                const int s = hu % Rin;
+                const double2 b = root_of_unity((long long)t * s, tot, 1.0), rho = root_of_unity(256LL * s, tot, 1.0);
+                tmem_st1(c.tm_g + 1 * TG::kColsPerC, mk<T>((T)b.x, (T)b.y));
+                tmem_st1(c.tm_g + 2 * TG::kColsPerC, mk<T>((T)rho.x, (T)rho.y));
+#pragma unroll
+                for (int q4 = 0; q4 < 4; ++q4) {           // TMEM chunk q4 = bins k3 = q4, q4 + 4, q4 + 8, q4 + 12
+                    C tmp[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) tmp[i] = ldg<T>(hp + (q4 + 4 * i) * 256);
+                    tmem_st4(tm_h + 4 * q4 * TG::kColsPerC, tmp);
+                }
+                tmem_wait_st();
+            }
+        }
         C* buf = a.wbuf + ((size_t)row * units_per_row + hu) * kL0;
+        // (a bulk L2 prefetch of the group's next unit, issued here a whole unit time ahead, was measured: cfg5 5.38 against 5.33 ms
+        //  for 296 rows, cfg3 3.78 against 3.75 ms -- the unit loads are not what the core waits for)
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] = buf[t + 256 * i];
         forward_4096<T>(v, c, nullptr, 0, [] {}, [] {});
