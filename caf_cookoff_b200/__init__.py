@@ -8,7 +8,7 @@ from .api import (CafB200, CafB200F32, CafError, CafFFTW, CafPanic, CafRustFFT, 
                   CafRustFFTIterRayon, CafRustFFTRayon, CafRustFFTThreadpool, CafRustFFTThreads,
                   CafSurface, CafSurfaceRow, Handle, Surface, Xcor, XcorF32, batch_arrays, default_handle,
                   peak_pack, peak_resolve, surface_arrays)
-from .io import bench_shifts, gen_float_shifts, read_file_c64, write_file_binary
+from .io import DeviceSamples, bench_shifts, gen_float_shifts, read_file_c64, read_file_c64_dev, write_file_binary
 from .siblings import GoSibling, PythonSibling, surface_layout
 
 __all__ = [n for n in dir() if not n.startswith("_")]

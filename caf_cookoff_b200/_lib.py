@@ -84,6 +84,12 @@ SYMBOLS = {
     "caf_b200_debug_trace": (_int, [_vp, _vp, _sz]),
     "caf_b200_host_alloc": (_int, [C.POINTER(_vp), _sz]),
     "caf_b200_host_free": (_int, [_vp]),
+    "caf_b200_load_c64_dev_f64": (_int, [_vp, C.c_char_p, _sz, _sz, C.POINTER(_vp), C.POINTER(_sz)]),
+    "caf_b200_load_c64_dev_f32": (_int, [_vp, C.c_char_p, _sz, _sz, C.POINTER(_vp), C.POINTER(_sz)]),
+    "caf_b200_dev_free": (_int, [_vp]),
+    "caf_b200_dev_alloc": (_int, [_vp, _sz, C.POINTER(_vp)]),
+    "caf_b200_dev_upload": (_int, [_vp, _vp, _vp, _sz]),
+    "caf_b200_dev_download": (_int, [_vp, _vp, _vp, _sz]),
     "caf_b200_apply_freq_shift_f64": (_int, _shift),
     "caf_b200_apply_freq_shift_f32": (_int, _shift),
     "caf_b200_apply_shift_f64": (_int, _shift),

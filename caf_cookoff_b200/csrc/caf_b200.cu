@@ -874,6 +874,55 @@ int run_xcor(caf_b200_handle h, const caf::cx<T>* a_, const caf::cx<T>* b_, size
     return CAF_B200_OK;
 }
 
+// read_file_c64 (utils.rs:10-35) onto the device: see include/caf_b200.h
+template <typename T>
+int load_c64_dev(caf_b200_handle h, const char* path, size_t first, size_t max_samples, void** dev_out, size_t* n_out) {
+    if (!h || !path || !dev_out || !n_out) return fail(CAF_B200_EINVAL, "null argument");
+    *dev_out = nullptr; *n_out = 0;
+    FILE* f = std::fopen(path, "rb");
+    if (!f) return fail(CAF_B200_EIO, std::string("read_file_c64: cannot open ") + path);
+    struct Close { FILE* f; ~Close() { std::fclose(f); } } closer{f};
+    if (std::fseek(f, 0, SEEK_END) != 0) return fail(CAF_B200_EIO, "read_file_c64: seek failed");
+    const long long bytes = (long long)std::ftell(f);
+    if (bytes < 0) return fail(CAF_B200_EIO, "read_file_c64: tell failed");
+    if (bytes % 8) return fail(CAF_B200_EINVAL, "read_file_c64: trailing partial sample (utils.rs:19-32 indexes past the end)");
+    const size_t total = (size_t)bytes / 8;
+    if (first > total) first = total;
+    size_t n = total - first;
+    if (max_samples && n > max_samples) n = max_samples;
+    if (n == 0) return CAF_B200_OK;
+    CK(cudaSetDevice(h->device));
+    // file -> pinned staging (the read lands where the DMA starts) -> device, 8 bytes per sample
+    const size_t raw = n * 8;
+    if (h->h_stage_cap < raw) {
+        if (h->h_stage) cudaFreeHost(h->h_stage);
+        h->h_stage = nullptr; h->h_stage_cap = 0;
+        CK(cudaMallocHost(&h->h_stage, raw));
+        h->h_stage_cap = raw;
+    }
+    if (std::fseek(f, (long)(first * 8), SEEK_SET) != 0 || std::fread(h->h_stage, 1, raw, f) != raw)
+        return fail(CAF_B200_EIO, std::string("read_file_c64: short read from ") + path);
+    void* out = nullptr;
+    CK(cudaMalloc(&out, n * sizeof(caf::cx<T>)));
+    cudaError_t e;
+    if (std::is_same<T, float>::value) {
+        e = cudaMemcpyAsync(out, h->h_stage, raw, cudaMemcpyHostToDevice, h->stream);
+    } else {
+        e = h->scratch.ensure(raw);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(h->scratch.p, h->h_stage, raw, cudaMemcpyHostToDevice, h->stream);
+        if (e == cudaSuccess) {
+            long long blocks = (long long)((n + 255) / 256);
+            if (blocks > 8LL * h->sm_count) blocks = 8LL * h->sm_count;
+            caf::caf_widen_c64_kernel<<<(unsigned)blocks, 256, 0, h->stream>>>((const float2*)h->scratch.p, (double2*)out, (long long)n);
+            h->launches++;
+            e = cudaGetLastError();
+        }
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);      // the staging block is the handle's: free it for the next call
+    if (e != cudaSuccess) { cudaFree(out); return fail(CAF_B200_ECUDA, cudaGetErrorString(e)); }
+    *dev_out = out; *n_out = n;
+    return CAF_B200_OK;
+}
 }  // namespace
 
 // ================================================ C ABI ================================================
@@ -1054,6 +1103,41 @@ int caf_b200_host_free(void* p) {
         }
         CK(cudaFreeHost(p));
     }
+    return CAF_B200_OK;
+}
+
+int caf_b200_load_c64_dev_f64(caf_b200_handle h, const char* path, size_t first_sample, size_t max_samples, caf_c128** dev_out, size_t* n_out) {
+    return load_c64_dev<double>(h, path, first_sample, max_samples, reinterpret_cast<void**>(dev_out), n_out);
+}
+int caf_b200_load_c64_dev_f32(caf_b200_handle h, const char* path, size_t first_sample, size_t max_samples, caf_c64** dev_out, size_t* n_out) {
+    return load_c64_dev<float>(h, path, first_sample, max_samples, reinterpret_cast<void**>(dev_out), n_out);
+}
+int caf_b200_dev_free(void* dev_ptr) {
+    if (dev_ptr) CK(cudaFree(dev_ptr));
+    return CAF_B200_OK;
+}
+int caf_b200_dev_alloc(caf_b200_handle h, size_t bytes, void** dev_out) {
+    if (!h || !dev_out) return fail(CAF_B200_EINVAL, "null argument");
+    *dev_out = nullptr;
+    if (bytes == 0) return CAF_B200_OK;
+    CK(cudaSetDevice(h->device));
+    CK(cudaMalloc(dev_out, bytes));
+    return CAF_B200_OK;
+}
+int caf_b200_dev_upload(caf_b200_handle h, void* dev_dst, const void* host_src, size_t bytes) {
+    if (!h || (bytes && (!dev_dst || !host_src))) return fail(CAF_B200_EINVAL, "null argument");
+    if (bytes == 0) return CAF_B200_OK;
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemcpyAsync(dev_dst, host_src, bytes, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return CAF_B200_OK;
+}
+int caf_b200_dev_download(caf_b200_handle h, void* host_dst, const void* dev_src, size_t bytes) {
+    if (!h || (bytes && (!host_dst || !dev_src))) return fail(CAF_B200_EINVAL, "null argument");
+    if (bytes == 0) return CAF_B200_OK;
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemcpyAsync(host_dst, dev_src, bytes, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
     return CAF_B200_OK;
 }
 

@@ -1249,6 +1249,15 @@ __global__ void caf_apply_shift_kernel(const cx<T>* __restrict__ in, cx<T>* __re
     }
 }
 
+// read_file_c64's widening (utils.rs:19-32) on the device: packed f32 I/Q pairs as they sit in the file -> complex128.
+// f32 -> f64 is exact, so the samples equal the host loader's bit for bit.
+__global__ void caf_widen_c64_kernel(const float2* __restrict__ in, double2* __restrict__ out, long long n) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float2 x = in[i];
+        out[i] = make_double2((double)x.x, (double)x.y);
+    }
+}
+
 // Circular correlation of length n from the linear one computed with L = n in a row of big_n >= 2n cells:
 //   c[k] = R(k) + R(k - n) = y[k] + y[big_n - n + k]   (y = the complex row; big_n = 8192 for n <= 4096)
 template <typename T>

@@ -30,10 +30,21 @@ from .api import CafB200, CafPanic, Handle, _check, _ptr, default_handle
 LAYOUT_RUST, LAYOUT_PYTHON, LAYOUT_GO = 0, 1, 2
 
 
+def _whole_sample_rate(samp_rate) -> int:
+    """The siblings take a float sample rate (caf.py:28, caf.go:118); the C ABI takes the Rust crate's u32 (mod.rs:46).
+    A rate the u32 cannot hold exactly would silently give a different phasor than the sibling program: refuse it."""
+    fs = float(samp_rate)
+    if not (fs >= 1.0 and fs <= 4294967295.0 and fs == int(fs)):
+        raise ValueError(f"samp_rate must be a whole number of Hz in [1, 2^32 - 1] (got {samp_rate!r}): the library's "
+                         "sample rate is the Rust crate's u32 (mod.rs:46)")
+    return int(fs)
+
+
 def surface_layout(needle, haystack, freqs_hz, fs, layout: int, *, f32: bool = False, want_surface: bool = True,
                    handle: Optional[Handle] = None):
     """caf_b200_surface_layout_{f64,f32}: returns (surface [D, W] or None, Peak) in the sibling's layout."""
     cdt, rdt, sfx = (np.complex64, np.float32, "f32") if f32 else (np.complex128, np.float64, "f64")
+    fs = _whole_sample_rate(fs)
     n_ = np.ascontiguousarray(needle, dtype=cdt).ravel()
     h_ = np.ascontiguousarray(haystack, dtype=cdt).ravel()
     f_ = np.ascontiguousarray(freqs_hz, dtype=np.float64).ravel()
@@ -45,7 +56,7 @@ def surface_layout(needle, haystack, freqs_hz, fs, layout: int, *, f32: bool = F
     pk = _lib.Peak()
     h = handle or default_handle()
     fn = getattr(_lib.load(), "caf_b200_surface_layout_" + sfx)
-    _check(fn(h.raw, _ptr(n_), _ptr(h_), l, _ptr(f_), d, int(round(fs)), int(layout), _ptr(out),
+    _check(fn(h.raw, _ptr(n_), _ptr(h_), l, _ptr(f_), d, fs, int(layout), _ptr(out),
               C.cast(C.byref(pk), C.c_void_p)))
     return out, pk
 
@@ -55,7 +66,7 @@ class PythonSibling:
 
     @staticmethod
     def apply_fdoa(ray, fdoa: float, samp_rate: float) -> np.ndarray:
-        return CafB200.apply_freq_shift(ray, float(fdoa), int(round(samp_rate)))
+        return CafB200.apply_freq_shift(ray, float(fdoa), _whole_sample_rate(samp_rate))
 
     @staticmethod
     def amb_surf(needle, haystack, freqs_hz, samp_rate: float) -> np.ndarray:
@@ -78,7 +89,7 @@ class GoSibling:
 
     @staticmethod
     def apply_fdoa(ray, fdoa: float, samp_rate: float) -> np.ndarray:
-        return CafB200.apply_freq_shift(ray, float(fdoa), int(round(samp_rate)))
+        return CafB200.apply_freq_shift(ray, float(fdoa), _whole_sample_rate(samp_rate))
 
     @staticmethod
     def amb_surf(needle, haystack, freqs_hz, samp_rate: float) -> np.ndarray:

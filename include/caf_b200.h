@@ -58,7 +58,8 @@ typedef enum {
     CAF_B200_ECUDA = -4,         /* CUDA runtime error (message in last_error) */
     CAF_B200_ENODEVICE = -5,     /* no usable sm_100 GPU — there is no CPU fallback */
     CAF_B200_ENCCL = -6,         /* NCCL missing or an NCCL call failed (message in last_error) */
-    CAF_B200_EREMOTE = -7        /* sharded call: a PEER rank failed before the peak exchange (every rank still left the collective) */
+    CAF_B200_EREMOTE = -7,       /* sharded call: a PEER rank failed before the peak exchange (every rank still left the collective) */
+    CAF_B200_EIO = -8            /* a sample file could not be opened or read (utils.rs:10's io::Result Err) */
 } caf_b200_status;
 
 /* Result of CafSurface::find_peak (mod.rs:31-42).  When no row beats the dummy 0.0 row (empty or
@@ -98,6 +99,24 @@ int caf_b200_debug_trace(caf_b200_handle h, long long* out, size_t n_cta);
 /* pinned host buffers: surfaces DMA straight into them (any host pointer is accepted, pinned is faster) */
 int caf_b200_host_alloc(void** out, size_t bytes);
 int caf_b200_host_free(void* p);
+
+/* ---- read_file_c64 (utils.rs:10-35) straight onto the device ------------------------------------------------------
+ * The file's packed little-endian f32 I/Q pairs are read into pinned memory, cross PCIe as they are (8 bytes per sample
+ * instead of the 16 of the widened Vec<Complex64>) and are widened on the GPU (f32 -> f64 is exact: the device samples
+ * equal read_file_c64's bit for bit).  first_sample / max_samples select a window of the file (max_samples = 0: to its
+ * end).  *dev_out is device memory on the handle's device -- complex128 for _f64, complex64 for _f32 -- for the *_dev
+ * entry points; release it with caf_b200_dev_free.  A file that cannot be opened is CAF_B200_EIO (the reference returns
+ * io::Result Err, utils.rs:10); a trailing partial sample is CAF_B200_EINVAL (the reference's slice index panics). */
+int caf_b200_load_c64_dev_f64(caf_b200_handle h, const char* path, size_t first_sample, size_t max_samples,
+                              caf_c128** dev_out, size_t* n_out);
+int caf_b200_load_c64_dev_f32(caf_b200_handle h, const char* path, size_t first_sample, size_t max_samples,
+                              caf_c64** dev_out, size_t* n_out);
+int caf_b200_dev_free(void* dev_ptr);
+/* device memory for callers that do not link the CUDA runtime themselves (the Rust shim, the C++ mirror): what the *_dev
+ * entry points take and fill.  upload / download are synchronous on the handle's stream. */
+int caf_b200_dev_alloc(caf_b200_handle h, size_t bytes, void** dev_out);
+int caf_b200_dev_upload(caf_b200_handle h, void* dev_dst, const void* host_src, size_t bytes);
+int caf_b200_dev_download(caf_b200_handle h, void* host_dst, const void* dev_src, size_t bytes);
 
 /* ---- CafSurface::apply_freq_shift (mod.rs:46-65); README.md:124 calls it apply_shift ------------ */
 /* out[i] = in[i] * e^{+j 2 pi freq_hz i / fs}.  in == out allowed. */

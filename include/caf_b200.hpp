@@ -175,6 +175,13 @@ public:
 // [][]float64 of 2L columns, |xcor|, column k = Rust lag L - k; find_2d_peak (caf.go:183-195) is the first
 // strict-> maximum in row-major order; main.go:35 reports len(apple) - tdx.
 struct GoSibling {
+    // caf.go:118 takes a float64 sample rate, the C ABI the Rust crate's u32 (mod.rs:46): a rate the u32 cannot hold
+    // exactly would silently give a different phasor than the Go program, so it is refused
+    static uint32_t whole_sample_rate(double samp_rate) {
+        if (!(samp_rate >= 1.0 && samp_rate <= 4294967295.0) || samp_rate != (double)(uint64_t)samp_rate)
+            throw Panic("samp_rate must be a whole number of Hz in [1, 2^32 - 1] (the library's sample rate is the Rust crate's u32, mod.rs:46)");
+        return (uint32_t)samp_rate;
+    }
     static std::vector<std::vector<double>> amb_surf(const std::vector<Complex64>& needle, const std::vector<Complex64>& haystack,
                                                      const std::vector<double>& freqs_hz, double samp_rate) {
         if (needle.size() != haystack.size()) throw Panic("input arrays should be same size (caf.go:97-99)");
@@ -182,7 +189,7 @@ struct GoSibling {
         std::vector<double> flat(d * w);
         check(caf_b200_surface_layout_f64(thread_handle(), reinterpret_cast<const caf_c128*>(needle.data()),
                                           reinterpret_cast<const caf_c128*>(haystack.data()), l, freqs_hz.data(), d,
-                                          (uint32_t)(samp_rate + 0.5), CAF_B200_LAYOUT_GO, flat.data(), nullptr));
+                                          whole_sample_rate(samp_rate), CAF_B200_LAYOUT_GO, flat.data(), nullptr));
         std::vector<std::vector<double>> surf(d);
         for (std::size_t r = 0; r < d; ++r) surf[r].assign(flat.begin() + r * w, flat.begin() + (r + 1) * w);
         return surf;
@@ -243,6 +250,57 @@ inline std::vector<Complex64> read_file_c64(const std::string& filename) {
     const float* p = reinterpret_cast<const float*>(buf.data());
     for (std::size_t i = 0; i < out.size(); ++i) out[i] = Complex64((double)p[2 * i], (double)p[2 * i + 1]);
     return out;
+}
+
+// Samples resident on the GPU and the loader that puts them there: read_file_c64 (utils.rs:10-35) through pinned memory,
+// 8 bytes per sample across PCIe, widened on the device (bit-identical to the host loader).  window: first sample and
+// count (0 = to the end of the file; main.rs:15 truncates the haystack to the needle's length).
+class DeviceSamples {
+    caf_c128* p_ = nullptr;
+    std::size_t n_ = 0;
+public:
+    DeviceSamples() = default;
+    DeviceSamples(caf_c128* p, std::size_t n) : p_(p), n_(n) {}
+    DeviceSamples(const DeviceSamples&) = delete;
+    DeviceSamples& operator=(const DeviceSamples&) = delete;
+    DeviceSamples(DeviceSamples&& o) noexcept : p_(o.p_), n_(o.n_) { o.p_ = nullptr; o.n_ = 0; }
+    DeviceSamples& operator=(DeviceSamples&& o) noexcept { std::swap(p_, o.p_); std::swap(n_, o.n_); return *this; }
+    ~DeviceSamples() { if (p_) caf_b200_dev_free(p_); }
+    const caf_c128* data() const { return p_; }
+    std::size_t size() const { return n_; }
+    std::vector<Complex64> to_host() const {
+        std::vector<Complex64> out(n_);
+        check(caf_b200_dev_download(thread_handle(), out.data(), p_, n_ * sizeof(Complex64)));
+        return out;
+    }
+};
+inline DeviceSamples read_file_c64_dev(const std::string& filename, std::size_t first_sample = 0, std::size_t max_samples = 0) {
+    caf_c128* p = nullptr;
+    std::size_t n = 0;
+    const int rc = caf_b200_load_c64_dev_f64(thread_handle(), filename.c_str(), first_sample, max_samples, &p, &n);
+    if (rc == CAF_B200_EIO) throw std::runtime_error(std::string("read_file_c64: ") + caf_b200_last_error());   // io::Result Err
+    check(rc);
+    return DeviceSamples(p, n);
+}
+// caf_surface + find_peak on device-resident samples (caf_b200_batch_f64_dev): only the doppler grid goes up and the
+// 32-byte peak comes down
+inline std::pair<double, std::size_t> caf_peak_dev(const DeviceSamples& needle, const DeviceSamples& haystack,
+                                                   const std::vector<double>& freqs_hz, uint32_t fs) {
+    if (needle.size() != haystack.size()) throw Panic("assertion failed: a.len() == self.n (xcor_rustfft.rs:54-55)");
+    caf_b200_handle h = thread_handle();
+    void* scratch = nullptr;
+    const std::size_t fb = freqs_hz.size() * sizeof(double);
+    check(caf_b200_dev_alloc(h, fb + sizeof(caf_b200_peak), &scratch));
+    struct Free { void* p; ~Free() { if (p) caf_b200_dev_free(p); } } guard{scratch};
+    caf_b200_peak pk{0.0, 0.0, ~0ull, 0};
+    if (scratch) {
+        check(caf_b200_dev_upload(h, scratch, freqs_hz.data(), fb));
+        caf_b200_peak* d_pk = reinterpret_cast<caf_b200_peak*>(static_cast<char*>(scratch) + fb);
+        check(caf_b200_batch_f64_dev(h, needle.data(), haystack.data(), 1, needle.size(), static_cast<const double*>(scratch),
+                                     freqs_hz.size(), fs, nullptr, nullptr, nullptr, d_pk));
+        check(caf_b200_dev_download(h, &pk, d_pk, sizeof pk));
+    }
+    return {pk.freq_hz, (std::size_t)pk.delay_idx};
 }
 
 // utils.rs:39-63: raw little-endian f64 pairs (numpy complex128)

@@ -177,11 +177,13 @@ impl Drop for ShardedCaf {
 /// The Go program's surface (caf_go/caf.go:162-173): [d][2l] of |xcor|, column k = lag l - k.
 pub fn go_amb_surf(needle: &[Complex64], haystack: &[Complex64], freqs_hz: &[f64], samp_rate: f64) -> Vec<Vec<f64>> {
     assert!(needle.len() == haystack.len());
+    // caf.go:118 takes a float64 rate, the library the crate's u32 (mod.rs:46): refuse what the u32 cannot hold exactly
+    assert!(samp_rate >= 1.0 && samp_rate <= u32::MAX as f64 && samp_rate.fract() == 0.0, "samp_rate must be a whole number of Hz");
     let (l, d) = (needle.len(), freqs_hz.len());
     let mut flat = vec![0f64; d * 2 * l];
     ffi::HANDLE.with(|h| ffi::check(unsafe {
         ffi::caf_b200_surface_layout_f64(h.0, needle.as_ptr(), haystack.as_ptr(), l, freqs_hz.as_ptr(), d,
-                                         samp_rate.round() as u32, 2, flat.as_mut_ptr(), std::ptr::null_mut())
+                                         samp_rate as u32, 2, flat.as_mut_ptr(), std::ptr::null_mut())
     }));
     flat.chunks(2 * l).map(|r| r.to_vec()).collect()
 }

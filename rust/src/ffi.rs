@@ -37,6 +37,16 @@ extern "C" {
     pub fn caf_b200_surface_find_peak(s: caf_b200_surface, out: *mut caf_b200_peak) -> c_int;
     pub fn caf_b200_surface_fetch_rows(s: caf_b200_surface, row0: usize, count: usize, out: *mut c_void) -> c_int;
     pub fn caf_b200_surface_destroy(s: caf_b200_surface) -> c_int;
+    // read_file_c64 straight onto the device, and device memory for callers without a CUDA runtime of their own
+    pub fn caf_b200_load_c64_dev_f64(h: caf_b200_handle, path: *const c_char, first_sample: usize, max_samples: usize,
+                                     dev_out: *mut *mut Complex64, n_out: *mut usize) -> c_int;
+    pub fn caf_b200_dev_free(p: *mut c_void) -> c_int;
+    pub fn caf_b200_dev_alloc(h: caf_b200_handle, bytes: usize, dev_out: *mut *mut c_void) -> c_int;
+    pub fn caf_b200_dev_upload(h: caf_b200_handle, dev_dst: *mut c_void, host_src: *const c_void, bytes: usize) -> c_int;
+    pub fn caf_b200_dev_download(h: caf_b200_handle, host_dst: *mut c_void, dev_src: *const c_void, bytes: usize) -> c_int;
+    pub fn caf_b200_batch_f64_dev(h: caf_b200_handle, needles: *const Complex64, haystacks: *const Complex64, p: usize, l: usize,
+                                  freqs_hz: *const f64, d: usize, fs: u32, surface: *mut f64, row_peak_val: *mut f64,
+                                  row_peak_idx: *mut u64, peaks: *mut caf_b200_peak) -> c_int;
     pub fn caf_b200_host_alloc(out: *mut *mut c_void, bytes: usize) -> c_int;
     pub fn caf_b200_host_free(p: *mut c_void) -> c_int;
     // sibling layouts (caf_go / caf_python conventions): layout 1 = Python [d][l], 2 = Go [d][2l], |xcor|

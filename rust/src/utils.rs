@@ -33,3 +33,35 @@ impl BinaryIO for Vec<Complex64> {
         Ok(())
     }
 }
+
+/// Samples resident on the GPU: `read_file_c64` (caf_rust/src/utils.rs:10-35) through pinned memory straight onto the
+/// device -- 8 bytes per sample across PCIe, widened there, bit-identical to the host loader.
+pub struct DeviceSamples { ptr: *mut Complex64, len: usize }
+
+impl DeviceSamples {
+    pub fn len(&self) -> usize { self.len }
+    pub fn is_empty(&self) -> bool { self.len == 0 }
+    pub fn as_ptr(&self) -> *const Complex64 { self.ptr }
+    pub fn to_host(&self) -> Vec<Complex64> {
+        let mut out = vec![Complex64::new(0.0, 0.0); self.len];
+        crate::ffi::HANDLE.with(|h| crate::ffi::check(unsafe {
+            crate::ffi::caf_b200_dev_download(h.0, out.as_mut_ptr() as *mut _, self.ptr as *const _, self.len * 16)
+        }));
+        out
+    }
+}
+impl Drop for DeviceSamples {
+    fn drop(&mut self) { if !self.ptr.is_null() { unsafe { crate::ffi::caf_b200_dev_free(self.ptr as *mut _); } } }
+}
+
+/// `first_sample` / `max_samples` select a window of the file (0 = to its end; main.rs:15 truncates the haystack).
+pub fn read_file_c64_dev(filename: &str, first_sample: usize, max_samples: usize) -> io::Result<DeviceSamples> {
+    let path = std::ffi::CString::new(filename).map_err(|e| io::Error::new(io::ErrorKind::InvalidInput, e))?;
+    let (mut ptr, mut len) = (std::ptr::null_mut(), 0usize);
+    let rc = crate::ffi::HANDLE.with(|h| unsafe {
+        crate::ffi::caf_b200_load_c64_dev_f64(h.0, path.as_ptr(), first_sample, max_samples, &mut ptr, &mut len)
+    });
+    if rc == -8 { return Err(io::Error::new(io::ErrorKind::NotFound, "caf_b200: cannot open or read the sample file")); }
+    crate::ffi::check(rc);      // everything else panics, as the reference's slice index does on a partial sample
+    Ok(DeviceSamples { ptr, len })
+}

@@ -66,6 +66,11 @@ def test_cli_prints_what_main_rs_prints(tmp_path):
     res = subprocess.run([CLI, a, b], capture_output=True, text=True, timeout=120)
     assert res.returncode == 0, res.stderr
     assert res.stdout == "Frequency offset: 69.0Hz\nTime offset: 202 samples (4.208ms)\n"            # main.rs:29-31
+    # the same report with both files loaded through pinned memory straight onto the GPU (read_file_c64_dev, caf_peak_dev)
+    res = subprocess.run([CLI, a, b, "--device-load"], capture_output=True, text=True, timeout=120)
+    assert res.returncode == 0, res.stderr
+    assert res.stdout == "Frequency offset: 69.0Hz\nTime offset: 202 samples (4.208ms)\n"
+    assert subprocess.run([CLI, "/nonexistent_a", b, "--device-load"], capture_output=True, text=True, timeout=120).returncode == 1
     # a finer grid, as caf_rust/tests/test.rs uses, and the surface dumped the way caf.go:14-29 dumps it
     dump = str(tmp_path / "surf.bin")
     res = subprocess.run([CLI, a, b, "--fstep", "0.25", "--dump", dump], capture_output=True, text=True, timeout=120)

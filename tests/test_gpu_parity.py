@@ -197,6 +197,46 @@ def test_alternating_pairs_never_see_a_stale_haystack_spectrum():
         h.close()
 
 
+def test_device_loader_matches_read_file_c64(tmp_path):
+    """caf_b200_load_c64_dev_* (pinned direct-to-device loader) against the host loader
+    (utils.rs:10-35): same samples bit for bit, windows, complex64, error behaviour; and the *_dev entry point fed with the
+    loaded samples gives the host call's bits."""
+    from caf_cookoff_b200 import bench_shifts
+    a, b = os.path.join(DATA, "chirp_0_raw.c64"), os.path.join(DATA, "chirp_0_T+202samp_F+69.25Hz.c64")
+    host_a, host_b = caf.read_file_c64(a), caf.read_file_c64(b)
+    dev_a = caf.read_file_c64_dev(a)
+    assert dev_a.size == host_a.size and np.array_equal(dev_a.to_host(), host_a)
+    dev_b = caf.read_file_c64_dev(b, 0, host_a.size)                      # main.rs:15: haystack truncated to the needle
+    assert dev_b.size == host_a.size and np.array_equal(dev_b.to_host(), host_b[: host_a.size])
+    win = caf.read_file_c64_dev(b, 100, 50)
+    assert np.array_equal(win.to_host(), host_b[100:150])
+    assert caf.read_file_c64_dev(b, host_b.size + 5, 0).size == 0
+    f32 = caf.read_file_c64_dev(a, f32=True)
+    assert f32.to_host().dtype == np.complex64 and np.array_equal(f32.to_host(), host_a.astype(np.complex64))
+    with pytest.raises(caf.CafError) as ei:
+        caf.read_file_c64_dev(str(tmp_path / "missing.c64"))
+    assert ei.value.status == -8                                           # CAF_B200_EIO: io::Result Err in the reference
+    odd = tmp_path / "odd.c64"; odd.write_bytes(b"\0" * 12)
+    with pytest.raises(caf.CafError):
+        caf.read_file_c64_dev(str(odd))
+    # device-resident inputs through the *_dev entry point
+    lib = _lib.load(); h = api.default_handle()
+    shifts = bench_shifts(); D = shifts.size
+    scratch = C.c_void_p()
+    assert lib.caf_b200_dev_alloc(h.raw, D * 8 + 32 + D * 16, C.byref(scratch)) == 0
+    assert lib.caf_b200_dev_upload(h.raw, scratch, shifts.ctypes.data, D * 8) == 0
+    d_pk, d_rv, d_ri = scratch.value + D * 8, scratch.value + D * 8 + 32, scratch.value + D * 8 + 32 + D * 8
+    assert lib.caf_b200_batch_f64_dev(h.raw, dev_a.ptr, dev_b.ptr, 1, dev_a.size, scratch, D, FS, None, d_rv, d_ri, d_pk) == 0
+    pk = _lib.Peak(); rv = np.empty(D); ri = np.empty(D, dtype=np.uint64)
+    assert lib.caf_b200_dev_download(h.raw, C.byref(pk), d_pk, 32) == 0
+    assert lib.caf_b200_dev_download(h.raw, rv.ctypes.data, d_rv, D * 8) == 0 and lib.caf_b200_dev_download(h.raw, ri.ctypes.data, d_ri, D * 8) == 0
+    want = caf.surface_arrays(host_a, host_b[: host_a.size], shifts, FS, want_surface=False)
+    assert np.array_equal(ri, want[1]) and np.array_equal(rv, want[2])
+    assert (pk.value, pk.freq_hz, pk.doppler_idx, pk.delay_idx) == (want[3].value, want[3].freq_hz, want[3].doppler_idx, want[3].delay_idx)
+    assert (pk.freq_hz, int(pk.delay_idx)) == (69.0, 202)
+    lib.caf_b200_dev_free(scratch)
+
+
 def test_stress_bitwise_determinism_over_many_launches(chirp0):
     """compute-sanitizer is closed on this GPU pool (profiles/r02_sanitizer.txt), so the hand-rolled synchronisation of
     the row kernel -- named barriers per warp group, the mailbox mbarrier pair, the cross-CTA H publication flag, the

@@ -102,3 +102,16 @@ def test_peak_pack_resolve_matches_find_peak_model():
             assert (got.value, int(got.doppler_idx), int(got.delay_idx), got.freq_hz) == (best, brow, rows[brow][1], float(brow))
 
     check()
+
+
+def test_sibling_adapters_refuse_a_sample_rate_the_u32_cannot_hold():
+    """caf.py:28 / caf.go:118 take a float sample rate, the library takes the Rust crate's u32 (mod.rs:46).  Rounding a
+    fractional or sub-1 Hz rate would silently change the phasor: the adapters refuse it before any GPU work."""
+    from caf_cookoff_b200 import siblings
+    x = np.ones(8, dtype=np.complex128)
+    for bad in (47999.5, 0.25, 0.0, -48000.0, 2.0 ** 32, float("nan")):
+        with pytest.raises(ValueError):
+            siblings.PythonSibling.apply_fdoa(x, 1.0, bad)
+        with pytest.raises(ValueError):
+            siblings.PythonSibling.amb_surf(x, x, [0.0], bad)
+    assert siblings._whole_sample_rate(48000.0) == 48000 and siblings._whole_sample_rate(1) == 1

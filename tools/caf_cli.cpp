@@ -4,13 +4,15 @@
 // ("Use CLAP to take in two c64 files as arguments", main.rs:1-2).  This is that program with the arguments:
 //
 //   caf_cli NEEDLE.c64 HAYSTACK.c64 [--fmin HZ] [--fmax HZ] [--fstep HZ] [--fs HZ]
-//           [--layout rust|go|python] [--dump FILE] [--f32]
+//           [--layout rust|go|python] [--dump FILE] [--device-load]
 //
 // With no options it prints exactly what main.rs prints for the same two files:
 //     Frequency offset: 69.0Hz
 //     Time offset: 202 samples (4.208ms)
 // --dump writes the surface as row-major little-endian f64 (caf_go/caf.go:14-29 dump_surf); --layout picks the
 // sibling program's convention for the dump and for the reported delay (caf.go / caf.py, include/caf_b200.h).
+// --device-load reads both files through pinned memory straight onto the GPU (read_file_c64_dev): the samples never exist
+// as a widened Vec on the host.
 // Build: g++ -std=c++17 -O2 -Iinclude tools/caf_cli.cpp -Lcaf_cookoff_b200 -lcaf_b200 -Wl,-rpath,$PWD/caf_cookoff_b200
 #include <cstdio>
 #include <cstdlib>
@@ -27,6 +29,7 @@ int main(int argc, char** argv) {
     double fmin = -100.0, fmax = 100.0, fstep = 0.5;
     uint32_t fs = 48000;
     std::string layout = "rust", dump;
+    bool device_load = false;
     for (int i = 1; i < argc; ++i) {
         const std::string a = argv[i];
         auto need = [&](const char* what) -> const char* {
@@ -39,9 +42,10 @@ int main(int argc, char** argv) {
         else if (a == "--fs") fs = (uint32_t)std::atol(need("--fs"));
         else if (a == "--layout") layout = need("--layout");
         else if (a == "--dump") dump = need("--dump");
+        else if (a == "--device-load") device_load = true;
         else if (a == "-h" || a == "--help") {
             std::printf("usage: caf_cli NEEDLE.c64 HAYSTACK.c64 [--fmin HZ] [--fmax HZ] [--fstep HZ] [--fs HZ] "
-                        "[--layout rust|go|python] [--dump FILE]\n");
+                        "[--layout rust|go|python] [--dump FILE] [--device-load]\n");
             return 0;
         } else if (a.rfind("--", 0) == 0) { std::fprintf(stderr, "caf_cli: unknown option %s\n", a.c_str()); return 2; }
         else pos.push_back(a);
@@ -49,6 +53,14 @@ int main(int argc, char** argv) {
     if (pos.size() != 2) { std::fprintf(stderr, "caf_cli: expected NEEDLE.c64 HAYSTACK.c64 (see --help)\n"); return 2; }
     if (!(fstep > 0.0) || fs == 0) { std::fprintf(stderr, "caf_cli: --fstep and --fs must be positive\n"); return 2; }
     try {
+        if (device_load) {
+            if (layout != "rust" || !dump.empty()) { std::fprintf(stderr, "caf_cli: --device-load goes with the default report (no --layout / --dump)\n"); return 2; }
+            const auto needle_d = read_file_c64_dev(pos[0]);
+            const auto hay_d = read_file_c64_dev(pos[1], 0, needle_d.size());        // main.rs:15
+            const auto [freq, idx] = caf_peak_dev(needle_d, hay_d, gen_float_shifts(fmin, fmax, fstep), fs);
+            std::printf("Frequency offset: %.1fHz\nTime offset: %zu samples (%.3fms)\n", freq, idx, (double)idx / ((double)fs / 1e3));
+            return 0;
+        }
         auto needle = read_file_c64(pos[0]);
         auto haystack = read_file_c64(pos[1]);
         haystack.resize(needle.size());                                  // main.rs:15
