@@ -140,6 +140,7 @@ struct caf_b200_handle_s {
     const void* pull_src = nullptr;             // set by run_batch_host around ONE run_batch_dev call
     size_t pull_bytes = 0;
     bool allow_pull = true;                     // CAF_B200_PULL
+    int gather_ahead = 2;                       // two-level gather: L2 tile prefetch distance in blocks per SM (CAF_B200_GATHER_AHEAD, development)
     unsigned int* seq_ptr = nullptr;            // single-pair host calls: pinned word the fused find_peak signals (see run_batch_host)
     unsigned int seq_val = 0, seq_counter = 0;
     unsigned long long* pack_words = nullptr;   // sharded rows: find_peak also writes its result packed for the exchange
@@ -255,6 +256,35 @@ cudaError_t configure_fused() {
     return cudaFuncSetAttribute(caf::caf_large_gather2<T, RT, kFusedJ, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point query: no link-time dependency on libcuda
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn tensor_map_encoder() {
+    static EncodeTiledFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
+        return (EncodeTiledFn)p;
+    }();
+    return fn;
+}
+// The scratch buffer of a chunk as a 2-D tensor for the TMA engine: [units][4096 complex] seen as [units][8192 reals];
+// a box is `box_units` consecutive units x `j` positions (caf_large.cuh, Fused2).
+template <typename T>
+cudaError_t make_unit_map(CUtensorMap* tm, void* base, size_t units, int j, int box_units) {
+    EncodeTiledFn enc = tensor_map_encoder();
+    if (!enc) return cudaErrorNotSupported;
+    const cuuint64_t gdim[2] = {(cuuint64_t)(2 * caf::kL0), (cuuint64_t)units};
+    const cuuint64_t gstride[1] = {(cuuint64_t)(caf::kL0 * sizeof(caf::cx<T>))};
+    const cuuint32_t box[2] = {(cuuint32_t)(2 * j), (cuuint32_t)box_units};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = enc(tm, std::is_same<T, double>::value ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                           base, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
+}
+
 template <typename T>
 cudaError_t configure_all(int* occ) {
     cudaError_t e;
@@ -333,9 +363,18 @@ template <typename T, int RT, int J>
 cudaError_t launch_large_fused_rt(caf_b200_handle h, const caf::LargeArgs<T>& a, bool gather) {
     dim3 grid((unsigned)(caf::kL0 / J), (unsigned)a.rows);
     const size_t smem = sizeof(caf::cx<T>) * 2 * RT * 16 * J;
-    if (!gather) caf::caf_large_spread2<T, RT, J><<<grid, 16 * J, smem, h->stream>>>(a);
-    else if (a.cplx) caf::caf_large_gather2<T, RT, J, true><<<grid, 16 * J, smem, h->stream>>>(a);
-    else caf::caf_large_gather2<T, RT, J><<<grid, 16 * J, smem, h->stream>>>(a);
+    if (!gather) {
+        caf::caf_large_spread2<T, RT, J><<<grid, 16 * J, smem, h->stream>>>(a);
+    } else {
+        // the gather's tiles are prefetched into L2 by the TMA engine, `ahead` blocks ahead of the block that loads them
+        CUtensorMap tm;
+        const int box_units = 2 * RT * 16;
+        cudaError_t e = make_unit_map<T>(&tm, a.wbuf, (size_t)a.rows * box_units, J, box_units);
+        if (e != cudaSuccess) return e;
+        const int ahead = h->gather_ahead * h->sm_count;
+        if (a.cplx) caf::caf_large_gather2<T, RT, J, true><<<grid, 16 * J, smem, h->stream>>>(a, tm, ahead);
+        else caf::caf_large_gather2<T, RT, J><<<grid, 16 * J, smem, h->stream>>>(a, tm, ahead);
+    }
     h->launches++;
     return cudaGetLastError();
 }
@@ -405,7 +444,7 @@ int run_large_dev(caf_b200_handle h, const caf::cx<T>* needles, const caf::cx<T>
     }
     if (chunk < 1) chunk = 1;
     if (chunk > d) chunk = d;
-    if (chunk > 65535) chunk = 65535;                       // rows of a chunk are grid.y of the spread / gather launches
+    if (chunk > 65535) chunk = 65535;                       // rows of a chunk are grid.y of the one-level spread / gather launches
     const int nparts = two ? kL0 / kFusedJ : inner / 256;   // gather blocks per row (each leaves one partial maximum)
     CK(h->lwbuf.ensure(row_bytes * chunk));
     CK(h->lhtmp.ensure(row_bytes));
@@ -954,6 +993,7 @@ static int create_impl(int device, bool own_stream, void* cuda_stream, caf_b200_
     if (const char* e_ = getenv("CAF_B200_PIPELINE")) h->allow_pipeline = e_[0] != '0';
     if (const char* e_ = getenv("CAF_B200_PEAK_ZEROCOPY")) h->peak_zero_copy = e_[0] != '0';
     if (const char* e_ = getenv("CAF_B200_PULL")) h->allow_pull = e_[0] != '0';
+    if (const char* e_ = getenv("CAF_B200_GATHER_AHEAD")) h->gather_ahead = atoi(e_);
 
     if (!own_stream) { h->stream = (cudaStream_t)cuda_stream; h->own_stream = false; }   // 0 = legacy default stream
     else {

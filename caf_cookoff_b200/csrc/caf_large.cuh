@@ -15,6 +15,7 @@
 // buffers sized to stay inside the 126 MB L2 (rows are processed in chunks).  Reference semantics as in the small-row
 // kernel: xcor_rustfft.rs:51-78 per row, 1/N on the product.
 #pragma once
+#include <cuda.h>
 #include "caf_kernels.cuh"
 
 namespace caf {
@@ -396,10 +397,22 @@ __global__ void __launch_bounds__(16 * J, J == 16 ? 3 : J == 8 ? 6 : 1) caf_larg
     }
 }
 
+// `tmap` sees the scratch buffer as a 2-D tensor [units][8192 reals]; a block's tile is ONE box of it (2 RT 16 units x 2 J
+// reals).  The block does not load through it -- three resident blocks cannot spare a landing zone -- it PREFETCHES with
+// it: thread 0 issues one cp.async.bulk.prefetch.tensor for the tile of the block `ahead` positions later in launch order,
+// so that by the time that block runs its 16 loads per thread find the tile in L2 instead of HBM.
 template <typename T, int RT, int J, bool CPLX = false>
-__global__ void __launch_bounds__(16 * J, J == 16 ? 3 : J == 8 ? 6 : 1) caf_large_gather2(const LargeArgs<T> a) {
+__global__ void __launch_bounds__(16 * J, J == 16 ? 3 : J == 8 ? 6 : 1) caf_large_gather2(const LargeArgs<T> a, const __grid_constant__ CUtensorMap tmap, const int ahead) {
     using C = cx<T>;
     extern __shared__ __align__(16) unsigned char smem_raw2[];
+    if (threadIdx.x == 0 && ahead > 0) {
+        const long long q = (long long)blockIdx.y * gridDim.x + blockIdx.x + ahead;
+        if (q < (long long)gridDim.x * gridDim.y) {
+            const int prow = (int)(q / gridDim.x), pmt = (int)(q - (long long)prow * gridDim.x);
+            asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];\n"
+                         :: "l"(&tmap), "r"(pmt * J * 2), "r"(prow * 2 * RT * 16) : "memory");
+        }
+    }
     C* tile = reinterpret_cast<C*>(smem_raw2);                       // [r][s_top][k_mid][jj]
     __shared__ double sv[16];
     __shared__ int si[16];
