@@ -573,6 +573,12 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
     constexpr bool kUseTmem = (MODE == kSurface);   // H lives in TMEM and the needle in shared memory (the twiddle tables always do)
     T* const ndl_re = reinterpret_cast<T*>(smem_raw + SL::offNeedle);   // the current pair's needle, planar
     T* const ndl_im = ndl_re + kL0;
+    // (ncu: the 32 needle loads of a row take 2 x the ideal wavefronts -- a half-warp holds t = {0..7} + {16..23} of its
+    //  32-sample run, which fall on the same 16 banks: 84 % of the kernel's bank conflicts.  Flipping bit 3 of t by bit 4 in
+    //  the needle's index removes them; measured on one box: single surface flushed 46.3 -> 45.3 us, but back to back
+    //  37.85 -> 38.5 us and the batch instantiation's steady row 8.88 -> 9.46 us -- ptxas lands on a worse schedule at the
+    //  128-register limit.  Not applied.  Likewise a poll bound (trap after 2^26 rounds) on the two cross-CTA spins: +16 bytes
+    //  of stack and +0.4 .. 1.1 us per surface; co-residency of the grid is guaranteed by construction instead.)
 
     // ---- work split: contiguous ranges of (pair, row) items so a CTA changes pair as rarely as possible ----
     const int rows_per_pair = (MODE == kSurface) ? a.D : 1;
