@@ -284,6 +284,7 @@ def block_cfg3_sharded(ctx, d_total=4096, l=32768, steps=5):
     o = outp.cpu().numpy()
     got = (float(o.view(np.float64)[0]), float(o.view(np.float64)[1]), int(o[2]), int(o[3]))   # value, freq, row, delay
     remote_err = comm.remote_error()
+    p2p = comm.uses_p2p()
     # ---- the unsharded answer (and, at N > 1, the N = 1 time) on rank 0 --------------------------------------------
     n1_ms, ref = ms, got
     if ctx.world > 1:
@@ -321,7 +322,10 @@ def block_cfg3_sharded(ctx, d_total=4096, l=32768, steps=5):
     surf_bytes = d_total * n * 8
     return {
         "workload": f"cfg3: {d_total} doppler x {n} delay fp64 surface + peak, doppler rows sharded x{ctx.world} "
-                    f"(caf_b200_sharded_f64_dev: local rows + packed find_peak + ncclAllGather 32 B/rank + device resolve inside the step)",
+                    f"(caf_b200_sharded_f64_dev: local rows + packed find_peak + the 32 B/rank exchange inside the step: "
+                    + ("ONE kernel per rank posting into every peer's mailbox over NVLink peer memory and resolving)" if p2p
+                       else "ncclAllGather + device resolve)" if ctx.world > 1 else "world of one)"),
+        "peak_exchange": "p2p_mailbox_kernel" if p2p else "nccl_allgather",
         "scaling": "strong", "ms_per_step": ms, "cells_per_s": d_total * n / (ms * 1e-3), "steps": steps,
         "rows_per_gpu": d_loc, "launches_per_step": int(launches),
         "n1_ms_same_run": n1_ms, "efficiency_vs_n1": n1_ms / (ctx.world * ms),

@@ -126,6 +126,7 @@ SYMBOLS = {
     "caf_b200_peak_resolve_status": (_int, [C.POINTER(C.c_uint64), _sz, _PK]),
     "caf_b200_peak_allgather_async": (_int, [_vp, _vp, _vp, C.c_uint64, _vp]),
     "caf_b200_comm_remote_error": (_int, [_vp, C.POINTER(_int)]),
+    "caf_b200_comm_uses_p2p": (_int, [_vp, C.POINTER(_int)]),
     "caf_b200_sharded_f64_dev": (_int, [_vp, _vp, _vp, _vp, _sz, _vp, _sz, C.c_uint64, _u32, _vp, _vp, _vp, _vp]),
     "caf_b200_sharded_f32_dev": (_int, [_vp, _vp, _vp, _vp, _sz, _vp, _sz, C.c_uint64, _u32, _vp, _vp, _vp, _vp]),
 }

@@ -112,6 +112,14 @@ struct caf_b200_comm_s {
     unsigned long long* recv = nullptr;   // device: 4 * world words
     unsigned long long* host = nullptr;   // pinned: 4 * world words
     int* status = nullptr;                // pinned, device-addressable: 1 when a peer reported a failure in the last exchange
+    // find_peak across ranks over NVLink peer memory (caf_peak_exchange_kernel): this rank's mailbox, mapped by every peer
+    // through CUDA IPC, and the peers' mailboxes mapped here.  p2p is false (NCCL all-gather instead) when any rank could
+    // not map any peer, or with CAF_B200_P2P=0.
+    bool p2p = false;
+    unsigned long long* mail = nullptr;           // device: [2][world][8] words
+    unsigned long long** peer_mail = nullptr;     // device: [world] pointers (own entry = mail)
+    std::vector<void*> opened;                    // IPC mappings to close
+    unsigned long long p2p_epoch = 0;
 };
 
 struct caf_b200_handle_s {
@@ -1389,6 +1397,59 @@ int caf_b200_comm_unique_id(unsigned char id[CAF_B200_NCCL_ID_BYTES]) {
     return CAF_B200_OK;
 }
 
+// Map every peer's mailbox (one NCCL all-gather of the IPC handles, one of the outcomes: either every rank has every peer
+// mapped or all fall back to the NCCL exchange).  Collective: every rank of the communicator runs it, in comm_finish.
+static void setup_p2p(caf_b200_comm c) {
+    c->p2p = false;
+    if (c->world < 2) return;
+    bool want = true;
+    if (const char* e_ = getenv("CAF_B200_P2P")) want = e_[0] != '0';
+    cudaStream_t s = c->h->stream;
+    const size_t W = (size_t)c->world;
+    struct Rec { cudaIpcMemHandle_t hd; unsigned long long ok; };
+    static_assert(sizeof(Rec) % 8 == 0, "record is sent as u64 words");
+    Rec mine{}; mine.ok = 0;
+    if (want && cudaMalloc(&c->mail, 2 * W * 8 * 8) == cudaSuccess && cudaMemset(c->mail, 0, 2 * W * 8 * 8) == cudaSuccess &&
+        cudaIpcGetMemHandle(&mine.hd, c->mail) == cudaSuccess) mine.ok = 1;
+    (void)cudaGetLastError();
+    // the exchange of handles is itself collective: every rank takes part whatever its local outcome
+    void* d_send = nullptr; void* d_recv = nullptr;
+    std::vector<Rec> all(W);
+    bool moved = cudaMalloc(&d_send, sizeof(Rec)) == cudaSuccess && cudaMalloc(&d_recv, sizeof(Rec) * W) == cudaSuccess &&
+                 cudaMemcpyAsync(d_send, &mine, sizeof(Rec), cudaMemcpyHostToDevice, s) == cudaSuccess &&
+                 nccl_api().AllGather(d_send, d_recv, sizeof(Rec) / 8, kNcclUint64, c->comm, s) == 0 &&
+                 cudaMemcpyAsync(all.data(), d_recv, sizeof(Rec) * W, cudaMemcpyDeviceToHost, s) == cudaSuccess &&
+                 cudaStreamSynchronize(s) == cudaSuccess;
+    unsigned long long good = moved ? 1ull : 0ull;
+    for (size_t r = 0; good && r < W; ++r) good = all[r].ok;
+    std::vector<unsigned long long*> peers(W, nullptr);
+    for (size_t r = 0; good && r < W; ++r) {
+        if ((int)r == c->rank) { peers[r] = c->mail; continue; }
+        void* p = nullptr;
+        if (cudaIpcOpenMemHandle(&p, all[r].hd, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { good = 0; (void)cudaGetLastError(); break; }
+        c->opened.push_back(p);
+        peers[r] = (unsigned long long*)p;
+    }
+    if (good && (cudaMalloc(&c->peer_mail, sizeof(void*) * W) != cudaSuccess ||
+                 cudaMemcpy(c->peer_mail, peers.data(), sizeof(void*) * W, cudaMemcpyHostToDevice) != cudaSuccess)) good = 0;
+    // second round: everybody mapped everybody?
+    unsigned long long verdict = 0;
+    if (moved) {
+        std::vector<unsigned long long> oks(W, 0ull);
+        if (cudaMemcpyAsync(d_send, &good, 8, cudaMemcpyHostToDevice, s) == cudaSuccess &&
+            nccl_api().AllGather(d_send, d_recv, 1, kNcclUint64, c->comm, s) == 0 &&
+            cudaMemcpyAsync(oks.data(), d_recv, 8 * W, cudaMemcpyDeviceToHost, s) == cudaSuccess &&
+            cudaStreamSynchronize(s) == cudaSuccess) {
+            verdict = 1;
+            for (size_t r = 0; r < W; ++r) verdict &= oks[r];
+        }
+    }
+    if (d_send) cudaFree(d_send);
+    if (d_recv) cudaFree(d_recv);
+    (void)cudaGetLastError();
+    c->p2p = verdict != 0;
+}
+
 static int comm_finish(caf_b200_comm c, caf_b200_comm* out) {
     cudaError_t e;
     if ((e = cudaMalloc(&c->send, 8 * 4)) != cudaSuccess || (e = cudaMalloc(&c->recv, 8 * 4 * (size_t)c->world)) != cudaSuccess ||
@@ -1398,6 +1459,7 @@ static int comm_finish(caf_b200_comm c, caf_b200_comm* out) {
         return fail(CAF_B200_ECUDA, std::string("communicator buffers: ") + cudaGetErrorString(e));
     }
     *c->status = 0;
+    setup_p2p(c);
     *out = c;
     return CAF_B200_OK;
 }
@@ -1434,6 +1496,9 @@ int caf_b200_comm_adopt(caf_b200_handle h, void* nccl_comm, int world, int rank,
 int caf_b200_comm_destroy(caf_b200_comm c) {
     if (!c) return CAF_B200_OK;
     cudaSetDevice(c->device);             // the handle may already be gone: the communicator remembers its own device
+    for (void* p : c->opened) cudaIpcCloseMemHandle(p);
+    if (c->peer_mail) cudaFree(c->peer_mail);
+    if (c->mail) cudaFree(c->mail);
     if (c->send) cudaFree(c->send);
     if (c->recv) cudaFree(c->recv);
     if (c->host) cudaFreeHost(c->host);
@@ -1447,6 +1512,12 @@ int caf_b200_comm_shard(caf_b200_comm c, size_t n, size_t* lo, size_t* hi) {
     if (!c || !lo || !hi) return fail(CAF_B200_EINVAL, "null argument");
     *lo = n * (size_t)c->rank / (size_t)c->world;
     *hi = n * ((size_t)c->rank + 1) / (size_t)c->world;
+    return CAF_B200_OK;
+}
+
+int caf_b200_comm_uses_p2p(caf_b200_comm c, int* flag) {
+    if (!c || !flag) return fail(CAF_B200_EINVAL, "null argument");
+    *flag = c->p2p ? 1 : 0;
     return CAF_B200_OK;
 }
 
@@ -1466,6 +1537,14 @@ int check_comm(caf_b200_handle h, caf_b200_comm c) {
 // c->send holds this rank's packed words (device): all-gather them and resolve on the DEVICE into out_dev (device or
 // pinned host memory).  Everything is stream-ordered; nothing waits on the host.
 int exchange_async(caf_b200_handle h, caf_b200_comm c, caf_b200_peak* out_dev) {
+    if (c->p2p) {
+        // one kernel: post to every peer's mailbox over NVLink, collect the world's records, resolve
+        caf::caf_peak_exchange_kernel<<<1, 32, 0, h->stream>>>(c->send, c->peer_mail, c->mail, c->world, c->rank, ++c->p2p_epoch,
+                                                               (caf::PeakOut*)out_dev, c->status);
+        h->launches++;
+        CK(cudaGetLastError());
+        return CAF_B200_OK;
+    }
     CKN(nccl_api().AllGather(c->send, c->recv, 4, kNcclUint64, c->comm, h->stream));
     caf::caf_peak_resolve_kernel<<<1, 32, 0, h->stream>>>(c->recv, c->world, (caf::PeakOut*)out_dev, c->status);
     h->launches++;
@@ -1476,8 +1555,17 @@ int exchange_async(caf_b200_handle h, caf_b200_comm c, caf_b200_peak* out_dev) {
 int post_failure_and_exchange(caf_b200_handle h, caf_b200_comm c) {
     const unsigned long long w[4] = {0ull, caf::kPeakRemoteError, 0ull, 0ull};
     if (cudaMemcpyAsync(c->send, w, sizeof w, cudaMemcpyHostToDevice, h->stream) != cudaSuccess) return CAF_B200_ECUDA;
-    if (nccl_api().AllGather(c->send, c->recv, 4, kNcclUint64, c->comm, h->stream) != 0) return CAF_B200_ENCCL;
+    const int rc = exchange_async(h, c, reinterpret_cast<caf_b200_peak*>(c->host));     // the same transport the healthy ranks use
     cudaStreamSynchronize(h->stream);
+    return rc;
+}
+// c->send -> the world's resolved peak on the HOST (through the pinned block c->host), whichever transport is in use
+int exchange_sync(caf_b200_handle h, caf_b200_comm c, caf_b200_peak* out) {
+    int rc = exchange_async(h, c, reinterpret_cast<caf_b200_peak*>(c->host));
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(h->stream));
+    to_public(*reinterpret_cast<const caf::PeakOut*>(c->host), out);
+    if (*c->status) return fail(CAF_B200_EREMOTE, "a peer rank failed before the peak exchange");
     return CAF_B200_OK;
 }
 }  // namespace
@@ -1504,12 +1592,7 @@ int caf_b200_peak_allgather_dev(caf_b200_handle h, caf_b200_comm c, const caf_b2
     caf::caf_peak_pack_kernel<<<1, 32, 0, h->stream>>>((const caf::PeakOut*)local_dev, (unsigned long long)global_row_offset, c->send);
     h->launches++;
     CK(cudaGetLastError());
-    CKN(nccl_api().AllGather(c->send, c->recv, 4, kNcclUint64, c->comm, h->stream));
-    CK(cudaMemcpyAsync(c->host, c->recv, 8 * 4 * (size_t)c->world, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
-    if (caf_b200_peak_resolve_status((const uint64_t*)c->host, (size_t)c->world, out))
-        return fail(CAF_B200_EREMOTE, "a peer rank failed before the peak exchange");
-    return CAF_B200_OK;
+    return exchange_sync(h, c, out);
 }
 
 extern "C++" {
@@ -1561,12 +1644,7 @@ int run_sharded(caf_b200_handle h, caf_b200_comm c, const caf::cx<T>* needle, co
     uint64_t words[4];
     caf_b200_peak_pack(&local, lo, words);
     CK(cudaMemcpyAsync(c->send, words, sizeof words, cudaMemcpyHostToDevice, h->stream));
-    CKN(nccl_api().AllGather(c->send, c->recv, 4, kNcclUint64, c->comm, h->stream));
-    CK(cudaMemcpyAsync(c->host, c->recv, 8 * 4 * (size_t)c->world, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
-    if (caf_b200_peak_resolve_status((const uint64_t*)c->host, (size_t)c->world, peak))
-        return fail(CAF_B200_EREMOTE, "a peer rank failed before the peak exchange");
-    return CAF_B200_OK;
+    return exchange_sync(h, c, peak);
 }
 }  // namespace
 }  // extern "C++"

@@ -1197,6 +1197,63 @@ __global__ void caf_peak_resolve_kernel(const unsigned long long* __restrict__ w
     if (status) *status = st;
 }
 
+// find_peak across ranks in ONE kernel over NVLink peer memory (mod.rs:31-42 over rows that live on several GPUs).
+// Every rank owns a mailbox [2 parities][world sources][8 words] that all peers have mapped (CUDA IPC); lane s of the one
+// warp stores this rank's four packed words into peer s's mailbox -- a peer-to-peer store through NVSwitch -- then a
+// sequence tag with release at system scope; then lane s acquire-polls the tag of source s in this rank's own mailbox,
+// reads its words, and the warp folds the world's records exactly as caf_peak_resolve_kernel does (largest value, ties to
+// the lowest global doppler row).  Replaces ncclAllGather (one more kernel, ~10 us of protocol latency) + the resolve
+// kernel.  Two parities suffice: a rank reaches exchange e + 1 only after it has read every peer's record of exchange e,
+// which every peer posted after it had finished reading exchange e - 1.  A peer that never posts (a crashed process)
+// turns into status 1 after ~2^27 polls instead of a hang.
+__global__ void caf_peak_exchange_kernel(const unsigned long long* __restrict__ send, unsigned long long* const* __restrict__ peer_mail,
+                                         unsigned long long* mail, int world, int rank, unsigned long long epoch,
+                                         PeakOut* out, int* __restrict__ status) {
+    const int lane = threadIdx.x;
+    const size_t par = (size_t)(epoch & 1ull);
+    const unsigned long long w0 = send[0], w1 = send[1], w2 = send[2], w3 = send[3];
+    for (int s = lane; s < world; s += 32) {
+        unsigned long long* dst = peer_mail[s] + (par * world + rank) * 8;
+        asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};\n" :: "l"(dst), "l"(w0), "l"(w1) : "memory");
+        asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};\n" :: "l"(dst + 2), "l"(w2), "l"(w3) : "memory");
+        __threadfence_system();
+        asm volatile("st.release.sys.global.u64 [%0], %1;\n" :: "l"(dst + 4), "l"(epoch) : "memory");
+    }
+    double bv = 0.0, bf = 0.0;
+    unsigned long long brow = ~0ull, bdel = 0ull;
+    int st = 0;
+    for (int s = lane; s < world; s += 32) {
+        const unsigned long long* src = mail + (par * world + s) * 8;
+        unsigned long long tag = 0ull;
+        unsigned int polls = 0;
+        for (;;) {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];\n" : "=l"(tag) : "l"(src + 4) : "memory");
+            if (tag == epoch) break;
+            if (++polls == (1u << 27)) { st = 1; break; }
+        }
+        if (tag != epoch) continue;
+        unsigned long long r0, r1, r2, r3;
+        asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];\n" : "=l"(r0), "=l"(r1) : "l"(src) : "memory");
+        asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];\n" : "=l"(r2), "=l"(r3) : "l"(src + 2) : "memory");
+        if (r1 == kPeakRemoteError) { st = 1; continue; }
+        if (r1 == kPeakNone) continue;
+        const double v = __longlong_as_double((long long)r0);
+        if (v > bv || (v == bv && v > 0.0 && r1 < brow)) { bv = v; bf = __longlong_as_double((long long)r3); brow = r1; bdel = r2; }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, bv, off), of = __shfl_xor_sync(0xffffffffu, bf, off);
+        const unsigned long long orow = __shfl_xor_sync(0xffffffffu, brow, off), odel = __shfl_xor_sync(0xffffffffu, bdel, off);
+        st |= __shfl_xor_sync(0xffffffffu, st, off);
+        if (ov > bv || (ov == bv && ov > 0.0 && orow < brow)) { bv = ov; bf = of; brow = orow; bdel = odel; }
+    }
+    if (lane == 0) {
+        PeakOut best; best.value = bv; best.freq_hz = bf; best.doppler_idx = brow; best.delay_idx = bdel;
+        *out = best;
+        if (status) *status = st;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Sibling-program layouts of one surface.  The Go and Python programs of the reference
 // compute the same correlation with the operands swapped and store |.| instead of |.|^2:

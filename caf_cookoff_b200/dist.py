@@ -227,6 +227,13 @@ class Comm:
         _check(fn(self.handle.raw, self._c, vp(needle_dev), vp(hay_dev), int(l), vp(freqs_local_dev), int(d_local),
                   int(row_offset), int(fs), vp(surface_local_dev), vp(row_val_dev), vp(row_idx_dev), vp(peak_out_dev)))
 
+    def uses_p2p(self) -> bool:
+        """True when the exchange is the one-kernel peer-memory mailbox (NVLink), False when it is ncclAllGather."""
+        import ctypes as C
+        flag = C.c_int()
+        _check(self._lib.caf_b200_comm_uses_p2p(self._c, C.byref(flag)))
+        return bool(flag.value)
+
     def remote_error(self) -> bool:
         """After a synchronise: did a peer report a failure in the last exchange?"""
         import ctypes as C

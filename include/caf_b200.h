@@ -27,6 +27,7 @@
  *    CAF_B200_PEAK_ZEROCOPY=0  single-pair host calls: copy the peak back instead of storing it into pinned host memory
  *    CAF_B200_PULL=0         single-pair host calls: one H2D copy in front of the kernel instead of the kernel's own CTAs
  *                            reading the pinned input block across PCIe
+ *    CAF_B200_P2P=0          cross-rank find_peak by ncclAllGather instead of the peer-memory mailbox kernel (read at comm creation)
  *    CAF_B200_NCCL_LIB=<so>  which libnccl to dlopen for caf_b200_comm_* (default: the loaded one, then libnccl.so.2)
  *
  * Sizes.  l = samples per input signal (needle and haystack must be equal length, as the reference's
@@ -251,6 +252,12 @@ int caf_b200_peak_allgather_dev(caf_b200_handle h, caf_b200_comm c, const caf_b2
 int caf_b200_peak_allgather_async(caf_b200_handle h, caf_b200_comm c, const caf_b200_peak* local_peak_dev,
                                   uint64_t global_row_offset, caf_b200_peak* out_dev);
 int caf_b200_comm_remote_error(caf_b200_comm c, int* flag);
+/* Transport of the 32-byte exchange.  When every rank of the communicator could map every peer's mailbox at creation (CUDA
+ * IPC over NVLink / NVSwitch peer memory; the handles travel in one ncclAllGather), the exchange is ONE kernel per rank:
+ * it stores this rank's packed words straight into every peer's mailbox, acquire-polls its own mailbox for the world's
+ * records and resolves them (caf_peak_exchange_kernel) -- flag = 1.  Otherwise, or with CAF_B200_P2P=0 in the environment
+ * at creation, ncclAllGather + a resolve kernel -- flag = 0.  Same results either way. */
+int caf_b200_comm_uses_p2p(caf_b200_comm c, int* flag);
 /* Device-resident sharded surface (mod.rs:185 par_iter over rows + mod.rs:31-42 across GPUs), fully asynchronous:
  * this rank's rows freqs_local[0..d_local) are global rows row_offset.., every pointer is device memory; the local
  * find_peak writes its result already packed for the exchange, then ONE ncclAllGather of 32 bytes per rank and a
