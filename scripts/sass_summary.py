@@ -1,6 +1,6 @@
 """Per-kernel SASS evidence for profiles/: registers, spill bytes, shared memory (cuobjdump --dump-resource-usage) and
 the counts of the opcodes that say what a kernel is made of -- fp64 / fp32 arithmetic, tensor-memory traffic
-(LDTM / STTM / UTCATOMSWS = tcgen05.ld / .st / .alloc), TMA (UTMALDG / UTMASTG / UBLKCP), tensor-core MMA (UTC*MMA), local
+(LDTM / STTM / UTCATOMSWS = tcgen05.ld / .st / .alloc), TMA (UTMALDG / UTMASTG / UTMAPF = cp.async.bulk.prefetch.tensor / UBLKCP), tensor-core MMA (UTC*MMA), local
 memory (LDL / STL = spills), shared and global memory instructions.
     python scripts/sass_summary.py [path/to/libcaf_b200.so] > profiles/r02_sass_summary.txt
 Needs no GPU."""
@@ -31,7 +31,7 @@ for line in sass.splitlines():
     m = re.match(r"\s+/\*[0-9a-f]{4,}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_]+)", line)
     if m and cur:
         kern[cur][m.group(1)] += 1
-cols = ["DFMA", "DADD", "DMUL", "FFMA", "FFMA2", "FADD2", "LDTM", "STTM", "UTCATOMSWS", "UTMALDG", "UTMASTG", "UBLKCP", "UTCHMMA",
+cols = ["DFMA", "DADD", "DMUL", "FFMA", "FFMA2", "FADD2", "LDTM", "STTM", "UTCATOMSWS", "UTMALDG", "UTMASTG", "UTMAPF", "UBLKCP", "UTCHMMA",
         "LDS", "STS", "LDG", "STG", "LDL", "STL", "BAR", "SYNCS", "SHFL"]
 demangle = lambda n: subprocess.run(["c++filt", n], capture_output=True, text=True).stdout.strip()
 print(f"# SASS summary of {os.path.relpath(so, ROOT)}: arch = {sorted(arch)}, {len(kern)} kernels (static instruction counts)")
