@@ -620,6 +620,10 @@ def run_b200(args):
         if rc != 0:
             raise RuntimeError(lib.caf_b200_last_error().decode())
 
+    # consecutive steps touch disjoint buffers and nothing else is enqueued between them, which is what the library's
+    # overlap switch asks of a caller: a launch may then start on the SMs its predecessor has already left (the same
+    # rotation with the launches serialised is timed right after the headline: `launches_serialised`)
+    lib.caf_b200_set_overlap(h.raw, 1)
     warm = max(args.warmup, 3)
     for k in range(warm):
         step_rot(k)
@@ -645,6 +649,21 @@ def run_b200(args):
     cells_step = D * N
     value = world * cells_step * args.steps / (total_ms_max * 1e-3)
     step_ms = total_ms_max / args.steps
+    # the same K steps with every launch waiting for the one before it (round 2's figure before the overlap existed)
+    lib.caf_b200_set_overlap(h.raw, 0)
+    for k in range(warm):
+        step_rot(k)
+    barrier()
+    s0_ = torch.cuda.Event(enable_timing=True); s1_ = torch.cuda.Event(enable_timing=True)
+    s0_.record(stream)
+    for k in range(warm, warm + args.steps):
+        step_rot(k)
+    s1_.record(stream)
+    barrier()
+    ts_ = torch.tensor([float(s0_.elapsed_time(s1_))], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ts_, op=dist.ReduceOp.MAX)
+    serial_ms = float(ts_.item()) / args.steps
 
     # correctness of what was just timed (asserted below: a wrong peak marks the line check_ok = false and the process
     # exits non-zero): every pair that ran sits on its planted lag, on a doppler bin next to the planted offset; the
@@ -707,6 +726,10 @@ def run_b200(args):
                 "peak_source": "MEASURED_PEAKS.json (measured)" if mp else "fallback 6650 GB/s"},
         "step_share": {"spectrum_ms": 0.0, "rows_ms": rows_avg_ms, "peak_ms": 0.0,
                        "note": "one fused launch per step: FFT(s1), the rows and find_peak are the same kernel"},
+        "kernel_ms_note": "the timed region holds K launches of this kernel and nothing else: kernel_ms = region / K.  Consecutive launches "
+                          "overlap (launch k+1 starts on the SMs launch k has left), so this is a launch's SHARE of the region, not its latency; "
+                          "launches_serialised is the same figure with every launch waiting for the one before it",
+        "launches_serialised": {"kernel_ms": serial_ms, "frac": row_flops / (serial_ms * 1e-3) / 1e12 / tf.value if tf.value else None},
         "flushed_per_step": {"kernel_ms": rows_flushed_ms, "frac": row_flops / (rows_flushed_ms * 1e-3) / 1e12 / tf.value if tf.value else None,
                              "note": "the same kernel timed alone by CUDA events inside the library, L2 flushed before every launch (round 1's figure)"},
     }
@@ -883,6 +906,9 @@ def run_b200(args):
                        "doppler_rows": D, "delay_cells": N, "pairs_per_step_per_gpu": 1,
                        "l2": "working set larger than L2: the steps rotate over 320 seeded pairs and 8 surface buffers (252 MB); one CUDA "
                              "event pair around the K back-to-back steps (flushed_per_step = round 1's method, beside it)",
+                       "launch_overlap": "caf_b200_set_overlap(1): a step touches no buffer of the two steps before it, so its launch does not "
+                                         "wait for the previous grid (its CTAs start on the SMs that grid has left); launches_serialised = the same "
+                                         "rotation with overlap off",
                        "pairs_in_rotation": n_pairs, "surface_buffers": n_surf,
                        "parallelism": f"pairs sharded x{world}, no data-path collective",
                        "host_cpus_bound_to_gpu": numa},
@@ -893,6 +919,8 @@ def run_b200(args):
             "e2e_peak_only": e2e_peak, "e2e_peak_only_pageable": e2e_peak_pageable, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
             "flushed_per_step": {"ms_per_step": flushed_ms, "cells_per_s": world * cells_step / (flushed_ms * 1e-3), "steps": fl_steps,
                                  "method": "L2 flushed (256 MiB overwrite) before every step, one CUDA event pair per step, summed"},
+            "launches_serialised": {"ms_per_step": serial_ms, "cells_per_s": world * cells_step / (serial_ms * 1e-3), "steps": args.steps,
+                                    "method": "the headline's rotation with caf_b200_set_overlap(0): every launch waits for the one before it"},
             "sharded": sharded, **extra,
             "clocks": sampler.summary(),
             "check": {"peak_freq_hz": peak_freq, "peak_delay": peak_delay, "checks": checks},

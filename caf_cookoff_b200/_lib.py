@@ -78,6 +78,7 @@ SYMBOLS = {
     "caf_b200_last_error": (C.c_char_p, []),
     "caf_b200_version": (C.c_char_p, []),
     "caf_b200_launch_count": (C.c_uint64, [_vp]),
+    "caf_b200_set_overlap": (_int, [_vp, _int]),
     "caf_b200_set_profiling": (_int, [_vp, _int]),
     "caf_b200_last_kernel_ms": (_int, [_vp, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "caf_b200_probe_fma_tflops": (_int, [_vp, _int, C.POINTER(C.c_double)]),

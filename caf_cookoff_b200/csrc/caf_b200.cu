@@ -138,9 +138,18 @@ struct caf_b200_handle_s {
     size_t h_stage_cap = 0;
     DevBuf lwbuf, lhtmp, lhbig, lpart;      // long-row path: chunk scratch, scratch of the H transform, H, partial row maxima
     long long* trace = nullptr;   // CAF_TRACE builds: device buffer for phase stamps
-    unsigned int* done_counter = nullptr;   // last-CTA-done ticket of the fused find_peak
-    void* hshare = nullptr;                 // single-pair launches: H published by CTA 0 (8192 complex128)
-    unsigned int* hflag = nullptr;          // [2] publish counters, monotonic
+    unsigned int* done_counter = nullptr;   // [2] last-CTA-done tickets of the fused find_peak, one per launch parity
+    void* hshare = nullptr;                 // single-pair launches: H published by CTA 0 (2 x 8192 complex128, one per launch parity)
+    unsigned int* hflag = nullptr;          // [2 parities][2] publish counters, monotonic
+    // Overlap of consecutive single-pair surface launches (RowArgs::flags bit 0).  A launch whose buffers are disjoint from
+    // the previous launch's does not wait for it; the launch-private state above is double-buffered by launch parity (a
+    // third launch cannot start before the first has completed: it needs every CTA of the second to be resident).
+    bool overlap_ok = false;                // caf_b200_set_overlap: opt-in, the caller's promise (include/caf_b200.h)
+    struct Range { const char* p; size_t n; };
+    Range prev_in[2][3] = {}, prev_out[2][6] = {};   // buffers of the previous two overlappable launches ([0] = the latest)
+    int prev_valid = 0;                              // how many of them are valid (consecutive, full-grid launches)
+    unsigned long long prev_launch_no = ~0ull;       // value of `launches` right after the previous overlappable launch
+    unsigned int done_total[2] = {0u, 0u};        // tickets drawn so far from done_counter[parity]
     unsigned int epoch = 0;
     // small single-pair host calls: the kernel pulls its inputs out of pinned host memory itself (RowArgs::pull_*)
     unsigned int* pull_counter = nullptr;       // device word the grid meets on, monotonic
@@ -559,12 +568,15 @@ int run_batch_dev(caf_b200_handle h, const caf::cx<T>* needles, const caf::cx<T>
         a.peak_seq = h->seq_ptr; a.seq_val = h->seq_val;
     }
     if (p == 1 && d > 1) {                        // one pair over many CTAs: CTA 0 publishes H, the rest consume it
-        a.hshare = reinterpret_cast<cx<T>*>(h->hshare); a.hflag = h->hflag; a.epoch = ++h->epoch;
+        a.epoch = ++h->epoch;
+        const unsigned int par = a.epoch & 1u;
+        a.hshare = reinterpret_cast<cx<T>*>(reinterpret_cast<double2*>(h->hshare) + (size_t)par * caf::kM); a.hflag = h->hflag + 2 * par;
         // H_1's publisher: the lowest-index CTA other than 0 that owns the fewest rows (same split as the kernel)
         const long long n_items = (long long)d;
         const int occ = std::is_same<T, double>::value ? h->occ_d : h->occ_f;
         const long long cap = (long long)h->sm_count * occ;
         const long long grid = n_items < cap ? n_items : cap;
+        if (fused_peak) { a.done_counter = h->done_counter + par; a.done_last = h->done_total[par] + (unsigned int)grid - 1u; }
         a.hprod1 = 0;
         long long best = -1;
         for (long long b = 1; b < grid; ++b) {
@@ -587,9 +599,54 @@ int run_batch_dev(caf_b200_handle h, const caf::cx<T>* needles, const caf::cx<T>
         CK(cudaEventRecord(h->ev[1], h->stream));
     }
     // one fused launch: per pair FFT(s1) -> TMEM, then per row shift -> FFT -> xH -> IFFT -> |.|^2 -> argmax
+    // ---- may this launch overlap its predecessor?  Only a single-pair device launch that fills the GPU (one CTA per SM),
+    //      directly behind another such launch (no other library launch in between), with every buffer disjoint from
+    //      those of the previous TWO launches wherever one side writes.  Two, because that is how far the overlap reaches:
+    //      launch k's CTAs can be placed only once every CTA of k-1 has started (launch_dependents at entry), which on a
+    //      full grid means every CTA of k-2 has exited; everything older issued its last store more than a launch ago. ----
+    caf_b200_handle_s::Range cur_in[3] = {}, cur_out[6] = {};
+    bool overlappable = false;
+    {
+        const int occ_ = std::is_same<T, double>::value ? h->occ_d : h->occ_f;
+        const bool full_grid = (long long)p * (long long)d >= (long long)h->sm_count * occ_;
+        if (p == 1 && d > 1 && full_grid && h->overlap_ok && !a.pull_src && !a.peak_seq && !prof) {
+            overlappable = true;
+            cur_in[0] = {(const char*)needles, sizeof(cx<T>) * l}; cur_in[1] = {(const char*)hays, sizeof(cx<T>) * l};
+            cur_in[2] = {(const char*)freqs, sizeof(double) * d};
+            cur_out[0] = {(const char*)surface, surface ? sizeof(T) * d * 2 * l : 0};
+            cur_out[1] = {(const char*)rv, rv ? sizeof(T) * d : 0}; cur_out[2] = {(const char*)ri, ri ? sizeof(unsigned long long) * d : 0};
+            cur_out[3] = {(const char*)peaks, peaks ? sizeof(PeakOut) : 0};
+            cur_out[4] = {(const char*)h->pack_words, h->pack_words ? (size_t)32 : (size_t)0};
+            auto hit = [](const caf_b200_handle_s::Range& x, const caf_b200_handle_s::Range& y) {
+                return x.n && y.n && x.p < y.p + y.n && y.p < x.p + x.n;
+            };
+            if (h->prev_launch_no != h->launches) h->prev_valid = 0;          // something else ran in between
+            bool indep = h->prev_valid > 0;
+            for (int q = 0; indep && q < h->prev_valid; ++q) {
+                for (int i = 0; indep && i < 6; ++i) {
+                    for (int j = 0; indep && j < 6; ++j) if (hit(cur_out[i], h->prev_out[q][j])) indep = false;     // write after write
+                    for (int j = 0; indep && j < 3; ++j) if (hit(cur_out[i], h->prev_in[q][j])) indep = false;      // write after read
+                }
+                for (int i = 0; indep && i < 3; ++i)
+                    for (int j = 0; indep && j < 6; ++j) if (hit(cur_in[i], h->prev_out[q][j])) indep = false;      // read after write
+            }
+            if (indep) a.flags |= 1u;
+            else h->prev_valid = 0;      // this launch waits for everything before it: the history restarts here
+        }
+    }
     if (l == (size_t)kL0) CK((launch_rows<T, kSurface, true>(h, a, (long long)p * (long long)d)));
     else CK((launch_rows<T, kSurface, false>(h, a, (long long)p * (long long)d)));
+    if (overlappable) {
+        for (int i = 0; i < 3; ++i) { h->prev_in[1][i] = h->prev_in[0][i]; h->prev_in[0][i] = cur_in[i]; }
+        for (int i = 0; i < 6; ++i) { h->prev_out[1][i] = h->prev_out[0][i]; h->prev_out[0][i] = cur_out[i]; }
+        h->prev_valid = h->prev_valid < 2 ? h->prev_valid + 1 : 2;
+        h->prev_launch_no = h->launches;
+    } else {
+        h->prev_launch_no = ~0ull;
+        h->prev_valid = 0;
+    }
     if (a.pull_src) h->pull_total = a.pull_target;      // only a launch that was accepted moves the meeting point
+    if (a.done_counter) h->done_total[a.epoch & 1u] = a.done_last + 1u;
     if (prof) CK(cudaEventRecord(h->ev[2], h->stream));
     if (peaks && !fused_peak) {
         caf_peak_kernel<T><<<(unsigned)p, 256, 0, h->stream>>>(rv, ri, freqs, (int)d, peaks, h->pack_words, h->pack_offset);
@@ -1009,13 +1066,13 @@ static int create_impl(int device, bool own_stream, void* cuda_stream, caf_b200_
         if (e != cudaSuccess) { delete h; return fail(CAF_B200_ECUDA, cudaGetErrorString(e)); }
         h->own_stream = true;
     }
-    if ((e = cudaMalloc(&h->hshare, sizeof(double2) * caf::kM)) != cudaSuccess ||
-        (e = cudaMalloc(&h->hflag, 2 * sizeof(unsigned int))) != cudaSuccess ||
-        (e = cudaMemsetAsync(h->hflag, 0, 2 * sizeof(unsigned int), h->stream)) != cudaSuccess ||
+    if ((e = cudaMalloc(&h->hshare, 2 * sizeof(double2) * caf::kM)) != cudaSuccess ||
+        (e = cudaMalloc(&h->hflag, 4 * sizeof(unsigned int))) != cudaSuccess ||
+        (e = cudaMemsetAsync(h->hflag, 0, 4 * sizeof(unsigned int), h->stream)) != cudaSuccess ||
         (e = cudaMalloc(&h->pull_counter, sizeof(unsigned int))) != cudaSuccess ||
         (e = cudaMemsetAsync(h->pull_counter, 0, sizeof(unsigned int), h->stream)) != cudaSuccess ||
-        (e = cudaMalloc(&h->done_counter, sizeof(unsigned int))) != cudaSuccess ||
-        (e = cudaMemsetAsync(h->done_counter, 0, sizeof(unsigned int), h->stream)) != cudaSuccess ||
+        (e = cudaMalloc(&h->done_counter, 2 * sizeof(unsigned int))) != cudaSuccess ||
+        (e = cudaMemsetAsync(h->done_counter, 0, 2 * sizeof(unsigned int), h->stream)) != cudaSuccess ||
         (e = upload_tables<double>(h->td, h->stream)) != cudaSuccess ||
         (e = upload_tables<float>(h->tf, h->stream)) != cudaSuccess ||
         (e = configure_all<double>(&h->occ_d)) != cudaSuccess ||
@@ -1069,6 +1126,13 @@ int caf_b200_sync(caf_b200_handle h) {
 
 uint64_t caf_b200_launch_count(caf_b200_handle h) { return h ? h->launches : 0; }
 
+int caf_b200_set_overlap(caf_b200_handle h, int on) {
+    if (!h) return fail(CAF_B200_EINVAL, "null handle");
+    h->overlap_ok = on != 0;
+    h->prev_launch_no = ~0ull;
+    h->prev_valid = 0;
+    return CAF_B200_OK;
+}
 int caf_b200_set_profiling(caf_b200_handle h, int on) {
     if (!h) return fail(CAF_B200_EINVAL, "null handle");
     h->profiling = on != 0;

@@ -77,7 +77,9 @@ struct RowArgs {
     unsigned long long row_offset;    // global index of this launch's first doppler row (rows sharded across ranks)
     unsigned int* peak_seq;           // kSurface, P == 1: host-visible word that receives seq_val once `peak` is written (or null)
     unsigned int seq_val;
-    unsigned int* done_counter;   // kSurface, P == 1: last-CTA-done ticket (self-resetting)
+    unsigned int* done_counter;   // kSurface, P == 1: last-CTA-done ticket, monotonic across launches (never reset: a launch that
+                                  // overlaps its predecessor must not depend on the order of a reset and a later increment)
+    unsigned int done_last;       // the ticket the last CTA of THIS launch draws
     const cx<T>* tw1;       // [16][256]  W_4096^{k1 t}
     const cx<T>* tw2;       // [16][16]   W_256^{a b}
     const cx<T>* g;         // [4096]     W_8192^{-n}   (first 256 entries are staged in smem)
@@ -97,6 +99,13 @@ struct RowArgs {
     unsigned int pull_n16;          // 16-byte chunks
     unsigned int* pull_counter;
     unsigned int pull_target;       // counter value once every pulling warp of THIS launch has arrived
+    // kSurface, P == 1: bit 0 = this launch shares no buffer with the previous TWO launches on the stream where either side
+    // writes -- the host has compared the ranges -- so it does not wait for the grid before it: its CTAs start their rows
+    // on the SMs that grid has already left (400 rows on 148 SMs: 44 CTAs own two rows instead of three and leave a row
+    // early).  Only full grids (one CTA per SM) are let through: a CTA of launch k can then be placed only after every CTA
+    // of k-1 has started, i.e. after every CTA of k-2 has exited, so the overlap never reaches further back than the two
+    // launches whose buffers were checked; anything older finished issuing its stores a whole launch (> 30 us) earlier.
+    unsigned int flags;
     long long* trace;       // CAF_TRACE builds only: [cta][warp][8 items][32 slots] clock64 stamps
 };
 
@@ -670,7 +679,7 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
     //      (Waiting earlier, right after the TMEM allocation, with the operand loads in flight behind the table generation,
     //      was measured: 39.8 against 39.25 us per surface back to back.) ----
     if constexpr (MODE == kSurface) {
-        asm volatile("griddepcontrol.wait;\n" ::: "memory");
+        if (!(SHARED && (a.flags & 1u))) asm volatile("griddepcontrol.wait;\n" ::: "memory");
         if constexpr (SHARED) {
             if (a.pull_src != nullptr) {
                 if (tid >= 448) {
@@ -1052,7 +1061,11 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
     {
         asm volatile("tcgen05.fence::before_thread_sync;\n");
         __syncthreads();
-        if (hw_warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" :: "r"(misc[0]), "n"(TG::kAlloc));
+        if (hw_warp == 0) {
+            // (A second griddepcontrol.wait HERE, at the end of a launch that skipped the one at entry, would make the order of
+            //  completion formal -- and was measured: it cancels the whole gain, 38.1-38.8 against 33.3 us per surface.)
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" :: "r"(misc[0]), "n"(TG::kAlloc));
+        }
     }
 
 #ifdef CAF_TRACE
@@ -1072,7 +1085,7 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
             unsigned int last = 0;
             if (lane == 0) {
                 __threadfence();
-                last = (atomicAdd(a.done_counter, 1u) == gridDim.x - 1) ? 1u : 0u;
+                last = (atomicAdd(a.done_counter, 1u) == a.done_last) ? 1u : 0u;
             }
             last = __shfl_sync(0xffffffffu, last, 0);
             if (last) {
@@ -1106,7 +1119,6 @@ __global__ void __launch_bounds__(kThreads, 1) caf_rows_kernel(const RowArgs<T> 
                     }
                     *a.peak = p;
                     if (a.peak_words) pack_peak_words(p, a.row_offset, a.peak_words);
-                    *a.done_counter = 0u;   // ready for the next launch on this stream
                     if (a.peak_seq) {       // the host spins on this word instead of paying a stream synchronise's wake-up
                         __threadfence_system();
                         *reinterpret_cast<volatile unsigned int*>(a.peak_seq) = a.seq_val;

@@ -20,7 +20,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-def measure(lib, h, stream, dev, *, pairs=320, surfaces=8, steps=300, warmup=40, f32=False):
+def measure(lib, h, stream, dev, *, pairs=320, surfaces=8, steps=300, warmup=40, f32=False, overlap=True):
     """Run the rotation on an existing handle / stream and return the result dict (bench.py calls this too)."""
     import ctypes as C
     import numpy as np
@@ -60,6 +60,9 @@ def measure(lib, h, stream, dev, *, pairs=320, surfaces=8, steps=300, warmup=40,
                 surfs[k % surfaces].data_ptr(), rv[i].data_ptr(), ri[i].data_ptr(), pk[i].data_ptr())
         assert rc == 0, lib.caf_b200_last_error().decode()
 
+    # consecutive steps touch disjoint buffers (different pair, different surface buffer, different peak slots) and nothing
+    # else is enqueued between them: the library may let a launch start on the SMs its predecessor has already left
+    lib.caf_b200_set_overlap(h.raw, 1 if overlap else 0)
     for k in range(warmup):
         step(k)
     torch.cuda.synchronize()
@@ -73,6 +76,7 @@ def measure(lib, h, stream, dev, *, pairs=320, surfaces=8, steps=300, warmup=40,
     torch.cuda.synchronize()
     us = e0.elapsed_time(e1) * 1e3 / steps
     launches = lib.caf_b200_launch_count(h.raw) - launches0
+    lib.caf_b200_set_overlap(h.raw, 0)
 
     # every pair that ran: the peak sits on the planted lag, at the grid point nearest the planted offset
     w = pk.cpu().numpy()
@@ -88,7 +92,7 @@ def measure(lib, h, stream, dev, *, pairs=320, surfaces=8, steps=300, warmup=40,
     assert lib.caf_b200_probe_fma_tflops(h.raw, 0 if f32 else 1, C.byref(tf)) == 0
     flops = D * (10.0 * N * np.log2(N) + 15.0 * N)
     return {
-        "method": "working set > L2, one event pair around K back-to-back launches",
+        "method": "working set > L2, one event pair around K back-to-back launches" + (", independent launches overlap (caf_b200_set_overlap)" if overlap else ", launches serialised"),
         "dtype": sfx, "us_per_surface": us, "cells_per_s": D * N / (us * 1e-6), "steps": steps, "warmup": warmup,
         "pairs": pairs, "surface_buffers": surfaces,
         "working_set_mb": (pairs * 2 * L * needles.itemsize + surfaces * D * N * surfs[0].element_size()) / 1e6,
@@ -104,6 +108,7 @@ def main():
     ap.add_argument("--pairs", type=int, default=1024)
     ap.add_argument("--surfaces", type=int, default=8)
     ap.add_argument("--f32", action="store_true")
+    ap.add_argument("--no-overlap", action="store_true")
     args = ap.parse_args()
 
     import torch
@@ -115,7 +120,7 @@ def main():
     lib = _lib.load()
     h = Handle(0, stream=stream.cuda_stream)
     line = measure(lib, h, stream, dev, pairs=args.pairs, surfaces=args.surfaces, steps=args.steps,
-                   warmup=args.warmup, f32=args.f32)
+                   warmup=args.warmup, f32=args.f32, overlap=not args.no_overlap)
     print(json.dumps(line))
     if line["peaks_off"]:
         sys.exit(1)

@@ -50,6 +50,10 @@ class _FakeLib:
         self.launches += 1
         return 0
 
+    def caf_b200_set_overlap(self, h, on):
+        self.overlap_calls = getattr(self, "overlap_calls", []) + [int(on)]
+        return 0
+
     def caf_b200_launch_count(self, h):
         return self.launches
 

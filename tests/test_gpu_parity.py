@@ -237,6 +237,66 @@ def test_device_loader_matches_read_file_c64(tmp_path):
     lib.caf_b200_dev_free(scratch)
 
 
+def test_overlapping_launches_give_the_serialised_bits():
+    """caf_b200_set_overlap: a single-pair device launch that directly follows another one and shares no buffer with it
+    (where either writes) does not wait for it -- its CTAs start on the SMs the earlier launch has left.  Launch-private
+    state (H publication buffer and flags, the find_peak ticket) is double-buffered by launch parity.  Over a long mixed
+    sequence -- rotating pairs, three surface buffers, grids of 7 / 147 / 148 CTAs, 1-3 rows per CTA, and launches that DO
+    alias their predecessor's outputs and must therefore serialise -- every row peak, every peak and the final content
+    of every surface buffer equals what the same sequence gives with overlap switched off."""
+    import torch
+    from caf_cookoff_b200 import bench_shifts
+    from oracle import oracle as O
+    cases = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "known_answers.json")))["cases"][:4]
+    dev = torch.device("cuda", 0)
+    stream = torch.cuda.Stream(device=dev)
+    lib = _lib.load()
+    h = api.Handle(0, stream=stream.cuda_stream)
+    L = 4096
+    nd, hd = [], []
+    for c in cases:
+        n = O.read_file_c64(os.path.join(DATA, "chirp_%d_raw.c64" % c["chirp"]))
+        nd.append(torch.from_numpy(n).to(dev)); hd.append(torch.from_numpy(O.read_file_c64(os.path.join(DATA, c["haystack"]))[:L].copy()).to(dev))
+    shifts = bench_shifts()
+    fd = torch.from_numpy(shifts).to(dev)
+    K = 72
+    plan = []
+    for k in range(K):
+        d = (400, 147, 7, 300, 148, 2)[k % 6]
+        alias_prev = (k % 9 == 5)                      # same surface buffer and peak slot as the launch before: must serialise
+        plan.append((k % len(cases), d, alias_prev))
+
+    def run(overlap):
+        lib.caf_b200_set_overlap(h.raw, 1 if overlap else 0)
+        surfs = [torch.zeros((400, 2 * L), dtype=torch.float64, device=dev) for _ in range(3)]
+        rv = torch.zeros((K, 400), dtype=torch.float64, device=dev); ri = torch.zeros((K, 400), dtype=torch.int64, device=dev)
+        pk = torch.zeros((K, 4), dtype=torch.int64, device=dev)
+        with torch.cuda.stream(stream):
+            sb, slot = 0, 0
+            for k, (pi, d, alias_prev) in enumerate(plan):
+                if not alias_prev:
+                    sb, slot = (sb + 1) % 3, k
+                rc = lib.caf_b200_batch_f64_dev(h.raw, nd[pi].data_ptr(), hd[pi].data_ptr(), 1, L, fd.data_ptr(), d, FS,
+                                                surfs[sb].data_ptr(), rv[slot].data_ptr(), ri[slot].data_ptr(), pk[slot].data_ptr())
+                assert rc == 0, lib.caf_b200_last_error()
+        torch.cuda.synchronize()
+        return [s_.cpu().numpy() for s_ in surfs], rv.cpu().numpy(), ri.cpu().numpy(), pk.cpu().numpy()
+
+    want = run(False)
+    for rep in range(3):
+        got = run(True)
+        for a_, b_ in zip(want[0], got[0]):
+            assert np.array_equal(a_, b_), rep
+        assert np.array_equal(want[1], got[1]) and np.array_equal(want[2], got[2]) and np.array_equal(want[3], got[3]), rep
+    # and the serialised reference itself is the known answer of each pair on the full grid
+    for k, (pi, d, alias_prev) in enumerate(plan):
+        if d == 400 and not alias_prev and not (k + 1 < K and plan[k + 1][2]):
+            w = want[3][k]
+            assert int(w.view(np.uint64)[3]) == cases[pi]["samp_idx"] and abs(float(w.view(np.float64)[1]) - cases[pi]["freq"]) <= 0.5
+    lib.caf_b200_set_overlap(h.raw, 0)
+    h.close()
+
+
 def test_stress_bitwise_determinism_over_many_launches(chirp0):
     """compute-sanitizer is closed on this GPU pool (profiles/r02_sanitizer.txt), so the hand-rolled synchronisation of
     the row kernel -- named barriers per warp group, the mailbox mbarrier pair, the cross-CTA H publication flag, the
