@@ -425,17 +425,20 @@ def block_cfg2(ctx, steps=40):
     got = (float(p.view(np.float64)[1]), int(p.view(np.uint64)[3]))
     del surf
     rot = bench_stream.measure(lib, h, ctx.stream, dev, pairs=320, surfaces=16, steps=200, warmup=40, f32=True)
+    ser = bench_stream.measure(lib, h, ctx.stream, dev, pairs=320, surfaces=16, steps=200, warmup=40, f32=True, overlap=False)
     ms = rot["us_per_surface"] * 1e-3
     fl = d * _row_flops(N)
     return {"workload": "cfg2: 400 doppler x 8192 delay CAF surface + peak in complex64/float32, working set larger than L2 "
-                        "(320 seeded pairs, 16 surface buffers), one event pair around 200 back-to-back launches",
+                        "(320 seeded pairs, 16 surface buffers), one event pair around 200 back-to-back launches, independent launches overlap",
             "ms_per_step": ms, "cells_per_s": d * N / (ms * 1e-3), "steps": rot["steps"],
             "working_set_mb": rot["working_set_mb"], "pairs_checked": rot["pairs_checked"], "peaks_off": rot["peaks_off"],
             "roofline": {"bound": "fp32", "achieved": fl / (ms * 1e-3) / 1e12, "peak": ctx.tf32, "unit": "TFLOP/s",
                          "frac": fl / (ms * 1e-3) / 1e12 / ctx.tf32 if ctx.tf32 else None},
+            "launches_serialised": {"ms_per_step": ser["us_per_surface"] * 1e-3, "frac": ser["frac"], "peaks_off": ser["peaks_off"],
+                                    "method": "the same rotation with caf_b200_set_overlap(0)"},
             "flushed_per_step": {"ms_per_step": ms_flushed, "frac": fl / (ms_flushed * 1e-3) / 1e12 / ctx.tf32 if ctx.tf32 else None,
                                  "method": "L2 flushed (256 MiB overwrite) before every step, one CUDA event pair per step (round 1's figure)"},
-            "peak": list(got), "check_ok": got == (69.0, 202) and not rot["peaks_off"]}
+            "peak": list(got), "check_ok": got == (69.0, 202) and not rot["peaks_off"] and not ser["peaks_off"]}
 
 
 def block_cfg5_rows(ctx, rows=296, l=1 << 19, steps=2):

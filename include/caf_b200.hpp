@@ -33,6 +33,7 @@ inline void check(int rc) {
 }
 
 // one lazily created handle per thread: the trait functions are static and must be callable from any thread
+// (caf::set_overlap(true) lets consecutive independent device launches of this thread's handle overlap, caf_b200.h)
 inline caf_b200_handle thread_handle() {
     struct Holder {
         caf_b200_handle h = nullptr;
@@ -90,6 +91,8 @@ public:
     const std::shared_ptr<const DeviceSurface>& surface() const { return surf_; }
     std::size_t row() const { return row_; }
 };
+
+inline void set_overlap(bool on) { check(caf_b200_set_overlap(thread_handle(), on ? 1 : 0)); }
 
 struct CafB200 {
     // mod.rs:121-166 (every strategy struct computes this).  Costs a peak-only call: inputs up, one fused launch, the

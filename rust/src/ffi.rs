@@ -20,6 +20,7 @@ extern "C" {
     pub fn caf_b200_create(device: c_int, out: *mut caf_b200_handle) -> c_int;
     pub fn caf_b200_destroy(h: caf_b200_handle) -> c_int;
     pub fn caf_b200_last_error() -> *const c_char;
+    pub fn caf_b200_set_overlap(h: caf_b200_handle, on: c_int) -> c_int;
     pub fn caf_b200_apply_freq_shift_f64(h: caf_b200_handle, input: *const Complex64, n: usize, freq_hz: f64,
                                          fs: u32, out: *mut Complex64) -> c_int;
     pub fn caf_b200_xcor_f64(h: caf_b200_handle, a: *const Complex64, b: *const Complex64, n: usize,
