@@ -775,17 +775,34 @@ def run_b200(args):
     d2h = surf_h.numel() * surf_h.element_size() + rv_h.numel() * rv_h.element_size() + ri_h.numel() * 8 + 32
 
     def time_host(step):
+        # A host call is synchronous: what its caller pays is wall-clock time.  The event pair around a call only measures
+        # that if the GPU is IDLE when the call begins -- with the L2 flush still running, the call's host-side work (staging
+        # memcpy, launch) would hide behind it and the events would read ~10 us less than the caller waits (as rounds 1 and
+        # early 2 did).  So: flush, SYNCHRONISE, then event / call / event.  The plain wall clock per call of an unflushed
+        # loop is reported beside it.
         for _ in range(3):
             step()
         barrier()
-        t0 = time.perf_counter()
-        evs = timed_pass(step, e2e_steps)
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(e2e_steps)]
+        wall_flushed = 0.0
+        for s0, s1 in evs:
+            flush.zero_()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            s0.record(stream)
+            step()
+            s1.record(stream)
+            wall_flushed += time.perf_counter() - t0
         barrier()
-        wall = time.perf_counter() - t0
         tt = torch.tensor([float(sum(a.elapsed_time(b) for a, b in evs))], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        return float(tt.item()) / e2e_steps, 1e3 * wall / e2e_steps
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            step()
+        wall_loop = time.perf_counter() - t0
+        time_host.last_wall_unflushed_ms = 1e3 * wall_loop / e2e_steps
+        return float(tt.item()) / e2e_steps, 1e3 * wall_flushed / e2e_steps
 
     def surface_call(n_, h_, f_, s_, rv_, ri_, pk_):
         def step():
@@ -804,7 +821,8 @@ def run_b200(args):
     pk_h = _lib.Peak()
     ms, wall_ms = time_host(surface_call(needle_h, hay_h, freqs_h, surf_h.data_ptr(), rv_h.data_ptr(), ri_h.data_ptr(), pk_h))
     e2e = {"value": world * cells_step / (ms * 1e-3), "unit": "cells/s", "ms_per_step": ms, "steps": e2e_steps,
-           "wall_ms_per_step_incl_flush": wall_ms, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+           "wall_ms_per_step": wall_ms, "wall_ms_per_step_unflushed_loop": time_host.last_wall_unflushed_ms,
+           "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
            "host_buffers": "pinned: inputs in one caf_b200_host_alloc block (one H2D), outputs in pinned memory",
            "peak": [pk_h.freq_hz, int(pk_h.delay_idx)]}
     checks["e2e_surface_to_host"] = peak_is_planted(rank, pk_h.freq_hz, int(pk_h.delay_idx)) and float(surf_h[int(pk_h.doppler_idx), int(pk_h.delay_idx)]) == pk_h.value
@@ -812,8 +830,9 @@ def run_b200(args):
     # the same call without the surface crossing PCIe: caf_b200_peak_* (what caf_bench.rs's closure observes:
     # find_peak(caf_surface(..)) returns (freq, delay); CafSurfaceRow's fields are private, mod.rs:17-22)
     pk2 = _lib.Peak()
-    ms, _ = time_host(peak_call(needle_h, hay_h, freqs_h, pk2))
+    ms, wall_ms = time_host(peak_call(needle_h, hay_h, freqs_h, pk2))
     e2e_peak = {"value": world * cells_step / (ms * 1e-3), "unit": "cells/s", "ms_per_step": ms,
+                "wall_ms_per_step": wall_ms, "wall_ms_per_step_unflushed_loop": time_host.last_wall_unflushed_ms,
                 "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 32 + 4, "peak": [pk2.freq_hz, int(pk2.delay_idx)],
                 "note": "host inputs in (one pinned block, read across PCIe by the kernel's own CTAs: no H2D DMA in front of the launch), "
                         "(freq, delay) out: the surface stays on the GPU (caf_b200_peak_*); the kernel stores the peak into pinned "
@@ -829,8 +848,9 @@ def run_b200(args):
                     "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "peak": [pk3.freq_hz, int(pk3.delay_idx)],
                     "host_buffers": "pageable numpy arrays for inputs AND outputs (std::vector / Vec<Complex64> callers)"}
     checks["e2e_surface_to_host_pageable"] = peak_is_planted(rank, pk3.freq_hz, int(pk3.delay_idx)) and float(surf_pg[int(pk3.doppler_idx), int(pk3.delay_idx)]) == pk3.value
-    ms, _ = time_host(peak_call(n_pg, h_pg, f_pg, pk4))
+    ms, wall_ms = time_host(peak_call(n_pg, h_pg, f_pg, pk4))
     e2e_peak_pageable = {"value": world * cells_step / (ms * 1e-3), "unit": "cells/s", "ms_per_step": ms,
+                         "wall_ms_per_step": wall_ms, "wall_ms_per_step_unflushed_loop": time_host.last_wall_unflushed_ms,
                          "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 32 + 4, "peak": [pk4.freq_hz, int(pk4.delay_idx)],
                          "host_buffers": "pageable numpy inputs (one memcpy into the library's pinned block, which the kernel reads across PCIe itself)"}
     checks["e2e_peak_only_pageable"] = peak_is_planted(rank, pk4.freq_hz, int(pk4.delay_idx))
@@ -846,8 +866,10 @@ def run_b200(args):
             raise RuntimeError(lib.caf_b200_last_error().decode())
         lib.caf_b200_surface_find_peak(so, C.byref(pk5))
         lib.caf_b200_surface_destroy(so)
-    ms, _ = time_host(step_dropin)
+    ms, wall_ms = time_host(step_dropin)
     e2e_dropin = {"value": world * cells_step / (ms * 1e-3), "unit": "cells/s", "ms_per_step": ms,
+                  "wall_ms_per_step": wall_ms, "wall_ms_per_step_unflushed_loop": time_host.last_wall_unflushed_ms,
+                  "timing": "L2 flushed, GPU idle (synchronised) when the call begins, one CUDA event pair around the call; wall clock beside it",
                   "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 32 + 4, "peak": [pk5.freq_hz, int(pk5.delay_idx)],
                   "note": "caf_surface + find_peak as rust/src/caf/mod.rs and include/caf_b200.hpp issue them: device-resident "
                           "surface object with lazy rows (caf_bench.rs:163-167's closure); pageable inputs, one memcpy into the library's pinned "
