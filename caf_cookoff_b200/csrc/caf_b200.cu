@@ -17,6 +17,9 @@
 
 #include <cuda_runtime.h>
 #include <dlfcn.h>
+#if defined(__x86_64__)
+#include <emmintrin.h>
+#endif
 
 #include "../../include/caf_b200.h"
 #include "caf_kernels.cuh"
@@ -194,6 +197,32 @@ struct caf_b200_surface_s {
 };
 
 namespace {
+
+// Copy into the pinned staging block the GPU is about to read across PCIe.  The CPU never reads that block again, so the
+// stores are non-temporal: no read-for-ownership of 134 KB of lines the previous call's PCIe reads pushed out of the caches,
+// and the data is on its way to DRAM when the kernel's loads arrive.  dst is 16-byte aligned (offsets in the block are).
+inline void stage_copy(void* dst, const void* src, size_t n) {
+#if defined(__x86_64__)
+    if (((uintptr_t)dst & 15) == 0) {
+        char* d = (char*)dst; const char* s_ = (const char*)src;
+        size_t i = 0;
+        for (; i + 64 <= n; i += 64) {
+            const __m128i a0 = _mm_loadu_si128((const __m128i*)(s_ + i)), a1 = _mm_loadu_si128((const __m128i*)(s_ + i + 16));
+            const __m128i a2 = _mm_loadu_si128((const __m128i*)(s_ + i + 32)), a3 = _mm_loadu_si128((const __m128i*)(s_ + i + 48));
+            _mm_stream_si128((__m128i*)(d + i), a0); _mm_stream_si128((__m128i*)(d + i + 16), a1);
+            _mm_stream_si128((__m128i*)(d + i + 32), a2); _mm_stream_si128((__m128i*)(d + i + 48), a3);
+        }
+        if (i < n) std::memcpy(d + i, s_ + i, n - i);
+        return;
+    }
+#endif
+    std::memcpy(dst, src, n);
+}
+inline void stage_fence() {
+#if defined(__x86_64__)
+    _mm_sfence();      // the streamed data is globally visible before the launch's doorbell is rung
+#endif
+}
 
 // blocks handed out by caf_b200_host_alloc: pinned and device-addressable, so a kernel may read inputs straight from them
 std::mutex g_pinned_mu;
@@ -719,7 +748,8 @@ int run_batch_host(caf_b200_handle h, const caf::cx<T>* needles, const caf::cx<T
                     h->h_stage_cap = tot16 + tot16 / 4;
                 }
                 char* st = (char*)h->h_stage;
-                std::memcpy(st, needles, sig_bytes); std::memcpy(st + sig_pad, hays, sig_bytes); std::memcpy(st + 2 * sig_pad, freqs, fr_bytes);
+                stage_copy(st, needles, sig_bytes); stage_copy(st + sig_pad, hays, sig_bytes); stage_copy(st + 2 * sig_pad, freqs, fr_bytes);
+                stage_fence();
                 h->pull_src = st;
             }
             h->pull_bytes = tot16;
