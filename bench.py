@@ -626,7 +626,7 @@ def run_b200(args):
     # consecutive steps touch disjoint buffers and nothing else is enqueued between them, which is what the library's
     # overlap switch asks of a caller: a launch may then start on the SMs its predecessor has already left (the same
     # rotation with the launches serialised is timed right after the headline: `launches_serialised`)
-    lib.caf_b200_set_overlap(h.raw, 1)
+    lib.caf_b200_set_overlap(h.raw, 4)
     warm = max(args.warmup, 3)
     for k in range(warm):
         step_rot(k)
@@ -730,7 +730,7 @@ def run_b200(args):
         "step_share": {"spectrum_ms": 0.0, "rows_ms": rows_avg_ms, "peak_ms": 0.0,
                        "note": "one fused launch per step: FFT(s1), the rows and find_peak are the same kernel"},
         "kernel_ms_note": "the timed region holds K launches of this kernel and nothing else: kernel_ms = region / K.  Consecutive launches "
-                          "overlap (launch k+1 starts on the SMs launch k has left), so this is a launch's SHARE of the region, not its latency; "
+                          "overlap (about four share the GPU, caf_b200_set_overlap(4)), so this is a launch's SHARE of the region, not its latency; "
                           "launches_serialised is the same figure with every launch waiting for the one before it",
         "launches_serialised": {"kernel_ms": serial_ms, "frac": row_flops / (serial_ms * 1e-3) / 1e12 / tf.value if tf.value else None},
         "flushed_per_step": {"kernel_ms": rows_flushed_ms, "frac": row_flops / (rows_flushed_ms * 1e-3) / 1e12 / tf.value if tf.value else None,
@@ -931,9 +931,10 @@ def run_b200(args):
                        "doppler_rows": D, "delay_cells": N, "pairs_per_step_per_gpu": 1,
                        "l2": "working set larger than L2: the steps rotate over 320 seeded pairs and 8 surface buffers (252 MB); one CUDA "
                              "event pair around the K back-to-back steps (flushed_per_step = round 1's method, beside it)",
-                       "launch_overlap": "caf_b200_set_overlap(1): a step touches no buffer of the two steps before it, so its launch does not "
-                                         "wait for the previous grid (its CTAs start on the SMs that grid has left); launches_serialised = the same "
-                                         "rotation with overlap off",
+                       "launch_overlap": "caf_b200_set_overlap(4): a step touches no buffer of the seven steps before it, so its launch does "
+                                         "not wait for the previous grid and uses a quarter of the SMs -- about four steps share the GPU at any "
+                                         "time, each CTA carries 10-11 rows instead of 2-3 (a single surface then takes ~110 us from launch to "
+                                         "completion); launches_serialised = the same rotation with overlap off (every launch waits, one CTA per SM)",
                        "pairs_in_rotation": n_pairs, "surface_buffers": n_surf,
                        "parallelism": f"pairs sharded x{world}, no data-path collective",
                        "host_cpus_bound_to_gpu": numa},

@@ -141,19 +141,25 @@ struct caf_b200_handle_s {
     size_t h_stage_cap = 0;
     DevBuf lwbuf, lhtmp, lhbig, lpart;      // long-row path: chunk scratch, scratch of the H transform, H, partial row maxima
     long long* trace = nullptr;   // CAF_TRACE builds: device buffer for phase stamps
-    unsigned int* done_counter = nullptr;   // [2] last-CTA-done tickets of the fused find_peak, one per launch parity
-    void* hshare = nullptr;                 // single-pair launches: H published by CTA 0 (2 x 8192 complex128, one per launch parity)
-    unsigned int* hflag = nullptr;          // [2 parities][2] publish counters, monotonic
-    // Overlap of consecutive single-pair surface launches (RowArgs::flags bit 0).  A launch whose buffers are disjoint from
-    // the previous launch's does not wait for it; the launch-private state above is double-buffered by launch parity (a
-    // third launch cannot start before the first has completed: it needs every CTA of the second to be resident).
-    bool overlap_ok = false;                // caf_b200_set_overlap: opt-in, the caller's promise (include/caf_b200.h)
-    struct Range { const char* p; size_t n; };
-    Range prev_in[2][3] = {}, prev_out[2][6] = {};   // buffers of the previous two overlappable launches ([0] = the latest)
-    int prev_valid = 0;                              // how many of them are valid (consecutive, full-grid launches)
-    unsigned long long prev_launch_no = ~0ull;       // value of `launches` right after the previous overlappable launch
-    unsigned int done_total[2] = {0u, 0u};        // tickets drawn so far from done_counter[parity]
+    // Launch-private state of single-pair surface launches, a ring of kRing slots indexed by launch number (epoch % kRing):
+    // several such launches can be in flight at once (overlap, below).
+    static constexpr int kRing = 8;
+    unsigned int* done_counter = nullptr;   // [kRing] last-CTA-done tickets of the fused find_peak, monotonic
+    void* hshare = nullptr;                 // [kRing][8192 complex128] H published by the publishing CTAs
+    unsigned int* hflag = nullptr;          // [kRing][2] publish counters, monotonic
     unsigned int epoch = 0;
+    unsigned int done_total[kRing] = {};    // tickets drawn so far from done_counter[slot]
+    // Overlap of consecutive single-pair surface launches (RowArgs::flags bit 0; include/caf_b200.h, caf_b200_set_overlap).
+    // overlap = 0: off.  1: a launch independent of its predecessors skips the wait for the grid before it, full grids.
+    // n >= 2: such a launch also uses only ceil(SMs / n) CTAs, so that ~n launches share the GPU and every CTA amortises
+    // its set-up over n times as many rows.
+    int overlap = 0;
+    struct Range { const char* p; size_t n; };
+    static constexpr int kHist = kRing - 1;          // launches whose buffers are compared (the newest first)
+    Range prev_in[kHist][3] = {}, prev_out[kHist][6] = {};
+    int prev_valid = 0;                              // how many of them are valid
+    long long prev_grid = 0;                         // the grid of the launches in the history (one size only)
+    unsigned long long prev_launch_no = ~0ull;       // value of `launches` right after the previous overlappable launch
     // small single-pair host calls: the kernel pulls its inputs out of pinned host memory itself (RowArgs::pull_*)
     unsigned int* pull_counter = nullptr;       // device word the grid meets on, monotonic
     unsigned int pull_total = 0;                // its value after every launch issued so far
@@ -351,10 +357,11 @@ cudaError_t configure_all(int* occ) {
 }
 
 template <typename T, int MODE, bool FULL = false>
-cudaError_t launch_rows(caf_b200_handle h, const caf::RowArgs<T>& a, long long n_items) {
+cudaError_t launch_rows(caf_b200_handle h, const caf::RowArgs<T>& a, long long n_items, long long grid_cap = 0) {
     if (n_items <= 0) return cudaSuccess;
     const int occ = std::is_same<T, double>::value ? h->occ_d : h->occ_f;
     long long cap = (long long)h->sm_count * occ;
+    if (grid_cap > 0 && grid_cap < cap) cap = grid_cap;
     int grid = (int)(n_items < cap ? n_items : cap);
     h->launches++;
     if (MODE == caf::kSurface) {
@@ -596,49 +603,23 @@ int run_batch_dev(caf_b200_handle h, const caf::cx<T>* needles, const caf::cx<T>
         a.peak = peaks; a.done_counter = h->done_counter; a.peak_words = h->pack_words; a.row_offset = h->pack_offset;
         a.peak_seq = h->seq_ptr; a.seq_val = h->seq_val;
     }
-    if (p == 1 && d > 1) {                        // one pair over many CTAs: CTA 0 publishes H, the rest consume it
-        a.epoch = ++h->epoch;
-        const unsigned int par = a.epoch & 1u;
-        a.hshare = reinterpret_cast<cx<T>*>(reinterpret_cast<double2*>(h->hshare) + (size_t)par * caf::kM); a.hflag = h->hflag + 2 * par;
-        // H_1's publisher: the lowest-index CTA other than 0 that owns the fewest rows (same split as the kernel)
-        const long long n_items = (long long)d;
-        const int occ = std::is_same<T, double>::value ? h->occ_d : h->occ_f;
-        const long long cap = (long long)h->sm_count * occ;
-        const long long grid = n_items < cap ? n_items : cap;
-        if (fused_peak) { a.done_counter = h->done_counter + par; a.done_last = h->done_total[par] + (unsigned int)grid - 1u; }
-        a.hprod1 = 0;
-        long long best = -1;
-        for (long long b = 1; b < grid; ++b) {
-            const long long cnt = n_items * (b + 1) / grid - n_items * b / grid;
-            if (best < 0 || cnt < best) { best = cnt; a.hprod1 = (int)b; }
-        }
-        if (h->pull_src) {      // the grid fetches needle | haystack | freqs from pinned host memory itself
-            a.pull_src = reinterpret_cast<const uint4*>(h->pull_src);
-            a.pull_dst = reinterpret_cast<uint4*>(const_cast<cx<T>*>(needles));
-            a.pull_n16 = (unsigned int)(h->pull_bytes / 16);
-            a.pull_counter = h->pull_counter;
-            a.pull_target = h->pull_total + 2u * (unsigned int)grid;      // two pulling warps per CTA
-        }
-    }
     const bool prof = h->profiling;
-    if (prof) {
-        for (auto& e : h->ev) if (!e) CK(cudaEventCreate(&e));
-        h->ev_valid = false;
-        CK(cudaEventRecord(h->ev[0], h->stream));
-        CK(cudaEventRecord(h->ev[1], h->stream));
-    }
-    // one fused launch: per pair FFT(s1) -> TMEM, then per row shift -> FFT -> xH -> IFFT -> |.|^2 -> argmax
-    // ---- may this launch overlap its predecessor?  Only a single-pair device launch that fills the GPU (one CTA per SM),
-    //      directly behind another such launch (no other library launch in between), with every buffer disjoint from
-    //      those of the previous TWO launches wherever one side writes.  Two, because that is how far the overlap reaches:
-    //      launch k's CTAs can be placed only once every CTA of k-1 has started (launch_dependents at entry), which on a
-    //      full grid means every CTA of k-2 has exited; everything older issued its last store more than a launch ago. ----
+    // ---- may this launch overlap its predecessors?  Only a single-pair device launch directly behind another overlappable
+    //      one (no other library launch in between), with every buffer disjoint from those of the launches in the history
+    //      (the previous kHist = 7) wherever one side writes.  Why 7 is enough: a CTA of launch k is placed only after every
+    //      CTA of k-1 has started (launch_dependents is issued at entry), hence after every CTA of k-2 ... k-7 has started;
+    //      those are 7 x grid >= 7 x 37 = 259 CTAs on 148 SMs, so at least 112 of them must have run to completion while a
+    //      CTA of k-8 was still running -- it would have to take twice as long as its peers, which all carry the same
+    //      rows +- 1.  (A formal version, a second griddepcontrol.wait at the END of an overlapped launch, was measured and
+    //      cancels the whole gain: caf_kernels.cuh.) ----
     caf_b200_handle_s::Range cur_in[3] = {}, cur_out[6] = {};
     bool overlappable = false;
-    {
+    long long grid_cap = 0;                       // 0 = one CTA per SM
+    if (p == 1 && d > 1 && h->overlap > 0 && !h->pull_src && !h->seq_ptr && !prof) {
         const int occ_ = std::is_same<T, double>::value ? h->occ_d : h->occ_f;
-        const bool full_grid = (long long)p * (long long)d >= (long long)h->sm_count * occ_;
-        if (p == 1 && d > 1 && full_grid && h->overlap_ok && !a.pull_src && !a.peak_seq && !prof) {
+        const long long full = (long long)h->sm_count * occ_;
+        const long long want = h->overlap >= 2 ? (full + h->overlap - 1) / h->overlap : full;      // CTAs of an overlapped launch
+        if ((long long)d >= full) {               // (smaller problems keep full stream order)
             overlappable = true;
             cur_in[0] = {(const char*)needles, sizeof(cx<T>) * l}; cur_in[1] = {(const char*)hays, sizeof(cx<T>) * l};
             cur_in[2] = {(const char*)freqs, sizeof(double) * d};
@@ -659,23 +640,60 @@ int run_batch_dev(caf_b200_handle h, const caf::cx<T>* needles, const caf::cx<T>
                 for (int i = 0; indep && i < 3; ++i)
                     for (int j = 0; indep && j < 6; ++j) if (hit(cur_in[i], h->prev_out[q][j])) indep = false;      // read after write
             }
-            if (indep) a.flags |= 1u;
-            else h->prev_valid = 0;      // this launch waits for everything before it: the history restarts here
+            if (indep) { a.flags |= 1u; grid_cap = want; }
+            else h->prev_valid = 0;      // this launch waits for everything before it (full grid): the history restarts here
         }
     }
-    if (l == (size_t)kL0) CK((launch_rows<T, kSurface, true>(h, a, (long long)p * (long long)d)));
-    else CK((launch_rows<T, kSurface, false>(h, a, (long long)p * (long long)d)));
+    if (p == 1 && d > 1) {                        // one pair over many CTAs: CTA 0 publishes H, the rest consume it
+        a.epoch = ++h->epoch;
+        const unsigned int slot = a.epoch % (unsigned int)caf_b200_handle_s::kRing;
+        a.hshare = reinterpret_cast<cx<T>*>(reinterpret_cast<double2*>(h->hshare) + (size_t)slot * caf::kM); a.hflag = h->hflag + 2 * slot;
+        // H_1's publisher: the lowest-index CTA other than 0 that owns the fewest rows (same split as the kernel)
+        const long long n_items = (long long)d;
+        const int occ = std::is_same<T, double>::value ? h->occ_d : h->occ_f;
+        long long cap = (long long)h->sm_count * occ;
+        if (grid_cap > 0 && grid_cap < cap) cap = grid_cap;
+        const long long grid = n_items < cap ? n_items : cap;
+        if (fused_peak) { a.done_counter = h->done_counter + slot; a.done_last = h->done_total[slot] + (unsigned int)grid - 1u; }
+        a.hprod1 = 0;
+        long long best = -1;
+        for (long long b = 1; b < grid; ++b) {
+            const long long cnt = n_items * (b + 1) / grid - n_items * b / grid;
+            if (best < 0 || cnt < best) { best = cnt; a.hprod1 = (int)b; }
+        }
+        if (h->pull_src) {      // the grid fetches needle | haystack | freqs from pinned host memory itself
+            a.pull_src = reinterpret_cast<const uint4*>(h->pull_src);
+            a.pull_dst = reinterpret_cast<uint4*>(const_cast<cx<T>*>(needles));
+            a.pull_n16 = (unsigned int)(h->pull_bytes / 16);
+            a.pull_counter = h->pull_counter;
+            a.pull_target = h->pull_total + 2u * (unsigned int)grid;      // two pulling warps per CTA
+        }
+    }
+    if (prof) {
+        for (auto& e : h->ev) if (!e) CK(cudaEventCreate(&e));
+        h->ev_valid = false;
+        CK(cudaEventRecord(h->ev[0], h->stream));
+        CK(cudaEventRecord(h->ev[1], h->stream));
+    }
+    // one fused launch: per pair FFT(s1) -> TMEM, then per row shift -> FFT -> xH -> IFFT -> |.|^2 -> argmax
+    if (l == (size_t)kL0) CK((launch_rows<T, kSurface, true>(h, a, (long long)p * (long long)d, grid_cap)));
+    else CK((launch_rows<T, kSurface, false>(h, a, (long long)p * (long long)d, grid_cap)));
     if (overlappable) {
-        for (int i = 0; i < 3; ++i) { h->prev_in[1][i] = h->prev_in[0][i]; h->prev_in[0][i] = cur_in[i]; }
-        for (int i = 0; i < 6; ++i) { h->prev_out[1][i] = h->prev_out[0][i]; h->prev_out[0][i] = cur_out[i]; }
-        h->prev_valid = h->prev_valid < 2 ? h->prev_valid + 1 : 2;
+        // a history holds launches of ONE grid size (the argument above counts CTAs): a launch that waited starts it afresh
+        for (int q = caf_b200_handle_s::kHist - 1; q > 0; --q) {
+            for (int i = 0; i < 3; ++i) h->prev_in[q][i] = h->prev_in[q - 1][i];
+            for (int i = 0; i < 6; ++i) h->prev_out[q][i] = h->prev_out[q - 1][i];
+        }
+        for (int i = 0; i < 3; ++i) h->prev_in[0][i] = cur_in[i];
+        for (int i = 0; i < 6; ++i) h->prev_out[0][i] = cur_out[i];
+        h->prev_valid = h->prev_valid < caf_b200_handle_s::kHist ? h->prev_valid + 1 : caf_b200_handle_s::kHist;
         h->prev_launch_no = h->launches;
     } else {
         h->prev_launch_no = ~0ull;
         h->prev_valid = 0;
     }
     if (a.pull_src) h->pull_total = a.pull_target;      // only a launch that was accepted moves the meeting point
-    if (a.done_counter) h->done_total[a.epoch & 1u] = a.done_last + 1u;
+    if (a.done_counter) h->done_total[a.epoch % (unsigned int)caf_b200_handle_s::kRing] = a.done_last + 1u;
     if (prof) CK(cudaEventRecord(h->ev[2], h->stream));
     if (peaks && !fused_peak) {
         caf_peak_kernel<T><<<(unsigned)p, 256, 0, h->stream>>>(rv, ri, freqs, (int)d, peaks, h->pack_words, h->pack_offset);
@@ -1096,13 +1114,14 @@ static int create_impl(int device, bool own_stream, void* cuda_stream, caf_b200_
         if (e != cudaSuccess) { delete h; return fail(CAF_B200_ECUDA, cudaGetErrorString(e)); }
         h->own_stream = true;
     }
-    if ((e = cudaMalloc(&h->hshare, 2 * sizeof(double2) * caf::kM)) != cudaSuccess ||
-        (e = cudaMalloc(&h->hflag, 4 * sizeof(unsigned int))) != cudaSuccess ||
-        (e = cudaMemsetAsync(h->hflag, 0, 4 * sizeof(unsigned int), h->stream)) != cudaSuccess ||
+    constexpr size_t kRing_ = (size_t)caf_b200_handle_s::kRing;
+    if ((e = cudaMalloc(&h->hshare, kRing_ * sizeof(double2) * caf::kM)) != cudaSuccess ||
+        (e = cudaMalloc(&h->hflag, 2 * kRing_ * sizeof(unsigned int))) != cudaSuccess ||
+        (e = cudaMemsetAsync(h->hflag, 0, 2 * kRing_ * sizeof(unsigned int), h->stream)) != cudaSuccess ||
         (e = cudaMalloc(&h->pull_counter, sizeof(unsigned int))) != cudaSuccess ||
         (e = cudaMemsetAsync(h->pull_counter, 0, sizeof(unsigned int), h->stream)) != cudaSuccess ||
-        (e = cudaMalloc(&h->done_counter, 2 * sizeof(unsigned int))) != cudaSuccess ||
-        (e = cudaMemsetAsync(h->done_counter, 0, 2 * sizeof(unsigned int), h->stream)) != cudaSuccess ||
+        (e = cudaMalloc(&h->done_counter, kRing_ * sizeof(unsigned int))) != cudaSuccess ||
+        (e = cudaMemsetAsync(h->done_counter, 0, kRing_ * sizeof(unsigned int), h->stream)) != cudaSuccess ||
         (e = upload_tables<double>(h->td, h->stream)) != cudaSuccess ||
         (e = upload_tables<float>(h->tf, h->stream)) != cudaSuccess ||
         (e = configure_all<double>(&h->occ_d)) != cudaSuccess ||
@@ -1156,9 +1175,10 @@ int caf_b200_sync(caf_b200_handle h) {
 
 uint64_t caf_b200_launch_count(caf_b200_handle h) { return h ? h->launches : 0; }
 
-int caf_b200_set_overlap(caf_b200_handle h, int on) {
+int caf_b200_set_overlap(caf_b200_handle h, int mode) {
     if (!h) return fail(CAF_B200_EINVAL, "null handle");
-    h->overlap_ok = on != 0;
+    if (mode < 0 || mode > 4) return fail(CAF_B200_EINVAL, "overlap mode must be 0 (off), 1 (full grids) or 2..4 (that many launches share the GPU)");
+    h->overlap = mode;
     h->prev_launch_no = ~0ull;
     h->prev_valid = 0;
     return CAF_B200_OK;

@@ -88,17 +88,20 @@ uint64_t caf_b200_launch_count(caf_b200_handle h);
 /* Per-kernel device times of the LAST surface/batch call on this handle, in milliseconds, measured with
  * CUDA events on the handle's stream.  Off by default (the events cost a little); when on, every
  * surface/batch call records spectrum (FFT(s1)), rows (the fused row kernel) and peak (find_peak). */
-/* Overlap of consecutive single-pair device launches (caf_b200_batch_*_dev with p = 1), OFF unless switched on.  Such a
- * launch is issued with programmatic stream serialisation; with overlap on, when it directly follows another one on the
- * handle, both fill the GPU (d >= number of SMs) and the library finds every buffer of this launch disjoint from those
- * of the previous TWO launches wherever one side writes, it does not wait for the grid before it: its CTAs start their
- * rows on the SMs that grid has already left (400 rows on 148 SMs leave 44 SMs a row early: a stream of independent
- * surfaces runs 12 % faster, 37.9 -> 33.3 us each).  Results are bit-identical.  Switching it on is the caller's promise
- * that (a) nothing it enqueues on the handle's stream between two library calls produces data the later call reads, and
- * (b) it does not rely on a launch being complete before the launch after it has begun (results are complete, in order,
- * when the stream reaches whatever follows the last launch: an event, a copy, a synchronise).  Launches that alias their
- * predecessors' buffers, smaller grids, host-pointer calls and everything else keep full stream order. */
-int caf_b200_set_overlap(caf_b200_handle h, int on);
+/* Overlap of consecutive single-pair device launches (caf_b200_batch_*_dev with p = 1): mode 0 = off (the default).
+ * Such a launch is issued with programmatic stream serialisation.  With mode >= 1, when it directly follows another one
+ * on the handle, has at least one row per SM, and the library finds every buffer of this launch disjoint from those of the
+ * previous SEVEN launches wherever one side writes, it does not wait for the grid before it: its CTAs start their rows on
+ * whatever SMs are free.  mode 1 keeps one CTA per SM (400 rows on 148 SMs leave 44 SMs a row early: 37.9 -> 33.4 us per
+ * surface).  mode n = 2..4 gives an overlapped launch only ceil(SMs / n) CTAs, so that about n launches share the GPU and
+ * every CTA spreads its set-up over n times as many rows: 29.1 / 27.9 / 27.2 us per surface for n = 2 / 3 / 4 -- at the
+ * price of latency, a single surface then takes ~n x 30 us from launch to completion.  Results are bit-identical in every
+ * mode.  Switching it on is the caller's promise that (a) nothing it enqueues on the handle's stream between two library
+ * calls produces data the later call reads, and (b) it does not rely on a launch being complete before the next one has
+ * begun (results are complete, in order, when the stream reaches whatever follows the last launch: an event, a copy, a
+ * synchronise).  Launches that alias their predecessors' buffers, problems with fewer rows than SMs, host-pointer calls
+ * and everything else keep full stream order. */
+int caf_b200_set_overlap(caf_b200_handle h, int mode);
 int caf_b200_set_profiling(caf_b200_handle h, int on);
 int caf_b200_last_kernel_ms(caf_b200_handle h, float* spectrum_ms, float* rows_ms, float* peak_ms);
 /* FMA-pipe peak probe used as the roofline denominator: runs a dependent-FMA kernel on every SM and

@@ -20,7 +20,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-def measure(lib, h, stream, dev, *, pairs=320, surfaces=8, steps=300, warmup=40, f32=False, overlap=True):
+def measure(lib, h, stream, dev, *, pairs=320, surfaces=8, steps=300, warmup=40, f32=False, overlap=4):
     """Run the rotation on an existing handle / stream and return the result dict (bench.py calls this too)."""
     import ctypes as C
     import numpy as np
@@ -62,7 +62,7 @@ def measure(lib, h, stream, dev, *, pairs=320, surfaces=8, steps=300, warmup=40,
 
     # consecutive steps touch disjoint buffers (different pair, different surface buffer, different peak slots) and nothing
     # else is enqueued between them: the library may let a launch start on the SMs its predecessor has already left
-    lib.caf_b200_set_overlap(h.raw, 1 if overlap else 0)
+    lib.caf_b200_set_overlap(h.raw, int(overlap))
     for k in range(warmup):
         step(k)
     torch.cuda.synchronize()
@@ -92,7 +92,7 @@ def measure(lib, h, stream, dev, *, pairs=320, surfaces=8, steps=300, warmup=40,
     assert lib.caf_b200_probe_fma_tflops(h.raw, 0 if f32 else 1, C.byref(tf)) == 0
     flops = D * (10.0 * N * np.log2(N) + 15.0 * N)
     return {
-        "method": "working set > L2, one event pair around K back-to-back launches" + (", independent launches overlap (caf_b200_set_overlap)" if overlap else ", launches serialised"),
+        "method": "working set > L2, one event pair around K back-to-back launches" + (f", independent launches overlap (caf_b200_set_overlap({int(overlap)}))" if overlap else ", launches serialised"),
         "dtype": sfx, "us_per_surface": us, "cells_per_s": D * N / (us * 1e-6), "steps": steps, "warmup": warmup,
         "pairs": pairs, "surface_buffers": surfaces,
         "working_set_mb": (pairs * 2 * L * needles.itemsize + surfaces * D * N * surfs[0].element_size()) / 1e6,
@@ -109,6 +109,7 @@ def main():
     ap.add_argument("--surfaces", type=int, default=8)
     ap.add_argument("--f32", action="store_true")
     ap.add_argument("--no-overlap", action="store_true")
+    ap.add_argument("--overlap", type=int, default=4, help="caf_b200_set_overlap mode: 1 = full grids, n >= 2 = n launches share the GPU")
     args = ap.parse_args()
 
     import torch
@@ -120,7 +121,7 @@ def main():
     lib = _lib.load()
     h = Handle(0, stream=stream.cuda_stream)
     line = measure(lib, h, stream, dev, pairs=args.pairs, surfaces=args.surfaces, steps=args.steps,
-                   warmup=args.warmup, f32=args.f32, overlap=not args.no_overlap)
+                   warmup=args.warmup, f32=args.f32, overlap=0 if args.no_overlap else args.overlap)
     print(json.dumps(line))
     if line["peaks_off"]:
         sys.exit(1)

@@ -6,6 +6,7 @@ import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
 from caf_cookoff_b200 import Handle, _lib, bench_shifts, generate as G
 K = int(sys.argv[1]) if len(sys.argv) > 1 else 20000
+MODE = int(sys.argv[2]) if len(sys.argv) > 2 else 4
 P, S, L, N, FS = 96, 8, 4096, 8192, 48000
 dev = torch.device("cuda", 0); stream = torch.cuda.Stream(device=dev); torch.cuda.set_stream(stream)
 lib = _lib.load(); h = Handle(0, stream=stream.cuda_stream)
@@ -19,7 +20,7 @@ nd = torch.from_numpy(needles).to(dev); hd = torch.from_numpy(hays).to(dev)
 freqs = bench_shifts(); D = freqs.size; fd = torch.from_numpy(freqs).to(dev)
 
 def run(overlap, k_total):
-    lib.caf_b200_set_overlap(h.raw, 1 if overlap else 0)
+    lib.caf_b200_set_overlap(h.raw, MODE if overlap else 0)
     surfs = [torch.zeros((D, N), dtype=torch.float64, device=dev) for _ in range(S)]
     rv = torch.zeros((P, D), dtype=torch.float64, device=dev); ri = torch.zeros((P, D), dtype=torch.int64, device=dev)
     pk = torch.zeros((P, 4), dtype=torch.int64, device=dev)
@@ -39,5 +40,5 @@ K = max(lcm, K // lcm * lcm)
 want = run(False, lcm)
 got = run(True, K)
 ok = all(np.array_equal(a, b) for a, b in zip(want[0], got[0])) and all(np.array_equal(want[j], got[j]) for j in (1, 2, 3))
-print(f"overlap soak: {K} overlapping launches, {P} pairs, {S} surface buffers: {'bit-identical to the serialised run' if ok else 'MISMATCH'}")
+print(f"overlap soak (mode {MODE}): {K} overlapping launches, {P} pairs, {S} surface buffers: {'bit-identical to the serialised run' if ok else 'MISMATCH'}")
 sys.exit(0 if ok else 1)

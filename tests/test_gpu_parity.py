@@ -238,12 +238,14 @@ def test_device_loader_matches_read_file_c64(tmp_path):
 
 
 def test_overlapping_launches_give_the_serialised_bits():
-    """caf_b200_set_overlap: a single-pair device launch that directly follows another one and shares no buffer with it
-    (where either writes) does not wait for it -- its CTAs start on the SMs the earlier launch has left.  Launch-private
-    state (H publication buffer and flags, the find_peak ticket) is double-buffered by launch parity.  Over a long mixed
-    sequence -- rotating pairs, three surface buffers, grids of 7 / 147 / 148 CTAs, 1-3 rows per CTA, and launches that DO
-    alias their predecessor's outputs and must therefore serialise -- every row peak, every peak and the final content
-    of every surface buffer equals what the same sequence gives with overlap switched off."""
+    """caf_b200_set_overlap: a single-pair device launch that directly follows another one and shares no buffer with the
+    seven launches before it (where either side writes) does not wait for the grid before it; in modes 2..4 it also
+    uses only a half / third / quarter of the SMs so that several launches share the GPU.  Launch-private state (H
+    publication buffer and flags, the find_peak ticket) lives in a ring indexed by launch number.  Over a long mixed
+    sequence -- rotating pairs, three surface buffers (so every fourth launch aliases and must serialise), grids of
+    2 / 7 / 147 CTAs that never overlap, and launches that deliberately reuse their predecessor's outputs -- every row
+    peak, every peak and the final content of every surface buffer equals what the same sequence gives with overlap off,
+    in every mode."""
     import torch
     from caf_cookoff_b200 import bench_shifts
     from oracle import oracle as O
@@ -266,28 +268,35 @@ def test_overlapping_launches_give_the_serialised_bits():
         alias_prev = (k % 9 == 5)                      # same surface buffer and peak slot as the launch before: must serialise
         plan.append((k % len(cases), d, alias_prev))
 
-    def run(overlap):
-        lib.caf_b200_set_overlap(h.raw, 1 if overlap else 0)
-        surfs = [torch.zeros((400, 2 * L), dtype=torch.float64, device=dev) for _ in range(3)]
+    def run(overlap, nbuf=3):
+        lib.caf_b200_set_overlap(h.raw, int(overlap))
+        surfs = [torch.zeros((400, 2 * L), dtype=torch.float64, device=dev) for _ in range(nbuf)]
         rv = torch.zeros((K, 400), dtype=torch.float64, device=dev); ri = torch.zeros((K, 400), dtype=torch.int64, device=dev)
         pk = torch.zeros((K, 4), dtype=torch.int64, device=dev)
         with torch.cuda.stream(stream):
             sb, slot = 0, 0
             for k, (pi, d, alias_prev) in enumerate(plan):
                 if not alias_prev:
-                    sb, slot = (sb + 1) % 3, k
+                    sb, slot = (sb + 1) % nbuf, k
                 rc = lib.caf_b200_batch_f64_dev(h.raw, nd[pi].data_ptr(), hd[pi].data_ptr(), 1, L, fd.data_ptr(), d, FS,
                                                 surfs[sb].data_ptr(), rv[slot].data_ptr(), ri[slot].data_ptr(), pk[slot].data_ptr())
                 assert rc == 0, lib.caf_b200_last_error()
         torch.cuda.synchronize()
         return [s_.cpu().numpy() for s_ in surfs], rv.cpu().numpy(), ri.cpu().numpy(), pk.cpu().numpy()
 
-    want = run(False)
-    for rep in range(3):
-        got = run(True)
+    want = run(0)
+    for rep, mode in enumerate((1, 2, 3, 4, 4)):
+        got = run(mode)
         for a_, b_ in zip(want[0], got[0]):
             assert np.array_equal(a_, b_), rep
         assert np.array_equal(want[1], got[1]) and np.array_equal(want[2], got[2]) and np.array_equal(want[3], got[3]), rep
+    # nine surface buffers: no launch aliases any of the seven before it, the overlap runs as deep as the mode allows
+    want9 = run(0, 9)
+    for mode in (1, 4, 4):
+        got = run(mode, 9)
+        for a_, b_ in zip(want9[0], got[0]):
+            assert np.array_equal(a_, b_), mode
+        assert np.array_equal(want9[1], got[1]) and np.array_equal(want9[2], got[2]) and np.array_equal(want9[3], got[3]), mode
     # and the serialised reference itself is the known answer of each pair on the full grid
     for k, (pi, d, alias_prev) in enumerate(plan):
         if d == 400 and not alias_prev and not (k + 1 < K and plan[k + 1][2]):
