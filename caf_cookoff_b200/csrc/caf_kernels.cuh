@@ -99,12 +99,13 @@ struct RowArgs {
     unsigned int pull_n16;          // 16-byte chunks
     unsigned int* pull_counter;
     unsigned int pull_target;       // counter value once every pulling warp of THIS launch has arrived
-    // kSurface, P == 1: bit 0 = this launch shares no buffer with the previous TWO launches on the stream where either side
-    // writes -- the host has compared the ranges -- so it does not wait for the grid before it: its CTAs start their rows
-    // on the SMs that grid has already left (400 rows on 148 SMs: 44 CTAs own two rows instead of three and leave a row
-    // early).  Only full grids (one CTA per SM) are let through: a CTA of launch k can then be placed only after every CTA
-    // of k-1 has started, i.e. after every CTA of k-2 has exited, so the overlap never reaches further back than the two
-    // launches whose buffers were checked; anything older finished issuing its stores a whole launch (> 30 us) earlier.
+    // kSurface, P == 1: bit 0 = this launch shares no buffer with the previous SEVEN launches on the stream where either
+    // side writes -- the host has compared the ranges -- so it does not wait for the grid before it: its CTAs start their
+    // rows on whatever SMs are free, and the host may give it a fraction of the SMs so that several launches share the
+    // GPU (caf_b200_set_overlap).  A CTA of launch k can be placed only after every CTA of k-1 ... k-7 has started -- at
+    // least 7 x 37 CTAs on 148 SMs -- so 112 of them must have run to completion while a CTA of k-8 was still running:
+    // the overlap does not reach further back than the launches whose buffers were compared.  Launch-private state (H
+    // buffer, flags, find_peak ticket) lives in a ring of eight slots chosen by the host.
     unsigned int flags;
     long long* trace;       // CAF_TRACE builds only: [cta][warp][8 items][32 slots] clock64 stamps
 };
