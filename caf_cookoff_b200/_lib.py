@@ -25,7 +25,7 @@ NVCC_FLAGS = [
 
 
 def _sources():
-    return [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh"))] + [HEADER]
+    return [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh", ".hpp"))] + [HEADER]
 
 
 def needs_build() -> bool:

@@ -24,6 +24,7 @@
 #include "../../include/caf_b200.h"
 #include "caf_kernels.cuh"
 #include "caf_large.cuh"
+#include "overlap_policy.hpp"
 
 namespace {
 
@@ -154,12 +155,9 @@ struct caf_b200_handle_s {
     // n >= 2: such a launch also uses only ceil(SMs / n) CTAs, so that ~n launches share the GPU and every CTA amortises
     // its set-up over n times as many rows.
     int overlap = 0;
-    struct Range { const char* p; size_t n; };
-    static constexpr int kHist = kRing - 1;          // launches whose buffers are compared (the newest first)
-    Range prev_in[kHist][3] = {}, prev_out[kHist][6] = {};
-    int prev_valid = 0;                              // how many of them are valid
-    long long prev_grid = 0;                         // the grid of the launches in the history (one size only)
-    unsigned long long prev_launch_no = ~0ull;       // value of `launches` right after the previous overlappable launch
+    using Range = caf_host::Range;
+    static constexpr int kHist = kRing - 1;          // launches whose buffers are compared (overlap_policy.hpp)
+    caf_host::OverlapHistory<kHist> hist;
     // small single-pair host calls: the kernel pulls its inputs out of pinned host memory itself (RowArgs::pull_*)
     unsigned int* pull_counter = nullptr;       // device word the grid meets on, monotonic
     unsigned int pull_total = 0;                // its value after every launch issued so far
@@ -618,7 +616,7 @@ int run_batch_dev(caf_b200_handle h, const caf::cx<T>* needles, const caf::cx<T>
     if (p == 1 && d > 1 && h->overlap > 0 && !h->pull_src && !h->seq_ptr && !prof) {
         const int occ_ = std::is_same<T, double>::value ? h->occ_d : h->occ_f;
         const long long full = (long long)h->sm_count * occ_;
-        const long long want = h->overlap >= 2 ? (full + h->overlap - 1) / h->overlap : full;      // CTAs of an overlapped launch
+        const long long want = caf_host::overlapped_grid(full, h->overlap);      // CTAs of an overlapped launch
         if ((long long)d >= full) {               // (smaller problems keep full stream order)
             overlappable = true;
             cur_in[0] = {(const char*)needles, sizeof(cx<T>) * l}; cur_in[1] = {(const char*)hays, sizeof(cx<T>) * l};
@@ -627,21 +625,8 @@ int run_batch_dev(caf_b200_handle h, const caf::cx<T>* needles, const caf::cx<T>
             cur_out[1] = {(const char*)rv, rv ? sizeof(T) * d : 0}; cur_out[2] = {(const char*)ri, ri ? sizeof(unsigned long long) * d : 0};
             cur_out[3] = {(const char*)peaks, peaks ? sizeof(PeakOut) : 0};
             cur_out[4] = {(const char*)h->pack_words, h->pack_words ? (size_t)32 : (size_t)0};
-            auto hit = [](const caf_b200_handle_s::Range& x, const caf_b200_handle_s::Range& y) {
-                return x.n && y.n && x.p < y.p + y.n && y.p < x.p + x.n;
-            };
-            if (h->prev_launch_no != h->launches) h->prev_valid = 0;          // something else ran in between
-            bool indep = h->prev_valid > 0;
-            for (int q = 0; indep && q < h->prev_valid; ++q) {
-                for (int i = 0; indep && i < 6; ++i) {
-                    for (int j = 0; indep && j < 6; ++j) if (hit(cur_out[i], h->prev_out[q][j])) indep = false;     // write after write
-                    for (int j = 0; indep && j < 3; ++j) if (hit(cur_out[i], h->prev_in[q][j])) indep = false;      // write after read
-                }
-                for (int i = 0; indep && i < 3; ++i)
-                    for (int j = 0; indep && j < 6; ++j) if (hit(cur_in[i], h->prev_out[q][j])) indep = false;      // read after write
-            }
+            const bool indep = h->hist.independent(cur_in, cur_out, h->launches);
             if (indep) { a.flags |= 1u; grid_cap = want; }
-            else h->prev_valid = 0;      // this launch waits for everything before it (full grid): the history restarts here
         }
     }
     if (p == 1 && d > 1) {                        // one pair over many CTAs: CTA 0 publishes H, the rest consume it
@@ -678,20 +663,8 @@ int run_batch_dev(caf_b200_handle h, const caf::cx<T>* needles, const caf::cx<T>
     // one fused launch: per pair FFT(s1) -> TMEM, then per row shift -> FFT -> xH -> IFFT -> |.|^2 -> argmax
     if (l == (size_t)kL0) CK((launch_rows<T, kSurface, true>(h, a, (long long)p * (long long)d, grid_cap)));
     else CK((launch_rows<T, kSurface, false>(h, a, (long long)p * (long long)d, grid_cap)));
-    if (overlappable) {
-        // a history holds launches of ONE grid size (the argument above counts CTAs): a launch that waited starts it afresh
-        for (int q = caf_b200_handle_s::kHist - 1; q > 0; --q) {
-            for (int i = 0; i < 3; ++i) h->prev_in[q][i] = h->prev_in[q - 1][i];
-            for (int i = 0; i < 6; ++i) h->prev_out[q][i] = h->prev_out[q - 1][i];
-        }
-        for (int i = 0; i < 3; ++i) h->prev_in[0][i] = cur_in[i];
-        for (int i = 0; i < 6; ++i) h->prev_out[0][i] = cur_out[i];
-        h->prev_valid = h->prev_valid < caf_b200_handle_s::kHist ? h->prev_valid + 1 : caf_b200_handle_s::kHist;
-        h->prev_launch_no = h->launches;
-    } else {
-        h->prev_launch_no = ~0ull;
-        h->prev_valid = 0;
-    }
+    if (overlappable) h->hist.push(cur_in, cur_out, h->launches, !(a.flags & 1u));
+    else h->hist.reset();
     if (a.pull_src) h->pull_total = a.pull_target;      // only a launch that was accepted moves the meeting point
     if (a.done_counter) h->done_total[a.epoch % (unsigned int)caf_b200_handle_s::kRing] = a.done_last + 1u;
     if (prof) CK(cudaEventRecord(h->ev[2], h->stream));
@@ -1179,8 +1152,7 @@ int caf_b200_set_overlap(caf_b200_handle h, int mode) {
     if (!h) return fail(CAF_B200_EINVAL, "null handle");
     if (mode < 0 || mode > 4) return fail(CAF_B200_EINVAL, "overlap mode must be 0 (off), 1 (full grids) or 2..4 (that many launches share the GPU)");
     h->overlap = mode;
-    h->prev_launch_no = ~0ull;
-    h->prev_valid = 0;
+    h->hist.reset();
     return CAF_B200_OK;
 }
 int caf_b200_set_profiling(caf_b200_handle h, int on) {

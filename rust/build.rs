@@ -13,7 +13,7 @@ fn main() {
         return;
     }
     let csrc = PathBuf::from(env::var("CARGO_MANIFEST_DIR").unwrap()).join("../caf_cookoff_b200/csrc");
-    for f in ["caf_b200.cu", "caf_kernels.cuh", "caf_large.cuh", "fft16.cuh"].iter() {
+    for f in ["caf_b200.cu", "caf_kernels.cuh", "caf_large.cuh", "fft16.cuh", "overlap_policy.hpp"].iter() {
         println!("cargo:rerun-if-changed={}", csrc.join(f).display());
     }
     println!("cargo:rerun-if-changed=../include/caf_b200.h");
