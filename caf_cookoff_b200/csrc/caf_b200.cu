@@ -155,6 +155,7 @@ struct caf_b200_handle_s {
     // n >= 2: such a launch also uses only ceil(SMs / n) CTAs, so that ~n launches share the GPU and every CTA amortises
     // its set-up over n times as many rows.
     int overlap = 0;
+    bool overlap_killed = false;            // CAF_B200_OVERLAP=0 in the environment at handle creation
     using Range = caf_host::Range;
     static constexpr int kHist = kRing - 1;          // launches whose buffers are compared (overlap_policy.hpp)
     caf_host::OverlapHistory<kHist> hist;
@@ -1079,6 +1080,7 @@ static int create_impl(int device, bool own_stream, void* cuda_stream, caf_b200_
     if (const char* e_ = getenv("CAF_B200_PIPELINE")) h->allow_pipeline = e_[0] != '0';
     if (const char* e_ = getenv("CAF_B200_PEAK_ZEROCOPY")) h->peak_zero_copy = e_[0] != '0';
     if (const char* e_ = getenv("CAF_B200_PULL")) h->allow_pull = e_[0] != '0';
+    if (const char* e_ = getenv("CAF_B200_OVERLAP")) h->overlap_killed = e_[0] == '0';
     if (const char* e_ = getenv("CAF_B200_GATHER_AHEAD")) h->gather_ahead = atoi(e_);
 
     if (!own_stream) { h->stream = (cudaStream_t)cuda_stream; h->own_stream = false; }   // 0 = legacy default stream
@@ -1151,7 +1153,7 @@ uint64_t caf_b200_launch_count(caf_b200_handle h) { return h ? h->launches : 0; 
 int caf_b200_set_overlap(caf_b200_handle h, int mode) {
     if (!h) return fail(CAF_B200_EINVAL, "null handle");
     if (mode < 0 || mode > 4) return fail(CAF_B200_EINVAL, "overlap mode must be 0 (off), 1 (full grids) or 2..4 (that many launches share the GPU)");
-    h->overlap = mode;
+    h->overlap = h->overlap_killed ? 0 : mode;      // CAF_B200_OVERLAP=0: the switch is accepted and ignored
     h->hist.reset();
     return CAF_B200_OK;
 }

@@ -27,6 +27,7 @@
  *    CAF_B200_PEAK_ZEROCOPY=0  single-pair host calls: copy the peak back instead of storing it into pinned host memory
  *    CAF_B200_PULL=0         single-pair host calls: one H2D copy in front of the kernel instead of the kernel's own CTAs
  *                            reading the pinned input block across PCIe
+ *    CAF_B200_OVERLAP=0      caf_b200_set_overlap is accepted and ignored: every launch keeps full stream order
  *    CAF_B200_P2P=0          cross-rank find_peak by ncclAllGather instead of the peer-memory mailbox kernel (read at comm creation)
  *    CAF_B200_NCCL_LIB=<so>  which libnccl to dlopen for caf_b200_comm_* (default: the loaded one, then libnccl.so.2)
  *
