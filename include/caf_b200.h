@@ -101,7 +101,8 @@ uint64_t caf_b200_launch_count(caf_b200_handle h);
  * calls produces data the later call reads, and (b) it does not rely on a launch being complete before the next one has
  * begun (results are complete, in order, when the stream reaches whatever follows the last launch: an event, a copy, a
  * synchronise).  Launches that alias their predecessors' buffers, problems with fewer rows than SMs, host-pointer calls
- * and everything else keep full stream order. */
+ * and everything else keep full stream order -- so a caller who wants the overlap sustained rotates its output buffers
+ * (surface, row peaks, peak) over at least eight sets; inputs may be shared freely, they are only read. */
 int caf_b200_set_overlap(caf_b200_handle h, int mode);
 int caf_b200_set_profiling(caf_b200_handle h, int on);
 int caf_b200_last_kernel_ms(caf_b200_handle h, float* spectrum_ms, float* rows_ms, float* peak_ms);
